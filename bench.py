@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the data-parallel train step (BASELINE.json metric: images/sec, device-timed, max over ranks).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--arch efficientnet_b0] [--batch 256]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the reference's arithmetic (oracle port) on the host cores
+
+One "step" = one full train iteration of the reference's hot loop (dfd/runners/train.py:621-637) on a synthetic
+batch: forward, 2-class CE (sigmoid-BCE) loss + top-1, zero_grad, backward, [gradient all-reduce], SGD-nesterov
+update, on per-GPU batch 256 x 3 x 224 x 224 (weak scaling).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# algorithmic work per image per train step (SURVEY.md 8d / BASELINE.md section 3)
+WORK = {
+    "efficientnet_b0": dict(gflop=2.286, act_mb=68.00, bound="hbm", res=224),
+    "efficientnet_b4": dict(gflop=26.258, act_mb=495.94, bound="hbm", res=380),
+    "resnet50": dict(gflop=24.287, act_mb=108.44, bound="tensor", res=224),
+    "resnet18": dict(gflop=10.645, act_mb=23.03, bound="tensor", res=224),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------------
+# algorithmic bytes of one launch of each kernel family (ideal: every operand once, 2 B / element)
+# ---------------------------------------------------------------------------------------------------
+def op_bytes(name, a):
+    if name in ("dfd_gemm_tn",):
+        M, N, K = a[3], a[4], a[5]
+        return 2 * (M * K + N * K + M * N)
+    if name == "dfd_gemm_tn_mma":
+        M, N, K = a[4], a[5], a[6]
+        return 2 * (M * K + N * K + M * N)
+    if name == "dfd_gemm_wgrad_mma":
+        M, Nw, Kw = a[3], a[4], a[5]
+        return 2 * M * (Nw + Kw) + 4 * Nw * Kw
+    if name == "dfd_dwconv_fwd":
+        N, H, W, C, k, s = a[5:11]
+        return 2 * N * C * (H * W + ((H + s - 1) // s) * ((W + s - 1) // s))
+    if name == "dfd_dwconv_dgrad":
+        N, H, W, C, k, s, mode = a[13:20]
+        o = ((H + s - 1) // s) * ((W + s - 1) // s)
+        return 2 * N * C * ((2 * o if a[2] else o) + (2 if mode == 1 else 1) * H * W + (H * W if a[11] else 0))
+    if name == "dfd_dwconv_wgrad":
+        N, H, W, C, k, s = a[9:15]
+        o = ((H + s - 1) // s) * ((W + s - 1) // s)
+        return 2 * N * C * (H * W + (2 * o if a[5] else o))
+    if name in ("dfd_bn_act",):
+        n, hw, C = a[6], a[7], a[8]
+        return 2 * n * hw * C * (2 + (1 if a[4] else 0))
+    if name in ("dfd_pool", "dfd_colstats"):
+        idx = 4 if name == "dfd_pool" else 1
+        n, hw, C = a[idx], a[idx + 1], a[idx + 2]
+        return 2 * n * hw * C
+    if name in ("dfd_bn_bwd_reduce", "dfd_se_bwd_reduce"):
+        n, hw, C = a[5], a[6], a[7]
+        return 2 * n * hw * C * 2
+    if name == "dfd_bn_bwd_apply":
+        n, hw, C = a[7], a[8], a[9]
+        return 2 * n * hw * C * 3
+    if name == "dfd_act_bwd":
+        n, hw, C = a[9], a[10], a[11]
+        return 2 * n * hw * C * (3 if a[0] else 2)
+    if name == "dfd_add_inplace":
+        return 2 * a[2] * 3
+    if name == "dfd_stem_fwd":
+        N, Cin, H, W, Cout = a[3:8]
+        return 2 * N * (Cin * H * W + Cout * ((H + 1) // 2) * ((W + 1) // 2))
+    if name == "dfd_stem_wgrad":
+        N, Cin, H, W, Cout = a[7:12]
+        return 2 * N * (Cin * H * W + 2 * Cout * ((H + 1) // 2) * ((W + 1) // 2))
+    return 0
+
+
+def profile_plan(trainer, torch):
+    """Per-launch CUDA-event timing of one eager step (each kernel bracketed on the launching stream)."""
+    e = trainer.engine
+    stream = torch.cuda.current_stream()
+    st = stream.cuda_stream
+    e.zero_step_scratch(st, grads=True)
+    fam = {}
+    for ops, training in ((e.fwd_ops, True), (e.bwd_ops, True)):
+        for op in ops:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(stream)
+            e._run([op], st, training)
+            t1.record(stream)
+            t1.synchronize()
+            ms = t0.elapsed_time(t1)
+            f = fam.setdefault(op[1], dict(ms=0.0, bytes=0, launches=0))
+            f["ms"] += ms
+            f["bytes"] += op_bytes(op[1], op[2])
+            f["launches"] += 1
+        if ops is e.fwd_ops:
+            e.head(True, stream=st)
+    return fam
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from deepfake_detection_b200.trainer import Trainer
+    from oracle.weights import synth_state
+    from deepfake_detection_b200.arch import get_spec
+    arch, B = args.arch, args.batch
+    res = args.res or WORK[arch]["res"]
+    lr = 0.0001 * B * world          # args.lr = batch * world * basic_lr (train.py:814), basic_lr small for stability
+    tr = Trainer(arch, B, res, res, dtype=args.dtype, opt="sgd", lr=lr, momentum=0.9, weight_decay=1e-4,
+                 use_graph=not args.no_graph, gemm_impl=args.gemm)
+    spec = get_spec(arch)
+    torch.manual_seed(42)
+    tr.load_state_dict({k: v for k, v in synth_state(spec, seed=42).items()})
+    if tr.reducer is not None:
+        tr.reducer.broadcast_parameters()
+    e = tr.engine
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    x = torch.randn(B, spec.in_chans, res, res, device="cuda", generator=g)
+    y = torch.randint(0, 2, (B,), device="cuda", generator=g)
+    e.set_input(x)
+    e.set_target(y)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        tr.step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        tr.step_resident()
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    loss_final = float(e.loss)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+
+    # ---- end to end through the public API with HOST buffers (H2D of the batch + D2H of the loss every step) ----
+    xh = torch.empty(B, spec.in_chans, res, res, dtype=e.tdtype).pin_memory()
+    xh.copy_(x.to(e.tdtype))
+    yh = torch.empty(B, dtype=torch.int64).pin_memory()
+    yh.copy_(y)
+    for _ in range(3):
+        out = tr.train_step_host(xh, yh)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, args.steps // 2)
+    e0.record()
+    for _ in range(e2e_steps):
+        out = tr.train_step_host(xh, yh)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    img_s = B * world * args.steps / (ms / 1e3)
+    e2e_img_s = B * world * e2e_steps / (e2e_ms / 1e3)
+    w = WORK[arch]
+    fam = profile_plan(tr, torch)
+    tot_ms = sum(f["ms"] for f in fam.values())
+    top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    top_name, tf = top
+    ach = tf["bytes"] / (tf["ms"] / 1e3) / 1e9 if tf["ms"] > 0 else 0.0
+    roofline = dict(bound="hbm", kernel=top_name, achieved=round(ach, 1), peak=peaks["hbm_gbs"], unit="GB/s",
+                    frac=round(ach / peaks["hbm_gbs"], 4), traffic=None, peak_source=peaks["source"],
+                    kernel_share_of_step=round(tf["ms"] / tot_ms, 4), launches=tf["launches"],
+                    step_frac_of_ideal_fusion_roofline=round(img_s / world * w["act_mb"] * 1e6 / (peaks["hbm_gbs"] * 1e9), 4),
+                    step_frac_of_tensor_roofline=round(img_s / world * w["gflop"] * 1e9 / (peaks["tf_sustained"] * 1e12), 4),
+                    families={k: dict(ms=round(v["ms"], 3), gbs=round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1), n=v["launches"])
+                              for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:8]})
+    cpu = cpu_baseline(arch, sample_steps=args.cpu_steps) if world == 1 and not args.no_cpu else None
+    n_launch = e.n_launch["fwd"] + e.n_launch["bwd"] + 3 + 4   # + head, optimizer groups, transposes, memsets
+    line = dict(metric="images/sec (device-timed, max over ranks) %s 3x%dx%d train step" % (arch, res, res),
+                value=round(img_s, 1), unit="images/sec", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=round(ms / args.steps, 4), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype=args.dtype, data="synthetic",
+                config=dict(workload="%s bf16 train step, synthetic 3x%dx%d, per-GPU batch %d (BASELINE configs[1]%s)" % (
+                    arch, res, res, B, "; DDP weak scaling" if world > 1 else ""), global_batch=B * world,
+                    optimizer="sgd-nesterov", l2_policy="working set (activations ~6 GB/step) far exceeds the 126 MB L2",
+                    cuda_graph=tr._graph is not None, gemm=args.gemm, loss_final=loss_final),
+                roofline=roofline, cpu_baseline=cpu,
+                e2e=dict(value=round(e2e_img_s, 1), unit="images/sec",
+                         h2d_bytes_per_step=int(xh.numel() * xh.element_size() + yh.numel() * 8), d2h_bytes_per_step=16),
+                gpu_launches=n_launch * args.steps, clocks=clocks)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(arch, sample_steps=4, batch=None, world=1):
+    """The reference's arithmetic (oracle port: torch fp32 CPU, reference module semantics) timed on the host cores."""
+    import torch
+    from deepfake_detection_b200.arch import get_spec
+    from oracle import train as OT
+    from oracle.weights import synth_batch, synth_state
+    spec = get_spec(arch)
+    res = WORK[arch]["res"]
+    b = batch or {"efficientnet_b0": 32, "efficientnet_b4": 4, "resnet50": 16, "resnet18": 8}[arch]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth_state(spec, seed=42)
+    opt = OT.OptState(kind="sgd", lr=0.01, momentum=0.9, weight_decay=1e-4)
+    x, y = synth_batch(b, 3, res, res, seed=1234)
+    OT.train_step(spec, sd, x, y, opt)
+    t0 = time.perf_counter()
+    for _ in range(sample_steps):
+        OT.train_step(spec, sd, x, y, opt)
+    dt = time.perf_counter() - t0
+    return dict(value=round(b * sample_steps / dt, 2), unit="images/sec", cores=torch.get_num_threads(), kind="port",
+                sample="%d train steps of %s fp32, batch %d, 3x%dx%d, torch CPU ops (oracle port of dfd.timm modules)" % (
+                    sample_steps, arch, b, res, res), ms_per_step=round(dt / sample_steps * 1e3, 1))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    arch = args.arch
+    res = WORK[arch]["res"]
+    steps = min(args.steps, 6)
+    cb = cpu_baseline(arch, sample_steps=steps)
+    line = dict(impl="reference", metric="images/sec (device-timed, max over ranks) %s 3x%dx%d train step" % (arch, res, res),
+                value=cb["value"], unit="images/sec", n_gpus=int(os.environ.get("WORLD_SIZE", "1")), steps=steps,
+                warmup=1, ms_per_step=cb["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", config=dict(workload="%s train step on host cores, bounded sample (%s)" % (arch, cb["sample"])),
+                cpu_baseline=cb, e2e=dict(value=cb["value"], unit="images/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native")
+    ap.add_argument("--arch", default="efficientnet_b0")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--res", type=int, default=0)
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--gemm", default="tc")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,541 @@
+// Channel-wise streaming kernels: BN statistics / finalise / apply, activation, SE gating, residual,
+// global pooling, and their backward passes.  All are HBM-bound single passes over NHWC tensors.
+//
+// Thread geometry ("row geometry"): blockDim = (V, RY) with V = C/8 channel vectors; a thread owns ONE
+// 8-channel vector (its per-channel parameters live in registers) and walks rows r = ty, ty+RY, ...
+// Consecutive threads therefore touch consecutive 16-byte chunks (a warp covers >=512 contiguous bytes,
+// spanning rows when V < 32 because the row pitch is exactly V*16 bytes).
+// grid = (row chunks, images): per-image parameters (SE gate, pooled gradients) index blockIdx.y.
+//
+// Reference semantics restated here:
+//   BN train/eval        torch.nn.BatchNorm2d as constructed at dfd/timm/models/efficientnet_blocks.py:154,166,280,287,300
+//   Swish fwd/bwd        dfd/timm/models/layers/activations.py:19-33
+//   SE gate, residual    dfd/timm/models/efficientnet_blocks.py:104-110, 343-346
+//   global average pool  dfd/timm/models/efficientnet.py:340-343
+#include "common.cuh"
+
+namespace {
+
+struct RowGeom {
+    dim3 block;
+    dim3 grid;
+    int rows_per_block;
+};
+
+// hw rows per image, n images; target enough CTAs to fill 148 SMs a few times over
+static RowGeom make_geom(int C, long long hw, int n, int target_blocks = 148 * 6) {
+    RowGeom g;
+    int V = C / 8;
+    int RY = V >= 256 ? 1 : (256 / V);
+    if (RY > 64) RY = 64;
+    if ((long long)RY > hw) RY = (int)hw;
+    if (RY < 1) RY = 1;
+    g.block = dim3(V, RY, 1);
+    long long chunks = (target_blocks + n - 1) / n;
+    long long max_chunks = (hw + RY - 1) / RY;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    long long rpb = (hw + chunks - 1) / chunks;
+    rpb = ((rpb + RY - 1) / RY) * RY;
+    chunks = (hw + rpb - 1) / rpb;
+    g.rows_per_block = (int)rpb;
+    g.grid = dim3((unsigned)chunks, (unsigned)n, 1);
+    return g;
+}
+
+// block-level reduction of per-thread 8-vectors across threadIdx.y, then `fn(channel, value)` once per channel
+// smem: float[RY][V*8] (caller provides dynamic smem)
+template <typename F>
+__device__ __forceinline__ void reduce_rows_and_emit(float* sm, const float* acc, F fn) {
+    const int V = blockDim.x, RY = blockDim.y;
+    const int C = V * 8;
+    float* mine = sm + (size_t)threadIdx.y * C + threadIdx.x * 8;
+#pragma unroll
+    for (int i = 0; i < 8; i++) mine[i] = acc[i];
+    __syncthreads();
+    const int tid = threadIdx.y * V + threadIdx.x;
+    for (int c = tid; c < C; c += V * RY) {
+        float s = 0.f;
+        for (int r = 0; r < RY; r++) s += sm[(size_t)r * C + c];
+        fn(c, s);
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// column statistics of a [M, C] tensor: dsum[c] += sum_m y, dsq[c] += sum_m y^2   (fp64 atomics)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void colstats_kernel(const T* __restrict__ y, long long hw, int rows_per_block,
+                                double* __restrict__ dsum, double* __restrict__ dsq) {
+    extern __shared__ float sm[];
+    const int V = blockDim.x, C = V * 8;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > hw) r1 = hw;
+    const T* base = y + (size_t)blockIdx.y * hw * C + threadIdx.x * 8;
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { s[i] = 0.f; q[i] = 0.f; }
+    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        float f[8];
+        unpack8<T>(ldg16(base + (size_t)r * C), f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    }
+    double* ps = stat_slot(dsum, C);
+    double* pq = stat_slot(dsq, C);
+    reduce_rows_and_emit(sm, s, [&](int c, float v) { atomicAdd(ps + c, (double)v); });
+    reduce_rows_and_emit(sm, q, [&](int c, float v) { atomicAdd(pq + c, (double)v); });
+}
+
+// ---------------------------------------------------------------------------------------------
+// BN finalise: batch statistics -> (scale, shift, mean, rstd) + running-stat EMA (unbiased var)
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* __restrict__ dsum, const double* __restrict__ dsq, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ nbt, float momentum, float eps, int training, int C,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && training && nbt) *nbt += 1;
+    if (c >= C) return;
+    float mean, var;
+    if (training) {
+        double m = stat_total(dsum, C, c) / count;
+        double v = stat_total(dsq, C, c) / count - m * m;
+        if (v < 0) v = 0;
+        mean = (float)m;
+        var = (float)v;
+        double unb = count > 1 ? v * count / (count - 1) : v;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    } else {
+        mean = running_mean[c];
+        var = running_var[c];
+    }
+    float rstd = rsqrtf(var + eps);
+    // rsqrtf is 2 ulp; refine once so that eval-mode folding matches torch's 1/sqrt to fp32 round-off
+    rstd = rstd * (1.5f - 0.5f * (var + eps) * rstd * rstd);
+    float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - mean * sc;
+    mean_out[c] = mean;
+    rstd_out[c] = rstd;
+}
+
+// ---------------------------------------------------------------------------------------------
+// out = act(scale*y + shift) [* gate[n,c]] [+ res] [relu after the add]
+// RES: 0 none, 1 add, 2 add then relu (ResNet block tail, resnet.py:172-173,243-244)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int ACT, bool GATE, int RES>
+__global__ void bn_act_kernel(const T* __restrict__ y, const float* __restrict__ scale,
+                              const float* __restrict__ shift, const float* __restrict__ gate,
+                              const T* __restrict__ res, T* __restrict__ out, long long hw, int rows_per_block) {
+    const int V = blockDim.x, C = V * 8;
+    const int c0 = threadIdx.x * 8;
+    float sc[8], sh[8], gt[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        sc[i] = scale ? scale[c0 + i] : 1.f;
+        sh[i] = shift ? shift[c0 + i] : 0.f;
+        gt[i] = GATE ? gate[(size_t)blockIdx.y * C + c0 + i] : 1.f;
+    }
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > hw) r1 = hw;
+    const size_t img = (size_t)blockIdx.y * hw * C + c0;
+    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        size_t off = img + (size_t)r * C;
+        float f[8];
+        unpack8<T>(ldg16(y + off), f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float u = fmaf(f[i], sc[i], sh[i]);
+            f[i] = act_fwd<ACT>(u);
+            if (GATE) f[i] *= gt[i];
+        }
+        if (RES) {
+            float g[8];
+            unpack8<T>(ldg16(res + off), g);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                f[i] += g[i];
+                if (RES == 2) f[i] = fmaxf(f[i], 0.f);
+            }
+        }
+        stg16(out + off, pack8<T>(f));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pooled[n,c] = mean_hw act(scale*y + shift)       (one CTA per image: deterministic, no atomics)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int ACT>
+__global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ scale,
+                            const float* __restrict__ shift, float* __restrict__ pooled, long long hw) {
+    extern __shared__ float sm[];
+    const int V = blockDim.x, C = V * 8;
+    const int c0 = threadIdx.x * 8;
+    float sc[8], sh[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        sc[i] = scale ? scale[c0 + i] : 1.f;
+        sh[i] = shift ? shift[c0 + i] : 0.f;
+        acc[i] = 0.f;
+    }
+    const T* base = y + (size_t)blockIdx.y * hw * C + c0;
+    for (long long r = threadIdx.y; r < hw; r += blockDim.y) {
+        float f[8];
+        unpack8<T>(ldg16(base + (size_t)r * C), f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] += act_fwd<ACT>(fmaf(f[i], sc[i], sh[i]));
+    }
+    const float inv = 1.f / (float)hw;
+    float* dst = pooled + (size_t)blockIdx.y * C;
+    reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v * inv; });
+}
+
+// ---------------------------------------------------------------------------------------------
+// BN backward, phase 1: s1[c] += sum g, s2[c] += sum g * xhat, xhat = (y - mean) * rstd
+// RELU_MASK: g is first masked by (out > 0) (ResNet: gradient through the post-add ReLU)
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool RELU_MASK>
+__global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ y, const T* __restrict__ out,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     long long hw, int rows_per_block, double* __restrict__ s1,
+                                     double* __restrict__ s2) {
+    extern __shared__ float sm[];
+    const int V = blockDim.x, C = V * 8;
+    const int c0 = threadIdx.x * 8;
+    float mu[8], rs[8], a1[8], a2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { mu[i] = mean[c0 + i]; rs[i] = rstd[c0 + i]; a1[i] = 0.f; a2[i] = 0.f; }
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > hw) r1 = hw;
+    const size_t img = (size_t)blockIdx.y * hw * C + c0;
+    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        size_t off = img + (size_t)r * C;
+        float gg[8], yy[8];
+        unpack8<T>(ldg16(g + off), gg);
+        unpack8<T>(ldg16(y + off), yy);
+        if (RELU_MASK) {
+            float oo[8];
+            unpack8<T>(ldg16(out + off), oo);
+#pragma unroll
+            for (int i = 0; i < 8; i++) gg[i] = oo[i] > 0.f ? gg[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            a1[i] += gg[i];
+            a2[i] = fmaf(gg[i], (yy[i] - mu[i]) * rs[i], a2[i]);
+        }
+    }
+    double* p1 = stat_slot(s1, C);
+    double* p2 = stat_slot(s2, C);
+    reduce_rows_and_emit(sm, a1, [&](int c, float v) { atomicAdd(p1 + c, (double)v); });
+    reduce_rows_and_emit(sm, a2, [&](int c, float v) { atomicAdd(p2 + c, (double)v); });
+}
+
+// BN backward, phase 2 (per channel): parameter gradients and the affine coefficients of
+//   dy = A*g + B*y + C  with A = gamma*rstd, B = -gamma*rstd^2*m2, C = -A*m1 - B*mean,
+//   m1 = s1/count, m2 = s2/count.
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ s1, const double* __restrict__ s2, double count,
+                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ cA, float* __restrict__ cB,
+                                       float* __restrict__ cC, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double sum_g = stat_total(s1, C, c), sum_gx = stat_total(s2, C, c);
+    dgamma[c] += (float)sum_gx;
+    dbeta[c] += (float)sum_g;
+    float m1 = (float)(sum_g / count), m2 = (float)(sum_gx / count);
+    float A = gamma[c] * rstd[c];
+    float B = -A * rstd[c] * m2;
+    cA[c] = A;
+    cB[c] = B;
+    cC[c] = -A * m1 - B * mean[c];
+}
+
+// BN backward, phase 3: dy = A*g*mask + B*y + C  (materialised; the GEMMs consume plain operands)
+template <typename T, bool RELU_MASK>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ y, const T* __restrict__ out,
+                                    const float* __restrict__ cA, const float* __restrict__ cB,
+                                    const float* __restrict__ cC, T* __restrict__ dy, long long hw,
+                                    int rows_per_block) {
+    const int V = blockDim.x, C = V * 8;
+    const int c0 = threadIdx.x * 8;
+    float A[8], B[8], Cc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { A[i] = cA[c0 + i]; B[i] = cB[c0 + i]; Cc[i] = cC[c0 + i]; }
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > hw) r1 = hw;
+    const size_t img = (size_t)blockIdx.y * hw * C + c0;
+    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        size_t off = img + (size_t)r * C;
+        float gg[8], yy[8];
+        unpack8<T>(ldg16(g + off), gg);
+        unpack8<T>(ldg16(y + off), yy);
+        if (RELU_MASK) {
+            float oo[8];
+            unpack8<T>(ldg16(out + off), oo);
+#pragma unroll
+            for (int i = 0; i < 8; i++) gg[i] = oo[i] > 0.f ? gg[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) gg[i] = fmaf(A[i], gg[i], fmaf(B[i], yy[i], Cc[i]));
+        stg16(dy + off, pack8<T>(gg));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SE backward reduce: draw[n,c] = sum_hw da[n,hw,c] * act(scale*y + shift)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int ACT>
+__global__ void se_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     float* __restrict__ draw, long long hw) {
+    extern __shared__ float sm[];
+    const int V = blockDim.x, C = V * 8;
+    const int c0 = threadIdx.x * 8;
+    float sc[8], sh[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { sc[i] = scale[c0 + i]; sh[i] = shift[c0 + i]; acc[i] = 0.f; }
+    const size_t img = (size_t)blockIdx.y * hw * C + c0;
+    for (long long r = threadIdx.y; r < hw; r += blockDim.y) {
+        size_t off = img + (size_t)r * C;
+        float d[8], f[8];
+        unpack8<T>(ldg16(da + off), d);
+        unpack8<T>(ldg16(y + off), f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = fmaf(d[i], act_fwd<ACT>(fmaf(f[i], sc[i], sh[i])), acc[i]);
+    }
+    float* dst = draw + (size_t)blockIdx.y * C;
+    reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v; });
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient w.r.t. the BN output u = scale*y + shift behind an activation (+ optional SE gate and pooling):
+//   gu = (da * gate[n,c] + dpool[n,c] * inv_hw) * act'(u)        (HAS_DA: da present; dpool may be null)
+// plus the BN backward reductions of gu: s1 += sum gu, s2 += sum gu * xhat.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int ACT, bool HAS_DA>
+__global__ void act_bwd_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
+                               const float* __restrict__ shift, const float* __restrict__ mean,
+                               const float* __restrict__ rstd, const float* __restrict__ gate,
+                               const float* __restrict__ dpool, float inv_hw, T* __restrict__ gu, long long hw,
+                               int rows_per_block, double* __restrict__ s1, double* __restrict__ s2) {
+    extern __shared__ float sm[];
+    const int V = blockDim.x, C = V * 8;
+    const int c0 = threadIdx.x * 8;
+    float sc[8], sh[8], mu[8], rs[8], gt[8], dp[8], a1[8], a2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        sc[i] = scale[c0 + i]; sh[i] = shift[c0 + i]; mu[i] = mean[c0 + i]; rs[i] = rstd[c0 + i];
+        gt[i] = gate ? gate[(size_t)blockIdx.y * C + c0 + i] : 1.f;
+        dp[i] = dpool ? dpool[(size_t)blockIdx.y * C + c0 + i] * inv_hw : 0.f;
+        a1[i] = 0.f; a2[i] = 0.f;
+    }
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > hw) r1 = hw;
+    const size_t img = (size_t)blockIdx.y * hw * C + c0;
+    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        size_t off = img + (size_t)r * C;
+        float d[8], f[8];
+        if (HAS_DA) unpack8<T>(ldg16(da + off), d);
+        unpack8<T>(ldg16(y + off), f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float u = fmaf(f[i], sc[i], sh[i]);
+            float gin = HAS_DA ? fmaf(d[i], gt[i], dp[i]) : dp[i];
+            float o = gin * act_bwd<ACT>(u);
+            // the stored (rounded) value is what the consumers see: reduce the rounded value
+            o = round_t<T>(o);
+            d[i] = o;
+            a1[i] += o;
+            a2[i] = fmaf(o, (f[i] - mu[i]) * rs[i], a2[i]);
+        }
+        stg16(gu + off, pack8<T>(d));
+    }
+    double* p1 = stat_slot(s1, C);
+    double* p2 = stat_slot(s2, C);
+    reduce_rows_and_emit(sm, a1, [&](int c, float v) { atomicAdd(p1 + c, (double)v); });
+    reduce_rows_and_emit(sm, a2, [&](int c, float v) { atomicAdd(p2 + c, (double)v); });
+}
+
+// elementwise a += b (residual gradient accumulation) over a flat 16-bit tensor
+template <typename T>
+__global__ void add_inplace_kernel(T* __restrict__ a, const T* __restrict__ b, size_t nvec) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < nvec; i += stride) {
+        float x[8], z[8];
+        unpack8<T>(ldg16(a + i * 8), x);
+        unpack8<T>(ldg16(b + i * 8), z);
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[k] += z[k];
+        stg16(a + i * 8, pack8<T>(x));
+    }
+}
+
+static size_t reduce_smem(const RowGeom& g) { return (size_t)g.block.x * 8 * g.block.y * sizeof(float); }
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+#define DISPATCH_T(dt, ...)                                              \
+    if ((dt) == DFD_DT_BF16) { typedef bf16 T; __VA_ARGS__; }            \
+    else if ((dt) == DFD_DT_FP16) { typedef __half T; __VA_ARGS__; }     \
+    else return dfd_set_error(DFD_ERR_ARG, "bad dtype");
+
+extern "C" {
+
+int dfd_colstats(const void* y, int n, long long hw, int C, int dt, double* dsum, double* dsq, void* stream) {
+    if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_colstats: C%8, sizes");
+    RowGeom g = make_geom(C, hw, n);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dt, (colstats_kernel<T><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)y, hw, g.rows_per_block, dsum, dsq)));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_bn_finalize(const double* dsum, const double* dsq, double count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
+                    int training, int C, float* scale, float* shift, float* mean, float* rstd, void* stream) {
+    if (C <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_bn_finalize: C");
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(dsum, dsq, count, gamma, beta, running_mean,
+                                                                         running_var, nbt, momentum, eps, training, C,
+                                                                         scale, shift, mean, rstd);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_bn_act(const void* y, const float* scale, const float* shift, const float* gate, const void* res, void* out,
+               int n, long long hw, int C, int act, int res_mode, int dt, void* stream) {
+    if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_bn_act: C%8, sizes");
+    if ((res_mode != 0) != (res != nullptr)) return dfd_set_error(DFD_ERR_ARG, "dfd_bn_act: res/res_mode");
+    RowGeom g = make_geom(C, hw, n);
+    cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(ACT, GATE, RES)                                                                                    \
+    bn_act_kernel<T, ACT, GATE, RES><<<g.grid, g.block, 0, st>>>((const T*)y, scale, shift, gate, (const T*)res, \
+                                                                   (T*)out, hw, g.rows_per_block)
+    int key = act * 100 + (gate ? 10 : 0) + res_mode;
+    DISPATCH_T(dt, {
+        switch (key) {
+            case 0: LAUNCH(0, false, 0); break;
+            case 1: LAUNCH(0, false, 1); break;
+            case 2: LAUNCH(0, false, 2); break;
+            case 100: LAUNCH(1, false, 0); break;
+            case 110: LAUNCH(1, true, 0); break;
+            case 200: LAUNCH(2, false, 0); break;
+            default: return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_bn_act: (act, gate, res) combination");
+        }
+    });
+#undef LAUNCH
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_pool(const void* y, const float* scale, const float* shift, float* pooled, int n, long long hw, int C,
+             int act, int dt, void* stream) {
+    if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_pool: C%8, sizes");
+    RowGeom g = make_geom(C, hw, n, 1);
+    g.grid = dim3(1, n, 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dt, {
+        if (act == DFD_ACT_SWISH) pool_kernel<T, 1><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)y, scale, shift, pooled, hw);
+        else if (act == DFD_ACT_RELU) pool_kernel<T, 2><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)y, scale, shift, pooled, hw);
+        else pool_kernel<T, 0><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)y, scale, shift, pooled, hw);
+    });
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_bn_bwd_reduce(const void* g_, const void* y, const void* out, const float* mean, const float* rstd, int n,
+                      long long hw, int C, int dt, double* s1, double* s2, void* stream) {
+    if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_bn_bwd_reduce: C%8, sizes");
+    RowGeom g = make_geom(C, hw, n);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dt, {
+        if (out) bn_bwd_reduce_kernel<T, true><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)g_, (const T*)y, (const T*)out, mean, rstd, hw, g.rows_per_block, s1, s2);
+        else bn_bwd_reduce_kernel<T, false><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)g_, (const T*)y, nullptr, mean, rstd, hw, g.rows_per_block, s1, s2);
+    });
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_bn_bwd_finalize(const double* s1, const double* s2, double count, const float* gamma, const float* mean,
+                        const float* rstd, float* dgamma, float* dbeta, float* cA, float* cB, float* cC, int C,
+                        void* stream) {
+    if (C <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_bn_bwd_finalize: C");
+    bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(s1, s2, count, gamma, mean, rstd, dgamma,
+                                                                             dbeta, cA, cB, cC, C);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_bn_bwd_apply(const void* g_, const void* y, const void* out, const float* cA, const float* cB,
+                     const float* cC, void* dy, int n, long long hw, int C, int dt, void* stream) {
+    if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_bn_bwd_apply: C%8, sizes");
+    RowGeom g = make_geom(C, hw, n);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dt, {
+        if (out) bn_bwd_apply_kernel<T, true><<<g.grid, g.block, 0, st>>>((const T*)g_, (const T*)y, (const T*)out, cA, cB, cC, (T*)dy, hw, g.rows_per_block);
+        else bn_bwd_apply_kernel<T, false><<<g.grid, g.block, 0, st>>>((const T*)g_, (const T*)y, nullptr, cA, cB, cC, (T*)dy, hw, g.rows_per_block);
+    });
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_se_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift, float* draw, int n,
+                      long long hw, int C, int dt, void* stream) {
+    if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_bwd_reduce: C%8, sizes");
+    RowGeom g = make_geom(C, hw, n, 1);
+    g.grid = dim3(1, n, 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dt, (se_bwd_reduce_kernel<T, 1><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)da, (const T*)y, scale, shift, draw, hw)));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_act_bwd(const void* da, const void* y, const float* scale, const float* shift, const float* mean,
+                const float* rstd, const float* gate, const float* dpool, void* gu, int n, long long hw, int C,
+                int act, int dt, double* s1, double* s2, void* stream) {
+    if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_act_bwd: C%8, sizes");
+    if (!da && !dpool) return dfd_set_error(DFD_ERR_ARG, "dfd_act_bwd: need da or dpool");
+    RowGeom g = make_geom(C, hw, n);
+    cudaStream_t st = (cudaStream_t)stream;
+    float inv_hw = 1.f / (float)hw;
+#define LAUNCH(ACT, HAS)                                                                                            \
+    act_bwd_kernel<T, ACT, HAS><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)da, (const T*)y, scale, shift, mean, \
+                                                                            rstd, gate, dpool, inv_hw, (T*)gu, hw,     \
+                                                                            g.rows_per_block, s1, s2)
+    DISPATCH_T(dt, {
+        if (act == DFD_ACT_SWISH) { if (da) LAUNCH(1, true); else LAUNCH(1, false); }
+        else if (act == DFD_ACT_RELU) { if (da) LAUNCH(2, true); else LAUNCH(2, false); }
+        else { if (da) LAUNCH(0, true); else LAUNCH(0, false); }
+    });
+#undef LAUNCH
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_add_inplace(void* a, const void* b, long long numel, int dt, void* stream) {
+    if (numel % 8) return dfd_set_error(DFD_ERR_ARG, "dfd_add_inplace: numel%8");
+    size_t nvec = (size_t)(numel / 8);
+    int blocks = (int)((nvec + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dt, (add_inplace_kernel<T><<<blocks, 256, 0, st>>>((T*)a, (const T*)b, nvec)));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+}  // extern "C"

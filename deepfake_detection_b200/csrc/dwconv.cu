@@ -1,0 +1,485 @@
+// Depthwise k x k convolution (k in {3,5}, stride in {1,2}) forward, input-gradient and weight-gradient,
+// NHWC 16-bit activations, fp32 accumulation.   Reference: nn.Conv2d(groups=C) built by
+// dfd/timm/models/layers/create_conv2d.py:11-30 at dfd/timm/models/efficientnet_blocks.py:152-153,283-285
+// with symmetric padding (k-1)//2 (layers/padding.py:12-14).
+//
+// Design (B200): these layers are HBM-bound with k*k-fold reuse of every input element, and the preceding
+// BN + Swish is fused into the load, so:
+//   * a CTA stages an input tile (+halo) for 64 channels in shared memory ONCE, applying BN scale/shift and the
+//     activation exactly once per element (sigmoid = one MUFU tanh), stored as packed 16-bit pairs;
+//   * lane l of every warp owns channel pair (2l, 2l+1): shared-memory reads are 32 consecutive 4-byte words
+//     (conflict free), global stores are 128 contiguous bytes per pixel;
+//   * each warp computes strips of P=8 consecutive output columns with the k*k weights of its two channels
+//     held in registers (sliding-window reuse: (P-1)*s+k smem reads feed P*k FMAs per kernel row);
+//   * per-channel BN statistics of the (rounded) outputs are reduced in the epilogue: one fp64 atomic per
+//     channel per CTA.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CB = 64;       // channels per CTA
+constexpr int P = 8;         // output columns per strip
+constexpr int NTHREADS = 256;
+
+struct DwGeom {
+    int N, H, W, C, Ho, Wo, pad;
+    int TH, TW;              // output tile (TW multiple of 8)
+    int IH, IW;              // staged input tile
+    int tiles_x, tiles_y;
+};
+
+__device__ __forceinline__ void load_chan_params(const float* p, int cbase, int C, float* out, float dflt) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = (p && cbase + i < C) ? p[cbase + i] : dflt;
+}
+
+// Stage act(scale*x+shift) for rows [iy0, iy0+IH) x cols [ix0, ix0+IW) x channels [c0, c0+64) of image `img`
+// (zero outside the image / beyond C) into tile[(r*IW + c)*32 + word].
+template <typename T, int ACT, bool AFFINE>
+__device__ __forceinline__ void stage_input_tile(uint32_t* tile, const T* __restrict__ img, int H, int W, int C,
+                                                 int c0, int iy0, int ix0, int IH, int IW,
+                                                 const float* __restrict__ scale, const float* __restrict__ shift) {
+    const int v = threadIdx.x & 7;
+    const int cbase = c0 + v * 8;
+    const bool cvalid = cbase < C;
+    float sc[8], sh[8];
+    if (AFFINE) { load_chan_params(scale, cbase, C, sc, 1.f); load_chan_params(shift, cbase, C, sh, 0.f); }
+    const int npix = IH * IW;
+    for (int pix = threadIdx.x >> 3; pix < npix; pix += NTHREADS / 8) {
+        int r = pix / IW, c = pix - r * IW;
+        int iy = iy0 + r, ix = ix0 + c;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (cvalid && iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            uint4 raw = ldg16(img + ((size_t)iy * W + ix) * C + cbase);
+            if (AFFINE || ACT != DFD_ACT_NONE) {
+                float f[8];
+                unpack8<T>(raw, f);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    float u = AFFINE ? fmaf(f[i], sc[i], sh[i]) : f[i];
+                    f[i] = act_fwd<ACT>(u);
+                }
+                o = pack8<T>(f);
+            } else {
+                o = raw;
+            }
+        }
+        *reinterpret_cast<uint4*>(tile + (size_t)pix * 32 + v * 4) = o;
+    }
+}
+
+// Stage the zero-upsampled output gradient dy = A*g + B*y + C (BN backward folded into the load) in INPUT pixel
+// coordinates: tile pixel (r, c) <-> U[uy0 + r, ux0 + c], U[a,b] = dy[a/S, b/S] when a, b are multiples of S.
+template <typename T, int S, bool AFFINE>
+__device__ __forceinline__ void stage_grad_tile(uint32_t* tile, const T* __restrict__ g, const T* __restrict__ y,
+                                                int Ho, int Wo, int C, int c0, int uy0, int ux0, int IH, int IW,
+                                                const float* __restrict__ cA, const float* __restrict__ cB,
+                                                const float* __restrict__ cC) {
+    const int v = threadIdx.x & 7;
+    const int cbase = c0 + v * 8;
+    const bool cvalid = cbase < C;
+    float A[8], B[8], Cc[8];
+    if (AFFINE) { load_chan_params(cA, cbase, C, A, 1.f); load_chan_params(cB, cbase, C, B, 0.f); load_chan_params(cC, cbase, C, Cc, 0.f); }
+    const int npix = IH * IW;
+    for (int pix = threadIdx.x >> 3; pix < npix; pix += NTHREADS / 8) {
+        int r = pix / IW, c = pix - r * IW;
+        int a = uy0 + r, b = ux0 + c;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (cvalid && a >= 0 && b >= 0 && (a % S) == 0 && (b % S) == 0) {
+            int oy = a / S, ox = b / S;
+            if (oy < Ho && ox < Wo) {
+                size_t off = ((size_t)oy * Wo + ox) * C + cbase;
+                uint4 graw = ldg16(g + off);
+                if (AFFINE) {
+                    float gg[8], yy[8];
+                    unpack8<T>(graw, gg);
+                    unpack8<T>(ldg16(y + off), yy);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) gg[i] = fmaf(A[i], gg[i], fmaf(B[i], yy[i], Cc[i]));
+                    o = pack8<T>(gg);
+                } else {
+                    o = graw;
+                }
+            }
+        }
+        *reinterpret_cast<uint4*>(tile + (size_t)pix * 32 + v * 4) = o;
+    }
+}
+
+// acc[p][:] += sum_{kh,kw} tile[r0+kh][c0 + p*S + kw] * w[kh*K+kw]
+template <typename T, int K, int S>
+__device__ __forceinline__ void strip_conv(const uint32_t* __restrict__ tile, int IW, int r0, int c0, int lane,
+                                           const float (&w)[K * K][2], float (&acc)[P][2]) {
+#pragma unroll
+    for (int kh = 0; kh < K; kh++) {
+        const uint32_t* row = tile + ((size_t)(r0 + kh) * IW + c0) * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < (P - 1) * S + K; j++) {
+            float2 x = unpack2<T>(row[j * 32]);
+#pragma unroll
+            for (int kw = 0; kw < K; kw++) {
+                int pj = j - kw;
+                if (pj >= 0 && (pj % S) == 0 && pj / S < P) {
+                    acc[pj / S][0] = fmaf(x.x, w[kh * K + kw][0], acc[pj / S][0]);
+                    acc[pj / S][1] = fmaf(x.y, w[kh * K + kw][1], acc[pj / S][1]);
+                }
+            }
+        }
+    }
+}
+
+// block reduction of per-thread channel-pair values across the 8 warps, then fn(channel_in_block, value)
+template <typename F>
+__device__ __forceinline__ void reduce_warps_emit(float* sm, float a, float b, F fn) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    sm[warp * 64 + lane * 2] = a;
+    sm[warp * 64 + lane * 2 + 1] = b;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < NTHREADS / 32; w++) s += sm[w * 64 + threadIdx.x];
+        fn(threadIdx.x, s);
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <typename T, int K, int S, int ACT, bool AFFINE>
+__global__ void __launch_bounds__(NTHREADS)
+dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                  const float* __restrict__ wgt, T* __restrict__ out, double* __restrict__ dsum,
+                  double* __restrict__ dsq, DwGeom g) {
+    extern __shared__ __align__(16) uint32_t tile[];
+    __shared__ float red[NTHREADS / 32 * 64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x % g.tiles_x, ty = blockIdx.x / g.tiles_x;
+    const int c0 = blockIdx.y * CB, n = blockIdx.z;
+    const int oy0 = ty * g.TH, ox0 = tx * g.TW;
+    const T* img = x + (size_t)n * g.H * g.W * g.C;
+    stage_input_tile<T, ACT, AFFINE>(tile, img, g.H, g.W, g.C, c0, oy0 * S - g.pad, ox0 * S - g.pad, g.IH, g.IW, scale, shift);
+
+    const int ch = c0 + lane * 2;
+    const bool chv = ch < g.C;
+    float w[K * K][2];
+#pragma unroll
+    for (int i = 0; i < K * K; i++) {
+        w[i][0] = chv ? wgt[(size_t)ch * K * K + i] : 0.f;
+        w[i][1] = chv ? wgt[(size_t)(ch + 1) * K * K + i] : 0.f;
+    }
+    __syncthreads();
+
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    const int strips_x = g.TW / P;
+    const int nstrips = g.TH * strips_x;
+    T* oimg = out + (size_t)n * g.Ho * g.Wo * g.C;
+    for (int s = warp; s < nstrips; s += NTHREADS / 32) {
+        int sy = s / strips_x, sx = (s - sy * strips_x) * P;
+        int oy = oy0 + sy, ox = ox0 + sx;
+        if (oy >= g.Ho || ox >= g.Wo) continue;
+        float acc[P][2];
+#pragma unroll
+        for (int p = 0; p < P; p++) { acc[p][0] = 0.f; acc[p][1] = 0.f; }
+        strip_conv<T, K, S>(tile, g.IW, sy * S, sx * S, lane, w, acc);
+        if (chv) {
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                if (ox + p < g.Wo) {
+                    uint32_t pk = pack2<T>(acc[p][0], acc[p][1]);
+                    *reinterpret_cast<uint32_t*>(oimg + ((size_t)oy * g.Wo + ox + p) * g.C + ch) = pk;
+                    float2 r = unpack2<T>(pk);
+                    s0 += r.x; s1 += r.y;
+                    q0 = fmaf(r.x, r.x, q0); q1 = fmaf(r.y, r.y, q1);
+                }
+            }
+        }
+    }
+    if (dsum) {
+        double* ps = stat_slot(dsum, g.C);
+        double* pq = stat_slot(dsq, g.C);
+        reduce_warps_emit(red, s0, s1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(ps + c0 + c, (double)v); });
+        reduce_warps_emit(red, q0, q1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(pq + c0 + c, (double)v); });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// input gradient.  Tile is in INPUT pixel space (H x W); the staged operand is the zero-upsampled dy.
+//   ga[h,w] = sum_{kh',kw'} U[h - p' + kh', w - p' + kw'] * wflip[kh',kw'],  p' = K-1-pad
+// MODE 0: dx = ga (+ add)                                   (DS block: dw conv reads the block input directly)
+// MODE 1: gu = ga * act'(scale*xin + shift); BN-backward reductions s1 += gu, s2 += gu*xhat
+// ---------------------------------------------------------------------------------------------
+template <typename T, int K, int S, int MODE, bool AFFINE>
+__global__ void __launch_bounds__(NTHREADS)
+dwconv_dgrad_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const float* __restrict__ cA,
+                    const float* __restrict__ cB, const float* __restrict__ cC, const float* __restrict__ wgt,
+                    const T* __restrict__ xin, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ add,
+                    T* __restrict__ gx, double* __restrict__ ds1, double* __restrict__ ds2, DwGeom g) {
+    extern __shared__ __align__(16) uint32_t tile[];
+    __shared__ float red[NTHREADS / 32 * 64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x % g.tiles_x, ty = blockIdx.x / g.tiles_x;
+    const int c0 = blockIdx.y * CB, n = blockIdx.z;
+    const int y0 = ty * g.TH, x0 = tx * g.TW;           // input-space tile origin
+    const int pp = K - 1 - g.pad;
+    const size_t ooff = (size_t)n * g.Ho * g.Wo * g.C;
+    stage_grad_tile<T, S, AFFINE>(tile, gy + ooff, AFFINE ? yout + ooff : nullptr, g.Ho, g.Wo, g.C, c0, y0 - pp, x0 - pp,
+                                  g.IH, g.IW, cA, cB, cC);
+    const int ch = c0 + lane * 2;
+    const bool chv = ch < g.C;
+    float w[K * K][2];
+#pragma unroll
+    for (int i = 0; i < K * K; i++) {       // flipped taps
+        w[i][0] = chv ? wgt[(size_t)ch * K * K + (K * K - 1 - i)] : 0.f;
+        w[i][1] = chv ? wgt[(size_t)(ch + 1) * K * K + (K * K - 1 - i)] : 0.f;
+    }
+    float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f, mu0 = 0.f, mu1 = 0.f, rs0 = 0.f, rs1 = 0.f;
+    if (MODE == 1 && chv) {
+        sc0 = scale[ch]; sc1 = scale[ch + 1]; sh0 = shift[ch]; sh1 = shift[ch + 1];
+        mu0 = mean[ch]; mu1 = mean[ch + 1]; rs0 = rstd[ch]; rs1 = rstd[ch + 1];
+    }
+    __syncthreads();
+
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    const int strips_x = g.TW / P;
+    const int nstrips = g.TH * strips_x;
+    const size_t ioff = (size_t)n * g.H * g.W * g.C;
+    for (int s = warp; s < nstrips; s += NTHREADS / 32) {
+        int sy = s / strips_x, sx = (s - sy * strips_x) * P;
+        int iy = y0 + sy, ix = x0 + sx;
+        if (iy >= g.H || ix >= g.W) continue;
+        float acc[P][2];
+#pragma unroll
+        for (int p = 0; p < P; p++) { acc[p][0] = 0.f; acc[p][1] = 0.f; }
+        strip_conv<T, K, 1>(tile, g.IW, sy, sx, lane, w, acc);
+        if (chv) {
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                if (ix + p < g.W) {
+                    size_t off = ioff + ((size_t)iy * g.W + ix + p) * g.C + ch;
+                    float v0 = acc[p][0], v1 = acc[p][1];
+                    if (MODE == 1) {
+                        float2 xi = unpack2<T>(*reinterpret_cast<const uint32_t*>(xin + off));
+                        v0 *= act_bwd<DFD_ACT_SWISH>(fmaf(xi.x, sc0, sh0));
+                        v1 *= act_bwd<DFD_ACT_SWISH>(fmaf(xi.y, sc1, sh1));
+                        uint32_t pk = pack2<T>(v0, v1);
+                        *reinterpret_cast<uint32_t*>(gx + off) = pk;
+                        float2 r = unpack2<T>(pk);
+                        a0 += r.x; a1 += r.y;
+                        b0 = fmaf(r.x, (xi.x - mu0) * rs0, b0);
+                        b1 = fmaf(r.y, (xi.y - mu1) * rs1, b1);
+                    } else {
+                        if (add) {
+                            float2 ad = unpack2<T>(*reinterpret_cast<const uint32_t*>(add + off));
+                            v0 += ad.x; v1 += ad.y;
+                        }
+                        *reinterpret_cast<uint32_t*>(gx + off) = pack2<T>(v0, v1);
+                    }
+                }
+            }
+        }
+    }
+    if (MODE == 1) {
+        double* p1 = stat_slot(ds1, g.C);
+        double* p2 = stat_slot(ds2, g.C);
+        reduce_warps_emit(red, a0, a1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p1 + c0 + c, (double)v); });
+        reduce_warps_emit(red, b0, b1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p2 + c0 + c, (double)v); });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient: dW[c,kh,kw] += sum_{n,oy,ox} dy[n,oy,ox,c] * a[n, oy*S-pad+kh, ox*S-pad+kw, c]
+// a = act(scale*x+shift) is re-staged like the forward; dy = A*g + B*y + C is formed per strip.
+// gridDim.z image groups: each CTA loops over images z, z+gridDim.z, ... to bound the number of atomics.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int K, int S, int ACT, bool AFFINE_IN, bool AFFINE_G>
+__global__ void __launch_bounds__(NTHREADS)
+dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const T* __restrict__ gy, const T* __restrict__ yout, const float* __restrict__ cA,
+                    const float* __restrict__ cB, const float* __restrict__ cC, float* __restrict__ dW, DwGeom g) {
+    extern __shared__ __align__(16) uint32_t tile[];
+    __shared__ float red[NTHREADS / 32 * 64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx = blockIdx.x % g.tiles_x, ty = blockIdx.x / g.tiles_x;
+    const int c0 = blockIdx.y * CB;
+    const int oy0 = ty * g.TH, ox0 = tx * g.TW;
+    const int ch = c0 + lane * 2;
+    const bool chv = ch < g.C;
+    float A0 = 1.f, A1 = 1.f, B0 = 0.f, B1 = 0.f, C0 = 0.f, C1 = 0.f;
+    if (AFFINE_G && chv) { A0 = cA[ch]; A1 = cA[ch + 1]; B0 = cB[ch]; B1 = cB[ch + 1]; C0 = cC[ch]; C1 = cC[ch + 1]; }
+    float wacc[K * K][2];
+#pragma unroll
+    for (int i = 0; i < K * K; i++) { wacc[i][0] = 0.f; wacc[i][1] = 0.f; }
+    const int strips_x = g.TW / P;
+    const int nstrips = g.TH * strips_x;
+
+    for (int n = blockIdx.z; n < g.N; n += gridDim.z) {
+        const T* img = x + (size_t)n * g.H * g.W * g.C;
+        __syncthreads();    // previous image's tile fully consumed
+        stage_input_tile<T, ACT, AFFINE_IN>(tile, img, g.H, g.W, g.C, c0, oy0 * S - g.pad, ox0 * S - g.pad, g.IH, g.IW, scale, shift);
+        __syncthreads();
+        const size_t ooff = (size_t)n * g.Ho * g.Wo * g.C;
+        for (int s = warp; s < nstrips; s += NTHREADS / 32) {
+            int sy = s / strips_x, sx = (s - sy * strips_x) * P;
+            int oy = oy0 + sy, ox = ox0 + sx;
+            if (oy >= g.Ho || ox >= g.Wo || !chv) continue;
+            float dy[P][2];
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                dy[p][0] = 0.f; dy[p][1] = 0.f;
+                if (ox + p < g.Wo) {
+                    size_t off = ooff + ((size_t)oy * g.Wo + ox + p) * g.C + ch;
+                    float2 gg = unpack2<T>(*reinterpret_cast<const uint32_t*>(gy + off));
+                    if (AFFINE_G) {
+                        float2 yy = unpack2<T>(*reinterpret_cast<const uint32_t*>(yout + off));
+                        // round like the staged operand of the dgrad kernel so both see the same dy
+                        float2 r = unpack2<T>(pack2<T>(fmaf(A0, gg.x, fmaf(B0, yy.x, C0)), fmaf(A1, gg.y, fmaf(B1, yy.y, C1))));
+                        gg = r;
+                    }
+                    dy[p][0] = gg.x; dy[p][1] = gg.y;
+                }
+            }
+#pragma unroll
+            for (int kh = 0; kh < K; kh++) {
+                const uint32_t* row = tile + ((size_t)(sy * S + kh) * g.IW + sx * S) * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < (P - 1) * S + K; j++) {
+                    float2 a = unpack2<T>(row[j * 32]);
+#pragma unroll
+                    for (int kw = 0; kw < K; kw++) {
+                        int pj = j - kw;
+                        if (pj >= 0 && (pj % S) == 0 && pj / S < P) {
+                            wacc[kh * K + kw][0] = fmaf(a.x, dy[pj / S][0], wacc[kh * K + kw][0]);
+                            wacc[kh * K + kw][1] = fmaf(a.y, dy[pj / S][1], wacc[kh * K + kw][1]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // reduce the 8 warps' partial sums, one tap at a time, then one fp32 atomic per (channel, tap) per CTA
+#pragma unroll
+    for (int i = 0; i < K * K; i++) {
+        reduce_warps_emit(red, wacc[i][0], wacc[i][1], [&](int c, float v) {
+            if (c0 + c < g.C) atomicAdd(dW + (size_t)(c0 + c) * K * K + i, v);
+        });
+    }
+}
+
+static int fill_geom(DwGeom& g, int N, int H, int W, int C, int K, int S, bool input_space) {
+    g.N = N; g.H = H; g.W = W; g.C = C; g.pad = (K - 1) / 2;
+    g.Ho = (H + 2 * g.pad - K) / S + 1;
+    g.Wo = (W + 2 * g.pad - K) / S + 1;
+    int th_dim = input_space ? H : g.Ho, tw_dim = input_space ? W : g.Wo;
+    int eff_s = input_space ? 1 : S;
+    g.TW = tw_dim <= 8 ? 8 : ((tw_dim <= 16 || eff_s == 2) ? 16 : 32);   // stride-2 tiles stage 2x the columns
+    g.TH = th_dim < 8 ? th_dim : 8;
+    g.IW = (g.TW - 1) * eff_s + K;
+    g.IH = (g.TH - 1) * eff_s + K;
+    g.tiles_x = (tw_dim + g.TW - 1) / g.TW;
+    g.tiles_y = (th_dim + g.TH - 1) / g.TH;
+    return g.IH * g.IW * 32 * (int)sizeof(uint32_t);
+}
+
+template <typename KernelT>
+static int set_smem(KernelT k, int bytes) {
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return dfd_set_cuda_error(e, __FILE__, __LINE__);
+    }
+    return DFD_OK;
+}
+
+}  // namespace
+
+#define DW_DISPATCH_KS(K_, S_, ...)                                               \
+    if (K_ == 3 && S_ == 1) { constexpr int K = 3, S = 1; __VA_ARGS__; }          \
+    else if (K_ == 3 && S_ == 2) { constexpr int K = 3, S = 2; __VA_ARGS__; }     \
+    else if (K_ == 5 && S_ == 1) { constexpr int K = 5, S = 1; __VA_ARGS__; }     \
+    else if (K_ == 5 && S_ == 2) { constexpr int K = 5, S = 2; __VA_ARGS__; }     \
+    else return dfd_set_error(DFD_ERR_UNSUPPORTED, "depthwise conv: k in {3,5}, stride in {1,2}");
+
+#define DW_DISPATCH_T(dt, ...)                                           \
+    if ((dt) == DFD_DT_BF16) { typedef bf16 T; __VA_ARGS__; }            \
+    else if ((dt) == DFD_DT_FP16) { typedef __half T; __VA_ARGS__; }     \
+    else return dfd_set_error(DFD_ERR_ARG, "bad dtype");
+
+#define DW_LAUNCH(kern, grid, smem, st, ...)                         \
+    do {                                                             \
+        auto kfn__ = kern;                                           \
+        int rc__ = set_smem(kfn__, smem);                            \
+        if (rc__) return rc__;                                       \
+        kfn__<<<grid, NTHREADS, smem, st>>>(__VA_ARGS__);            \
+    } while (0)
+
+extern "C" {
+
+// out[N,Ho,Wo,C] = dwconv(act_in(scale*x + shift)); scale == NULL: x is consumed as is (act_in must be 0).
+// dsum/dsq (optional): per-channel sum / sum of squares of the rounded outputs (fp64, accumulated).
+int dfd_dwconv_fwd(const void* x, const float* scale, const float* shift, const float* w, void* out, int N, int H,
+                   int W, int C, int k, int stride, int act_in, int dt, double* dsum, double* dsq, void* stream) {
+    if (C % 8 || N <= 0 || H <= 0 || W <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_fwd: sizes");
+    if (!scale && act_in != DFD_ACT_NONE) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_fwd: act without BN");
+    if (scale && act_in != DFD_ACT_SWISH) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_dwconv_fwd: BN input implies Swish");
+    DwGeom g;
+    int smem = fill_geom(g, N, H, W, C, k, stride, false);
+    dim3 grid(g.tiles_x * g.tiles_y, (C + CB - 1) / CB, N);
+    cudaStream_t st = (cudaStream_t)stream;
+    DW_DISPATCH_T(dt, DW_DISPATCH_KS(k, stride, {
+        if (scale) DW_LAUNCH((dwconv_fwd_kernel<T, K, S, DFD_ACT_SWISH, true>), grid, smem, st, (const T*)x, scale, shift, w, (T*)out, dsum, dsq, g);
+        else DW_LAUNCH((dwconv_fwd_kernel<T, K, S, DFD_ACT_NONE, false>), grid, smem, st, (const T*)x, scale, shift, w, (T*)out, dsum, dsq, g);
+    }));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+// Input gradient of the depthwise conv.
+//   gy [N,Ho,Wo,C]: gradient w.r.t. the BN output behind the conv (cA != NULL: dy = cA*gy + cB*yout + cC is formed on load)
+//   mode 0: gx = dgrad (+ add)                       (block input consumed directly)
+//   mode 1: gx = dgrad * swish'(scale*xin + shift), and s1 += sum gx, s2 += sum gx * (xin-mean)*rstd
+int dfd_dwconv_dgrad(const void* gy, const void* yout, const float* cA, const float* cB, const float* cC,
+                     const float* w, const void* xin, const float* scale, const float* shift, const float* mean,
+                     const float* rstd, const void* add, void* gx, int N, int H, int W, int C, int k, int stride,
+                     int mode, int dt, double* s1, double* s2, void* stream) {
+    if (C % 8 || N <= 0 || H <= 0 || W <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_dgrad: sizes");
+    if (mode == 1 && (!xin || !scale || !s1 || !s2)) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_dgrad: mode 1 operands");
+    DwGeom g;
+    int smem = fill_geom(g, N, H, W, C, k, stride, true);
+    dim3 grid(g.tiles_x * g.tiles_y, (C + CB - 1) / CB, N);
+    cudaStream_t st = (cudaStream_t)stream;
+#define DG(MODE, AFF) DW_LAUNCH((dwconv_dgrad_kernel<T, K, S, MODE, AFF>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, s1, s2, g)
+    DW_DISPATCH_T(dt, DW_DISPATCH_KS(k, stride, {
+        if (mode == 1) { if (cA) DG(1, true); else DG(1, false); }
+        else { if (cA) DG(0, true); else DG(0, false); }
+    }));
+#undef DG
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+// dW[C,1,k,k] (fp32, accumulated with atomics) of the depthwise conv; operands as in fwd / dgrad.
+int dfd_dwconv_wgrad(const void* x, const float* scale, const float* shift, const void* gy, const void* yout,
+                     const float* cA, const float* cB, const float* cC, float* dW, int N, int H, int W, int C, int k,
+                     int stride, int dt, void* stream) {
+    if (C % 8 || N <= 0 || H <= 0 || W <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_wgrad: sizes");
+    DwGeom g;
+    int smem = fill_geom(g, N, H, W, C, k, stride, false);
+    int tiles = g.tiles_x * g.tiles_y, cbs = (C + CB - 1) / CB;
+    int gz = (148 * 6 + tiles * cbs - 1) / (tiles * cbs);
+    if (gz > N) gz = N;
+    if (gz < 1) gz = 1;
+    dim3 grid(tiles, cbs, gz);
+    cudaStream_t st = (cudaStream_t)stream;
+#define WG(ACT, AIN, AG) DW_LAUNCH((dwconv_wgrad_kernel<T, K, S, ACT, AIN, AG>), grid, smem, st, (const T*)x, scale, shift, (const T*)gy, (const T*)yout, cA, cB, cC, dW, g)
+    DW_DISPATCH_T(dt, DW_DISPATCH_KS(k, stride, {
+        if (scale) { if (cA) WG(DFD_ACT_SWISH, true, true); else WG(DFD_ACT_SWISH, true, false); }
+        else { if (cA) WG(DFD_ACT_NONE, false, true); else WG(DFD_ACT_NONE, false, false); }
+    }));
+#undef WG
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+}  // extern "C"

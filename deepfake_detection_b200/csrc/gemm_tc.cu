@@ -1,0 +1,420 @@
+// Pointwise (1x1) convolution GEMM on the Blackwell tensor-core path: TMA -> shared memory (128B swizzle) ->
+// tcgen05.mma (cta_group::1, kind::f16, fp32 accumulators in TMEM) -> tcgen05.ld epilogue -> swizzled smem ->
+// TMA store, with the per-channel BatchNorm statistics of the stored tile reduced in the same epilogue.
+//
+//   C[M,N] = A[M,K] * B[N,K]^T          A: NHWC activations / output gradients (K-contiguous rows)
+//                                        B: conv weight [Cout,Cin] (forward) or its transpose [Cin,Cout] (dgrad)
+//
+// Replaces nn.Conv2d 1x1 (cuDNN/cuBLAS in the reference: dfd/timm/models/efficientnet_blocks.py:165,277,299,
+// efficientnet.py:292, resnet.py:192,199) and its input-gradient (autograd, train.py:634-636).
+//
+// Shape regime: M = N*H*W is 12.5k .. 3.2M, K and N are 16 .. 1280 -> every instance is
+// HBM-bound (AI << 219 FLOP/B), so the design goal is to stream A and C at HBM rate, not MMA peak:
+//   * persistent CTAs (one per SM), tiles 128 x BLOCK_N, BLOCK_N = whole N when N <= 256 (A is read once);
+//   * K/N/M tails need no padding copies: TMA zero-fills out-of-bounds loads and clips stores;
+//   * 2 TMEM accumulator stages so the epilogue of tile i overlaps the loads + MMAs of tile i+1;
+//   * warp roles: w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue (TMEM lane quarter = warp%4).
+#include <cuda.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 x 2 B = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int SLAB = 64;             // epilogue / TMA-store column slab
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_THREADS = 128;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;      // TMEM column offset between the two accumulator stages
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_addr(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+
+// ---- TMA ------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_addr(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// ---- tcgen05 --------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16/fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64))
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                 // LBO: unused for swizzled K-major
+    d |= (uint64_t)(1024 >> 4) << 32;       // SBO = 1024 B between 8-row core-matrix groups
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 (1) [4,6), a/b format [7,10)/[10,13) (F16=0, BF16=1),
+// a/b major K (0) bits 15/16, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int is_bf16, int n) {
+    uint32_t d = 0;
+    d |= 1u << 4;
+    d |= (uint32_t)(is_bf16 ? 1 : 0) << 7;
+    d |= (uint32_t)(is_bf16 ? 1 : 0) << 10;
+    d |= (uint32_t)(n >> 3) << 17;
+    d |= (uint32_t)(BLOCK_M >> 4) << 24;
+    return d;
+}
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+struct TcParams {
+    int M, N, K;
+    int block_n;          // multiple of 16, <= 256
+    int num_m_tiles, num_n_tiles, num_k_blocks;
+    int stages;
+    int is_bf16;
+    double* dsum;         // optional [DFD_STAT_SLOTS][N]
+    double* dsq;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_c, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // SWIZZLE_128B tiles must sit on 1024-byte boundaries of the shared address space
+    uint8_t* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    // carve-up (all tile bases 1024-byte aligned): [A stages][B stages][2 C slabs][barriers]
+    const uint32_t a_bytes = BLOCK_M * BLOCK_K * 2;
+    const uint32_t b_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
+    const uint32_t b_stride = (b_bytes + 1023) & ~1023u;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem_a + (size_t)p.stages * a_bytes;
+    uint8_t* smem_c = smem_b + (size_t)p.stages * b_stride;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * BLOCK_M * SLAB * 2);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + 8;
+    uint64_t* tmem_full = bars + 16;
+    uint64_t* tmem_empty = bars + 18;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+    float* red = reinterpret_cast<float*>(bars + 22);        // [2][2][64]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        prefetch_tmap(&tmap_c);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(tmem_full + i, 1); mbar_init(tmem_empty + i, EPI_THREADS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_idx = tile / p.num_n_tiles, n_idx = tile - m_idx * p.num_n_tiles;
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    mbar_arrive_expect_tx(full_bar + stage, a_bytes + b_bytes);
+                    tma_load_2d(smem_a + (size_t)stage * a_bytes, &tmap_a, full_bar + stage, kb * BLOCK_K, m_idx * BLOCK_M);
+                    tma_load_2d(smem_b + (size_t)stage * b_stride, &tmap_b, full_bar + stage, kb * BLOCK_K, n_idx * p.block_n);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(p.is_bf16, p.block_n);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+                for (int kb = 0; kb < p.num_k_blocks; kb++) {
+                    mbar_wait(full_bar + stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_addr(smem_a + (size_t)stage * a_bytes);
+                    const uint32_t b_addr = smem_addr(smem_b + (size_t)stage * b_stride);
+                    int krem = p.K - kb * BLOCK_K;
+                    int nk = krem >= BLOCK_K ? BLOCK_K / UMMA_K : (krem + UMMA_K - 1) / UMMA_K;
+                    for (int k = 0; k < nk; k++) {
+                        uint64_t adesc = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 2);
+                        uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 2);
+                        umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar + stage);          // frees the smem stage when the MMAs have read it
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tmem_full + acc);                // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int et = threadIdx.x - (NUM_THREADS - EPI_THREADS);     // 0..127 == TMEM lane == tile row
+        const int q = warp & 3;                                       // TMEM lane quarter this warp may access
+        const bool leader = et == 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t slab_count = 0;
+        const int nslabs = (p.block_n + SLAB - 1) / SLAB;
+        const bool keep = p.num_n_tiles == 1;          // column identity is fixed -> keep sums in registers
+        float ks[4] = {0.f, 0.f, 0.f, 0.f}, kq[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_idx = tile / p.num_n_tiles, n_idx = tile - m_idx * p.num_n_tiles;
+            mbar_wait(tmem_full + acc, acc_phase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+            for (int s = 0; s < nslabs; s++) {
+                uint8_t* cbuf = smem_c + (size_t)(slab_count & 1) * (BLOCK_M * SLAB * 2);
+                if (leader) tma_store_wait_read<1>();       // the store that last used this buffer has drained
+                epi_barrier();
+                const int ncols = min(SLAB, p.block_n - s * SLAB);
+                for (int c16 = 0; c16 < ncols; c16 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(t_base + s * SLAB + c16, v);
+                    tmem_ld_wait();
+                    uint4 lo, hi;
+                    lo.x = pack2<T>(__uint_as_float(v[0]), __uint_as_float(v[1]));
+                    lo.y = pack2<T>(__uint_as_float(v[2]), __uint_as_float(v[3]));
+                    lo.z = pack2<T>(__uint_as_float(v[4]), __uint_as_float(v[5]));
+                    lo.w = pack2<T>(__uint_as_float(v[6]), __uint_as_float(v[7]));
+                    hi.x = pack2<T>(__uint_as_float(v[8]), __uint_as_float(v[9]));
+                    hi.y = pack2<T>(__uint_as_float(v[10]), __uint_as_float(v[11]));
+                    hi.z = pack2<T>(__uint_as_float(v[12]), __uint_as_float(v[13]));
+                    hi.w = pack2<T>(__uint_as_float(v[14]), __uint_as_float(v[15]));
+                    const int j = c16 >> 3;              // logical 16-byte chunk index within the 128-byte row
+                    uint8_t* row = cbuf + et * 128;
+                    *reinterpret_cast<uint4*>(row + ((j ^ (et & 7)) << 4)) = lo;
+                    *reinterpret_cast<uint4*>(row + (((j + 1) ^ (et & 7)) << 4)) = hi;
+                }
+                if (s == nslabs - 1) {
+                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(tmem_empty + acc);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                epi_barrier();
+                if (leader) {
+                    tma_store_2d(&tmap_c, cbuf, n_idx * p.block_n + s * SLAB, m_idx * BLOCK_M);
+                    tma_store_commit();
+                }
+                if (p.dsum) {
+                    // column statistics of the stored (rounded) slab; rows past M are exact zeros
+                    const int c = et & 63, half = et >> 6;
+                    float sum = 0.f, sq = 0.f;
+                    if (c < ncols) {
+                        const uint8_t* colp = cbuf + (c & 7) * 2;
+                        const int jc = c >> 3;
+#pragma unroll 8
+                        for (int r = half * 64; r < half * 64 + 64; r++) {
+                            float x = to_f<T>(*reinterpret_cast<const T*>(colp + r * 128 + ((jc ^ (r & 7)) << 4)));
+                            sum += x;
+                            sq = fmaf(x, x, sq);
+                        }
+                    }
+                    red[(0 * 2 + half) * 64 + c] = sum;
+                    red[(1 * 2 + half) * 64 + c] = sq;
+                    epi_barrier();
+                    if (et < 64) {
+                        float ts = red[et] + red[64 + et], tq = red[128 + et] + red[192 + et];
+                        if (keep) { ks[s] += ts; kq[s] += tq; }
+                        else {
+                            int gc = n_idx * p.block_n + s * SLAB + et;
+                            if (et < ncols && gc < p.N) {
+                                atomicAdd(stat_slot(p.dsum, p.N) + gc, (double)ts);
+                                atomicAdd(stat_slot(p.dsq, p.N) + gc, (double)tq);
+                            }
+                        }
+                    }
+                }
+                slab_count++;
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (p.dsum && keep && et < 64) {
+            for (int s = 0; s < nslabs; s++) {
+                int gc = s * SLAB + et;
+                if (gc < p.N && gc < p.block_n) {
+                    atomicAdd(stat_slot(p.dsum, p.N) + gc, (double)ks[s]);
+                    atomicAdd(stat_slot(p.dsq, p.N) + gc, (double)kq[s]);
+                }
+            }
+        }
+        if (leader) tma_store_wait_read<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D row-major [rows, cols] 16-bit tensor, box = [box_rows, 64 cols], 128-byte swizzle, OOB -> zeros / clipped
+static int make_map(CUtensorMap* m, const void* base, long long rows, int cols, int box_rows, int is_bf16) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return dfd_set_error(DFD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d box_rows=%d", (int)r, rows, cols, box_rows);
+        return dfd_set_error(DFD_ERR_CUDA, buf);
+    }
+    return DFD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// C[M,N] = A[M,K] * B[N,K]^T on tcgen05; optional fp64 column statistics of the stored C ([8][N] slots).
+// All pointers must be 16-byte aligned, K % 8 == 0 and N % 8 == 0 (TMA global strides are multiples of 16 B).
+int dfd_gemm_tn(const void* A, const void* B, void* C, long long M, int N, int K, int dt, double* dsum, double* dsq,
+                void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0 || (N % 8) || (K % 8)) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn: N%8, K%8");
+    if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn: dtype");
+    TcParams p;
+    p.M = (int)M; p.N = N; p.K = K;
+    p.is_bf16 = dt == DFD_DT_BF16;
+    p.block_n = N <= 256 ? ((N + 15) / 16) * 16 : 256;
+    p.num_m_tiles = cdiv(M, BLOCK_M);
+    p.num_n_tiles = cdiv(N, p.block_n);
+    p.num_k_blocks = cdiv(K, BLOCK_K);
+    p.dsum = dsum; p.dsq = dsq;
+    const int a_bytes = BLOCK_M * BLOCK_K * 2;
+    const int b_stride = ((p.block_n * BLOCK_K * 2) + 1023) & ~1023;
+    const int fixed = 2 * BLOCK_M * SLAB * 2 + 22 * 8 + 4 * 64 * 4 + 1024 /* alignment slack */;
+    int stages = (227 * 1024 - fixed) / (a_bytes + b_stride);
+    if (stages > 6) stages = 6;
+    if (stages < 2) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_gemm_tn: smem");
+    p.stages = stages;
+    size_t smem = (size_t)stages * (a_bytes + b_stride) + fixed;
+
+    CUtensorMap ma, mb, mc;
+    int rc;
+    if ((rc = make_map(&ma, A, M, K, BLOCK_M, p.is_bf16))) return rc;
+    if ((rc = make_map(&mb, B, N, K, p.block_n, p.is_bf16))) return rc;
+    if ((rc = make_map(&mc, C, M, N, BLOCK_M, p.is_bf16))) return rc;
+
+    int device = 0, sms = 148;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int grid = p.num_m_tiles * p.num_n_tiles;
+    if (grid > sms) grid = sms;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.is_bf16) {
+        auto kf = gemm_tc_kernel<bf16>;
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+        kf<<<grid, NUM_THREADS, smem, st>>>(ma, mb, mc, p);
+    } else {
+        auto kf = gemm_tc_kernel<__half>;
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+        kf<<<grid, NUM_THREADS, smem, st>>>(ma, mb, mc, p);
+    }
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+}  // extern "C"

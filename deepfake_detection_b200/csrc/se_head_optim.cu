@@ -1,0 +1,456 @@
+// Small per-image kernels (squeeze-excite FCs, classifier + sigmoid-BCE loss) and the flat-arena
+// optimizer / weight-preparation kernels.
+//
+// Reference semantics restated here:
+//   SqueezeExcite.forward         dfd/timm/models/efficientnet_blocks.py:104-110  (FC+bias, Swish, FC+bias, sigmoid)
+//   classifier + loss             dfd/timm/models/efficientnet.py:348, dfd/timm/loss/cross_entropy.py:20-36,
+//                                 nn.CrossEntropyLoss (dfd/runners/train.py:509-520); 2-class CE == sigmoid-BCE on z1-z0
+//   accuracy                      dfd/timm/utils.py:170-186
+//   SGD nesterov                  torch.optim.SGD as configured by dfd/timm/optim/optim_factory.py:48-50
+//   Adam / AdamW                  optim_factory.py:51-56, dfd/timm/optim/adamw.py:55-117
+//   RMSpropTF                     dfd/timm/optim/rmsprop_tf.py:57-122
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float swish_precise(float x) { return x * sigmoid_precise(x); }
+__device__ __forceinline__ float softplus_precise(float x) {
+    // log(1 + exp(x)), stable
+    return fmaxf(x, 0.f) + log1pf(__expf(-fabsf(x)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// SE excite, one CTA per image: gate[n,:] = sigmoid(We * swish(Wr * pooled[n,:] + br) + be)
+// ---------------------------------------------------------------------------------------------
+__global__ void se_fc_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ Wr,
+                                 const float* __restrict__ br, const float* __restrict__ We,
+                                 const float* __restrict__ be, float* __restrict__ gate, int C, int Cse) {
+    extern __shared__ float sm[];
+    float* p = sm;           // [C]
+    float* r = sm + C;       // [Cse]
+    const int n = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    for (int c = tid; c < C; c += nt) p[c] = pooled[(size_t)n * C + c];
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    for (int j = warp; j < Cse; j += nw) {
+        const float* w = Wr + (size_t)j * C;
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(w[c], p[c], s);
+        s = warp_sum(s);
+        if (lane == 0) r[j] = swish_precise(s + br[j]);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += nt) {
+        const float* w = We + (size_t)c * Cse;
+        float s = be[c];
+        for (int j = 0; j < Cse; j++) s = fmaf(w[j], r[j], s);
+        gate[(size_t)n * C + c] = sigmoid_precise(s);
+    }
+}
+
+// SE backward, per image: from draw = dL/dgate recompute the FC chain and emit
+//   d_e [N,C], r [N,Cse], d_rpre [N,Cse] (for the parameter-gradient kernel) and dpool [N,C].
+__global__ void se_fc_bwd_kernel(const float* __restrict__ draw, const float* __restrict__ pooled,
+                                 const float* __restrict__ Wr, const float* __restrict__ br,
+                                 const float* __restrict__ We, const float* __restrict__ be,
+                                 float* __restrict__ d_e, float* __restrict__ r_out, float* __restrict__ d_rpre,
+                                 float* __restrict__ dpool, int C, int Cse) {
+    extern __shared__ float sm[];
+    float* p = sm;                 // [C]
+    float* de = sm + C;            // [C]
+    float* rpre = sm + 2 * C;      // [Cse]
+    float* r = rpre + Cse;         // [Cse]
+    float* drp = r + Cse;          // [Cse]
+    const int n = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    for (int c = tid; c < C; c += nt) p[c] = pooled[(size_t)n * C + c];
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    for (int j = warp; j < Cse; j += nw) {
+        const float* w = Wr + (size_t)j * C;
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(w[c], p[c], s);
+        s = warp_sum(s);
+        if (lane == 0) { rpre[j] = s + br[j]; r[j] = swish_precise(s + br[j]); }
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += nt) {
+        const float* w = We + (size_t)c * Cse;
+        float s = be[c];
+        for (int j = 0; j < Cse; j++) s = fmaf(w[j], r[j], s);
+        float g = sigmoid_precise(s);
+        float v = draw[(size_t)n * C + c] * g * (1.f - g);
+        de[c] = v;
+        d_e[(size_t)n * C + c] = v;
+    }
+    __syncthreads();
+    for (int j = warp; j < Cse; j += nw) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(We[(size_t)c * Cse + j], de[c], s);
+        s = warp_sum(s);
+        if (lane == 0) {
+            float x = rpre[j];
+            float sg = sigmoid_precise(x);
+            float v = s * (sg * (1.f + x * (1.f - sg)));
+            drp[j] = v;
+            d_rpre[(size_t)n * Cse + j] = v;
+            r_out[(size_t)n * Cse + j] = r[j];
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += nt) {
+        float s = 0.f;
+        for (int j = 0; j < Cse; j++) s = fmaf(Wr[(size_t)j * C + c], drp[j], s);
+        dpool[(size_t)n * C + c] = s;
+    }
+}
+
+// SE parameter gradients: one thread per (c, j); contraction over the N images.
+__global__ void se_fc_wgrad_kernel(const float* __restrict__ d_e, const float* __restrict__ r,
+                                   const float* __restrict__ d_rpre, const float* __restrict__ pooled,
+                                   float* __restrict__ dWr, float* __restrict__ dbr, float* __restrict__ dWe,
+                                   float* __restrict__ dbe, int N, int C, int Cse) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= C * Cse) return;
+    int c = idx / Cse, j = idx - c * Cse;
+    float awe = 0.f, awr = 0.f, abe = 0.f, abr = 0.f;
+    for (int n = 0; n < N; n++) {
+        float de = d_e[(size_t)n * C + c], rr = r[(size_t)n * Cse + j];
+        float dr = d_rpre[(size_t)n * Cse + j], pp = pooled[(size_t)n * C + c];
+        awe = fmaf(de, rr, awe);
+        awr = fmaf(dr, pp, awr);
+        abe += de;
+        abr += dr;
+    }
+    dWe[(size_t)c * Cse + j] += awe;
+    dWr[(size_t)j * C + c] += awr;
+    if (j == 0) dbe[c] += abe;
+    if (c == 0) dbr[j] += abr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// classifier: logits[n,k] = W[k,:] . pooled[n,:] + b[k]   (one CTA per image, one warp per class round-robin)
+// fused 2-class loss (sigmoid-BCE on d = z1 - z0 == softmax-CE), top-1, and dL/dlogits.
+// target: int64 hard labels (tgt_i) or float soft targets [N,2] (tgt_f).
+// ---------------------------------------------------------------------------------------------
+__global__ void head_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ W,
+                                const float* __restrict__ b, float* __restrict__ logits, int F, int K,
+                                const long long* __restrict__ tgt_i, const float* __restrict__ tgt_f, float smoothing,
+                                float inv_n, float loss_scale, float* __restrict__ loss_acc,
+                                float* __restrict__ correct_acc, float* __restrict__ dlogits) {
+    __shared__ float z[32];
+    const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const float* p = pooled + (size_t)n * F;
+    for (int k = warp; k < K; k += nw) {
+        const float* w = W + (size_t)k * F;
+        float s = 0.f;
+        for (int f = lane; f < F; f += 32) s = fmaf(w[f], p[f], s);
+        s = warp_sum(s);
+        if (lane == 0) { z[k] = s + b[k]; logits[(size_t)n * K + k] = s + b[k]; }
+    }
+    if (!loss_acc) return;
+    __syncthreads();
+    if (threadIdx.x == 0 && K == 2) {
+        float t0, t1;
+        if (tgt_f) { t0 = tgt_f[n * 2]; t1 = tgt_f[n * 2 + 1]; }
+        else {
+            int y = (int)tgt_i[n];
+            t1 = y ? 1.f - 0.5f * smoothing : 0.5f * smoothing;
+            t0 = y ? 0.5f * smoothing : 1.f - 0.5f * smoothing;
+        }
+        float d = z[1] - z[0];
+        float loss = t0 * softplus_precise(d) + t1 * softplus_precise(-d);
+        float sg = sigmoid_precise(d);
+        float g1 = (t0 + t1) * sg - t1;
+        atomicAdd(loss_acc, loss * inv_n);
+        int pred = z[1] > z[0] ? 1 : 0;      // topk(1) returns the first index on ties
+        int lab = t1 > t0 ? 1 : 0;
+        if (pred == lab) atomicAdd(correct_acc, 1.f);
+        if (dlogits) {
+            dlogits[n * 2] = -g1 * inv_n * loss_scale;
+            dlogits[n * 2 + 1] = g1 * inv_n * loss_scale;
+        }
+    }
+}
+
+// dpooled[n,f] = sum_k dlogits[n,k] W[k,f]
+__global__ void head_dgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ W,
+                                  float* __restrict__ dpooled, int N, int F, int K) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)N * F) return;
+    int n = (int)(idx / F), f = (int)(idx - (size_t)n * F);
+    float s = 0.f;
+    for (int k = 0; k < K; k++) s = fmaf(dlogits[(size_t)n * K + k], W[(size_t)k * F + f], s);
+    dpooled[idx] = s;
+}
+// dW[k,f] += sum_n dlogits[n,k] pooled[n,f]; db[k] += sum_n dlogits[n,k]
+__global__ void head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ pooled,
+                                  float* __restrict__ dW, float* __restrict__ db, int N, int F, int K) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * F) return;
+    int k = idx / F, f = idx - k * F;
+    float s = 0.f, sb = 0.f;
+    for (int n = 0; n < N; n++) {
+        float d = dlogits[(size_t)n * K + k];
+        s = fmaf(d, pooled[(size_t)n * F + f], s);
+        sb += d;
+    }
+    dW[idx] += s;
+    if (f == 0) db[k] += sb;
+}
+
+// ---------------------------------------------------------------------------------------------
+// flat-arena optimizers.  One launch per parameter group (decay / no-decay ranges of the arena).
+// g is multiplied by grad_scale (1/world for the DDP mean, 1/loss_scale for fp16) before use.
+// If `skip` is non-null and *skip != 0 the step is skipped (fp16 overflow).  p16 (optional) receives the
+// 16-bit copy of the updated weights that the GEMM / depthwise kernels read.
+// ---------------------------------------------------------------------------------------------
+template <typename T16>
+__device__ __forceinline__ void store16(void* p16, size_t i, float v) {
+    if (p16) reinterpret_cast<T16*>(p16)[i] = from_f<T16>(v);
+}
+
+template <typename T16>
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, size_t n,
+                           float lr, float momentum, float wd, int nesterov, float grad_scale,
+                           const int* __restrict__ skip, void* __restrict__ p16) {
+    if (skip && *skip) return;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float w = p[i];
+        float gg = fmaf(wd, w, g[i] * grad_scale);
+        float buf = fmaf(momentum, m[i], gg);     // first step: m == 0 -> buf = g (torch clones the gradient)
+        m[i] = buf;
+        float upd = nesterov ? fmaf(momentum, buf, gg) : buf;
+        w = fmaf(-lr, upd, w);
+        p[i] = w;
+        store16<T16>(p16, i, w);
+    }
+}
+
+template <typename T16>
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                            int decoupled, float bc1, float bc2_sqrt, float grad_scale,
+                            const int* __restrict__ skip, void* __restrict__ p16) {
+    if (skip && *skip) return;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float w = p[i];
+        float gg = g[i] * grad_scale;
+        if (decoupled) w *= (1.f - lr * wd);       // adamw.py:72
+        else gg = fmaf(wd, w, gg);                 // torch.optim.Adam L2
+        float mm = fmaf(b1, m[i], (1.f - b1) * gg);
+        float vv = fmaf(b2, v[i], (1.f - b2) * gg * gg);
+        m[i] = mm;
+        v[i] = vv;
+        float denom = sqrtf(vv) / bc2_sqrt + eps;
+        w -= (lr / bc1) * (mm / denom);
+        p[i] = w;
+        store16<T16>(p16, i, w);
+    }
+}
+
+template <typename T16>
+__global__ void rmsprop_tf_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq,
+                                  float* __restrict__ mom, size_t n, float lr, float alpha, float eps, float wd,
+                                  float momentum, float grad_scale, const int* __restrict__ skip,
+                                  void* __restrict__ p16) {
+    if (skip && *skip) return;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float w = p[i];
+        float gg = fmaf(wd, w, g[i] * grad_scale);
+        float s = sq[i];
+        s = fmaf(1.f - alpha, gg * gg - s, s);     // rmsprop_tf.py:100 (TF op order)
+        sq[i] = s;
+        float avg = sqrtf(s + eps);                // eps inside the sqrt, :107
+        if (momentum > 0.f) {
+            float b = fmaf(momentum, mom[i], lr * gg / avg);   // lr folded into the buffer, :112-114
+            mom[i] = b;
+            w -= b;
+        } else {
+            w -= lr * gg / avg;
+        }
+        p[i] = w;
+        store16<T16>(p16, i, w);
+    }
+}
+
+template <typename T16>
+__global__ void cast_arena_kernel(const float* __restrict__ p, T16* __restrict__ p16, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p16[i] = from_f<T16>(p[i]);
+}
+
+// any non-finite gradient -> *flag = 1   (fp16 dynamic loss scaling, apex O1 semantics train.py:353,632-634)
+__global__ void check_finite_kernel(const float* __restrict__ g, size_t n, int* __restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (; i < n; i += stride) {
+        float x = g[i];
+        if (!(fabsf(x) <= 3.0e38f)) bad = 1;
+    }
+    if (bad) *flag = 1;
+}
+
+// dynamic loss scale update on the device (no host sync): halve on overflow, double after `interval` clean steps
+__global__ void update_loss_scale_kernel(int* __restrict__ flag, float* __restrict__ scale, int* __restrict__ good,
+                                         int interval, float* __restrict__ inv_scale_out) {
+    if (*flag) {
+        *scale = fmaxf(*scale * 0.5f, 1.f);
+        *good = 0;
+    } else {
+        int g = *good + 1;
+        if (g >= interval) { *scale = fminf(*scale * 2.f, 16777216.f); g = 0; }
+        *good = g;
+    }
+    if (inv_scale_out) *inv_scale_out = 1.f / *scale;
+}
+
+// transposed 16-bit copies of the 1x1-conv weights for dgrad: src [O, I] -> dst [I, O]
+struct TransposeDesc {
+    const void* src;
+    void* dst;
+    int O;
+    int I;
+};
+template <typename T16>
+__global__ void transpose_weights_kernel(const TransposeDesc* __restrict__ table) {
+    __shared__ T16 tile[32][33];
+    TransposeDesc d = table[blockIdx.z];
+    const T16* src = (const T16*)d.src;
+    T16* dst = (T16*)d.dst;
+    for (int o0 = blockIdx.y * 32; o0 < d.O; o0 += gridDim.y * 32) {
+        for (int i0 = blockIdx.x * 32; i0 < d.I; i0 += gridDim.x * 32) {
+            for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+                int o = o0 + r, i = i0 + threadIdx.x;
+                if (o < d.O && i < d.I) tile[r][threadIdx.x] = src[(size_t)o * d.I + i];
+            }
+            __syncthreads();
+            for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+                int i = i0 + r, o = o0 + threadIdx.x;
+                if (o < d.O && i < d.I) dst[(size_t)i * d.O + o] = tile[threadIdx.x][r];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+static int flat_blocks(size_t n) {
+    size_t b = (n + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dfd_se_fc_fwd(const float* pooled, const float* Wr, const float* br, const float* We, const float* be,
+                  float* gate, int N, int C, int Cse, void* stream) {
+    if (N <= 0 || C <= 0 || Cse <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_fc_fwd: sizes");
+    size_t smem = (size_t)(C + Cse) * sizeof(float);
+    se_fc_fwd_kernel<<<N, 256, smem, (cudaStream_t)stream>>>(pooled, Wr, br, We, be, gate, C, Cse);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_se_fc_bwd(const float* draw, const float* pooled, const float* Wr, const float* br, const float* We,
+                  const float* be, float* d_e, float* r, float* d_rpre, float* dpool, float* dWr, float* dbr,
+                  float* dWe, float* dbe, int N, int C, int Cse, void* stream) {
+    if (N <= 0 || C <= 0 || Cse <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_fc_bwd: sizes");
+    size_t smem = (size_t)(2 * C + 3 * Cse) * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    se_fc_bwd_kernel<<<N, 256, smem, st>>>(draw, pooled, Wr, br, We, be, d_e, r, d_rpre, dpool, C, Cse);
+    DFD_LAUNCH_CHECK();
+    se_fc_wgrad_kernel<<<cdiv((long long)C * Cse, 128), 128, 0, st>>>(d_e, r, d_rpre, pooled, dWr, dbr, dWe, dbe, N, C, Cse);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_head_fwd(const float* pooled, const float* W, const float* b, float* logits, int N, int F, int K,
+                 const long long* tgt_i, const float* tgt_f, float smoothing, float loss_scale, float* loss_acc,
+                 float* correct_acc, float* dlogits, void* stream) {
+    if (N <= 0 || F <= 0 || K <= 0 || K > 32) return dfd_set_error(DFD_ERR_ARG, "dfd_head_fwd: sizes");
+    if (loss_acc && K != 2) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_head_fwd: fused sigmoid-BCE needs num_classes == 2");
+    if (loss_acc && !tgt_i && !tgt_f) return dfd_set_error(DFD_ERR_ARG, "dfd_head_fwd: loss without target");
+    head_fwd_kernel<<<N, 64, 0, (cudaStream_t)stream>>>(pooled, W, b, logits, F, K, tgt_i, tgt_f, smoothing,
+                                                         1.f / (float)N, loss_scale, loss_acc, correct_acc, dlogits);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_head_bwd(const float* dlogits, const float* pooled, const float* W, float* dW, float* db, float* dpooled,
+                 int N, int F, int K, void* stream) {
+    if (N <= 0 || F <= 0 || K <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_head_bwd: sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    head_dgrad_kernel<<<cdiv((long long)N * F, 256), 256, 0, st>>>(dlogits, W, dpooled, N, F, K);
+    DFD_LAUNCH_CHECK();
+    head_wgrad_kernel<<<cdiv((long long)K * F, 128), 128, 0, st>>>(dlogits, pooled, dW, db, N, F, K);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+#define DISPATCH_16(dt, ...)                                          \
+    if ((dt) == DFD_DT_FP16) { typedef __half T16; __VA_ARGS__; }     \
+    else { typedef bf16 T16; __VA_ARGS__; }
+
+int dfd_sgd_step(float* p, const float* g, float* m, long long n, float lr, float momentum, float wd, int nesterov,
+                 float grad_scale, const int* skip, void* p16, int dt, void* stream) {
+    if (n <= 0) return DFD_OK;
+    DISPATCH_16(dt, (sgd_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, (size_t)n, lr, momentum, wd, nesterov, grad_scale, skip, p16)));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                  float wd, int decoupled, int step, float grad_scale, const int* skip, void* p16, int dt,
+                  void* stream) {
+    if (n <= 0) return DFD_OK;
+    float bc1 = 1.f - powf(b1, (float)step);
+    float bc2s = sqrtf(1.f - powf(b2, (float)step));
+    DISPATCH_16(dt, (adam_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (size_t)n, lr, b1, b2, eps, wd, decoupled, bc1, bc2s, grad_scale, skip, p16)));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_rmsprop_tf_step(float* p, const float* g, float* sq, float* mom, long long n, float lr, float alpha,
+                        float eps, float wd, float momentum, float grad_scale, const int* skip, void* p16, int dt,
+                        void* stream) {
+    if (n <= 0) return DFD_OK;
+    DISPATCH_16(dt, (rmsprop_tf_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, sq, mom, (size_t)n, lr, alpha, eps, wd, momentum, grad_scale, skip, p16)));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_cast_arena(const float* p, void* p16, long long n, int dt, void* stream) {
+    if (n <= 0) return DFD_OK;
+    DISPATCH_16(dt, (cast_arena_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, (T16*)p16, (size_t)n)));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_check_finite(const float* g, long long n, int* flag, void* stream) {
+    if (n <= 0) return DFD_OK;
+    check_finite_kernel<<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(g, (size_t)n, flag);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_update_loss_scale(int* flag, float* scale, int* good_steps, int interval, float* inv_scale_out, void* stream) {
+    update_loss_scale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, scale, good_steps, interval, inv_scale_out);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+// table: device array of {src, dst, O, I} (see TransposeDesc); all tensors share dtype dt
+int dfd_transpose_weights(const void* table, int count, int dt, void* stream) {
+    if (count <= 0) return DFD_OK;
+    dim3 grid(4, 4, count), block(32, 8, 1);
+    DISPATCH_16(dt, (transpose_weights_kernel<T16><<<grid, block, 0, (cudaStream_t)stream>>>((const TransposeDesc*)table)));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,486 @@
+"""Native train / validate engine: lays the network out in HBM and drives the sm_100a kernels.
+
+This is the host side of the hot path (dfd/runners/train.py:610-649): given an architecture spec it
+  * owns the flat fp32 parameter / gradient arenas (reference tensor names, OIHW shapes) plus their 16-bit
+    copies in the layouts the kernels read ([Cout,Cin] and transposed [Cin,Cout] for the 1x1 convs),
+  * keeps every conv output NHWC in 16-bit (the only activation tensors that touch HBM),
+  * builds, once, the ordered list of C-ABI calls ("plan") for forward, backward and the optimizer, and
+  * replays the plan on the caller's current CUDA stream (optionally captured into a CUDA graph).
+
+PyTorch is used for device memory and streams only; there is no PyTorch compute on the hot path and no CPU
+fallback: constructing an Engine without a CUDA device or without libdfd_b200.so raises.
+"""
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+from .arch import get_spec, is_no_decay, param_entries, state_entries
+
+ACT_NONE, ACT_SWISH, ACT_RELU = _lib.ACT_NONE, _lib.ACT_SWISH, _lib.ACT_RELU
+
+
+def _ptr(t, off_elems=0):
+    return t.data_ptr() + off_elems * t.element_size()
+
+
+class _BN:
+    """Pointers of one BatchNorm layer (parameters, running stats, per-step statistics, bwd coefficients)."""
+    __slots__ = ("name", "C", "gamma", "beta", "dgamma", "dbeta", "rm", "rv", "nbt", "scale", "shift", "mean",
+                 "rstd", "cA", "cB", "cC", "fsum", "fsq", "bs1", "bs2")
+
+
+class Engine:
+    def __init__(self, arch, batch, height=None, width=None, num_classes=2, in_chans=3, dtype="bf16",
+                 bn_momentum=0.1, bn_eps=1e-5, device=None, gemm_impl="tc"):
+        # _plan_only: build the arenas and the call plan on the CPU for host-logic tests; nothing can be executed
+        self._plan_only = device == "plan-only"
+        if self._plan_only:
+            device = "cpu"
+        elif not torch.cuda.is_available():
+            raise _lib.NativeError("deepfake_detection_b200.Engine needs a CUDA device (B200, sm_100a); "
+                                   "there is no CPU path")
+        self.L = _lib.lib()
+        self.spec = spec = get_spec(arch, num_classes=num_classes, in_chans=in_chans)
+        if spec.family != "efficientnet":
+            raise _lib.NativeError("native path for %s is not built yet (round 1 covers the EfficientNet family)" % arch)
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.N = int(batch)
+        self.H = int(height or spec.input_size[1])
+        self.W = int(width or spec.input_size[2])
+        self.dt = _lib.DT_BF16 if dtype in ("bf16", torch.bfloat16) else _lib.DT_FP16
+        self.tdtype = torch.bfloat16 if self.dt == _lib.DT_BF16 else torch.float16
+        self.bn_momentum = float(bn_momentum)
+        self.bn_eps = float(bn_eps)
+        self.gemm_impl = gemm_impl
+        self.training = True
+        self.n_launch = {"fwd": 0, "bwd": 0, "opt": 0}
+        self._layout_params()
+        self._build()
+
+    # ------------------------------------------------------------------------------------------
+    # parameter / buffer arenas
+    # ------------------------------------------------------------------------------------------
+    def _layout_params(self):
+        spec, dev = self.spec, self.device
+        entries = param_entries(spec)
+        decay = [(n, s) for n, s, _ in entries if not is_no_decay(n, s)]
+        nodecay = [(n, s) for n, s, _ in entries if is_no_decay(n, s)]
+        self.p_off = OrderedDict()
+        off = 0
+        for n, s in decay + nodecay:
+            numel = 1
+            for d in s:
+                numel *= d
+            self.p_off[n] = (off, tuple(s), numel)
+            off += (numel + 3) // 4 * 4          # keep every tensor 16-byte aligned in fp32 and 8-byte in 16-bit
+            if n == decay[-1][0]:
+                off = (off + 7) // 8 * 8
+                self.n_decay = off
+        self.n_params = off
+        self.param_names = [n for n, _, _ in entries]
+        self.params32 = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grads32 = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.params16 = torch.zeros(off, dtype=self.tdtype, device=dev)
+        # buffers (running stats): flat fp32 + int64 counters
+        self.b_off = OrderedDict()
+        boff = 0
+        self.bn_names = []
+        for n, s, role in state_entries(spec):
+            if role in ("bn_rm", "bn_rv"):
+                self.b_off[n] = (boff, s[0])
+                boff += (s[0] + 3) // 4 * 4
+            elif role == "bn_nbt":
+                self.bn_names.append(n[: -len(".num_batches_tracked")])
+        self.buffers32 = torch.zeros(boff, dtype=torch.float32, device=dev)
+        for n, (o, c) in self.b_off.items():
+            if n.endswith("running_var"):
+                self.buffers32[o:o + c] = 1.0
+        self.nbt = torch.zeros(len(self.bn_names), dtype=torch.int64, device=dev)
+        # transposed 16-bit copies of the 1x1 conv weights (dgrad B operand)
+        self.t_off = OrderedDict()
+        toff = 0
+        for n, s, role in entries:
+            if role == "conv_w" and s[2] == 1 and s[3] == 1:
+                self.t_off[n] = (toff, s[0], s[1])
+                toff += (s[0] * s[1] + 7) // 8 * 8
+        self.paramsT16 = torch.zeros(max(toff, 8), dtype=self.tdtype, device=dev)
+        import struct
+        raw = b"".join(struct.pack("<QQii", _ptr(self.params16, self.p_off[n][0]), _ptr(self.paramsT16, o), O, I)
+                       for n, (o, O, I) in self.t_off.items())
+        self._ttable = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self._ttable_count = len(self.t_off)
+
+    def param_view(self, name):
+        o, s, n = self.p_off[name]
+        return self.params32[o:o + n].view(s)
+
+    def grad_view(self, name):
+        o, s, n = self.p_off[name]
+        return self.grads32[o:o + n].view(s)
+
+    def buffer_view(self, name):
+        if name.endswith("num_batches_tracked"):
+            return self.nbt[self.bn_names.index(name[: -len(".num_batches_tracked")])]
+        o, c = self.b_off[name]
+        return self.buffers32[o:o + c]
+
+    def state_dict(self):
+        """Reference-layout state dict (fp32 master weights, OIHW), a copy."""
+        sd = OrderedDict()
+        for n, s, role in state_entries(self.spec):
+            if role in ("bn_rm", "bn_rv", "bn_nbt"):
+                sd[n] = self.buffer_view(n).clone()
+            else:
+                sd[n] = self.param_view(n).clone()
+        return sd
+
+    def load_state_dict(self, sd, strict=True):
+        missing = []
+        with torch.no_grad():
+            for n, s, role in state_entries(self.spec):
+                if n not in sd:
+                    missing.append(n)
+                    continue
+                src = sd[n].to(self.device)
+                if role in ("bn_rm", "bn_rv"):
+                    self.buffer_view(n).copy_(src.float())
+                elif role == "bn_nbt":
+                    self.nbt[self.bn_names.index(n[: -len(".num_batches_tracked")])] = int(src)
+                else:
+                    self.param_view(n).copy_(src.float().reshape(self.p_off[n][1]))
+        if strict and missing:
+            raise KeyError("missing keys in state_dict: %s" % missing[:5])
+        self.sync_weights()
+        return missing
+
+    def sync_weights(self):
+        """fp32 master -> 16-bit kernel copies (call after any out-of-band weight change)."""
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.call("dfd_cast_arena", _ptr(self.params32), _ptr(self.params16), self.n_params, self.dt, st)
+        _lib.call("dfd_transpose_weights", _ptr(self._ttable), self._ttable_count, self.dt, st)
+
+    # ------------------------------------------------------------------------------------------
+    # plan construction
+    # ------------------------------------------------------------------------------------------
+    def _alloc16(self, *shape):
+        return torch.empty(shape, dtype=self.tdtype, device=self.device)
+
+    def _build(self):
+        spec, N, dev, L = self.spec, self.N, self.device, self.L
+        S = L.stat_slots
+        self.acts = {}
+        fwd, bwd = [], []
+        bn_list = []
+
+        # ---- pass 1: shapes --------------------------------------------------------------------
+        Hs = (self.H + 2 - 3) // 2 + 1
+        Ws = (self.W + 2 - 3) // 2 + 1
+        blocks = []
+        h, w = Hs, Ws
+        for b in spec.blocks:
+            ho = (h + 2 * b.pad - b.k) // b.stride + 1
+            wo = (w + 2 * b.pad - b.k) // b.stride + 1
+            blocks.append((b, h, w, ho, wo))
+            h, w = ho, wo
+        Hf, Wf = h, w
+
+        # ---- BN bookkeeping arenas ---------------------------------------------------------------
+        bn_specs = [("bn1", spec.stem)]
+        for b in spec.blocks:
+            if b.kind == "ir":
+                bn_specs += [(b.name + ".bn1", b.cmid), (b.name + ".bn2", b.cmid), (b.name + ".bn3", b.cout)]
+            else:
+                bn_specs += [(b.name + ".bn1", b.cmid), (b.name + ".bn2", b.cout)]
+        bn_specs.append(("bn2", spec.num_features))
+        tot_c = sum((c + 3) // 4 * 4 for _, c in bn_specs)
+        self.bnstate = torch.zeros(7 * tot_c, dtype=torch.float32, device=dev)      # scale shift mean rstd cA cB cC
+        self.stats = torch.zeros(4 * S * tot_c + 8, dtype=torch.float64, device=dev)  # fsum fsq bs1 bs2 (+ loss/correct)
+        self.bns = {}
+        co = 0
+        for name, c in bn_specs:
+            bn = _BN()
+            bn.name, bn.C = name, c
+            bn.gamma = _ptr(self.params32, self.p_off[name + ".weight"][0])
+            bn.beta = _ptr(self.params32, self.p_off[name + ".bias"][0])
+            bn.dgamma = _ptr(self.grads32, self.p_off[name + ".weight"][0])
+            bn.dbeta = _ptr(self.grads32, self.p_off[name + ".bias"][0])
+            bn.rm = _ptr(self.buffers32, self.b_off[name + ".running_mean"][0])
+            bn.rv = _ptr(self.buffers32, self.b_off[name + ".running_var"][0])
+            bn.nbt = _ptr(self.nbt, self.bn_names.index(name))
+            for i, f in enumerate(("scale", "shift", "mean", "rstd", "cA", "cB", "cC")):
+                setattr(bn, f, _ptr(self.bnstate, i * tot_c + co))
+            for i, f in enumerate(("fsum", "fsq", "bs1", "bs2")):
+                setattr(bn, f, _ptr(self.stats, (i * tot_c + co) * S))
+            co += (c + 3) // 4 * 4
+            self.bns[name] = bn
+        self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)     # loss_acc, correct_acc, (spare)
+        self.loss_scale_state = torch.ones(2, dtype=torch.float32, device=dev)   # scale, 1/scale
+        self.flags = torch.zeros(2, dtype=torch.int32, device=dev)          # found_inf, good_steps
+
+        P32 = lambda n: _ptr(self.params32, self.p_off[n][0])
+        G32 = lambda n: _ptr(self.grads32, self.p_off[n][0])
+        P16 = lambda n: _ptr(self.params16, self.p_off[n][0])
+        T16 = lambda n: _ptr(self.paramsT16, self.t_off[n][0])
+        dt = self.dt
+        mom, eps = self.bn_momentum, self.bn_eps
+
+        def gemm(A, B, C, M, Nn, K, bn=None):
+            fs, fq = (bn.fsum, bn.fsq) if bn is not None else (None, None)
+            if self.gemm_impl == "tc":
+                return ("dfd_gemm_tn", (A, B, C, M, Nn, K, dt, fs, fq))
+            return ("dfd_gemm_tn_mma", (A, B, C, None, M, Nn, K, dt, fs, fq))
+
+        def finalize(bn, count):
+            # training flag is patched at run time (see _run)
+            return ("dfd_bn_finalize", [bn.fsum, bn.fsq, float(count), bn.gamma, bn.beta, bn.rm, bn.rv, bn.nbt, mom, eps,
+                                        "TRAINING", bn.C, bn.scale, bn.shift, bn.mean, bn.rstd])
+
+        def bwd_finalize(bn, count):
+            return ("dfd_bn_bwd_finalize", (bn.bs1, bn.bs2, float(count), bn.gamma, bn.mean, bn.rstd, bn.dgamma, bn.dbeta,
+                                            bn.cA, bn.cB, bn.cC, bn.C))
+
+        # ---- scratch for backward ----------------------------------------------------------------
+        mid_max = max([N * h * w * b.cmid for b, h, w, ho, wo in blocks if b.kind == "ir"] +
+                      [N * ho * wo * b.cmid for b, h, w, ho, wo in blocks] + [N * Hf * Wf * spec.num_features] +
+                      [N * Hs * Ws * spec.stem])
+        small_max = max([N * h * w * b.cin for b, h, w, ho, wo in blocks] +
+                        [N * ho * wo * b.cout for b, h, w, ho, wo in blocks])
+        self.mid = [self._alloc16(mid_max) for _ in range(2)]
+        self.small = [self._alloc16(small_max) for _ in range(3)]
+        mid_a, mid_b = _ptr(self.mid[0]), _ptr(self.mid[1])
+        sm = [_ptr(t) for t in self.small]
+        se_max_c = max([b.cmid for b in spec.blocks if b.cse] + [8])
+        se_max_r = max([b.cse for b in spec.blocks if b.cse] + [8])
+        self.se_tmp = torch.zeros(3 * N * se_max_c + 2 * N * se_max_r, dtype=torch.float32, device=dev)
+        se_draw = _ptr(self.se_tmp)
+        se_de = _ptr(self.se_tmp, N * se_max_c)
+        se_dpool = _ptr(self.se_tmp, 2 * N * se_max_c)
+        se_r = _ptr(self.se_tmp, 3 * N * se_max_c)
+        se_drp = _ptr(self.se_tmp, 3 * N * se_max_c + N * se_max_r)
+
+        # ---- forward -----------------------------------------------------------------------------
+        self.x_in = torch.zeros(N, spec.in_chans, self.H, self.W, dtype=self.tdtype, device=dev)
+        y0 = self._alloc16(N, Hs, Ws, spec.stem)
+        stem_out = self._alloc16(N, Hs, Ws, spec.stem)
+        self.acts["conv_stem"] = y0
+        self.acts["stem.out"] = stem_out
+        bn = self.bns["bn1"]
+        fwd.append(("dfd_stem_fwd", (_ptr(self.x_in), P32("conv_stem.weight"), _ptr(y0), N, spec.in_chans, self.H, self.W,
+                                     spec.stem, 3, 2, 1, dt, bn.fsum, bn.fsq)))
+        fwd.append(finalize(bn, N * Hs * Ws))
+        fwd.append(("dfd_bn_act", (_ptr(y0), bn.scale, bn.shift, None, None, _ptr(stem_out), N, Hs * Ws, spec.stem,
+                                   ACT_SWISH, 0, dt)))
+        x = stem_out
+        recs = []
+        for b, h, w, ho, wo in blocks:
+            p = b.name
+            M1, M2 = N * h * w, N * ho * wo
+            rec = dict(b=b, h=h, w=w, ho=ho, wo=wo, x=x)
+            if b.kind == "ir":
+                bn1, bn2, bn3 = self.bns[p + ".bn1"], self.bns[p + ".bn2"], self.bns[p + ".bn3"]
+                y1 = self._alloc16(N, h, w, b.cmid)
+                self.acts[p + ".conv_pw"] = y1
+                fwd.append(gemm(_ptr(x), P16(p + ".conv_pw.weight"), _ptr(y1), M1, b.cmid, b.cin, bn1))
+                fwd.append(finalize(bn1, M1))
+                dw_in, dw_bn, bn_mid, bn_out, pw_name = y1, bn1, bn2, bn3, ".conv_pwl"
+                rec.update(y1=y1)
+            else:
+                dw_in, dw_bn, bn_mid, bn_out, pw_name = x, None, self.bns[p + ".bn1"], self.bns[p + ".bn2"], ".conv_pw"
+            y2 = self._alloc16(N, ho, wo, b.cmid)
+            self.acts[p + ".conv_dw"] = y2
+            fwd.append(("dfd_dwconv_fwd", (_ptr(dw_in), dw_bn.scale if dw_bn else None, dw_bn.shift if dw_bn else None,
+                                           P32(p + ".conv_dw.weight"), _ptr(y2), N, h, w, b.cmid, b.k, b.stride,
+                                           ACT_SWISH if dw_bn else ACT_NONE, dt, bn_mid.fsum, bn_mid.fsq)))
+            fwd.append(finalize(bn_mid, M2))
+            gate_ptr = None
+            if b.cse:
+                pooled = torch.zeros(N, b.cmid, dtype=torch.float32, device=dev)
+                gate = torch.zeros(N, b.cmid, dtype=torch.float32, device=dev)
+                rec.update(pooled=pooled, gate=gate)
+                fwd.append(("dfd_pool", (_ptr(y2), bn_mid.scale, bn_mid.shift, _ptr(pooled), N, ho * wo, b.cmid, ACT_SWISH, dt)))
+                fwd.append(("dfd_se_fc_fwd", (_ptr(pooled), P32(p + ".se.conv_reduce.weight"), P32(p + ".se.conv_reduce.bias"),
+                                              P32(p + ".se.conv_expand.weight"), P32(p + ".se.conv_expand.bias"),
+                                              _ptr(gate), N, b.cmid, b.cse)))
+                gate_ptr = _ptr(gate)
+            a2 = self._alloc16(N, ho, wo, b.cmid)
+            fwd.append(("dfd_bn_act", (_ptr(y2), bn_mid.scale, bn_mid.shift, gate_ptr, None, _ptr(a2), N, ho * wo, b.cmid,
+                                       ACT_SWISH, 0, dt)))
+            y3 = self._alloc16(N, ho, wo, b.cout)
+            self.acts[p + pw_name] = y3
+            fwd.append(gemm(_ptr(a2), P16(p + pw_name + ".weight"), _ptr(y3), M2, b.cout, b.cmid, bn_out))
+            fwd.append(finalize(bn_out, M2))
+            out = self._alloc16(N, ho, wo, b.cout)
+            self.acts[p + ".out"] = out
+            fwd.append(("dfd_bn_act", (_ptr(y3), bn_out.scale, bn_out.shift, None, _ptr(x) if b.has_residual else None,
+                                       _ptr(out), N, ho * wo, b.cout, ACT_NONE, 1 if b.has_residual else 0, dt)))
+            rec.update(y2=y2, a2=a2, y3=y3, out=out, dw_bn=dw_bn, bn_mid=bn_mid, bn_out=bn_out, pw_name=pw_name)
+            recs.append(rec)
+            x = out
+        # head
+        F = spec.num_features
+        Mf = N * Hf * Wf
+        bnh = self.bns["bn2"]
+        yh = self._alloc16(N, Hf, Wf, F)
+        self.acts["conv_head"] = yh
+        fwd.append(gemm(_ptr(x), P16("conv_head.weight"), _ptr(yh), Mf, F, spec.head_in, bnh))
+        fwd.append(finalize(bnh, Mf))
+        self.pooled = torch.zeros(N, F, dtype=torch.float32, device=dev)
+        fwd.append(("dfd_pool", (_ptr(yh), bnh.scale, bnh.shift, _ptr(self.pooled), N, Hf * Wf, F, ACT_SWISH, dt)))
+        K = spec.num_classes
+        self.logits = torch.zeros(N, K, dtype=torch.float32, device=dev)
+        self.dlogits = torch.zeros(N, K, dtype=torch.float32, device=dev)
+        self.dpooled = torch.zeros(N, F, dtype=torch.float32, device=dev)
+        self.target_i = torch.zeros(N, dtype=torch.int64, device=dev)
+        self.target_f = torch.zeros(N, K, dtype=torch.float32, device=dev)
+        self._head_in = x
+
+        # ---- backward ----------------------------------------------------------------------------
+        bwd.append(("dfd_head_bwd", (_ptr(self.dlogits), _ptr(self.pooled), P32("classifier.weight"),
+                                     G32("classifier.weight"), G32("classifier.bias"), _ptr(self.dpooled), N, F, K)))
+        bwd.append(("dfd_act_bwd", (None, _ptr(yh), bnh.scale, bnh.shift, bnh.mean, bnh.rstd, None, _ptr(self.dpooled),
+                                    mid_a, N, Hf * Wf, F, ACT_SWISH, dt, bnh.bs1, bnh.bs2)))
+        bwd.append(bwd_finalize(bnh, Mf))
+        bwd.append(("dfd_bn_bwd_apply", (mid_a, _ptr(yh), None, bnh.cA, bnh.cB, bnh.cC, mid_b, N, Hf * Wf, F, dt)))
+        cur = 0
+        bwd.append(gemm(mid_b, T16("conv_head.weight"), sm[cur], Mf, spec.head_in, F))
+        bwd.append(("dfd_gemm_wgrad_mma", (mid_b, _ptr(self._head_in), G32("conv_head.weight"), Mf, F, spec.head_in, dt)))
+        for rec in reversed(recs):
+            b, h, w, ho, wo, xin = rec["b"], rec["h"], rec["w"], rec["ho"], rec["wo"], rec["x"]
+            p = b.name
+            M1, M2 = N * h * w, N * ho * wo
+            bn_out, bn_mid, dw_bn, pw_name = rec["bn_out"], rec["bn_mid"], rec["dw_bn"], rec["pw_name"]
+            y2, a2, y3 = rec["y2"], rec["a2"], rec["y3"]
+            dout = sm[cur]
+            t1, t2 = sm[(cur + 1) % 3], sm[(cur + 2) % 3]
+            bwd.append(("dfd_bn_bwd_reduce", (dout, _ptr(y3), None, bn_out.mean, bn_out.rstd, N, ho * wo, b.cout, dt,
+                                              bn_out.bs1, bn_out.bs2)))
+            bwd.append(bwd_finalize(bn_out, M2))
+            bwd.append(("dfd_bn_bwd_apply", (dout, _ptr(y3), None, bn_out.cA, bn_out.cB, bn_out.cC, t1, N, ho * wo, b.cout, dt)))
+            bwd.append(gemm(t1, T16(p + pw_name + ".weight"), mid_a, M2, b.cmid, b.cout))
+            bwd.append(("dfd_gemm_wgrad_mma", (t1, _ptr(a2), G32(p + pw_name + ".weight"), M2, b.cout, b.cmid, dt)))
+            gate_ptr = dpool_ptr = None
+            if b.cse:
+                gate_ptr, dpool_ptr = _ptr(rec["gate"]), se_dpool
+                bwd.append(("dfd_se_bwd_reduce", (mid_a, _ptr(y2), bn_mid.scale, bn_mid.shift, se_draw, N, ho * wo, b.cmid, dt)))
+                bwd.append(("dfd_se_fc_bwd", (se_draw, _ptr(rec["pooled"]), P32(p + ".se.conv_reduce.weight"),
+                                              P32(p + ".se.conv_reduce.bias"), P32(p + ".se.conv_expand.weight"),
+                                              P32(p + ".se.conv_expand.bias"), se_de, se_r, se_drp, se_dpool,
+                                              G32(p + ".se.conv_reduce.weight"), G32(p + ".se.conv_reduce.bias"),
+                                              G32(p + ".se.conv_expand.weight"), G32(p + ".se.conv_expand.bias"),
+                                              N, b.cmid, b.cse)))
+            bwd.append(("dfd_act_bwd", (mid_a, _ptr(y2), bn_mid.scale, bn_mid.shift, bn_mid.mean, bn_mid.rstd, gate_ptr,
+                                        dpool_ptr, mid_b, N, ho * wo, b.cmid, ACT_SWISH, dt, bn_mid.bs1, bn_mid.bs2)))
+            bwd.append(bwd_finalize(bn_mid, M2))
+            if b.kind == "ir":
+                y1 = rec["y1"]
+                bwd.append(("dfd_dwconv_dgrad", (mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
+                                                 _ptr(y1), dw_bn.scale, dw_bn.shift, dw_bn.mean, dw_bn.rstd, None, mid_a,
+                                                 N, h, w, b.cmid, b.k, b.stride, 1, dt, dw_bn.bs1, dw_bn.bs2)))
+                bwd.append(("dfd_dwconv_wgrad", (_ptr(y1), dw_bn.scale, dw_bn.shift, mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB,
+                                                 bn_mid.cC, G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt)))
+                bwd.append(bwd_finalize(dw_bn, M1))
+                bwd.append(("dfd_bn_bwd_apply", (mid_a, _ptr(y1), None, dw_bn.cA, dw_bn.cB, dw_bn.cC, mid_b, N, h * w, b.cmid, dt)))
+                bwd.append(gemm(mid_b, T16(p + ".conv_pw.weight"), t2, M1, b.cin, b.cmid))
+                if b.has_residual:
+                    bwd.append(("dfd_add_inplace", (t2, dout, M1 * b.cin, dt)))
+                bwd.append(("dfd_gemm_wgrad_mma", (mid_b, _ptr(xin), G32(p + ".conv_pw.weight"), M1, b.cmid, b.cin, dt)))
+            else:
+                bwd.append(("dfd_dwconv_dgrad", (mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
+                                                 None, None, None, None, None, dout if b.has_residual else None, t2,
+                                                 N, h, w, b.cmid, b.k, b.stride, 0, dt, None, None)))
+                bwd.append(("dfd_dwconv_wgrad", (_ptr(xin), None, None, mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC,
+                                                 G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt)))
+            cur = (cur + 2) % 3
+        # stem
+        bn = self.bns["bn1"]
+        bwd.append(("dfd_act_bwd", (sm[cur], _ptr(y0), bn.scale, bn.shift, bn.mean, bn.rstd, None, None, mid_a, N, Hs * Ws,
+                                    spec.stem, ACT_SWISH, dt, bn.bs1, bn.bs2)))
+        bwd.append(bwd_finalize(bn, N * Hs * Ws))
+        bwd.append(("dfd_stem_wgrad", (_ptr(self.x_in), mid_a, _ptr(y0), bn.cA, bn.cB, bn.cC, G32("conv_stem.weight"), N,
+                                       spec.in_chans, self.H, self.W, spec.stem, 3, 2, 1, dt)))
+        for n, a in fwd + bwd:      # arity / type check of the plan against the ABI table
+            codes = _lib.SIGNATURES[n]
+            if len(a) != len(codes) - 1:
+                raise AssertionError("%s: %d args for signature %r" % (n, len(a), codes))
+            for v, c in zip(a, codes):
+                ok = (v is None or isinstance(v, int)) if c == "p" else (
+                    isinstance(v, int) if c in "il" else (isinstance(v, (int, float)) or v == "TRAINING"))
+                if not (ok or v == "TRAINING"):
+                    raise AssertionError("%s: argument %r does not fit code %r" % (n, v, c))
+        self.fwd_ops = [(getattr(L, n), n, a) for n, a in fwd]
+        self.bwd_ops = [(getattr(L, n), n, tuple(a)) for n, a in bwd]
+        self.n_launch["fwd"] = len(fwd)
+        self.n_launch["bwd"] = len(bwd)
+
+    # ------------------------------------------------------------------------------------------
+    # execution
+    # ------------------------------------------------------------------------------------------
+    def _run(self, ops, stream, training=None):
+        if self._plan_only:
+            raise _lib.NativeError("plan-only engine cannot execute (no CUDA device)")
+        L = self.L
+        for fn, name, args in ops:
+            if name == "dfd_bn_finalize":
+                args = tuple((1 if training else 0) if a == "TRAINING" else a for a in args)
+                if not training:
+                    args = (None, None) + args[2:]
+            elif not training and name in ("dfd_gemm_tn", "dfd_gemm_tn_mma", "dfd_dwconv_fwd", "dfd_stem_fwd"):
+                args = tuple(args[:-2]) + (None, None)      # eval: no batch statistics
+            rc = fn(*args, stream)
+            if rc != 0:
+                raise _lib.NativeError("%s failed (%d): %s" % (name, rc, L.last_error()))
+
+    def set_input(self, x):
+        """x: [N, C, H, W] (NCHW, any float dtype / device)."""
+        if tuple(x.shape) != tuple(self.x_in.shape):
+            raise ValueError("input shape %s != engine shape %s" % (tuple(x.shape), tuple(self.x_in.shape)))
+        self.x_in.copy_(x, non_blocking=True)
+
+    def set_target(self, target):
+        if target.dtype.is_floating_point:
+            self.target_f.copy_(target, non_blocking=True)
+            self._soft = True
+        else:
+            self.target_i.copy_(target, non_blocking=True)
+            self._soft = False
+
+    def zero_step_scratch(self, stream, grads=True):
+        _lib.call("dfd_memset_async", _ptr(self.stats), 0, self.stats.numel() * 8, stream)
+        _lib.call("dfd_memset_async", _ptr(self.scalars), 0, self.scalars.numel() * 4, stream)
+        if grads:
+            _lib.call("dfd_memset_async", _ptr(self.grads32), 0, self.grads32.numel() * 4, stream)
+
+    def forward(self, training=True, stream=None):
+        """Runs the network on self.x_in; logits land in self.logits ([N, num_classes] fp32)."""
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        self._run(self.fwd_ops, st, training)
+        return self.logits
+
+    def head(self, with_loss, smoothing=0.0, loss_scale=1.0, soft=False, stream=None):
+        """classifier (+ fused sigmoid-BCE loss, top-1 count and dL/dlogits when with_loss)."""
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        spec = self.spec
+        pw = _ptr(self.params32, self.p_off["classifier.weight"][0])
+        pb = _ptr(self.params32, self.p_off["classifier.bias"][0])
+        if with_loss:
+            _lib.call("dfd_head_fwd", _ptr(self.pooled), pw, pb, _ptr(self.logits), self.N, spec.num_features,
+                      spec.num_classes, None if soft else _ptr(self.target_i), _ptr(self.target_f) if soft else None,
+                      float(smoothing), float(loss_scale), _ptr(self.scalars), _ptr(self.scalars, 1), _ptr(self.dlogits), st)
+        else:
+            _lib.call("dfd_head_fwd", _ptr(self.pooled), pw, pb, _ptr(self.logits), self.N, spec.num_features,
+                      spec.num_classes, None, None, 0.0, 1.0, None, None, None, st)
+
+    def backward(self, stream=None):
+        """Back-propagates self.dlogits; gradients are ACCUMULATED into self.grads32 (zero it per step)."""
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        self._run(self.bwd_ops, st, True)
+
+    @property
+    def loss(self):
+        return self.scalars[0]
+
+    @property
+    def correct(self):
+        return self.scalars[1]

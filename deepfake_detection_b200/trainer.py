@@ -1,0 +1,118 @@
+"""One-call train / validate steps over the native engine — the public API `bench.py` and the runner mirror use.
+
+A `Trainer` owns an Engine + ArenaOptimizer (+ the DDP gradient reducer when torch.distributed is initialised) and
+executes the body of the reference's hot loop (dfd/runners/train.py:621-637):
+
+    output = model(input); loss = loss_fn(output, target); prec1 = accuracy(output, target)
+    optimizer.zero_grad(); loss.backward() [DDP all-reduce]; optimizer.step()
+
+as one replayable sequence of kernel launches, optionally captured in a CUDA graph.  The per-step host
+synchronisation + two `.item()` reads of the reference (train.py:639-645) are not part of the step: loss and the
+correct-count stay on the device until the caller asks for them.
+"""
+import torch
+
+from . import _lib
+from .engine import Engine, _ptr
+from .optim import ArenaOptimizer
+
+
+class Trainer:
+    def __init__(self, arch, batch, height=None, width=None, dtype="bf16", opt="sgd", lr=0.01, momentum=0.9,
+                 weight_decay=1e-4, opt_eps=1e-8, smoothing=0.0, num_classes=2, in_chans=3, bn_momentum=0.1,
+                 bn_eps=1e-5, use_graph=True, gemm_impl="tc", process_group=None, bucket_mb=8.0):
+        self.engine = Engine(arch, batch, height, width, num_classes=num_classes, in_chans=in_chans, dtype=dtype,
+                             bn_momentum=bn_momentum, bn_eps=bn_eps, gemm_impl=gemm_impl)
+        self.optimizer = ArenaOptimizer(self.engine, opt=opt, lr=lr, momentum=momentum, weight_decay=weight_decay,
+                                        eps=opt_eps)
+        self.smoothing = float(smoothing)
+        self.use_graph = bool(use_graph) and self.optimizer.kind in ("sgd", "rmsproptf")
+        self._graph = None
+        self._graph_key = None
+        self.reducer = None
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+            from .ddp import GradReducer
+            self.reducer = GradReducer(self.engine, process_group, bucket_mb=bucket_mb)
+            self.optimizer.grad_scale = 1.0 / dist.get_world_size(process_group)
+            self.reducer.broadcast_parameters()
+        # pinned staging for the host-buffer (end-to-end) entry point
+        e = self.engine
+        self._pin_x = torch.empty(e.x_in.shape, dtype=e.tdtype).pin_memory()
+        self._pin_y = torch.empty(e.N, dtype=torch.int64).pin_memory()
+        self._pin_out = torch.empty(4, dtype=torch.float32).pin_memory()
+
+    # ---- state ------------------------------------------------------------------------------------
+    def state_dict(self):
+        return self.engine.state_dict()
+
+    def load_state_dict(self, sd, strict=True):
+        return self.engine.load_state_dict(sd, strict=strict)
+
+    # ---- the step ---------------------------------------------------------------------------------
+    def _launch_step(self, soft):
+        e = self.engine
+        st = torch.cuda.current_stream().cuda_stream
+        e.zero_step_scratch(st, grads=True)
+        e.forward(training=True, stream=st)
+        e.head(True, smoothing=self.smoothing, soft=soft, stream=st)
+        if self.reducer is not None:
+            self.reducer.backward_and_reduce()
+        else:
+            e.backward(stream=st)
+        self.optimizer.step(stream=st)
+
+    def _graph_signature(self, soft):
+        return (soft, self.smoothing, tuple((g["lr"], g["momentum"], g["weight_decay"]) for g in self.optimizer.param_groups),
+                self.optimizer.grad_scale)
+
+    def step_resident(self, soft=False):
+        """One full train step on the batch already resident in engine.x_in / target_i|target_f."""
+        if not self.use_graph:
+            self._launch_step(soft)
+            return
+        key = self._graph_signature(soft)
+        if self._graph is None or key != self._graph_key:
+            # warm-up launch outside capture (module loading, cudaFuncSetAttribute, tensor-map encoding paths)
+            self._launch_step(soft)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch_step(soft)
+            self._graph, self._graph_key = g, key
+            return
+        self._graph.replay()
+
+    def train_step(self, x, target):
+        """x: [N,C,H,W] on any device; target: int64 [N] or float [N,2]. Returns (loss, correct) DEVICE scalars."""
+        e = self.engine
+        e.set_input(x)
+        e.set_target(target)
+        self.step_resident(soft=target.dtype.is_floating_point)
+        return e.loss, e.correct
+
+    def train_step_host(self, x_pinned, y_pinned):
+        """End-to-end entry: pinned HOST buffers in, loss/correct read back to the host (async, call
+        torch.cuda.current_stream().synchronize() before reading the returned pinned tensor)."""
+        e = self.engine
+        e.x_in.copy_(x_pinned, non_blocking=True)
+        e.target_i.copy_(y_pinned, non_blocking=True)
+        self.step_resident(soft=False)
+        self._pin_out.copy_(e.scalars, non_blocking=True)
+        return self._pin_out
+
+    @torch.no_grad()
+    def validate_step(self, x, target=None):
+        """Eval-mode forward (BN running statistics, no dropout): returns logits [N, num_classes] (device, fp32)
+        and, when a target is given, fills engine.loss / engine.correct (train.py:719-731)."""
+        e = self.engine
+        st = torch.cuda.current_stream().cuda_stream
+        e.set_input(x)
+        e.zero_step_scratch(st, grads=False)
+        e.forward(training=False, stream=st)
+        if target is not None:
+            e.set_target(target)
+            e.head(True, smoothing=0.0, soft=target.dtype.is_floating_point, stream=st)
+        else:
+            e.head(False, stream=st)
+        return e.logits

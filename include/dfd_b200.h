@@ -1,0 +1,138 @@
+/* dfd_b200.h — C ABI of libdfd_b200.so: the sm_100a device kernels behind the data-parallel train / validate
+ * step of TARTRL/Deepfake_Detection (dfd/runners/train.py:610-649, :713-746).
+ *
+ * The reference has NO native/FFI layer: every entry point below replaces a stock
+ * PyTorch op (ATen / cuDNN / cuBLAS dispatch) that the reference's nn.Module tree issues on the hot path; the
+ * citation on each function is the reference call site it stands in for.  INTEGRATION.md shows the binding a
+ * maintainer adds on the reference side (ctypes, because the reference is pure Python).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the caller (no ownership transfer);
+ *   - activations are NHWC, 16-bit: dt = DFD_DT_BF16 (0) or DFD_DT_FP16 (1); parameters, gradients, BN
+ *     statistics, SE vectors, logits and the loss are fp32; channel counts are multiples of 8;
+ *   - `stream` is a cudaStream_t; kernels are enqueued on it and nothing synchronises the host;
+ *   - return value: 0 on success, negative DFD_ERR_* otherwise (dfd_last_error() gives the message); the
+ *     Python host raises RuntimeError, the reference's only error convention;
+ *   - per-channel statistics buffers hold DFD_STAT_SLOTS (= dfd_stat_slots() = 8) interleaved fp64 copies,
+ *     i.e. [8][C] doubles, accumulated with atomics and zeroed by the caller once per step.
+ */
+#ifndef DFD_B200_H
+#define DFD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFD_OK 0
+#define DFD_ERR_ARG (-1)
+#define DFD_ERR_CUDA (-2)
+#define DFD_ERR_UNSUPPORTED (-3)
+
+#define DFD_DT_BF16 0
+#define DFD_DT_FP16 1
+
+#define DFD_ACT_NONE 0
+#define DFD_ACT_SWISH 1
+#define DFD_ACT_RELU 2
+
+/* ---- runtime ---------------------------------------------------------------------------------------- */
+const char* dfd_last_error(void);
+int dfd_abi_version(void);
+int dfd_stat_slots(void);
+/* optimizer.zero_grad() (train.py:631) and per-step scratch clearing */
+int dfd_memset_async(void* p, int value, long long bytes, void* stream);
+
+/* ---- pointwise (1x1) convolution: nn.Conv2d via create_conv2d, efficientnet_blocks.py:165,277,299,
+ *      efficientnet.py:292, resnet.py:192,199 -------------------------------------------------------- */
+/* C[M,N] = A[M,K] * B[N,K]^T on tcgen05 (TMA in/out, TMEM accumulators). Forward: A = input [N*H*W, Cin],
+ * B = weight [Cout, Cin]. Input gradient: A = dY [N*H*W, Cout], B = weight^T [Cin, Cout].
+ * dsum/dsq (optional): per-column sum / sum of squares of the stored C for the following BatchNorm. */
+int dfd_gemm_tn(const void* A, const void* B, void* C, long long M, int N, int K, int dt, double* dsum, double* dsq,
+                void* stream);
+/* same contract on the warp-level mma.sync path (+ optional residual `add` [M,N]); cross-check / fallback */
+int dfd_gemm_tn_mma(const void* A, const void* B, void* C, const void* add, long long M, int N, int K, int dt,
+                    double* dsum, double* dsq, void* stream);
+/* weight gradient dW[Nw,Kw] (fp32, accumulated) += G[M,Nw]^T * X[M,Kw]  (autograd of the conv, train.py:634) */
+int dfd_gemm_wgrad_mma(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* stream);
+
+/* ---- depthwise k x k convolution: nn.Conv2d(groups=C), efficientnet_blocks.py:152-153,283-285 -------- */
+int dfd_dwconv_fwd(const void* x, const float* scale, const float* shift, const float* w, void* out, int N, int H,
+                   int W, int C, int k, int stride, int act_in, int dt, double* dsum, double* dsq, void* stream);
+int dfd_dwconv_dgrad(const void* gy, const void* yout, const float* cA, const float* cB, const float* cC,
+                     const float* w, const void* xin, const float* scale, const float* shift, const float* mean,
+                     const float* rstd, const void* add, void* gx, int N, int H, int W, int C, int k, int stride,
+                     int mode, int dt, double* s1, double* s2, void* stream);
+int dfd_dwconv_wgrad(const void* x, const float* scale, const float* shift, const void* gy, const void* yout,
+                     const float* cA, const float* cB, const float* cC, float* dW, int N, int H, int W, int C, int k,
+                     int stride, int dt, void* stream);
+
+/* ---- stem convolution: conv_stem 3x3 s2 (efficientnet.py:275,321) / conv1 7x7 s2 (resnet.py:379,451) ---- */
+int dfd_stem_fwd(const void* x_nchw, const float* w, void* out_nhwc, int N, int Cin, int H, int W, int Cout, int k,
+                 int stride, int pad, int dt, double* dsum, double* dsq, void* stream);
+int dfd_stem_wgrad(const void* x_nchw, const void* g, const void* y, const float* cA, const float* cB,
+                   const float* cC, float* dW, int N, int Cin, int H, int W, int Cout, int k, int stride, int pad,
+                   int dt, void* stream);
+
+/* ---- BatchNorm2d (train + eval), Swish, SE gating, residual, global pool and their backward:
+ *      efficientnet_blocks.py:104-110,154,166,180-194,280-348; layers/activations.py:19-33;
+ *      efficientnet.py:323-343; resnet.py:154-173 ---------------------------------------------------- */
+int dfd_colstats(const void* y, int n, long long hw, int C, int dt, double* dsum, double* dsq, void* stream);
+int dfd_bn_finalize(const double* dsum, const double* dsq, double count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                    float eps, int training, int C, float* scale, float* shift, float* mean, float* rstd,
+                    void* stream);
+int dfd_bn_act(const void* y, const float* scale, const float* shift, const float* gate, const void* res, void* out,
+               int n, long long hw, int C, int act, int res_mode, int dt, void* stream);
+int dfd_pool(const void* y, const float* scale, const float* shift, float* pooled, int n, long long hw, int C,
+             int act, int dt, void* stream);
+int dfd_bn_bwd_reduce(const void* g, const void* y, const void* out, const float* mean, const float* rstd, int n,
+                      long long hw, int C, int dt, double* s1, double* s2, void* stream);
+int dfd_bn_bwd_finalize(const double* s1, const double* s2, double count, const float* gamma, const float* mean,
+                        const float* rstd, float* dgamma, float* dbeta, float* cA, float* cB, float* cC, int C,
+                        void* stream);
+int dfd_bn_bwd_apply(const void* g, const void* y, const void* out, const float* cA, const float* cB,
+                     const float* cC, void* dy, int n, long long hw, int C, int dt, void* stream);
+int dfd_se_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift, float* draw, int n,
+                      long long hw, int C, int dt, void* stream);
+int dfd_act_bwd(const void* da, const void* y, const float* scale, const float* shift, const float* mean,
+                const float* rstd, const float* gate, const float* dpool, void* gu, int n, long long hw, int C,
+                int act, int dt, double* s1, double* s2, void* stream);
+int dfd_add_inplace(void* a, const void* b, long long numel, int dt, void* stream);
+
+/* ---- squeeze-excite FCs: SqueezeExcite.forward, efficientnet_blocks.py:104-110 ------------------------ */
+int dfd_se_fc_fwd(const float* pooled, const float* Wr, const float* br, const float* We, const float* be,
+                  float* gate, int N, int C, int Cse, void* stream);
+int dfd_se_fc_bwd(const float* draw, const float* pooled, const float* Wr, const float* br, const float* We,
+                  const float* be, float* d_e, float* r, float* d_rpre, float* dpool, float* dWr, float* dbr,
+                  float* dWe, float* dbe, int N, int C, int Cse, void* stream);
+
+/* ---- classifier + loss + accuracy: nn.Linear (efficientnet.py:348, resnet.py:467), LabelSmoothing /
+ *      SoftTarget / nn.CrossEntropyLoss (loss/cross_entropy.py:20-36, train.py:509-520), accuracy
+ *      (utils.py:170-186).  2-class softmax-CE is computed as sigmoid-BCE on z1 - z0 (exactly equal). ----- */
+int dfd_head_fwd(const float* pooled, const float* W, const float* b, float* logits, int N, int F, int K,
+                 const long long* target_i64, const float* target_soft, float smoothing, float loss_scale,
+                 float* loss_acc, float* correct_acc, float* dlogits, void* stream);
+int dfd_head_bwd(const float* dlogits, const float* pooled, const float* W, float* dW, float* db, float* dpooled,
+                 int N, int F, int K, void* stream);
+
+/* ---- optimizers over the flat fp32 parameter arena: create_optimizer, optim_factory.py:26-100;
+ *      RMSpropTF rmsprop_tf.py:57-122; AdamW adamw.py:55-117; apex AMP loss scaling train.py:353,632-634 ---- */
+int dfd_sgd_step(float* p, const float* g, float* m, long long n, float lr, float momentum, float wd, int nesterov,
+                 float grad_scale, const int* skip, void* p16, int dt, void* stream);
+int dfd_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                  float wd, int decoupled, int step, float grad_scale, const int* skip, void* p16, int dt,
+                  void* stream);
+int dfd_rmsprop_tf_step(float* p, const float* g, float* sq, float* mom, long long n, float lr, float alpha,
+                        float eps, float wd, float momentum, float grad_scale, const int* skip, void* p16, int dt,
+                        void* stream);
+int dfd_cast_arena(const float* p, void* p16, long long n, int dt, void* stream);
+int dfd_check_finite(const float* g, long long n, int* flag, void* stream);
+int dfd_update_loss_scale(int* flag, float* scale, int* good_steps, int interval, float* inv_scale_out,
+                          void* stream);
+/* table: device array of { const void* src; void* dst; int O; int I; } — dst[I,O] = transpose(src[O,I]) */
+int dfd_transpose_weights(const void* table, int count, int dt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFD_B200_H */

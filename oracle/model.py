@@ -97,7 +97,9 @@ def _mb_block(x, sd, b, bn, act_dtype, taps):
         x = q(F.conv2d(x, sd[p + ".conv_pw.weight"]), act_dtype)
         if taps is not None:
             taps[p + ".conv_pw"] = x
-        x = swish(batch_norm(x, sd, p + ".bn1", bn))
+        # the native depthwise kernel stages its activated input in 16-bit shared memory (as apex AMP O1 casts
+        # the conv input to half in the reference's GPU path): one more rounding point in emulation mode
+        x = q(swish(batch_norm(x, sd, p + ".bn1", bn)), act_dtype)
         x = q(F.conv2d(x, sd[p + ".conv_dw.weight"], stride=b.stride, padding=b.pad, groups=b.cmid), act_dtype)
         if taps is not None:
             taps[p + ".conv_dw"] = x

@@ -1,0 +1,356 @@
+"""GPU parity checks of every C-ABI kernel against plain PyTorch fp32 arithmetic ON THE SAME ROUNDED INPUTS.
+Each check returns {metric: value}; thresholds live in the pytest wrappers (tests/test_kernels_gpu.py).
+Shared by tools/gpu_diag.py, which runs them all without stopping at the first failure.
+
+Tolerances (written here once): tensors stored in bf16 carry 2^-9 relative rounding per element, so
+  * max |err| <= 2^-7 * (|ref| + scale)   for 16-bit outputs (scale = rms of the reference tensor),
+  * rel-L2 <= 2e-3                        for fp32 reductions (statistics, weight gradients) of bf16 data,
+  * 1e-5 relative for pure fp32 kernels (optimizers, SE FCs, head).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from deepfake_detection_b200 import _lib
+
+DT = {torch.bfloat16: 0, torch.float16: 1}
+
+
+def P(t):
+    return None if t is None else t.data_ptr()
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def relerr(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def maxerr_scaled(a, b):
+    """max |a-b| / (|b| + rms(b))"""
+    a, b = a.double(), b.double()
+    scale = b.pow(2).mean().sqrt() + 1e-30
+    return float(((a - b).abs() / (b.abs() + scale)).max())
+
+
+def slots():
+    return _lib.lib().stat_slots
+
+
+def stat_buf(C, dev="cuda"):
+    return torch.zeros(slots(), C, dtype=torch.float64, device=dev)
+
+
+def nhwc(x):  # [N,C,H,W] -> [N,H,W,C] contiguous
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+def check_gemm(impl, M, K, N, dtype=torch.bfloat16, with_stats=True, with_add=False, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(dtype)
+    B = (torch.randn(N, K, device="cuda", generator=g) * (1.0 / math.sqrt(K))).to(dtype)
+    C = torch.full((M, N), float("nan"), device="cuda", dtype=dtype)
+    add = (torch.randn(M, N, device="cuda", generator=g)).to(dtype) if with_add else None
+    s1, s2 = (stat_buf(N), stat_buf(N)) if with_stats else (None, None)
+    if impl == "tc":
+        assert not with_add
+        _lib.call("dfd_gemm_tn", P(A), P(B), P(C), M, N, K, DT[dtype], P(s1), P(s2), st())
+    else:
+        _lib.call("dfd_gemm_tn_mma", P(A), P(B), P(C), P(add), M, N, K, DT[dtype], P(s1), P(s2), st())
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    if with_add:
+        ref = ref.to(dtype).float() + add.float()
+    out = dict(out_max=maxerr_scaled(C.float(), ref), out_rel=relerr(C.float(), ref), nan=int(torch.isnan(C.float()).sum()))
+    if with_stats:
+        cf = C.double()
+        out["sum_rel"] = relerr(s1.sum(0), cf.sum(0))
+        out["sq_rel"] = relerr(s2.sum(0), (cf * cf).sum(0))
+    return out
+
+
+def check_wgrad(M, Nw, Kw, dtype=torch.bfloat16, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    G = (torch.randn(M, Nw, device="cuda", generator=g) * 0.3).to(dtype)
+    X = (torch.randn(M, Kw, device="cuda", generator=g)).to(dtype)
+    dW = torch.zeros(Nw, Kw, device="cuda")
+    _lib.call("dfd_gemm_wgrad_mma", P(G), P(X), P(dW), M, Nw, Kw, DT[dtype], st())
+    torch.cuda.synchronize()
+    ref = G.double().t() @ X.double()
+    return dict(rel=relerr(dW, ref))
+
+
+def _bn_params(C, g):
+    scale = 1.0 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    shift = 0.3 * torch.randn(C, device="cuda", generator=g)
+    return scale, shift
+
+
+def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0):
+    """fwd + dgrad (both modes) + wgrad against F.conv2d autograd on the rounded operands."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    pad = (k - 1) // 2
+    x = torch.randn(N, H, W, C, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(C, 1, k, k, device="cuda", generator=g) * (1.0 / k)).contiguous()
+    scale, shift = _bn_params(C, g)
+    Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    out = torch.full((N, Ho, Wo, C), float("nan"), device="cuda", dtype=dtype)
+    s1, s2 = stat_buf(C), stat_buf(C)
+    act = 1 if affine else 0
+    _lib.call("dfd_dwconv_fwd", P(x), P(scale) if affine else None, P(shift) if affine else None, P(w), P(out), N, H, W, C,
+              k, s, act, DT[dtype], P(s1), P(s2), st())
+    torch.cuda.synchronize()
+    # reference (fp32, same rounding points: activated input rounded to `dtype`)
+    xr = nchw(x.float()).requires_grad_(True)
+    if affine:
+        u = xr * scale.view(1, C, 1, 1) + shift.view(1, C, 1, 1)
+        a = u * torch.sigmoid(u)
+    else:
+        a = xr
+    a_q = a.to(dtype).float() + (a - a.detach())          # straight-through rounding
+    wr = w.clone().requires_grad_(True)
+    ref = F.conv2d(a_q, wr, stride=s, padding=pad, groups=C)
+    res = dict(fwd_max=maxerr_scaled(nchw(out.float()), ref.detach()), fwd_rel=relerr(nchw(out.float()), ref.detach()),
+               nan=int(torch.isnan(out.float()).sum()))
+    of = out.double()
+    res["sum_rel"] = relerr(s1.sum(0), of.sum((0, 1, 2)))
+    res["sq_rel"] = relerr(s2.sum(0), (of * of).sum((0, 1, 2)))
+    # backward: gy is the gradient w.r.t. the BN output behind the conv; dy = cA*gy + cB*yout + cC
+    gy = (torch.randn(N, Ho, Wo, C, device="cuda", generator=g) * 0.1).to(dtype)
+    cA = 1.0 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    cB = 0.05 * torch.randn(C, device="cuda", generator=g)
+    cC = 0.01 * torch.randn(C, device="cuda", generator=g)
+    dy = (cA * gy.float() + cB * out.float() + cC).to(dtype).float()
+    ref.backward(nchw(dy))
+    dW = torch.zeros_like(w)
+    _lib.call("dfd_dwconv_wgrad", P(x), P(scale) if affine else None, P(shift) if affine else None, P(gy), P(out), P(cA), P(cB),
+              P(cC), P(dW), N, H, W, C, k, s, DT[dtype], st())
+    torch.cuda.synchronize()
+    res["wgrad_rel"] = relerr(dW, wr.grad)
+    gx = torch.full((N, H, W, C), float("nan"), device="cuda", dtype=dtype)
+    if affine:
+        mean = 0.1 * torch.randn(C, device="cuda", generator=g)
+        rstd = 1.0 + 0.1 * torch.rand(C, device="cuda", generator=g)
+        b1, b2 = stat_buf(C), stat_buf(C)
+        _lib.call("dfd_dwconv_dgrad", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), P(scale), P(shift), P(mean), P(rstd), None,
+                  P(gx), N, H, W, C, k, s, 1, DT[dtype], P(b1), P(b2), st())
+        torch.cuda.synchronize()
+        # xr.grad is d/dx of the whole chain = scale * (dgrad * swish'(u)); the kernel emits gu = dgrad*swish'(u)
+        gu_ref = xr.grad / scale.view(1, C, 1, 1)
+        res["dgrad_max"] = maxerr_scaled(nchw(gx.float()), gu_ref)
+        res["dgrad_rel"] = relerr(nchw(gx.float()), gu_ref)
+        gxd = gx.double()
+        xhat = (x.double() - mean.double()) * rstd.double()
+        res["bs1_rel"] = relerr(b1.sum(0), gxd.sum((0, 1, 2)))
+        res["bs2_rel"] = relerr(b2.sum(0), (gxd * xhat).sum((0, 1, 2)))
+    else:
+        add = torch.randn(N, H, W, C, device="cuda", generator=g).to(dtype)
+        _lib.call("dfd_dwconv_dgrad", P(gy), P(out), P(cA), P(cB), P(cC), P(w), None, None, None, None, None, P(add), P(gx), N, H,
+                  W, C, k, s, 0, DT[dtype], None, None, st())
+        torch.cuda.synchronize()
+        ref_gx = xr.grad + nchw(add.float())
+        res["dgrad_max"] = maxerr_scaled(nchw(gx.float()), ref_gx)
+        res["dgrad_rel"] = relerr(nchw(gx.float()), ref_gx)
+    res["nan_b"] = int(torch.isnan(gx.float()).sum())
+    return res
+
+
+def check_stem(N, Cin, H, W, Cout, k, dtype=torch.bfloat16, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    pad = (k - 1) // 2 if k == 3 else 3
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / math.sqrt(Cin * k * k)).contiguous()
+    Ho, Wo = (H + 2 * pad - k) // 2 + 1, (W + 2 * pad - k) // 2 + 1
+    out = torch.full((N, Ho, Wo, Cout), float("nan"), device="cuda", dtype=dtype)
+    s1, s2 = stat_buf(Cout), stat_buf(Cout)
+    _lib.call("dfd_stem_fwd", P(x), P(w), P(out), N, Cin, H, W, Cout, k, 2, pad, DT[dtype], P(s1), P(s2), st())
+    torch.cuda.synchronize()
+    wr = w.clone().requires_grad_(True)
+    ref = F.conv2d(x.float(), wr, stride=2, padding=pad)
+    res = dict(fwd_max=maxerr_scaled(nchw(out.float()), ref.detach()), nan=int(torch.isnan(out.float()).sum()))
+    of = out.double()
+    res["sum_rel"] = relerr(s1.sum(0), of.sum((0, 1, 2)))
+    res["sq_rel"] = relerr(s2.sum(0), (of * of).sum((0, 1, 2)))
+    gy = (torch.randn(N, Ho, Wo, Cout, device="cuda", generator=g) * 0.1).to(dtype)
+    cA = 1.0 + 0.1 * torch.randn(Cout, device="cuda", generator=g)
+    cB = 0.05 * torch.randn(Cout, device="cuda", generator=g)
+    cC = 0.01 * torch.randn(Cout, device="cuda", generator=g)
+    dy = cA * gy.float() + cB * out.float() + cC
+    ref.backward(nchw(dy))
+    dW = torch.zeros_like(w)
+    _lib.call("dfd_stem_wgrad", P(x), P(gy), P(out), P(cA), P(cB), P(cC), P(dW), N, Cin, H, W, Cout, k, 2, pad, DT[dtype], st())
+    torch.cuda.synchronize()
+    res["wgrad_rel"] = relerr(dW, wr.grad)
+    return res
+
+
+def check_bn_chain(N, HW, C, dtype=torch.bfloat16, seed=0):
+    """colstats -> bn_finalize -> bn_act(+gate,+res) / pool, then act_bwd -> bn_bwd_finalize -> bn_bwd_apply,
+    against torch.nn.functional.batch_norm + swish autograd (train mode, running-stat EMA included)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    y = (torch.randn(N, HW, C, device="cuda", generator=g) * 1.5 + 0.3).to(dtype)
+    gamma = 1.0 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    rm = 0.05 * torch.randn(C, device="cuda", generator=g)
+    rv = 1.0 + 0.1 * torch.rand(C, device="cuda", generator=g)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    nbt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    s1, s2 = stat_buf(C), stat_buf(C)
+    scale, shift, mean, rstd = (torch.zeros(C, device="cuda") for _ in range(4))
+    d = DT[dtype]
+    _lib.call("dfd_colstats", P(y), N, HW, C, d, P(s1), P(s2), st())
+    _lib.call("dfd_bn_finalize", P(s1), P(s2), float(N * HW), P(gamma), P(beta), P(rm), P(rv), P(nbt), 0.1, 1e-5, 1, C, P(scale),
+              P(shift), P(mean), P(rstd), st())
+    gate = torch.sigmoid(torch.randn(N, C, device="cuda", generator=g))
+    a2 = torch.full((N, HW, C), float("nan"), device="cuda", dtype=dtype)
+    _lib.call("dfd_bn_act", P(y), P(scale), P(shift), P(gate), None, P(a2), N, HW, C, 1, 0, d, st())
+    res_t = torch.randn(N, HW, C, device="cuda", generator=g).to(dtype)
+    o_res = torch.full((N, HW, C), float("nan"), device="cuda", dtype=dtype)
+    _lib.call("dfd_bn_act", P(y), P(scale), P(shift), None, P(res_t), P(o_res), N, HW, C, 0, 1, d, st())
+    pooled = torch.zeros(N, C, device="cuda")
+    _lib.call("dfd_pool", P(y), P(scale), P(shift), P(pooled), N, HW, C, 1, d, st())
+    torch.cuda.synchronize()
+    # reference
+    yr = y.float().permute(0, 2, 1).reshape(N, C, HW, 1).requires_grad_(True)
+    gr = gamma.clone().requires_grad_(True)
+    br = beta.clone().requires_grad_(True)
+    u = F.batch_norm(yr, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5)
+    sw = u * torch.sigmoid(u)
+    res = dict(
+        rm_rel=relerr(rm, rm_ref), rv_rel=relerr(rv, rv_ref), nbt=int(nbt.item()),
+        gate_max=maxerr_scaled(a2.float().permute(0, 2, 1), (sw.squeeze(-1) * gate.unsqueeze(-1)).detach()),
+        res_max=maxerr_scaled(o_res.float().permute(0, 2, 1), (u.squeeze(-1) + res_t.float().permute(0, 2, 1)).detach()),
+        pool_rel=relerr(pooled, sw.mean((2, 3)).detach()))
+    # backward: gu = (da*gate + dpool/HW) * swish'(u); then BN backward
+    da = (torch.randn(N, HW, C, device="cuda", generator=g) * 0.1).to(dtype)
+    dpool = torch.randn(N, C, device="cuda", generator=g) * 0.1
+    gu = torch.full((N, HW, C), float("nan"), device="cuda", dtype=dtype)
+    b1, b2 = stat_buf(C), stat_buf(C)
+    _lib.call("dfd_act_bwd", P(da), P(y), P(scale), P(shift), P(mean), P(rstd), P(gate), P(dpool), P(gu), N, HW, C, 1, d, P(b1), P(b2), st())
+    dgamma, dbeta, cA, cB, cC = (torch.zeros(C, device="cuda") for _ in range(5))
+    _lib.call("dfd_bn_bwd_finalize", P(b1), P(b2), float(N * HW), P(gamma), P(mean), P(rstd), P(dgamma), P(dbeta), P(cA), P(cB), P(cC), C, st())
+    dy = torch.full((N, HW, C), float("nan"), device="cuda", dtype=dtype)
+    _lib.call("dfd_bn_bwd_apply", P(gu), P(y), None, P(cA), P(cB), P(cC), P(dy), N, HW, C, d, st())
+    # also the two-pass reduce variant used for un-activated BN outputs
+    c1, c2 = stat_buf(C), stat_buf(C)
+    _lib.call("dfd_bn_bwd_reduce", P(da), P(y), None, P(mean), P(rstd), N, HW, C, d, P(c1), P(c2), st())
+    draw = torch.zeros(N, C, device="cuda")
+    _lib.call("dfd_se_bwd_reduce", P(da), P(y), P(scale), P(shift), P(draw), N, HW, C, d, st())
+    torch.cuda.synchronize()
+    loss = (sw * gate.view(N, C, 1, 1) * da.float().permute(0, 2, 1).unsqueeze(-1)).sum() + (sw.mean((2, 3)) * dpool).sum()
+    loss.backward()
+    res["dy_max"] = maxerr_scaled(dy.float().permute(0, 2, 1), yr.grad.squeeze(-1))
+    res["dy_rel"] = relerr(dy.float().permute(0, 2, 1), yr.grad.squeeze(-1))
+    res["dgamma_rel"] = relerr(dgamma, gr.grad)
+    res["dbeta_rel"] = relerr(dbeta, br.grad)
+    xhat = (y.double() - mean.double()) * rstd.double()
+    res["reduce1_rel"] = relerr(c1.sum(0), da.double().sum((0, 1)))
+    res["reduce2_rel"] = relerr(c2.sum(0), (da.double() * xhat).sum((0, 1)))
+    res["draw_rel"] = relerr(draw, (da.float().permute(0, 2, 1) * sw.squeeze(-1).detach()).sum(2))
+    res["nan"] = int(torch.isnan(dy.float()).sum() + torch.isnan(a2.float()).sum())
+    return res
+
+
+def check_se_fc(N, C, Cse, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    pooled = torch.randn(N, C, device="cuda", generator=g)
+    Wr = (torch.randn(Cse, C, device="cuda", generator=g) / math.sqrt(C)).requires_grad_(True)
+    br = (0.1 * torch.randn(Cse, device="cuda", generator=g)).requires_grad_(True)
+    We = (torch.randn(C, Cse, device="cuda", generator=g) / math.sqrt(Cse)).requires_grad_(True)
+    be = (0.1 * torch.randn(C, device="cuda", generator=g)).requires_grad_(True)
+    gate = torch.zeros(N, C, device="cuda")
+    _lib.call("dfd_se_fc_fwd", P(pooled), P(Wr), P(br), P(We), P(be), P(gate), N, C, Cse, st())
+    pr = pooled.clone().requires_grad_(True)
+    r = F.linear(pr, Wr, br)
+    r = r * torch.sigmoid(r)
+    ref = torch.sigmoid(F.linear(r, We, be))
+    draw = torch.randn(N, C, device="cuda", generator=g)
+    ref.backward(draw)
+    d_e, dpool = torch.zeros(N, C, device="cuda"), torch.zeros(N, C, device="cuda")
+    rr, drp = torch.zeros(N, Cse, device="cuda"), torch.zeros(N, Cse, device="cuda")
+    dWr, dbr, dWe, dbe = torch.zeros_like(Wr), torch.zeros_like(br), torch.zeros_like(We), torch.zeros_like(be)
+    _lib.call("dfd_se_fc_bwd", P(draw), P(pooled), P(Wr), P(br), P(We), P(be), P(d_e), P(rr), P(drp), P(dpool), P(dWr), P(dbr), P(dWe),
+              P(dbe), N, C, Cse, st())
+    torch.cuda.synchronize()
+    return dict(gate_rel=relerr(gate, ref.detach()), dpool_rel=relerr(dpool, pr.grad), dWr_rel=relerr(dWr, Wr.grad),
+                dbr_rel=relerr(dbr, br.grad), dWe_rel=relerr(dWe, We.grad), dbe_rel=relerr(dbe, be.grad))
+
+
+def check_head(N, Fdim, smoothing=0.0, soft=False, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    pooled = torch.randn(N, Fdim, device="cuda", generator=g)
+    W = (torch.randn(2, Fdim, device="cuda", generator=g) / math.sqrt(Fdim)).requires_grad_(True)
+    b = (0.1 * torch.randn(2, device="cuda", generator=g)).requires_grad_(True)
+    y = torch.randint(0, 2, (N,), device="cuda", generator=g)
+    tf = torch.softmax(torch.randn(N, 2, device="cuda", generator=g), -1)
+    logits = torch.zeros(N, 2, device="cuda")
+    dlog = torch.zeros(N, 2, device="cuda")
+    acc = torch.zeros(2, device="cuda")
+    _lib.call("dfd_head_fwd", P(pooled), P(W), P(b), P(logits), N, Fdim, 2, None if soft else P(y), P(tf) if soft else None,
+              smoothing, 1.0, P(acc), P(acc) + 4, P(dlog), st())
+    pr = pooled.clone().requires_grad_(True)
+    z = F.linear(pr, W, b)
+    logp = F.log_softmax(z, -1)
+    if soft:
+        loss = torch.sum(-tf * logp, -1).mean()
+        lab = tf.argmax(1)
+    else:
+        nll = -logp.gather(-1, y.unsqueeze(1)).squeeze(1)
+        loss = ((1 - smoothing) * nll + smoothing * (-logp.mean(-1))).mean()
+        lab = y
+    z.retain_grad()
+    loss.backward()
+    dW, db, dpooled = torch.zeros_like(W), torch.zeros_like(b), torch.zeros(N, Fdim, device="cuda")
+    _lib.call("dfd_head_bwd", P(dlog), P(pooled), P(W), P(dW), P(db), P(dpooled), N, Fdim, 2, st())
+    torch.cuda.synchronize()
+    correct = float((z.argmax(1) == lab).sum())
+    return dict(logits_rel=relerr(logits, z.detach()), loss_rel=abs(float(acc[0]) - float(loss)) / abs(float(loss)),
+                correct_diff=abs(float(acc[1]) - correct), dlogits_rel=relerr(dlog, z.grad), dW_rel=relerr(dW, W.grad),
+                db_rel=relerr(db, b.grad), dpooled_rel=relerr(dpooled, pr.grad))
+
+
+def check_optimizer(kind, n=10007, steps=3, dtype=torch.bfloat16, seed=0):
+    from oracle import train as OT
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    p = torch.randn(n, device="cuda", generator=g)
+    p_ref = {"w": p.cpu().clone().view(n, 1)}           # 2-D name without 'bias' -> weight decay applies
+    lr, wd, mom, eps = 0.05, 1e-2, 0.9, 1e-3
+    opt = OT.OptState(kind=kind, lr=lr, momentum=mom, weight_decay=wd, eps=eps)
+    a = torch.ones(n, device="cuda") if kind == "rmsproptf" else torch.zeros(n, device="cuda")
+    b = torch.zeros(n, device="cuda")
+    p16 = torch.zeros(n, device="cuda", dtype=dtype)
+    worst = 0.0
+    for s in range(steps):
+        gr = torch.randn(n, device="cuda", generator=g)
+        OT.optimizer_step(opt, p_ref, {"w": gr.cpu().view(n, 1)})
+        if kind == "sgd":
+            _lib.call("dfd_sgd_step", P(p), P(gr), P(a), n, lr, mom, wd, 1, 1.0, None, P(p16), DT[dtype], st())
+        elif kind in ("adam", "adamw"):
+            _lib.call("dfd_adam_step", P(p), P(gr), P(a), P(b), n, lr, 0.9, 0.999, eps, wd, 1 if kind == "adamw" else 0, s + 1, 1.0,
+                      None, P(p16), DT[dtype], st())
+        else:
+            _lib.call("dfd_rmsprop_tf_step", P(p), P(gr), P(a), P(b), n, lr, 0.9, eps, wd, mom, 1.0, None, P(p16), DT[dtype], st())
+        torch.cuda.synchronize()
+        worst = max(worst, relerr(p.cpu(), p_ref["w"].view(-1)))
+    return dict(rel=worst, p16_rel=relerr(p16.float(), p.to(dtype).float()))
+
+
+def check_transpose(dtype=torch.bfloat16):
+    import struct
+    shapes = [(96, 16), (24, 144), (1280, 320), (40, 240)]
+    srcs = [torch.randn(o, i, device="cuda").to(dtype) for o, i in shapes]
+    dsts = [torch.zeros(i, o, device="cuda", dtype=dtype) for o, i in shapes]
+    raw = b"".join(struct.pack("<QQii", s.data_ptr(), d.data_ptr(), o, i) for s, d, (o, i) in zip(srcs, dsts, shapes))
+    table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
+    _lib.call("dfd_transpose_weights", P(table), len(shapes), DT[dtype], st())
+    torch.cuda.synchronize()
+    return dict(mismatch=sum(int((d != s.t()).sum()) for s, d in zip(srcs, dsts)))

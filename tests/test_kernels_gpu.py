@@ -1,0 +1,96 @@
+"""-m gpu: every C-ABI kernel against plain PyTorch fp32 on the same rounded inputs (see tests/gpu_checks.py for
+the tolerance rationale: OUT16 = 2^-7 scaled max error for 16-bit outputs, RED = 2e-3 rel-L2 for fp32 reductions)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+OUT16 = 2.0 ** -7
+RED = 2e-3
+F32 = 2e-5
+
+
+def _gc():
+    import gpu_checks
+    return gpu_checks
+
+
+GEMM_SHAPES = [(1000, 16, 96), (4096 + 37, 24, 144), (777, 1152, 320), (5000, 320, 1280), (130, 40, 24), (50176, 80, 480),
+               (300, 64, 64), (128, 64, 16), (256 * 49, 672, 192)]
+
+
+@pytest.mark.parametrize("M,K,N", GEMM_SHAPES)
+def test_gemm_tcgen05(M, K, N):
+    r = _gc().check_gemm("tc", M, K, N)
+    assert r["nan"] == 0 and r["out_max"] < OUT16 and r["sum_rel"] < RED and r["sq_rel"] < RED, r
+
+
+def test_gemm_tcgen05_fp16():
+    r = _gc().check_gemm("tc", 3000, 144, 40, dtype=torch.float16)
+    assert r["nan"] == 0 and r["out_max"] < 2.0 ** -9 and r["sum_rel"] < RED, r
+
+
+@pytest.mark.parametrize("M,K,N", GEMM_SHAPES[:5])
+def test_gemm_mma(M, K, N):
+    r = _gc().check_gemm("mma", M, K, N, with_add=(N == 24))
+    assert r["nan"] == 0 and r["out_max"] < OUT16 and r["sum_rel"] < RED and r["sq_rel"] < RED, r
+
+
+@pytest.mark.parametrize("M,Nw,Kw", [(5000, 96, 16), (12345, 144, 24), (3000, 1152, 192), (777, 320, 1280), (64, 24, 144)])
+def test_wgrad(M, Nw, Kw):
+    assert _gc().check_wgrad(M, Nw, Kw)["rel"] < 1e-4
+
+
+@pytest.mark.parametrize("N,H,W,C,k,s,aff", [(2, 16, 16, 32, 3, 1, True), (2, 17, 19, 96, 3, 2, True), (2, 14, 14, 144, 5, 1, True),
+                                              (2, 15, 15, 240, 5, 2, True), (3, 7, 7, 1152, 5, 1, True), (2, 40, 40, 32, 3, 1, False),
+                                              (1, 33, 33, 24, 3, 1, False), (2, 56, 56, 144, 5, 2, True)])
+def test_dwconv(N, H, W, C, k, s, aff):
+    r = _gc().check_dwconv(N, H, W, C, k, s, affine=aff)
+    assert r["nan"] == 0 and r["nan_b"] == 0, r
+    assert r["fwd_max"] < OUT16 and r["sum_rel"] < RED and r["sq_rel"] < RED, r
+    assert r["dgrad_rel"] < 8e-3 and r["wgrad_rel"] < RED, r      # tanh.approx sigmoid: 2^-11 relative
+    if aff:
+        assert r["bs1_rel"] < RED and r["bs2_rel"] < RED, r
+
+
+def test_dwconv_fp16():
+    r = _gc().check_dwconv(2, 14, 14, 80, 3, 1, dtype=torch.float16)
+    assert r["fwd_rel"] < 2e-3 and r["dgrad_rel"] < 4e-3 and r["wgrad_rel"] < RED, r
+
+
+@pytest.mark.parametrize("N,Cin,H,Cout,k", [(2, 3, 32, 32, 3), (2, 3, 38, 48, 3), (1, 12, 20, 256, 3), (2, 3, 32, 64, 7)])
+def test_stem(N, Cin, H, Cout, k):
+    r = _gc().check_stem(N, Cin, H, H, Cout, k)
+    assert r["nan"] == 0 and r["fwd_max"] < OUT16 and r["sum_rel"] < RED and r["sq_rel"] < RED and r["wgrad_rel"] < 1e-4, r
+
+
+@pytest.mark.parametrize("N,HW,C", [(3, 64, 32), (2, 49, 1152), (4, 200, 144), (2, 1000, 16)])
+def test_bn_chain(N, HW, C):
+    r = _gc().check_bn_chain(N, HW, C)
+    assert r["nan"] == 0 and r["nbt"] == 1, r
+    assert r["rm_rel"] < 1e-5 and r["rv_rel"] < 1e-5, r
+    assert r["gate_max"] < OUT16 and r["res_max"] < OUT16 and r["pool_rel"] < RED, r
+    assert r["dy_rel"] < 1e-2 and r["dgamma_rel"] < 5e-3 and r["dbeta_rel"] < 5e-3, r
+    assert r["reduce1_rel"] < 1e-5 and r["reduce2_rel"] < 1e-5 and r["draw_rel"] < RED, r
+
+
+@pytest.mark.parametrize("N,C,Cse", [(5, 144, 6), (3, 1152, 48)])
+def test_se_fc(N, C, Cse):
+    r = _gc().check_se_fc(N, C, Cse)
+    assert max(r.values()) < F32 * 5, r
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(smoothing=0.1), dict(soft=True)])
+def test_head_loss(kw):
+    r = _gc().check_head(16, 1280, **kw)
+    assert r["correct_diff"] == 0 and max(v for k, v in r.items() if k != "correct_diff") < F32 * 5, r
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adam", "adamw", "rmsproptf"])
+def test_optimizer(kind):
+    r = _gc().check_optimizer(kind)
+    assert r["rel"] < F32 and r["p16_rel"] == 0.0, r
+
+
+def test_transpose():
+    assert _gc().check_transpose()["mismatch"] == 0
