@@ -20,6 +20,7 @@ namespace {
 constexpr int CB = 64;       // channels per CTA
 constexpr int P = 8;         // output columns per strip
 constexpr int NTHREADS = 256;
+constexpr int DW_MAX_SMEM = 200 * 1024;
 
 struct DwGeom {
     int N, H, W, C, Ho, Wo, pad;
@@ -385,10 +386,8 @@ static int fill_geom(DwGeom& g, int N, int H, int W, int C, int K, int S, bool i
 
 template <typename KernelT>
 static int set_smem(KernelT k, int bytes) {
-    if (bytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        if (e != cudaSuccess) return dfd_set_cuda_error(e, __FILE__, __LINE__);
-    }
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return dfd_set_cuda_error(e, __FILE__, __LINE__);
     return DFD_OK;
 }
 
@@ -409,8 +408,13 @@ static int set_smem(KernelT k, int bytes) {
 #define DW_LAUNCH(kern, grid, smem, st, ...)                         \
     do {                                                             \
         auto kfn__ = kern;                                           \
-        int rc__ = set_smem(kfn__, smem);                            \
-        if (rc__) return rc__;                                       \
+        static bool attr_done__ = false;   /* once per instantiation: a per-launch value would be stale at graph replay */ \
+        if (!attr_done__) {                                          \
+            int rc__ = set_smem(kfn__, DW_MAX_SMEM);                 \
+            if (rc__) return rc__;                                   \
+            attr_done__ = true;                                      \
+        }                                                            \
+        if (smem > DW_MAX_SMEM) return dfd_set_error(DFD_ERR_UNSUPPORTED, "depthwise tile exceeds shared memory"); \
         kfn__<<<grid, NTHREADS, smem, st>>>(__VA_ARGS__);            \
     } while (0)
 

@@ -180,10 +180,11 @@ extern "C" {
 // x: [N,Cin,H,W] (NCHW, 16-bit) ; w: [Cout,Cin,k,k] fp32 ; out: [N,Ho,Wo,Cout] (NHWC, 16-bit)
 int dfd_stem_fwd(const void* x, const float* w, void* out, int N, int Cin, int H, int W, int Cout, int k, int stride,
                  int pad, int dt, double* dsum, double* dsq, void* stream) {
-    if (Cout % 8 || Cout > 256 || 256 % (Cout / 8) || (k != 3 && k != 7))
-        return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_stem_fwd: Cout/8 must divide 256, k in {3,7}");
+    if (Cout % 8 || Cout > 256 || (k != 3 && k != 7))
+        return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_stem_fwd: Cout % 8 == 0, Cout <= 256, k in {3,7}");
     int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     int G = Cout / 8, ppb = 256 / G;
+    const int nthreads = G * ppb;            // whole pixels only (e.g. Cout = 48: 6 groups x 42 pixels = 252 threads)
     long long total = (long long)N * Ho * Wo;
     int blocks = cdiv(total, ppb);
     size_t smem = (size_t)Cin * k * k * Cout * sizeof(float);
@@ -192,11 +193,11 @@ int dfd_stem_fwd(const void* x, const float* w, void* out, int N, int Cin, int H
         if (k == 3) {
             auto kf = stem_fwd_kernel<T, 3>;
             if (smem > 48 * 1024) cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kf<<<blocks, 256, smem, st>>>((const T*)x, w, (T*)out, N, Cin, H, W, Cout, Ho, Wo, stride, pad, dsum, dsq);
+            kf<<<blocks, nthreads, smem, st>>>((const T*)x, w, (T*)out, N, Cin, H, W, Cout, Ho, Wo, stride, pad, dsum, dsq);
         } else {
             auto kf = stem_fwd_kernel<T, 7>;
             if (smem > 48 * 1024) cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kf<<<blocks, 256, smem, st>>>((const T*)x, w, (T*)out, N, Cin, H, W, Cout, Ho, Wo, stride, pad, dsum, dsq);
+            kf<<<blocks, nthreads, smem, st>>>((const T*)x, w, (T*)out, N, Cin, H, W, Cout, Ho, Wo, stride, pad, dsum, dsq);
         }
     });
     DFD_LAUNCH_CHECK();

@@ -62,6 +62,7 @@ def run_parity(arch, batch, H, W, dtype="bf16", steps=2, gemm_impl="tc", opt_kin
         x, y = synth_batch(batch, spec.in_chans, H, W, seed=1234 + step, soft=soft)
         engine_step(eng, opt, x.cuda(), y.cuda(), smoothing)
         rec = {}
+        keep = {}
         for key, (sd, ost, adt) in oracles.items():
             taps = {} if (key == "emul" and step == 0) else None
             # capture the oracle gradients before the update changes the weights
@@ -77,6 +78,7 @@ def run_parity(arch, batch, H, W, dtype="bf16", steps=2, gemm_impl="tc", opt_kin
             tot_n = torch.cat([eng.grad_view(n).flatten().cpu() for n in pnames])
             tot_o = torch.cat([out["grads"][n].flatten() for n in pnames])
             r["grad_rel_total"] = relerr(tot_n, tot_o)
+            keep[key] = (out["logits"].clone(), tot_o, float(out["loss"]))
             perr = {n: relerr(eng.param_view(n), sd[n]) for n in pnames}
             r["param_rel_worst"] = sorted(perr.items(), key=lambda kv: -kv[1])[:3]
             berr = {n: relerr(eng.buffer_view(n).float(), sd[n].float()) for n in sd if n not in pnames}
@@ -91,6 +93,10 @@ def run_parity(arch, batch, H, W, dtype="bf16", steps=2, gemm_impl="tc", opt_kin
                 if verbose:
                     r["taps"] = tl
             rec[key] = r
+        # the yardstick: how far the oracle's own 16-bit emulation is from the fp32 reference arithmetic. A perfect
+        # 16-bit implementation cannot be closer to fp32 than this, so the bf16 tolerance is stated relative to it.
+        rec["yard"] = dict(logits_rel=relerr(keep["emul"][0], keep["fp32"][0]), grad_rel_total=relerr(keep["emul"][1], keep["fp32"][1]),
+                           loss_abs=abs(keep["emul"][2] - keep["fp32"][2]))
         report["steps"].append(rec)
     # eval-mode forward with the trained running statistics (validate path)
     x, y = synth_batch(batch, spec.in_chans, H, W, seed=999)

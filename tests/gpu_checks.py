@@ -116,7 +116,7 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0):
         a = u * torch.sigmoid(u)
     else:
         a = xr
-    a_q = a.to(dtype).float() + (a - a.detach())          # straight-through rounding
+    a_q = a + (a.to(dtype).float() - a).detach()          # straight-through rounding (value rounded, gradient 1)
     wr = w.clone().requires_grad_(True)
     ref = F.conv2d(a_q, wr, stride=s, padding=pad, groups=C)
     res = dict(fwd_max=maxerr_scaled(nchw(out.float()), ref.detach()), fwd_rel=relerr(nchw(out.float()), ref.detach()),

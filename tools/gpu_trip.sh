@@ -5,6 +5,9 @@ mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/gpu.txt 2>&1
 for g in "$@"; do
   case "$g" in
+    blocking_*)
+      impl="${g#blocking_}"
+      CUDA_LAUNCH_BLOCKING=1 timeout 900 python bench.py --steps 2 --warmup 1 --gemm "$impl" --no-graph --no-cpu > gpurun_out/$g.log 2>&1; echo "$g exit $?" ;;
     bench_*)
       impl="${g#bench_}"
       timeout 900 python bench.py --steps 10 --warmup 3 --gemm "$impl" > gpurun_out/$g.log 2>&1; echo "$g exit $?" ;;
