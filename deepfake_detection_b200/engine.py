@@ -165,11 +165,15 @@ class Engine:
     # plan construction
     # ------------------------------------------------------------------------------------------
     def _alloc16(self, *shape):
-        return torch.empty(shape, dtype=self.tdtype, device=self.device)
+        # the plan holds RAW pointers: every buffer must stay referenced for the engine's lifetime
+        t = torch.empty(shape, dtype=self.tdtype, device=self.device)
+        self._keep.append(t)
+        return t
 
     def _build(self):
         spec, N, dev, L = self.spec, self.N, self.device, self.L
         S = L.stat_slots
+        self._keep = []
         self.acts = {}
         fwd, bwd = [], []
         bn_list = []
@@ -298,6 +302,7 @@ class Engine:
             if b.cse:
                 pooled = torch.zeros(N, b.cmid, dtype=torch.float32, device=dev)
                 gate = torch.zeros(N, b.cmid, dtype=torch.float32, device=dev)
+                self._keep += [pooled, gate]
                 rec.update(pooled=pooled, gate=gate)
                 fwd.append(("dfd_pool", (_ptr(y2), bn_mid.scale, bn_mid.shift, _ptr(pooled), N, ho * wo, b.cmid, ACT_SWISH, dt)))
                 fwd.append(("dfd_se_fc_fwd", (_ptr(pooled), P32(p + ".se.conv_reduce.weight"), P32(p + ".se.conv_reduce.bias"),
