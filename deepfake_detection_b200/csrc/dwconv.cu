@@ -36,6 +36,9 @@ __device__ __forceinline__ void load_chan_params(const float* p, int cbase, int 
 
 // Stage act(scale*x+shift) for rows [iy0, iy0+IH) x cols [ix0, ix0+IW) x channels [c0, c0+64) of image `img`
 // (zero outside the image / beyond C) into tile[(r*IW + c)*32 + word].
+// UNR independent 16-byte loads are issued per thread before any is consumed (memory-level parallelism: with one
+// load in flight per thread the kernel is latency-bound at ~1/3 of HBM speed).
+constexpr int UNR = 4;
 template <typename T, int ACT, bool AFFINE>
 __device__ __forceinline__ void stage_input_tile(uint32_t* tile, const T* __restrict__ img, int H, int W, int C,
                                                  int c0, int iy0, int ix0, int IH, int IW,
@@ -46,34 +49,48 @@ __device__ __forceinline__ void stage_input_tile(uint32_t* tile, const T* __rest
     float sc[8], sh[8];
     if (AFFINE) { load_chan_params(scale, cbase, C, sc, 1.f); load_chan_params(shift, cbase, C, sh, 0.f); }
     const int npix = IH * IW;
-    for (int pix = threadIdx.x >> 3; pix < npix; pix += NTHREADS / 8) {
-        int r = pix / IW, c = pix - r * IW;
-        int iy = iy0 + r, ix = ix0 + c;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if (cvalid && iy >= 0 && iy < H && ix >= 0 && ix < W) {
-            uint4 raw = ldg16(img + ((size_t)iy * W + ix) * C + cbase);
-            if (AFFINE || ACT != DFD_ACT_NONE) {
-                float f[8];
-                unpack8<T>(raw, f);
+    constexpr int PSTEP = NTHREADS / 8;
+    for (int base = threadIdx.x >> 3; base < npix; base += PSTEP * UNR) {
+        uint4 raw[UNR];
+        bool ok[UNR];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    float u = AFFINE ? fmaf(f[i], sc[i], sh[i]) : f[i];
-                    f[i] = act_fwd<ACT>(u);
-                }
-                o = pack8<T>(f);
-            } else {
-                o = raw;
-            }
+        for (int u = 0; u < UNR; u++) {
+            int pix = base + u * PSTEP;
+            int r = pix / IW, c = pix - r * IW;
+            int iy = iy0 + r, ix = ix0 + c;
+            ok[u] = pix < npix && cvalid && iy >= 0 && iy < H && ix >= 0 && ix < W;
+            if (ok[u]) raw[u] = ldg16(img + ((size_t)iy * W + ix) * C + cbase);
         }
-        *reinterpret_cast<uint4*>(tile + (size_t)pix * 32 + v * 4) = o;
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            int pix = base + u * PSTEP;
+            if (pix >= npix) break;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (ok[u]) {
+                if (AFFINE || ACT != DFD_ACT_NONE) {
+                    float f[8];
+                    unpack8<T>(raw[u], f);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        float uu = AFFINE ? fmaf(f[i], sc[i], sh[i]) : f[i];
+                        f[i] = act_fwd<ACT>(uu);
+                    }
+                    o = pack8<T>(f);
+                } else {
+                    o = raw[u];
+                }
+            }
+            *reinterpret_cast<uint4*>(tile + (size_t)pix * 32 + v * 4) = o;
+        }
     }
 }
 
-// Stage the zero-upsampled output gradient dy = A*g + B*y + C (BN backward folded into the load) in INPUT pixel
-// coordinates: tile pixel (r, c) <-> U[uy0 + r, ux0 + c], U[a,b] = dy[a/S, b/S] when a, b are multiples of S.
-template <typename T, int S, bool AFFINE>
+// Stage the output gradient dy = A*g + B*y + C (BN backward folded into the load): tile pixel (r, c) <-> dy[oy0 + r,
+// ox0 + c], zero outside [0,Ho) x [0,Wo).  (Compact: the stride-2 input-gradient kernel indexes it by parity, nothing is
+// zero-upsampled.)
+template <typename T, bool AFFINE>
 __device__ __forceinline__ void stage_grad_tile(uint32_t* tile, const T* __restrict__ g, const T* __restrict__ y,
-                                                int Ho, int Wo, int C, int c0, int uy0, int ux0, int IH, int IW,
+                                                int Ho, int Wo, int C, int c0, int oy0, int ox0, int IH, int IW,
                                                 const float* __restrict__ cA, const float* __restrict__ cB,
                                                 const float* __restrict__ cC) {
     const int v = threadIdx.x & 7;
@@ -82,28 +99,73 @@ __device__ __forceinline__ void stage_grad_tile(uint32_t* tile, const T* __restr
     float A[8], B[8], Cc[8];
     if (AFFINE) { load_chan_params(cA, cbase, C, A, 1.f); load_chan_params(cB, cbase, C, B, 0.f); load_chan_params(cC, cbase, C, Cc, 0.f); }
     const int npix = IH * IW;
-    for (int pix = threadIdx.x >> 3; pix < npix; pix += NTHREADS / 8) {
-        int r = pix / IW, c = pix - r * IW;
-        int a = uy0 + r, b = ux0 + c;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if (cvalid && a >= 0 && b >= 0 && (a % S) == 0 && (b % S) == 0) {
-            int oy = a / S, ox = b / S;
-            if (oy < Ho && ox < Wo) {
+    constexpr int PSTEP = NTHREADS / 8;
+    constexpr int UG = AFFINE ? 2 : 4;     // two tensors are read when the BN backward is folded in
+    for (int base = threadIdx.x >> 3; base < npix; base += PSTEP * UG) {
+        uint4 graw[UG], yraw[UG];
+        bool ok[UG];
+#pragma unroll
+        for (int u = 0; u < UG; u++) {
+            int pix = base + u * PSTEP;
+            int r = pix / IW, c = pix - r * IW;
+            int oy = oy0 + r, ox = ox0 + c;
+            ok[u] = pix < npix && cvalid && oy >= 0 && oy < Ho && ox >= 0 && ox < Wo;
+            if (ok[u]) {
                 size_t off = ((size_t)oy * Wo + ox) * C + cbase;
-                uint4 graw = ldg16(g + off);
+                graw[u] = ldg16(g + off);
+                if (AFFINE) yraw[u] = ldg16(y + off);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UG; u++) {
+            int pix = base + u * PSTEP;
+            if (pix >= npix) break;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (ok[u]) {
                 if (AFFINE) {
                     float gg[8], yy[8];
-                    unpack8<T>(graw, gg);
-                    unpack8<T>(ldg16(y + off), yy);
+                    unpack8<T>(graw[u], gg);
+                    unpack8<T>(yraw[u], yy);
 #pragma unroll
                     for (int i = 0; i < 8; i++) gg[i] = fmaf(A[i], gg[i], fmaf(B[i], yy[i], Cc[i]));
                     o = pack8<T>(gg);
                 } else {
-                    o = graw;
+                    o = graw[u];
+                }
+            }
+            *reinterpret_cast<uint4*>(tile + (size_t)pix * 32 + v * 4) = o;
+        }
+    }
+}
+
+// stride-2 input gradient of one strip of P input columns (ix0 even) in input row `sy` (relative to the even tile
+// origin): ga[p] = sum over taps with (sy+pad-kh) and (p+pad-kw) even of dy[(sy+pad-kh)/2, (sx+p+pad-kw)/2] * w[kh,kw].
+// The compact dy tile starts at (y0/2 - 1, x0/2 - 1).
+template <typename T, int K>
+__device__ __forceinline__ void strip_dgrad_s2(const uint32_t* __restrict__ tile, int IW, int sy, int sx, int lane,
+                                               const float (&w)[K * K][2], float (&acc)[P][2]) {
+    constexpr int PAD = (K - 1) / 2;
+#pragma unroll
+    for (int kh = 0; kh < K; kh++) {
+        const int q = sy + PAD - kh;
+        if (q & 1) continue;                          // warp-uniform
+        const int row = (q >> 1) + 1;
+        const uint32_t* rp = tile + ((size_t)row * IW + (sx >> 1)) * 32 + lane;
+        float2 vv[P / 2 + 2];
+#pragma unroll
+        for (int j = 0; j < P / 2 + 2; j++) vv[j] = unpack2<T>(rp[j * 32]);
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+#pragma unroll
+            for (int kw = 0; kw < K; kw++) {
+                const int e = p + PAD - kw;
+                if (((e % 2) + 2) % 2 == 0) {
+                    const int col = (e + 2) / 2;      // e/2 + 1 with e >= -2
+                    acc[p][0] = fmaf(vv[col].x, w[kh * K + kw][0], acc[p][0]);
+                    acc[p][1] = fmaf(vv[col].y, w[kh * K + kw][1], acc[p][1]);
                 }
             }
         }
-        *reinterpret_cast<uint4*>(tile + (size_t)pix * 32 + v * 4) = o;
     }
 }
 
@@ -226,15 +288,17 @@ dwconv_dgrad_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const 
     const int y0 = ty * g.TH, x0 = tx * g.TW;           // input-space tile origin
     const int pp = K - 1 - g.pad;
     const size_t ooff = (size_t)n * g.Ho * g.Wo * g.C;
-    stage_grad_tile<T, S, AFFINE>(tile, gy + ooff, AFFINE ? yout + ooff : nullptr, g.Ho, g.Wo, g.C, c0, y0 - pp, x0 - pp,
-                                  g.IH, g.IW, cA, cB, cC);
+    // stride 1: the dy tile is the input tile shifted by the flipped padding; stride 2: compact tile at (y0/2-1, x0/2-1)
+    stage_grad_tile<T, AFFINE>(tile, gy + ooff, AFFINE ? yout + ooff : nullptr, g.Ho, g.Wo, g.C, c0,
+                               S == 1 ? y0 - pp : (y0 >> 1) - 1, S == 1 ? x0 - pp : (x0 >> 1) - 1, g.IH, g.IW, cA, cB, cC);
     const int ch = c0 + lane * 2;
     const bool chv = ch < g.C;
     float w[K * K][2];
 #pragma unroll
-    for (int i = 0; i < K * K; i++) {       // flipped taps
-        w[i][0] = chv ? wgt[(size_t)ch * K * K + (K * K - 1 - i)] : 0.f;
-        w[i][1] = chv ? wgt[(size_t)(ch + 1) * K * K + (K * K - 1 - i)] : 0.f;
+    for (int i = 0; i < K * K; i++) {       // stride 1: flipped taps (correlation form); stride 2: direct taps
+        const int src = S == 1 ? (K * K - 1 - i) : i;
+        w[i][0] = chv ? wgt[(size_t)ch * K * K + src] : 0.f;
+        w[i][1] = chv ? wgt[(size_t)(ch + 1) * K * K + src] : 0.f;
     }
     float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f, mu0 = 0.f, mu1 = 0.f, rs0 = 0.f, rs1 = 0.f;
     if (MODE == 1 && chv) {
@@ -251,18 +315,28 @@ dwconv_dgrad_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const 
         int sy = s / strips_x, sx = (s - sy * strips_x) * P;
         int iy = y0 + sy, ix = x0 + sx;
         if (iy >= g.H || ix >= g.W) continue;
+        // issue the strip's global reads (pre-activation input / residual gradient) BEFORE the conv math so that
+        // their latency hides behind it instead of serialising with the stores
+        uint32_t pre[P];
+        const size_t off0 = ioff + ((size_t)iy * g.W + ix) * g.C + ch;
+        if (chv && (MODE == 1 || add)) {
+            const T* src = MODE == 1 ? xin : add;
+#pragma unroll
+            for (int p = 0; p < P; p++) pre[p] = (ix + p < g.W) ? __ldg(reinterpret_cast<const uint32_t*>(src + off0 + (size_t)p * g.C)) : 0u;
+        }
         float acc[P][2];
 #pragma unroll
         for (int p = 0; p < P; p++) { acc[p][0] = 0.f; acc[p][1] = 0.f; }
-        strip_conv<T, K, 1>(tile, g.IW, sy, sx, lane, w, acc);
+        if (S == 1) strip_conv<T, K, 1>(tile, g.IW, sy, sx, lane, w, acc);
+        else strip_dgrad_s2<T, K>(tile, g.IW, sy, sx, lane, w, acc);
         if (chv) {
 #pragma unroll
             for (int p = 0; p < P; p++) {
                 if (ix + p < g.W) {
-                    size_t off = ioff + ((size_t)iy * g.W + ix + p) * g.C + ch;
+                    size_t off = off0 + (size_t)p * g.C;
                     float v0 = acc[p][0], v1 = acc[p][1];
                     if (MODE == 1) {
-                        float2 xi = unpack2<T>(*reinterpret_cast<const uint32_t*>(xin + off));
+                        float2 xi = unpack2<T>(pre[p]);
                         v0 *= act_bwd<DFD_ACT_SWISH>(fmaf(xi.x, sc0, sh0));
                         v1 *= act_bwd<DFD_ACT_SWISH>(fmaf(xi.y, sc1, sh1));
                         uint32_t pk = pack2<T>(v0, v1);
@@ -273,7 +347,7 @@ dwconv_dgrad_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const 
                         b1 = fmaf(r.y, (xi.y - mu1) * rs1, b1);
                     } else {
                         if (add) {
-                            float2 ad = unpack2<T>(*reinterpret_cast<const uint32_t*>(add + off));
+                            float2 ad = unpack2<T>(pre[p]);
                             v0 += ad.x; v1 += ad.y;
                         }
                         *reinterpret_cast<uint32_t*>(gx + off) = pack2<T>(v0, v1);
@@ -318,30 +392,44 @@ dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, co
 
     for (int n = blockIdx.z; n < g.N; n += gridDim.z) {
         const T* img = x + (size_t)n * g.H * g.W * g.C;
+        const size_t ooff = (size_t)n * g.Ho * g.Wo * g.C;
+        // software pipeline: the raw gradient operands of a strip are fetched one strip ahead (the first one before
+        // the tile is staged) so that their global latency overlaps staging / the previous strip's FMAs
+        uint32_t gq[P], yq[P];
+        auto prefetch = [&](int s) {
+            int sy = s / strips_x, sx = (s - sy * strips_x) * P;
+            int oy = oy0 + sy, ox = ox0 + sx;
+            const bool rowok = chv && oy < g.Ho;
+            const size_t off0 = ooff + ((size_t)oy * g.Wo + ox) * g.C + ch;
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const bool ok = rowok && ox + p < g.Wo;
+                gq[p] = ok ? __ldg(reinterpret_cast<const uint32_t*>(gy + off0 + (size_t)p * g.C)) : 0u;
+                if (AFFINE_G) yq[p] = ok ? __ldg(reinterpret_cast<const uint32_t*>(yout + off0 + (size_t)p * g.C)) : 0u;
+            }
+        };
+        if (warp < nstrips) prefetch(warp);
         __syncthreads();    // previous image's tile fully consumed
         stage_input_tile<T, ACT, AFFINE_IN>(tile, img, g.H, g.W, g.C, c0, oy0 * S - g.pad, ox0 * S - g.pad, g.IH, g.IW, scale, shift);
         __syncthreads();
-        const size_t ooff = (size_t)n * g.Ho * g.Wo * g.C;
         for (int s = warp; s < nstrips; s += NTHREADS / 32) {
             int sy = s / strips_x, sx = (s - sy * strips_x) * P;
             int oy = oy0 + sy, ox = ox0 + sx;
-            if (oy >= g.Ho || ox >= g.Wo || !chv) continue;
             float dy[P][2];
 #pragma unroll
             for (int p = 0; p < P; p++) {
-                dy[p][0] = 0.f; dy[p][1] = 0.f;
-                if (ox + p < g.Wo) {
-                    size_t off = ooff + ((size_t)oy * g.Wo + ox + p) * g.C + ch;
-                    float2 gg = unpack2<T>(*reinterpret_cast<const uint32_t*>(gy + off));
-                    if (AFFINE_G) {
-                        float2 yy = unpack2<T>(*reinterpret_cast<const uint32_t*>(yout + off));
-                        // round like the staged operand of the dgrad kernel so both see the same dy
-                        float2 r = unpack2<T>(pack2<T>(fmaf(A0, gg.x, fmaf(B0, yy.x, C0)), fmaf(A1, gg.y, fmaf(B1, yy.y, C1))));
-                        gg = r;
-                    }
-                    dy[p][0] = gg.x; dy[p][1] = gg.y;
+                float2 gg = unpack2<T>(gq[p]);
+                const bool ok = chv && oy < g.Ho && ox + p < g.Wo;
+                if (AFFINE_G) {
+                    float2 yy = unpack2<T>(yq[p]);
+                    // round like the staged operand of the dgrad kernel so both see the same dy
+                    gg = unpack2<T>(pack2<T>(fmaf(A0, gg.x, fmaf(B0, yy.x, C0)), fmaf(A1, gg.y, fmaf(B1, yy.y, C1))));
                 }
+                dy[p][0] = ok ? gg.x : 0.f;
+                dy[p][1] = ok ? gg.y : 0.f;
             }
+            if (s + NTHREADS / 32 < nstrips) prefetch(s + NTHREADS / 32);
+            if (oy >= g.Ho || ox >= g.Wo || !chv) continue;
 #pragma unroll
             for (int kh = 0; kh < K; kh++) {
                 const uint32_t* row = tile + ((size_t)(sy * S + kh) * g.IW + sx * S) * 32 + lane;
@@ -370,6 +458,7 @@ dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, co
 }
 
 static int fill_geom(DwGeom& g, int N, int H, int W, int C, int K, int S, bool input_space) {
+    // input_space: tiles partition the INPUT pixels (dgrad); the staged tile is then dy: shifted (S=1) or compact (S=2)
     g.N = N; g.H = H; g.W = W; g.C = C; g.pad = (K - 1) / 2;
     g.Ho = (H + 2 * g.pad - K) / S + 1;
     g.Wo = (W + 2 * g.pad - K) / S + 1;
@@ -377,8 +466,13 @@ static int fill_geom(DwGeom& g, int N, int H, int W, int C, int K, int S, bool i
     int eff_s = input_space ? 1 : S;
     g.TW = tw_dim <= 8 ? 8 : ((tw_dim <= 16 || eff_s == 2) ? 16 : 32);   // stride-2 tiles stage 2x the columns
     g.TH = th_dim < 8 ? th_dim : 8;
-    g.IW = (g.TW - 1) * eff_s + K;
-    g.IH = (g.TH - 1) * eff_s + K;
+    if (input_space && S == 2) {
+        g.IW = g.TW / 2 + 2;
+        g.IH = (g.TH + 1) / 2 + 2;
+    } else {
+        g.IW = (g.TW - 1) * eff_s + K;
+        g.IH = (g.TH - 1) * eff_s + K;
+    }
     g.tiles_x = (tw_dim + g.TW - 1) / g.TW;
     g.tiles_y = (th_dim + g.TH - 1) / g.TH;
     return g.IH * g.IW * 32 * (int)sizeof(uint32_t);

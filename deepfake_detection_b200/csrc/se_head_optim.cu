@@ -112,8 +112,12 @@ __global__ void se_fc_wgrad_kernel(const float* __restrict__ d_e, const float* _
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= C * Cse) return;
     int c = idx / Cse, j = idx - c * Cse;
+    // blockIdx.y splits the images so that the serial chain per thread stays short; partial sums meet in fp32 atomics
+    const int per = (N + gridDim.y - 1) / gridDim.y;
+    const int n0 = blockIdx.y * per, n1 = min(N, n0 + per);
     float awe = 0.f, awr = 0.f, abe = 0.f, abr = 0.f;
-    for (int n = 0; n < N; n++) {
+#pragma unroll 4
+    for (int n = n0; n < n1; n++) {
         float de = d_e[(size_t)n * C + c], rr = r[(size_t)n * Cse + j];
         float dr = d_rpre[(size_t)n * Cse + j], pp = pooled[(size_t)n * C + c];
         awe = fmaf(de, rr, awe);
@@ -121,10 +125,10 @@ __global__ void se_fc_wgrad_kernel(const float* __restrict__ d_e, const float* _
         abe += de;
         abr += dr;
     }
-    dWe[(size_t)c * Cse + j] += awe;
-    dWr[(size_t)j * C + c] += awr;
-    if (j == 0) dbe[c] += abe;
-    if (c == 0) dbr[j] += abr;
+    atomicAdd(dWe + (size_t)c * Cse + j, awe);
+    atomicAdd(dWr + (size_t)j * C + c, awr);
+    if (j == 0) atomicAdd(dbe + c, abe);
+    if (c == 0) atomicAdd(dbr + j, abr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -364,7 +368,8 @@ int dfd_se_fc_bwd(const float* draw, const float* pooled, const float* Wr, const
     cudaStream_t st = (cudaStream_t)stream;
     se_fc_bwd_kernel<<<N, 256, smem, st>>>(draw, pooled, Wr, br, We, be, d_e, r, d_rpre, dpool, C, Cse);
     DFD_LAUNCH_CHECK();
-    se_fc_wgrad_kernel<<<cdiv((long long)C * Cse, 128), 128, 0, st>>>(d_e, r, d_rpre, pooled, dWr, dbr, dWe, dbe, N, C, Cse);
+    int nsplit = N >= 64 ? 16 : (N >= 8 ? 4 : 1);
+    se_fc_wgrad_kernel<<<dim3(cdiv((long long)C * Cse, 128), nsplit), 128, 0, st>>>(d_e, r, d_rpre, pooled, dWr, dbr, dWe, dbe, N, C, Cse);
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

@@ -102,24 +102,47 @@ stem_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ g, const T* __r
                   const float* __restrict__ cA, const float* __restrict__ cB, const float* __restrict__ cC,
                   float* __restrict__ dW, int N, int Cin, int H, int W, int Cout, int Ho, int Wo, int stride, int pad,
                   int pix_per_block) {
-    extern __shared__ float sdy[];           // [PIX][Cout]
+    extern __shared__ float sdy[];           // [PIX][Cout] dy, then int2[PIX] pixel coordinates
     constexpr int PIX = 64;
+    int2* spix = reinterpret_cast<int2*>(sdy + (size_t)PIX * Cout);    // {image base offset, (iy0 << 16) | (ix0 & 0xffff)}
     const int taps = Cin * K * K;
     const int G = Cout / 8;
     const int items = taps * G;
+    // when items < blockDim, several thread groups share the item set and split the pixels between them
+    const int groups = IPT == 1 ? max(1, (int)blockDim.x / items) : 1;
+    const int grp = IPT == 1 ? threadIdx.x / items : 0;
     const long long total = (long long)N * Ho * Wo;
     const long long p_begin = (long long)blockIdx.x * pix_per_block;
     long long p_end = p_begin + pix_per_block;
     if (p_end > total) p_end = total;
     float acc[IPT][8];
+    int it_ci_off[IPT], it_kh[IPT], it_kw[IPT], it_g[IPT];
 #pragma unroll
-    for (int a = 0; a < IPT; a++)
+    for (int a = 0; a < IPT; a++) {
 #pragma unroll
         for (int i = 0; i < 8; i++) acc[a][i] = 0.f;
+        int item = (IPT == 1 ? threadIdx.x % items : threadIdx.x) + a * blockDim.x;
+        bool valid = item < items && grp < groups;
+        int t = valid ? item / G : 0;
+        it_g[a] = valid ? item - t * G : -1;
+        int ci = t / (K * K), r = t - ci * K * K;
+        it_kh[a] = r / K;
+        it_kw[a] = r - it_kh[a] * K;
+        it_ci_off[a] = ci * H * W;
+    }
 
     for (long long p0 = p_begin; p0 < p_end; p0 += PIX) {
         int np = (int)((p_end - p0 < PIX) ? (p_end - p0) : PIX);
         __syncthreads();
+        if (threadIdx.x < np) {
+            long long pix = p0 + threadIdx.x;
+            int ox = (int)(pix % Wo);
+            long long t2 = pix / Wo;
+            int oy = (int)(t2 % Ho);
+            int n = (int)(t2 / Ho);
+            int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
+            spix[threadIdx.x] = make_int2(n * Cin * H * W, (iy0 << 16) | (ix0 & 0xffff));
+        }
         for (int i = threadIdx.x; i < np * G; i += blockDim.x) {
             int pp = i / G, gg = i - pp * G;
             size_t off = (size_t)(p0 + pp) * Cout + gg * 8;
@@ -135,20 +158,14 @@ stem_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ g, const T* __r
         __syncthreads();
 #pragma unroll
         for (int a = 0; a < IPT; a++) {
-            int item = threadIdx.x + a * blockDim.x;
-            if (item >= items) continue;
-            int t = item / G, gg = item - t * G;
-            int ci = t / (K * K), r = t - ci * K * K;
-            int kh = r / K, kw = r - kh * K;
-            for (int pp = 0; pp < np; pp++) {
-                long long pix = p0 + pp;
-                int ox = (int)(pix % Wo);
-                long long t2 = pix / Wo;
-                int oy = (int)(t2 % Ho);
-                int n = (int)(t2 / Ho);
-                int iy = oy * stride - pad + kh, ix = ox * stride - pad + kw;
+            if (it_g[a] < 0) continue;
+            const int kh = it_kh[a], kw = it_kw[a], cio = it_ci_off[a], gg = it_g[a];
+#pragma unroll 4
+            for (int pp = grp; pp < np; pp += groups) {
+                int2 pc = spix[pp];
+                int iy = (pc.y >> 16) + kh, ix = (int)(short)(pc.y & 0xffff) + kw;
                 if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-                float xv = to_f<T>(x[(((size_t)n * Cin + ci) * H + iy) * W + ix]);
+                float xv = to_f<T>(x[(size_t)pc.x + cio + iy * W + ix]);
                 const float4* dp = reinterpret_cast<const float4*>(sdy + (size_t)pp * Cout + gg * 8);
                 float4 d0 = dp[0], d1 = dp[1];
                 acc[a][0] = fmaf(xv, d0.x, acc[a][0]); acc[a][1] = fmaf(xv, d0.y, acc[a][1]);
@@ -160,11 +177,11 @@ stem_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ g, const T* __r
     }
 #pragma unroll
     for (int a = 0; a < IPT; a++) {
-        int item = threadIdx.x + a * blockDim.x;
-        if (item >= items) continue;
-        int t = item / G, gg = item - t * G;
+        if (it_g[a] < 0) continue;
+        int item = (IPT == 1 ? threadIdx.x % items : threadIdx.x) + a * blockDim.x;
+        int t = item / G;
 #pragma unroll
-        for (int i = 0; i < 8; i++) atomicAdd(dW + (size_t)(gg * 8 + i) * taps + t, acc[a][i]);
+        for (int i = 0; i < 8; i++) atomicAdd(dW + (size_t)(it_g[a] * 8 + i) * taps + t, acc[a][i]);
     }
 }
 
@@ -217,7 +234,8 @@ int dfd_stem_wgrad(const void* x, const void* g, const void* y, const float* cA,
     long long ppb = (total + blocks - 1) / blocks;
     ppb = ((ppb + 63) / 64) * 64;
     blocks = cdiv(total, ppb);
-    size_t smem = (size_t)64 * Cout * sizeof(float);
+    size_t smem = (size_t)64 * Cout * sizeof(float) + 64 * sizeof(int2);
+    if ((long long)N * Cin * H * W >= (1ll << 31)) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_stem_wgrad: image tensor >= 2^31 elements");
     cudaStream_t st = (cudaStream_t)stream;
 #define WG(KK, IPT)                                                                                               \
     do {                                                                                                          \
