@@ -54,7 +54,7 @@ class GradReducer:
         self.engine = e = engine
         self.group = group
         self.world = dist.get_world_size(group)
-        self.side = torch.cuda.Stream(device=e.device)
+        self.side = None if e._plan_only else torch.cuda.Stream(device=e.device)
         # cut the backward plan where a block's last gradient has been produced: op index -> arena ranges done.
         # Arena layout = [decay tensors in exec order | no-decay tensors in exec order]; backward walks both from
         # the end towards the start, so after the ops of a block the suffixes starting at that block's first
@@ -141,12 +141,18 @@ class GradReducer:
         e = self.engine
         dist.broadcast(e.params32, 0, group=self.group)
         dist.broadcast(e.buffers32, 0, group=self.group)
-        e.sync_weights()
+        if not e._plan_only:
+            e.sync_weights()
 
     def backward_and_reduce(self):
         """Runs the engine's backward plan on the current stream, launching each bucket's all-reduce on the side
         stream as soon as the ops that produce it have been enqueued; joins the side stream at the end."""
         e = self.engine
+        if e._plan_only:        # host-logic tests (gloo on CPU): no kernels, only the bucketed collectives
+            for _, spans in self.buckets:
+                for lo, hi in spans:
+                    dist.all_reduce(e.grads32[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+            return
         main = torch.cuda.current_stream()
         st = main.cuda_stream
         start = 0
