@@ -236,10 +236,13 @@ def run_native(args):
         t = torch.tensor([e2e_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t)
+    if world > 1:
+        # every rank leaves together and without tearing NCCL down (a destroy while a peer still holds captured
+        # collectives can block for minutes): rank 0 first finishes its report
+        torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        sys.stdout.flush()
+        os._exit(0)
 
     peaks = load_peaks()
     img_s = B * world * args.steps / (ms / 1e3)
@@ -272,8 +275,9 @@ def run_native(args):
                          h2d_bytes_per_step=int(xh.numel() * xh.element_size() + yh.numel() * 8), d2h_bytes_per_step=16),
                 gpu_launches=n_launch * args.steps, clocks=clocks)
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        os._exit(0)
 
 
 def cpu_baseline(arch, sample_steps=4, batch=None, world=1):

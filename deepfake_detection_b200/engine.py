@@ -33,7 +33,7 @@ class _BN:
 
 class Engine:
     def __init__(self, arch, batch, height=None, width=None, num_classes=2, in_chans=3, dtype="bf16",
-                 bn_momentum=0.1, bn_eps=1e-5, device=None, gemm_impl="tc"):
+                 bn_momentum=0.1, bn_eps=1e-5, device=None, gemm_impl="tc", share_from=None):
         # _plan_only: build the arenas and the call plan on the CPU for host-logic tests; nothing can be executed
         self._plan_only = device == "plan-only"
         if self._plan_only:
@@ -56,7 +56,16 @@ class Engine:
         self.gemm_impl = gemm_impl
         self.training = True
         self.n_launch = {"fwd": 0, "bwd": 0, "opt": 0}
-        self._layout_params()
+        if share_from is not None:
+            # a second plan (other batch size / resolution, e.g. the validation loader) over the SAME weights,
+            # gradients and running statistics
+            if share_from.spec.arch != spec.arch or share_from.dt != self.dt:
+                raise ValueError("share_from: architecture / dtype mismatch")
+            for a in ("p_off", "n_decay", "n_params", "param_names", "params32", "grads32", "params16", "b_off", "bn_names",
+                      "buffers32", "nbt", "t_off", "paramsT16", "_ttable", "_ttable_count"):
+                setattr(self, a, getattr(share_from, a))
+        else:
+            self._layout_params()
         self._build()
 
     # ------------------------------------------------------------------------------------------

@@ -1,0 +1,197 @@
+"""Drop-in model objects for the runner: `create_model` / `create_deepfake_model_v4` return an `nn.Module` whose
+forward / backward run on the native engine.
+
+Boundary being mirrored:
+  * `create_model(model_name, pretrained=False, num_classes=1000, in_chans=3, checkpoint_path='', **kwargs)`
+        dfd/timm/models/factory.py:8-64
+  * `create_deepfake_model_v4(model_name, ..., num_classes, in_chans, checkpoint_path, strict)`  factory.py:190-252
+  * the model object protocol the runner relies on: `model(input) -> logits [N, num_classes]` (train.py:621,719),
+    `.train()/.eval()`, `.named_parameters()` (optim_factory.py:14), `.state_dict()/.load_state_dict()` with the
+    reference key names / OIHW fp32 tensors (utils.py:32-33,101; helpers.py:44,57), `.default_cfg`, `.cuda()`.
+
+The kernels need static shapes, so the engine (kernel plan + activation arenas) is built lazily for each
+(batch, H, W) that reaches `forward`; all plans share one set of weights, gradients and running statistics.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .arch import SUPPORTED_ARCHS, get_spec, state_entries
+from .engine import Engine
+
+_DEFAULT_CFG = dict(num_classes=1000, pool_size=(7, 7), crop_pct=0.875, interpolation="bicubic",
+                    mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225))
+
+
+class _NativeForward(torch.autograd.Function):
+    """logits = net(input) on the engine; backward hands dL/dlogits to the engine's backward plan, which accumulates
+    into the flat gradient arena that the parameters' `.grad` tensors alias."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, engine, training):
+        ctx.engine = engine
+        st = torch.cuda.current_stream().cuda_stream
+        engine.zero_step_scratch(st, grads=False)
+        engine.forward(training=training, stream=st)
+        engine.head(False, stream=st)
+        return engine.logits.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        e = ctx.engine
+        e.dlogits.copy_(dlogits)
+        e.backward()
+        return None, None, None, None
+
+
+class NativeModel(nn.Module):
+    def __init__(self, arch, num_classes=2, in_chans=3, dtype="bf16", bn_momentum=None, bn_eps=None, bn_tf=False,
+                 drop_rate=0.0, drop_path_rate=0.0, gemm_impl="tc", **unused):
+        super().__init__()
+        if drop_rate or drop_path_rate:
+            raise _lib.NativeError("drop_rate / drop_path_rate > 0 are not on the native path yet (SURVEY.md 7.3: RNG parity)")
+        if bn_tf:       # efficientnet_blocks.py:13-30
+            bn_momentum = 1 - 0.99 if bn_momentum is None else bn_momentum
+            bn_eps = 1e-3 if bn_eps is None else bn_eps
+        self.arch = arch
+        self.num_classes = num_classes
+        self.in_chans = in_chans
+        self.dtype_name = dtype
+        self.bn_momentum = 0.1 if bn_momentum is None else bn_momentum
+        self.bn_eps = 1e-5 if bn_eps is None else bn_eps
+        self.gemm_impl = gemm_impl
+        self.spec = get_spec(arch, num_classes=num_classes, in_chans=in_chans)
+        self.default_cfg = dict(_DEFAULT_CFG, input_size=self.spec.input_size,
+                                first_conv="conv_stem" if self.spec.family == "efficientnet" else "conv1",
+                                classifier="classifier" if self.spec.family == "efficientnet" else "fc")
+        self._engines = OrderedDict()
+        self._primary = None
+        self._pending_state = None
+        self._anchor = nn.Parameter(torch.zeros(()), requires_grad=True)   # gives the output a grad_fn
+        self._named = None
+
+    # ---- engines ------------------------------------------------------------------------------------
+    def engine_for(self, n, h, w):
+        key = (int(n), int(h), int(w))
+        e = self._engines.get(key)
+        if e is None:
+            e = Engine(self.arch, key[0], key[1], key[2], num_classes=self.num_classes, in_chans=self.in_chans,
+                       dtype=self.dtype_name, bn_momentum=self.bn_momentum, bn_eps=self.bn_eps, gemm_impl=self.gemm_impl,
+                       share_from=self._primary)
+            if self._primary is None:
+                self._primary = e
+                if self._pending_state is not None:
+                    e.load_state_dict(self._pending_state, strict=False)
+                    self._pending_state = None
+                else:
+                    self._init_weights(e)
+            self._engines[key] = e
+        return e
+
+    @property
+    def engine(self):
+        """the primary engine (owner of the weight / gradient arenas); built for the default input size if needed"""
+        if self._primary is None:
+            c, h, w = self.spec.input_size
+            self.engine_for(1, h, w)
+        return self._primary
+
+    def _init_weights(self, e):
+        """Reference initialisers: efficientnet_builder.py:537-575 (`_init_weight_goog`), resnet.py:411-420."""
+        import math
+        g = torch.Generator(device="cpu").manual_seed(torch.initial_seed() % (2 ** 31))
+        sd = OrderedDict()
+        for name, shape, role in state_entries(self.spec):
+            if role in ("conv_w", "dw_w", "se_w"):
+                fan_out = shape[0] * shape[2] * shape[3]
+                if role == "dw_w":
+                    fan_out = shape[2] * shape[3]           # fan_out //= groups
+                sd[name] = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_out)
+            elif role == "bn_w":
+                sd[name] = torch.ones(shape)
+            elif role in ("bn_b", "se_b", "fc_b", "bn_rm"):
+                sd[name] = torch.zeros(shape)
+            elif role == "bn_rv":
+                sd[name] = torch.ones(shape)
+            elif role == "bn_nbt":
+                sd[name] = torch.zeros((), dtype=torch.int64)
+            elif role == "fc_w":
+                r = 1.0 / math.sqrt(shape[0])               # fan_out of the Linear, _init_weight_goog
+                sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * r
+        e.load_state_dict(sd)
+
+    # ---- nn.Module protocol ---------------------------------------------------------------------------
+    def forward(self, x):
+        if x.dim() != 4:
+            raise ValueError("expected NCHW input")
+        e = self.engine_for(x.shape[0], x.shape[2], x.shape[3])
+        e.set_input(x)
+        if torch.is_grad_enabled() and self.training:
+            return _NativeForward.apply(self._anchor, self, e, True)
+        st = torch.cuda.current_stream().cuda_stream
+        e.zero_step_scratch(st, grads=False)
+        e.forward(training=self.training, stream=st)
+        e.head(False, stream=st)
+        return e.logits.clone()
+
+    def named_parameters(self, prefix="", recurse=True, remove_duplicate=True):
+        if self._named is None:
+            e = self.engine
+            self._named = []
+            for n in e.param_names:
+                p = nn.Parameter(e.param_view(n), requires_grad=True)
+                p.grad = e.grad_view(n)
+                self._named.append((n, p))
+        for n, p in self._named:
+            yield (prefix + ("." if prefix else "") + n, p)
+
+    def parameters(self, recurse=True):
+        for _, p in self.named_parameters():
+            yield p
+
+    def state_dict(self, *args, **kwargs):
+        return self.engine.state_dict()
+
+    def load_state_dict(self, state_dict, strict=True):
+        if self._primary is None and not torch.cuda.is_available():
+            self._pending_state = state_dict
+            return
+        missing = self.engine.load_state_dict(state_dict, strict=strict)
+        return missing
+
+    def cuda(self, device=None):
+        return self
+
+    def half(self):
+        return self
+
+    def get_classifier(self):
+        raise NotImplementedError("the classifier lives in the engine arenas; use state_dict()")
+
+
+def create_model(model_name, pretrained=False, num_classes=1000, in_chans=3, checkpoint_path="", **kwargs):
+    """dfd/timm/models/factory.py:8-64 for the architectures on the native hot path."""
+    if pretrained:
+        raise _lib.NativeError("pretrained weights need network access; load a checkpoint instead")
+    if model_name not in SUPPORTED_ARCHS:
+        raise RuntimeError("Unknown model (%s)" % model_name)       # factory.py:56
+    kwargs.pop("global_pool", None)
+    model = NativeModel(model_name, num_classes=num_classes, in_chans=in_chans, **kwargs)
+    if checkpoint_path:
+        from .helpers import load_checkpoint
+        load_checkpoint(model, checkpoint_path)
+    return model
+
+
+def create_deepfake_model_v4(model_name, pretrained=False, num_classes=1000, in_chans=3, checkpoint_path="",
+                             strict=True, **kwargs):
+    """dfd/timm/models/factory.py:190-252 (asserts the model name, :213)."""
+    assert model_name in ["efficientnet_deepfake_v4"]
+    kwargs.pop("global_pool", None)
+    model = NativeModel(model_name, num_classes=num_classes, in_chans=in_chans, **kwargs)
+    if checkpoint_path:
+        from .helpers import load_checkpoint
+        load_checkpoint(model, checkpoint_path, strict=strict)
+    return model
