@@ -45,6 +45,14 @@ SIGNATURES = {
     "dfd_check_finite": "p" "l" "pp",
     "dfd_update_loss_scale": "ppp" "i" "pp",
     "dfd_transpose_weights": "p" "ii" "p",
+    "dfd_im2col": "pp" "iiiiiii" "i" "p",
+    "dfd_col2im": "ppp" "iiiiiii" "i" "p",
+    "dfd_repack_weights": "p" "ii" "p",
+    "dfd_unpack_grad": "pp" "iii" "p",
+    "dfd_maxpool_fwd": "ppp" "iiii" "i" "p",
+    "dfd_maxpool_bwd": "ppp" "iiii" "i" "p",
+    "dfd_relu_bwd": "ppp" "li" "p",
+    "dfd_pool_bwd": "pp" "ili" "i" "p",
 }
 
 DT_BF16, DT_FP16 = 0, 1

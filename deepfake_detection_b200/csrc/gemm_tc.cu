@@ -16,6 +16,7 @@
 //   * warp roles: w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue (TMEM lane quarter = warp%4).
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -27,8 +28,11 @@ constexpr int UMMA_K = 16;
 constexpr int SLAB = 64;             // epilogue / TMA-store column slab
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_THREADS = 128;
-constexpr int TMEM_COLS = 512;
-constexpr int ACC_STRIDE = 256;      // TMEM column offset between the two accumulator stages
+constexpr int TMEM_COLS = 256;         // per CTA; two CTAs share an SM's 512 columns
+constexpr int ACC_STRIDE = 128;      // TMEM column offset between the two accumulator stages
+constexpr int MAX_BLOCK_N = 128;
+constexpr int SMEM_BUDGET = 113 * 1024;   // two CTAs per SM: the epilogue of one overlaps the other's (measured: one
+                                          // epilogue warpgroup per SM leaves output-heavy tiles latency-bound at ~1.5 TB/s)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -132,16 +136,17 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" :
 
 struct TcParams {
     int M, N, K;
-    int block_n;          // multiple of 16, <= 256
+    int block_n;          // multiple of 16, <= MAX_BLOCK_N
     int num_m_tiles, num_n_tiles, num_k_blocks;
     int stages;
     int is_bf16;
     double* dsum;         // optional [DFD_STAT_SLOTS][N]
     double* dsq;
+    int dbg;              // debug switches (DFD_DBG env): 1 = skip TMA store, 2 = skip stats pass
 };
 
 template <typename T>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -246,26 +251,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t t_base = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
             for (int s = 0; s < nslabs; s++) {
                 uint8_t* cbuf = smem_c + (size_t)(slab_count & 1) * (BLOCK_M * SLAB * 2);
+                // all TMEM loads of the slab are issued back to back (one wait), BEFORE the staging buffer is known to be
+                // free: TMEM latency overlaps the wait for the TMA store that last read this buffer
+                const int ncols = min(SLAB, p.block_n - s * SLAB);
+                uint32_t v[SLAB / 16][16];
+#pragma unroll
+                for (int q4 = 0; q4 < SLAB / 16; q4++)
+                    if (q4 * 16 < ncols) tmem_ld16(t_base + s * SLAB + q4 * 16, v[q4]);
                 if (leader) tma_store_wait_read<1>();       // the store that last used this buffer has drained
                 epi_barrier();
-                const int ncols = min(SLAB, p.block_n - s * SLAB);
-                for (int c16 = 0; c16 < ncols; c16 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(t_base + s * SLAB + c16, v);
-                    tmem_ld_wait();
-                    uint4 lo, hi;
-                    lo.x = pack2<T>(__uint_as_float(v[0]), __uint_as_float(v[1]));
-                    lo.y = pack2<T>(__uint_as_float(v[2]), __uint_as_float(v[3]));
-                    lo.z = pack2<T>(__uint_as_float(v[4]), __uint_as_float(v[5]));
-                    lo.w = pack2<T>(__uint_as_float(v[6]), __uint_as_float(v[7]));
-                    hi.x = pack2<T>(__uint_as_float(v[8]), __uint_as_float(v[9]));
-                    hi.y = pack2<T>(__uint_as_float(v[10]), __uint_as_float(v[11]));
-                    hi.z = pack2<T>(__uint_as_float(v[12]), __uint_as_float(v[13]));
-                    hi.w = pack2<T>(__uint_as_float(v[14]), __uint_as_float(v[15]));
-                    const int j = c16 >> 3;              // logical 16-byte chunk index within the 128-byte row
-                    uint8_t* row = cbuf + et * 128;
-                    *reinterpret_cast<uint4*>(row + ((j ^ (et & 7)) << 4)) = lo;
-                    *reinterpret_cast<uint4*>(row + (((j + 1) ^ (et & 7)) << 4)) = hi;
+                tmem_ld_wait();
+#pragma unroll
+                for (int q4 = 0; q4 < SLAB / 16; q4++) {
+                    if (q4 * 16 < ncols) {
+                        uint4 lo, hi;
+                        lo.x = pack2<T>(__uint_as_float(v[q4][0]), __uint_as_float(v[q4][1]));
+                        lo.y = pack2<T>(__uint_as_float(v[q4][2]), __uint_as_float(v[q4][3]));
+                        lo.z = pack2<T>(__uint_as_float(v[q4][4]), __uint_as_float(v[q4][5]));
+                        lo.w = pack2<T>(__uint_as_float(v[q4][6]), __uint_as_float(v[q4][7]));
+                        hi.x = pack2<T>(__uint_as_float(v[q4][8]), __uint_as_float(v[q4][9]));
+                        hi.y = pack2<T>(__uint_as_float(v[q4][10]), __uint_as_float(v[q4][11]));
+                        hi.z = pack2<T>(__uint_as_float(v[q4][12]), __uint_as_float(v[q4][13]));
+                        hi.w = pack2<T>(__uint_as_float(v[q4][14]), __uint_as_float(v[q4][15]));
+                        const int j = q4 * 2;            // logical 16-byte chunk index within the 128-byte row
+                        uint8_t* row = cbuf + et * 128;
+                        *reinterpret_cast<uint4*>(row + ((j ^ (et & 7)) << 4)) = lo;
+                        *reinterpret_cast<uint4*>(row + (((j + 1) ^ (et & 7)) << 4)) = hi;
+                    }
                 }
                 if (s == nslabs - 1) {
                     // all TMEM reads of this accumulator are done: hand it back to the MMA warp
@@ -274,23 +286,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 epi_barrier();
-                if (leader) {
+                if (leader && !(p.dbg & 1)) {
                     tma_store_2d(&tmap_c, cbuf, n_idx * p.block_n + s * SLAB, m_idx * BLOCK_M);
                     tma_store_commit();
                 }
-                if (p.dsum) {
+                if (p.dsum && !(p.dbg & 2)) {
                     // column statistics of the stored (rounded) slab; rows past M are exact zeros
                     const int c = et & 63, half = et >> 6;
                     float sum = 0.f, sq = 0.f;
                     if (c < ncols) {
                         const uint8_t* colp = cbuf + (c & 7) * 2;
                         const int jc = c >> 3;
+                        float s1 = 0.f, q1 = 0.f;            // two chains: the adds are latency-, not throughput-bound
 #pragma unroll 8
-                        for (int r = half * 64; r < half * 64 + 64; r++) {
-                            float x = to_f<T>(*reinterpret_cast<const T*>(colp + r * 128 + ((jc ^ (r & 7)) << 4)));
-                            sum += x;
-                            sq = fmaf(x, x, sq);
+                        for (int r = half * 64; r < half * 64 + 64; r += 2) {
+                            float x0 = to_f<T>(*reinterpret_cast<const T*>(colp + r * 128 + ((jc ^ (r & 7)) << 4)));
+                            float x1 = to_f<T>(*reinterpret_cast<const T*>(colp + (r + 1) * 128 + ((jc ^ ((r + 1) & 7)) << 4)));
+                            sum += x0; s1 += x1;
+                            sq = fmaf(x0, x0, sq); q1 = fmaf(x1, x1, q1);
                         }
+                        sum += s1; sq += q1;
                     }
                     red[(0 * 2 + half) * 64 + c] = sum;
                     red[(1 * 2 + half) * 64 + c] = sq;
@@ -376,15 +391,16 @@ int dfd_gemm_tn(const void* A, const void* B, void* C, long long M, int N, int K
     TcParams p;
     p.M = (int)M; p.N = N; p.K = K;
     p.is_bf16 = dt == DFD_DT_BF16;
-    p.block_n = N <= 256 ? ((N + 15) / 16) * 16 : 256;
+    p.block_n = N <= MAX_BLOCK_N ? ((N + 15) / 16) * 16 : MAX_BLOCK_N;
     p.num_m_tiles = cdiv(M, BLOCK_M);
     p.num_n_tiles = cdiv(N, p.block_n);
     p.num_k_blocks = cdiv(K, BLOCK_K);
     p.dsum = dsum; p.dsq = dsq;
+    { const char* e = getenv("DFD_DBG"); p.dbg = e ? atoi(e) : 0; }
     const int a_bytes = BLOCK_M * BLOCK_K * 2;
     const int b_stride = ((p.block_n * BLOCK_K * 2) + 1023) & ~1023;
     const int fixed = 2 * BLOCK_M * SLAB * 2 + 22 * 8 + 4 * 64 * 4 + 1024 /* alignment slack */;
-    int stages = (227 * 1024 - fixed) / (a_bytes + b_stride);
+    int stages = (SMEM_BUDGET - fixed) / (a_bytes + b_stride);
     if (stages > 6) stages = 6;
     if (stages < 2) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_gemm_tn: smem");
     p.stages = stages;
@@ -400,17 +416,17 @@ int dfd_gemm_tn(const void* A, const void* B, void* C, long long M, int N, int K
     cudaGetDevice(&device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     int grid = p.num_m_tiles * p.num_n_tiles;
-    if (grid > sms) grid = sms;
+    if (grid > 2 * sms) grid = 2 * sms;
     cudaStream_t st = (cudaStream_t)stream;
     if (p.is_bf16) {
         auto kf = gemm_tc_kernel<bf16>;
         static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+        if (!attr) { cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET); attr = true; }
         kf<<<grid, NUM_THREADS, smem, st>>>(ma, mb, mc, p);
     } else {
         auto kf = gemm_tc_kernel<__half>;
         static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+        if (!attr) { cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET); attr = true; }
         kf<<<grid, NUM_THREADS, smem, st>>>(ma, mb, mc, p);
     }
     DFD_LAUNCH_CHECK();

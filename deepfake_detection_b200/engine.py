@@ -43,8 +43,7 @@ class Engine:
                                    "there is no CPU path")
         self.L = _lib.lib()
         self.spec = spec = get_spec(arch, num_classes=num_classes, in_chans=in_chans)
-        if spec.family != "efficientnet":
-            raise _lib.NativeError("native path for %s is not built yet (round 1 covers the EfficientNet family)" % arch)
+        self.cls_name = "classifier" if spec.family == "efficientnet" else "fc"
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.N = int(batch)
         self.H = int(height or spec.input_size[1])
@@ -168,7 +167,7 @@ class Engine:
         """fp32 master -> 16-bit kernel copies (call after any out-of-band weight change)."""
         st = torch.cuda.current_stream().cuda_stream
         _lib.call("dfd_cast_arena", _ptr(self.params32), _ptr(self.params16), self.n_params, self.dt, st)
-        _lib.call("dfd_transpose_weights", _ptr(self._ttable), self._ttable_count, self.dt, st)
+        self.refresh_weight_layouts(st)
 
     # ------------------------------------------------------------------------------------------
     # plan construction
@@ -179,7 +178,45 @@ class Engine:
         self._keep.append(t)
         return t
 
+    def refresh_weight_layouts(self, stream):
+        """derived 16-bit weight layouts (transposed 1x1, packed k x k) from the 16-bit arena"""
+        _lib.call("dfd_transpose_weights", _ptr(self._ttable), self._ttable_count, self.dt, stream)
+        if getattr(self, "_rtable_count", 0):
+            _lib.call("dfd_repack_weights", _ptr(self._rtable), self._rtable_count, self.dt, stream)
+
+    def _alloc_bn(self, bn_specs):
+        """per-BN pointers into the parameter / running-stat arenas + the per-step statistic and coefficient arenas"""
+        dev, S = self.device, self.L.stat_slots
+        tot_c = sum((c + 3) // 4 * 4 for _, c in bn_specs)
+        self.bnstate = torch.zeros(7 * tot_c, dtype=torch.float32, device=dev)      # scale shift mean rstd cA cB cC
+        self.stats = torch.zeros(4 * S * tot_c + 8, dtype=torch.float64, device=dev)  # fsum fsq bs1 bs2 (+ loss/correct)
+        self.bns = {}
+        co = 0
+        for name, c in bn_specs:
+            bn = _BN()
+            bn.name, bn.C = name, c
+            bn.gamma = _ptr(self.params32, self.p_off[name + ".weight"][0])
+            bn.beta = _ptr(self.params32, self.p_off[name + ".bias"][0])
+            bn.dgamma = _ptr(self.grads32, self.p_off[name + ".weight"][0])
+            bn.dbeta = _ptr(self.grads32, self.p_off[name + ".bias"][0])
+            bn.rm = _ptr(self.buffers32, self.b_off[name + ".running_mean"][0])
+            bn.rv = _ptr(self.buffers32, self.b_off[name + ".running_var"][0])
+            bn.nbt = _ptr(self.nbt, self.bn_names.index(name))
+            for i, f in enumerate(("scale", "shift", "mean", "rstd", "cA", "cB", "cC")):
+                setattr(bn, f, _ptr(self.bnstate, i * tot_c + co))
+            for i, f in enumerate(("fsum", "fsq", "bs1", "bs2")):
+                setattr(bn, f, _ptr(self.stats, (i * tot_c + co) * S))
+            co += (c + 3) // 4 * 4
+            self.bns[name] = bn
+        self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)     # loss_acc, correct_acc, (spare)
+        self.loss_scale_state = torch.ones(2, dtype=torch.float32, device=dev)   # scale, 1/scale
+        self.flags = torch.zeros(2, dtype=torch.int32, device=dev)          # found_inf, good_steps
+
+
     def _build(self):
+        if self.spec.family == "resnet":
+            from .engine_resnet import build_resnet
+            return build_resnet(self)
         spec, N, dev, L = self.spec, self.N, self.device, self.L
         S = L.stat_slots
         self._keep = []
@@ -207,30 +244,7 @@ class Engine:
             else:
                 bn_specs += [(b.name + ".bn1", b.cmid), (b.name + ".bn2", b.cout)]
         bn_specs.append(("bn2", spec.num_features))
-        tot_c = sum((c + 3) // 4 * 4 for _, c in bn_specs)
-        self.bnstate = torch.zeros(7 * tot_c, dtype=torch.float32, device=dev)      # scale shift mean rstd cA cB cC
-        self.stats = torch.zeros(4 * S * tot_c + 8, dtype=torch.float64, device=dev)  # fsum fsq bs1 bs2 (+ loss/correct)
-        self.bns = {}
-        co = 0
-        for name, c in bn_specs:
-            bn = _BN()
-            bn.name, bn.C = name, c
-            bn.gamma = _ptr(self.params32, self.p_off[name + ".weight"][0])
-            bn.beta = _ptr(self.params32, self.p_off[name + ".bias"][0])
-            bn.dgamma = _ptr(self.grads32, self.p_off[name + ".weight"][0])
-            bn.dbeta = _ptr(self.grads32, self.p_off[name + ".bias"][0])
-            bn.rm = _ptr(self.buffers32, self.b_off[name + ".running_mean"][0])
-            bn.rv = _ptr(self.buffers32, self.b_off[name + ".running_var"][0])
-            bn.nbt = _ptr(self.nbt, self.bn_names.index(name))
-            for i, f in enumerate(("scale", "shift", "mean", "rstd", "cA", "cB", "cC")):
-                setattr(bn, f, _ptr(self.bnstate, i * tot_c + co))
-            for i, f in enumerate(("fsum", "fsq", "bs1", "bs2")):
-                setattr(bn, f, _ptr(self.stats, (i * tot_c + co) * S))
-            co += (c + 3) // 4 * 4
-            self.bns[name] = bn
-        self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)     # loss_acc, correct_acc, (spare)
-        self.loss_scale_state = torch.ones(2, dtype=torch.float32, device=dev)   # scale, 1/scale
-        self.flags = torch.zeros(2, dtype=torch.int32, device=dev)          # found_inf, good_steps
+        self._alloc_bn(bn_specs)
 
         P32 = lambda n: _ptr(self.params32, self.p_off[n][0])
         G32 = lambda n: _ptr(self.grads32, self.p_off[n][0])
@@ -476,8 +490,8 @@ class Engine:
         """classifier (+ fused sigmoid-BCE loss, top-1 count and dL/dlogits when with_loss)."""
         st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
         spec = self.spec
-        pw = _ptr(self.params32, self.p_off["classifier.weight"][0])
-        pb = _ptr(self.params32, self.p_off["classifier.bias"][0])
+        pw = _ptr(self.params32, self.p_off[self.cls_name + ".weight"][0])
+        pb = _ptr(self.params32, self.p_off[self.cls_name + ".bias"][0])
         if with_loss:
             _lib.call("dfd_head_fwd", _ptr(self.pooled), pw, pb, _ptr(self.logits), self.N, spec.num_features,
                       spec.num_classes, None if soft else _ptr(self.target_i), _ptr(self.target_f) if soft else None,

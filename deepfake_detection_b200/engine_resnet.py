@@ -1,0 +1,276 @@
+"""Kernel plan of the ResNet family (resnet18 / resnet50) for `Engine` — host side only.
+
+Reference graph: dfd/timm/models/resnet.py:450-468 (stem 7x7 s2 -> BN -> ReLU -> maxpool 3x3 s2 -> 4 stages -> GAP
+-> fc), BasicBlock :150-175, Bottleneck :215-246 (stride on the 3x3, :195-197), downsample 1x1 conv + BN :249-260.
+
+Round-1 formulation of the dense k x k convolutions (see csrc/conv_dense.cu): materialised im2col -> tcgen05 GEMM
+(forward), GEMM -> col2im (input gradient), mma.sync wgrad GEMM on the re-computed im2col matrix. 1x1 convolutions are
+plain GEMMs on the NHWC tensors. BN + ReLU outputs are materialised (`dfd_bn_act`) because three consumers read them.
+"""
+import struct
+
+import torch
+
+from . import _lib
+from .engine import ACT_NONE, ACT_RELU, _ptr
+
+
+def conv_out(h, k, s, p):
+    return (h + 2 * p - k) // s + 1
+
+
+def build_resnet(e):
+    spec, N, dev, dt = e.spec, e.N, e.device, e.dt
+    e._keep = []
+    e.acts = {}
+    fwd, bwd = [], []
+    mom, eps = e.bn_momentum, e.bn_eps
+
+    # ---- packed (kh, kw, ci) copies of the k x k weights -------------------------------------------------
+    pk_off, off = {}, 0
+    for n in e.param_names:
+        o, s, k = e.p_off[n]
+        if len(s) == 4 and s[2] > 1 and not n.startswith("conv1."):
+            pk_off[n] = (off, s[0], s[1], s[2])
+            off += (k + 7) // 8 * 8
+    e.wpack16 = torch.zeros(max(off, 8), dtype=e.tdtype, device=dev)
+    e.wpackT16 = torch.zeros(max(off, 8), dtype=e.tdtype, device=dev)
+    raw = b"".join(struct.pack("<QQQiiii", _ptr(e.params16, e.p_off[n][0]), _ptr(e.wpack16, o), _ptr(e.wpackT16, o), O, I, k, 0)
+                   for n, (o, O, I, k) in pk_off.items())
+    e._rtable = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+    e._rtable_count = len(pk_off)
+    e.gperm = torch.zeros(max([O * I * k * k for (_, O, I, k) in pk_off.values()] + [8]), dtype=torch.float32, device=dev)
+
+    P32 = lambda n: _ptr(e.params32, e.p_off[n][0])
+    G32 = lambda n: _ptr(e.grads32, e.p_off[n][0])
+    P16 = lambda n: _ptr(e.params16, e.p_off[n][0])
+    T16 = lambda n: _ptr(e.paramsT16, e.t_off[n][0])
+    PK = lambda n: _ptr(e.wpack16, pk_off[n][0])
+    PKT = lambda n: _ptr(e.wpackT16, pk_off[n][0])
+
+    # ---- shapes ------------------------------------------------------------------------------------------
+    H1, W1 = conv_out(e.H, 7, 2, 3), conv_out(e.W, 7, 2, 3)
+    H2, W2 = conv_out(H1, 3, 2, 1), conv_out(W1, 3, 2, 1)
+    shapes = []
+    h, w = H2, W2
+    for b in spec.blocks:
+        ho, wo = conv_out(h, 3, b.stride, 1), conv_out(w, 3, b.stride, 1)
+        shapes.append((b, h, w, ho, wo))
+        h, w = ho, wo
+    Hf, Wf = h, w
+
+    # ---- BN arenas ---------------------------------------------------------------------------------------
+    bn_specs = [("bn1", 64)]
+    for b in spec.blocks:
+        if b.kind == "basic":
+            bn_specs += [(b.name + ".bn1", b.planes), (b.name + ".bn2", b.cout)]
+        else:
+            bn_specs += [(b.name + ".bn1", b.planes), (b.name + ".bn2", b.planes), (b.name + ".bn3", b.cout)]
+        if b.downsample:
+            bn_specs.append((b.name + ".downsample.1", b.cout))
+    e._alloc_bn(bn_specs)
+    bns = e.bns
+
+    def gemm(A, B, C, M, Nn, K, bn=None):
+        fs, fq = (bn.fsum, bn.fsq) if bn is not None else (None, None)
+        if e.gemm_impl == "tc":
+            return ("dfd_gemm_tn", (A, B, C, M, Nn, K, dt, fs, fq))
+        return ("dfd_gemm_tn_mma", (A, B, C, None, M, Nn, K, dt, fs, fq))
+
+    def finalize(bn, count):
+        return ("dfd_bn_finalize", [bn.fsum, bn.fsq, float(count), bn.gamma, bn.beta, bn.rm, bn.rv, bn.nbt, mom, eps,
+                                    "TRAINING", bn.C, bn.scale, bn.shift, bn.mean, bn.rstd])
+
+    def bwd_finalize(bn, count):
+        return ("dfd_bn_bwd_finalize", (bn.bs1, bn.bs2, float(count), bn.gamma, bn.mean, bn.rstd, bn.dgamma, bn.dbeta,
+                                        bn.cA, bn.cB, bn.cC, bn.C))
+
+    def bn_relu(y, bn, out, hw, C):
+        return ("dfd_bn_act", (_ptr(y), bn.scale, bn.shift, None, None, _ptr(out), N, hw, C, ACT_RELU, 0, dt))
+
+    # ---- scratch -----------------------------------------------------------------------------------------
+    max_act = max([N * H1 * W1 * 64] + [N * hh * ww * max(b.cin, b.planes) for b, hh, ww, ho, wo in shapes] +
+                  [N * ho * wo * b.cout for b, hh, ww, ho, wo in shapes])
+    max_cols = max([N * ho * wo * 9 * (b.cin if b.kind == "basic" else b.planes) for b, hh, ww, ho, wo in shapes] +
+                   [N * ho * wo * 9 * b.planes for b, hh, ww, ho, wo in shapes])
+    e.gbuf = [e._alloc16(max_act) for _ in range(5)]
+    e.cols = e._alloc16(max_cols)
+    COLS = _ptr(e.cols)
+    gA, gB, gC, gD, gE = [_ptr(t) for t in e.gbuf]
+
+    # ---- forward -----------------------------------------------------------------------------------------
+    e.x_in = torch.zeros(N, spec.in_chans, e.H, e.W, dtype=e.tdtype, device=dev)
+    y0 = e._alloc16(N, H1, W1, 64)
+    a0 = e._alloc16(N, H1, W1, 64)
+    x0 = e._alloc16(N, H2, W2, 64)
+    e.pool_idx = torch.zeros(N * H2 * W2 * 64, dtype=torch.uint8, device=dev)
+    bn0 = bns["bn1"]
+    fwd.append(("dfd_stem_fwd", (_ptr(e.x_in), P32("conv1.weight"), _ptr(y0), N, spec.in_chans, e.H, e.W, 64, 7, 2, 3, dt,
+                                 bn0.fsum, bn0.fsq)))
+    fwd.append(finalize(bn0, N * H1 * W1))
+    fwd.append(bn_relu(y0, bn0, a0, H1 * W1, 64))
+    fwd.append(("dfd_maxpool_fwd", (_ptr(a0), _ptr(x0), _ptr(e.pool_idx), N, H1, W1, 64, dt)))
+    e.acts["stem.out"] = x0
+    x = x0
+    recs = []
+    for b, h, w, ho, wo in shapes:
+        p = b.name
+        M1, M2 = N * h * w, N * ho * wo
+        rec = dict(b=b, h=h, w=w, ho=ho, wo=wo, x=x)
+        if b.kind == "basic":
+            bn1, bn2 = bns[p + ".bn1"], bns[p + ".bn2"]
+            y1 = e._alloc16(N, ho, wo, b.planes)
+            a1 = e._alloc16(N, ho, wo, b.planes)
+            y2 = e._alloc16(N, ho, wo, b.cout)
+            fwd.append(("dfd_im2col", (_ptr(x), COLS, N, h, w, b.cin, 3, b.stride, 1, dt)))
+            fwd.append(gemm(COLS, PK(p + ".conv1.weight"), _ptr(y1), M2, b.planes, 9 * b.cin, bn1))
+            fwd.append(finalize(bn1, M2))
+            fwd.append(bn_relu(y1, bn1, a1, ho * wo, b.planes))
+            fwd.append(("dfd_im2col", (_ptr(a1), COLS, N, ho, wo, b.planes, 3, 1, 1, dt)))
+            fwd.append(gemm(COLS, PK(p + ".conv2.weight"), _ptr(y2), M2, b.cout, 9 * b.planes, bn2))
+            fwd.append(finalize(bn2, M2))
+            rec.update(y1=y1, a1=a1, ylast=y2, bnlast=bn2)
+        else:
+            bn1, bn2, bn3 = bns[p + ".bn1"], bns[p + ".bn2"], bns[p + ".bn3"]
+            y1 = e._alloc16(N, h, w, b.planes)
+            a1 = e._alloc16(N, h, w, b.planes)
+            y2 = e._alloc16(N, ho, wo, b.planes)
+            a2 = e._alloc16(N, ho, wo, b.planes)
+            y3 = e._alloc16(N, ho, wo, b.cout)
+            fwd.append(gemm(_ptr(x), P16(p + ".conv1.weight"), _ptr(y1), M1, b.planes, b.cin, bn1))
+            fwd.append(finalize(bn1, M1))
+            fwd.append(bn_relu(y1, bn1, a1, h * w, b.planes))
+            fwd.append(("dfd_im2col", (_ptr(a1), COLS, N, h, w, b.planes, 3, b.stride, 1, dt)))
+            fwd.append(gemm(COLS, PK(p + ".conv2.weight"), _ptr(y2), M2, b.planes, 9 * b.planes, bn2))
+            fwd.append(finalize(bn2, M2))
+            fwd.append(bn_relu(y2, bn2, a2, ho * wo, b.planes))
+            fwd.append(gemm(_ptr(a2), P16(p + ".conv3.weight"), _ptr(y3), M2, b.cout, b.planes, bn3))
+            fwd.append(finalize(bn3, M2))
+            rec.update(y1=y1, a1=a1, y2=y2, a2=a2, ylast=y3, bnlast=bn3)
+        res = x
+        if b.downsample:
+            bnd = bns[p + ".downsample.1"]
+            yd = e._alloc16(N, ho, wo, b.cout)
+            r = e._alloc16(N, ho, wo, b.cout)
+            if b.stride == 1:
+                xs = x
+            else:
+                xs = e._alloc16(N, ho, wo, b.cin)
+                fwd.append(("dfd_im2col", (_ptr(x), _ptr(xs), N, h, w, b.cin, 1, b.stride, 0, dt)))
+            fwd.append(gemm(_ptr(xs), P16(p + ".downsample.0.weight"), _ptr(yd), M2, b.cout, b.cin, bnd))
+            fwd.append(finalize(bnd, M2))
+            fwd.append(("dfd_bn_act", (_ptr(yd), bnd.scale, bnd.shift, None, None, _ptr(r), N, ho * wo, b.cout, ACT_NONE, 0, dt)))
+            rec.update(yd=yd, xs=xs, bnd=bnd)
+            res = r
+        out = e._alloc16(N, ho, wo, b.cout)
+        bl = rec["bnlast"]
+        fwd.append(("dfd_bn_act", (_ptr(rec["ylast"]), bl.scale, bl.shift, None, _ptr(res), _ptr(out), N, ho * wo, b.cout,
+                                   ACT_NONE, 2, dt)))
+        e.acts[p + ".out"] = out
+        rec["out"] = out
+        recs.append(rec)
+        x = out
+    F, K = spec.num_features, spec.num_classes
+    e.pooled = torch.zeros(N, F, dtype=torch.float32, device=dev)
+    fwd.append(("dfd_pool", (_ptr(x), None, None, _ptr(e.pooled), N, Hf * Wf, F, ACT_NONE, dt)))
+    e.logits = torch.zeros(N, K, dtype=torch.float32, device=dev)
+    e.dlogits = torch.zeros(N, K, dtype=torch.float32, device=dev)
+    e.dpooled = torch.zeros(N, F, dtype=torch.float32, device=dev)
+    e.target_i = torch.zeros(N, dtype=torch.int64, device=dev)
+    e.target_f = torch.zeros(N, K, dtype=torch.float32, device=dev)
+
+    # ---- backward ----------------------------------------------------------------------------------------
+    def zero_gperm(numel):
+        return ("dfd_memset_async", (_ptr(e.gperm), 0, numel * 4))
+
+    def conv3x3_bwd(name, dy, M_out, Cin, Cout, xin_t, n_h, n_w, stride, dx_out, dx_add=None):
+        """dy [M_out, Cout] -> dx_out [N, n_h, n_w, Cin] (+dx_add) and the weight gradient of `name`"""
+        ops = [gemm(dy, PKT(name), COLS, M_out, 9 * Cin, Cout),
+               ("dfd_col2im", (COLS, dx_add, dx_out, N, n_h, n_w, Cin, 3, stride, 1, dt)),
+               ("dfd_im2col", (_ptr(xin_t), COLS, N, n_h, n_w, Cin, 3, stride, 1, dt)),
+               zero_gperm(Cout * 9 * Cin),
+               ("dfd_gemm_wgrad_mma", (dy, COLS, _ptr(e.gperm), M_out, Cout, 9 * Cin, dt)),
+               ("dfd_unpack_grad", (_ptr(e.gperm), G32(name), Cout, Cin, 3))]
+        return ops
+
+    bwd.append(("dfd_head_bwd", (_ptr(e.dlogits), _ptr(e.pooled), P32("fc.weight"), G32("fc.weight"), G32("fc.bias"),
+                                 _ptr(e.dpooled), N, F, K)))
+    bwd.append(("dfd_pool_bwd", (_ptr(e.dpooled), gA, N, Hf * Wf, F, dt)))
+    dout = gA
+    free = [gB, gC, gD, gE]
+    for rec in reversed(recs):
+        b, h, w, ho, wo, xin = rec["b"], rec["h"], rec["w"], rec["ho"], rec["wo"], rec["x"]
+        p = b.name
+        M1, M2 = N * h * w, N * ho * wo
+        gm, t1, t2, t3 = free
+        bl = rec["bnlast"]
+        bwd.append(("dfd_relu_bwd", (dout, _ptr(rec["out"]), gm, M2 * b.cout, dt)))
+        bwd.append(("dfd_bn_bwd_reduce", (gm, _ptr(rec["ylast"]), None, bl.mean, bl.rstd, N, ho * wo, b.cout, dt, bl.bs1, bl.bs2)))
+        bwd.append(bwd_finalize(bl, M2))
+        bwd.append(("dfd_bn_bwd_apply", (gm, _ptr(rec["ylast"]), None, bl.cA, bl.cB, bl.cC, t1, N, ho * wo, b.cout, dt)))
+        if b.kind == "basic":
+            bn1 = bns[p + ".bn1"]
+            # conv2 (3x3 s1): dy2 = t1 -> da1 = t2
+            bwd += conv3x3_bwd(p + ".conv2.weight", t1, M2, b.planes, b.cout, rec["a1"], ho, wo, 1, t2)
+            bwd.append(("dfd_act_bwd", (t2, _ptr(rec["y1"]), bn1.scale, bn1.shift, bn1.mean, bn1.rstd, None, None, t1, N,
+                                        ho * wo, b.planes, ACT_RELU, dt, bn1.bs1, bn1.bs2)))
+            bwd.append(bwd_finalize(bn1, M2))
+            bwd.append(("dfd_bn_bwd_apply", (t1, _ptr(rec["y1"]), None, bn1.cA, bn1.cB, bn1.cC, t2, N, ho * wo, b.planes, dt)))
+            # conv1 (3x3 stride s): dy1 = t2 -> dx = t3 [M1, cin]
+            bwd += conv3x3_bwd(p + ".conv1.weight", t2, M2, b.cin, b.planes, xin, h, w, b.stride, t3)
+        else:
+            bn1, bn2 = bns[p + ".bn1"], bns[p + ".bn2"]
+            # conv3 (1x1): dy3 = t1 -> da2 = t2
+            bwd.append(gemm(t1, T16(p + ".conv3.weight"), t2, M2, b.planes, b.cout))
+            bwd.append(("dfd_gemm_wgrad_mma", (t1, _ptr(rec["a2"]), G32(p + ".conv3.weight"), M2, b.cout, b.planes, dt)))
+            bwd.append(("dfd_act_bwd", (t2, _ptr(rec["y2"]), bn2.scale, bn2.shift, bn2.mean, bn2.rstd, None, None, t1, N,
+                                        ho * wo, b.planes, ACT_RELU, dt, bn2.bs1, bn2.bs2)))
+            bwd.append(bwd_finalize(bn2, M2))
+            bwd.append(("dfd_bn_bwd_apply", (t1, _ptr(rec["y2"]), None, bn2.cA, bn2.cB, bn2.cC, t2, N, ho * wo, b.planes, dt)))
+            # conv2 (3x3 stride s): dy2 = t2 -> da1 = t1 [M1, planes]
+            bwd += conv3x3_bwd(p + ".conv2.weight", t2, M2, b.planes, b.planes, rec["a1"], h, w, b.stride, t1)
+            bwd.append(("dfd_act_bwd", (t1, _ptr(rec["y1"]), bn1.scale, bn1.shift, bn1.mean, bn1.rstd, None, None, t2, N,
+                                        h * w, b.planes, ACT_RELU, dt, bn1.bs1, bn1.bs2)))
+            bwd.append(bwd_finalize(bn1, M1))
+            bwd.append(("dfd_bn_bwd_apply", (t2, _ptr(rec["y1"]), None, bn1.cA, bn1.cB, bn1.cC, t1, N, h * w, b.planes, dt)))
+            # conv1 (1x1): dy1 = t1 -> dx = t3 [M1, cin]
+            bwd.append(gemm(t1, T16(p + ".conv1.weight"), t3, M1, b.cin, b.planes))
+            bwd.append(("dfd_gemm_wgrad_mma", (t1, _ptr(xin), G32(p + ".conv1.weight"), M1, b.planes, b.cin, dt)))
+        # identity / downsample path: gradient gm flows to the block input too
+        if b.downsample:
+            bnd = rec["bnd"]
+            bwd.append(("dfd_bn_bwd_reduce", (gm, _ptr(rec["yd"]), None, bnd.mean, bnd.rstd, N, ho * wo, b.cout, dt, bnd.bs1, bnd.bs2)))
+            bwd.append(bwd_finalize(bnd, M2))
+            bwd.append(("dfd_bn_bwd_apply", (gm, _ptr(rec["yd"]), None, bnd.cA, bnd.cB, bnd.cC, t1, N, ho * wo, b.cout, dt)))
+            bwd.append(gemm(t1, T16(p + ".downsample.0.weight"), t2, M2, b.cin, b.cout))
+            bwd.append(("dfd_gemm_wgrad_mma", (t1, _ptr(rec["xs"]), G32(p + ".downsample.0.weight"), M2, b.cout, b.cin, dt)))
+            if b.stride == 1:
+                bwd.append(("dfd_add_inplace", (t3, t2, M1 * b.cin, dt)))
+                new_dout = t3
+            else:
+                # scatter the strided gradient back onto the input grid and add the main-path gradient
+                bwd.append(("dfd_col2im", (t2, t3, dout, N, h, w, b.cin, 1, b.stride, 0, dt)))
+                new_dout = dout
+        else:
+            bwd.append(("dfd_add_inplace", (t3, gm, M1 * b.cin, dt)))
+            new_dout = t3
+        allb = [dout] + free
+        free = [g for g in allb if g != new_dout]
+        dout = new_dout
+    # stem: maxpool -> relu/bn1 -> conv1 wgrad
+    t1, t2 = free[0], free[1]
+    bwd.append(("dfd_maxpool_bwd", (dout, _ptr(e.pool_idx), t1, N, H1, W1, 64, dt)))
+    bwd.append(("dfd_act_bwd", (t1, _ptr(y0), bn0.scale, bn0.shift, bn0.mean, bn0.rstd, None, None, t2, N, H1 * W1, 64,
+                                ACT_RELU, dt, bn0.bs1, bn0.bs2)))
+    bwd.append(bwd_finalize(bn0, N * H1 * W1))
+    bwd.append(("dfd_stem_wgrad", (_ptr(e.x_in), t2, _ptr(y0), bn0.cA, bn0.cB, bn0.cC, G32("conv1.weight"), N, spec.in_chans,
+                                   e.H, e.W, 64, 7, 2, 3, dt)))
+
+    for n, a in fwd + bwd:
+        codes = _lib.SIGNATURES[n]
+        if len(a) != len(codes) - 1:
+            raise AssertionError("%s: %d args for signature %r" % (n, len(a), codes))
+    L = e.L
+    e.fwd_ops = [(getattr(L, n), n, a) for n, a in fwd]
+    e.bwd_ops = [(getattr(L, n), n, tuple(a)) for n, a in bwd]
+    e.n_launch["fwd"], e.n_launch["bwd"] = len(fwd), len(bwd)

@@ -75,7 +75,7 @@ class ArenaOptimizer:
             else:
                 _lib.call("dfd_rmsprop_tf_step", p, gr, a, _ptr(self.state_b, lo), n, g["lr"], g["alpha"], g["eps"],
                           g["weight_decay"], g["momentum"], self.grad_scale, self.skip_flag, p16, e.dt, st)
-        _lib.call("dfd_transpose_weights", _ptr(e._ttable), e._ttable_count, e.dt, st)
+        e.refresh_weight_layouts(st)
 
     # ---- torch-compatible (de)serialisation so `--resume` works across backends -----------------
     _KEYS = {"sgd": ("momentum_buffer", None), "adam": ("exp_avg", "exp_avg_sq"), "adamw": ("exp_avg", "exp_avg_sq"),

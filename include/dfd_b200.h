@@ -73,6 +73,20 @@ int dfd_stem_wgrad(const void* x_nchw, const void* g, const void* y, const float
                    const float* cC, float* dW, int N, int Cin, int H, int W, int Cout, int k, int stride, int pad,
                    int dt, void* stream);
 
+/* ---- dense k x k convolution, max-pool, ReLU tail (ResNet: resnet.py:129-136,150-175,195-260,379-382,450-468).
+ *      conv = im2col -> dfd_gemm_tn; dgrad = dfd_gemm_tn -> col2im; wgrad = dfd_gemm_wgrad_mma on the im2col matrix.
+ *      Column order of the im2col matrix / packed weights: (kh, kw, ci). ------------------------------------------- */
+int dfd_im2col(const void* x, void* cols, int N, int H, int W, int C, int k, int stride, int pad, int dt, void* stream);
+int dfd_col2im(const void* dcols, const void* add, void* dx, int N, int H, int W, int C, int k, int stride, int pad, int dt,
+               void* stream);
+/* table: device array of { const void* src_OIHW16; void* dst_OHWI16; void* dstT_HWI_O16; int O; int I; int k; int pad; } */
+int dfd_repack_weights(const void* table, int count, int dt, void* stream);
+int dfd_unpack_grad(const float* g_ohwi, float* g_oihw_accum, int O, int I, int k, void* stream);
+int dfd_maxpool_fwd(const void* x, void* out, void* argmax_u8, int N, int H, int W, int C, int dt, void* stream);
+int dfd_maxpool_bwd(const void* gy, const void* argmax_u8, void* gx, int N, int H, int W, int C, int dt, void* stream);
+int dfd_relu_bwd(const void* g, const void* out, void* gm, long long numel, int dt, void* stream);
+int dfd_pool_bwd(const float* dpooled, void* dout, int N, long long hw, int C, int dt, void* stream);
+
 /* ---- BatchNorm2d (train + eval), Swish, SE gating, residual, global pool and their backward:
  *      efficientnet_blocks.py:104-110,154,166,180-194,280-348; layers/activations.py:19-33;
  *      efficientnet.py:323-343; resnet.py:154-173 ---------------------------------------------------- */

@@ -354,3 +354,70 @@ def check_transpose(dtype=torch.bfloat16):
     _lib.call("dfd_transpose_weights", P(table), len(shapes), DT[dtype], st())
     torch.cuda.synchronize()
     return dict(mismatch=sum(int((d != s.t()).sum()) for s, d in zip(srcs, dsts)))
+
+
+def check_conv_dense(N, H, W, Cin, Cout, k, s, dtype=torch.bfloat16, seed=0):
+    """k x k dense conv = im2col + tcgen05 GEMM; dgrad = GEMM + col2im; wgrad = mma GEMM on im2col + unpack, vs F.conv2d."""
+    import struct
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    pad = (k - 1) // 2
+    Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    M = N * Ho * Wo
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).to(dtype)
+    w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / math.sqrt(Cin * k * k)).to(dtype)
+    wp = torch.zeros(Cout * k * k * Cin, device="cuda", dtype=dtype)
+    wpT = torch.zeros_like(wp)
+    table = torch.frombuffer(bytearray(struct.pack("<QQQiiii", w.data_ptr(), wp.data_ptr(), wpT.data_ptr(), Cout, Cin, k, 0)),
+                             dtype=torch.uint8).cuda()
+    d = DT[dtype]
+    _lib.call("dfd_repack_weights", P(table), 1, d, st())
+    cols = torch.full((M, k * k * Cin), float("nan"), device="cuda", dtype=dtype)
+    y = torch.full((M, Cout), float("nan"), device="cuda", dtype=dtype)
+    _lib.call("dfd_im2col", P(x), P(cols), N, H, W, Cin, k, s, pad, d, st())
+    _lib.call("dfd_gemm_tn", P(cols), P(wp), P(y), M, Cout, k * k * Cin, d, None, None, st())
+    torch.cuda.synchronize()
+    xr = nchw(x.float()).requires_grad_(True)
+    wr = w.float().clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, stride=s, padding=pad)
+    res = dict(fwd_max=maxerr_scaled(nchw(y.view(N, Ho, Wo, Cout).float()), ref.detach()), nan=int(torch.isnan(y.float()).sum()))
+    dy = (torch.randn(M, Cout, device="cuda", generator=g) * 0.1).to(dtype)
+    ref.backward(nchw(dy.view(N, Ho, Wo, Cout).float()))
+    dcols = torch.full((M, k * k * Cin), float("nan"), device="cuda", dtype=dtype)
+    add = torch.randn(N, H, W, Cin, device="cuda", generator=g).to(dtype)
+    dx = torch.full((N, H, W, Cin), float("nan"), device="cuda", dtype=dtype)
+    _lib.call("dfd_gemm_tn", P(dy), P(wpT), P(dcols), M, k * k * Cin, Cout, d, None, None, st())
+    _lib.call("dfd_col2im", P(dcols), P(add), P(dx), N, H, W, Cin, k, s, pad, d, st())
+    gperm = torch.zeros(Cout, k * k * Cin, device="cuda")
+    gw = torch.zeros(Cout, Cin, k, k, device="cuda")
+    _lib.call("dfd_gemm_wgrad_mma", P(dy), P(cols), P(gperm), M, Cout, k * k * Cin, d, st())
+    _lib.call("dfd_unpack_grad", P(gperm), P(gw), Cout, Cin, k, st())
+    torch.cuda.synchronize()
+    res["dgrad_rel"] = relerr(nchw(dx.float()), xr.grad + nchw(add.float()))
+    res["wgrad_rel"] = relerr(gw, wr.grad)
+    res["nan_b"] = int(torch.isnan(dx.float()).sum())
+    return res
+
+
+def check_maxpool_relu_pool(N, H, W, C, dtype=torch.bfloat16, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.relu(torch.randn(N, H, W, C, device="cuda", generator=g)).to(dtype)        # many exact ties at 0
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.full((N, Ho, Wo, C), float("nan"), device="cuda", dtype=dtype)
+    idx = torch.zeros(N * Ho * Wo * C, dtype=torch.uint8, device="cuda")
+    d = DT[dtype]
+    _lib.call("dfd_maxpool_fwd", P(x), P(out), P(idx), N, H, W, C, d, st())
+    xr = nchw(x.float()).requires_grad_(True)
+    ref = F.max_pool2d(xr, 3, 2, 1)
+    gy = torch.randn(N, Ho, Wo, C, device="cuda", generator=g).to(dtype)
+    ref.backward(nchw(gy.float()))
+    gx = torch.full((N, H, W, C), float("nan"), device="cuda", dtype=dtype)
+    _lib.call("dfd_maxpool_bwd", P(gy), P(idx), P(gx), N, H, W, C, d, st())
+    gm = torch.zeros_like(gy)
+    _lib.call("dfd_relu_bwd", P(gy), P(out), P(gm), gy.numel(), d, st())
+    dp = torch.randn(N, C, device="cuda", generator=g)
+    bro = torch.zeros(N, Ho * Wo, C, device="cuda", dtype=dtype)
+    _lib.call("dfd_pool_bwd", P(dp), P(bro), N, Ho * Wo, C, d, st())
+    torch.cuda.synchronize()
+    return dict(fwd_exact=int((nchw(out.float()) != ref.detach()).sum()), bwd_rel=relerr(nchw(gx.float()), xr.grad),
+                relu_mismatch=int((gm.float() != gy.float() * (out.float() > 0)).sum()),
+                pool_bwd_rel=relerr(bro.float(), (dp / (Ho * Wo)).to(dtype).float().unsqueeze(1).expand(N, Ho * Wo, C)))

@@ -94,3 +94,16 @@ def test_optimizer(kind):
 
 def test_transpose():
     assert _gc().check_transpose()["mismatch"] == 0
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,s", [(2, 14, 14, 64, 64, 3, 1), (2, 15, 17, 64, 128, 3, 2), (1, 9, 9, 128, 40, 3, 1),
+                                                   (2, 12, 12, 64, 256, 1, 2)])
+def test_conv_dense(N, H, W, Cin, Cout, k, s):
+    r = _gc().check_conv_dense(N, H, W, Cin, Cout, k, s)
+    assert r["nan"] == 0 and r["nan_b"] == 0 and r["fwd_max"] < OUT16 and r["dgrad_rel"] < 6e-3 and r["wgrad_rel"] < 1e-4, r
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 16, 64), (3, 15, 13, 64)])
+def test_maxpool_relu_pool(N, H, W, C):
+    r = _gc().check_maxpool_relu_pool(N, H, W, C)
+    assert r["fwd_exact"] == 0 and r["bwd_rel"] < 1e-6 and r["relu_mismatch"] == 0 and r["pool_bwd_rel"] < 1e-6, r

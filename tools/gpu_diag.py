@@ -20,7 +20,7 @@ import torch  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
-    ap.add_argument("--gemm", default="mma")
+    ap.add_argument("--gemm", default="tc")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "diag"))
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
@@ -84,6 +84,15 @@ def main():
         for k in ("sgd", "adam", "adamw", "rmsproptf"):
             run("opt_" + k, GC.check_optimizer, k)
         run("transpose", GC.check_transpose)
+    if want("resnet"):
+        run("conv_dense_3x3", GC.check_conv_dense, 2, 14, 14, 64, 64, 3, 1)
+        run("conv_dense_3x3_s2", GC.check_conv_dense, 2, 15, 17, 64, 128, 3, 2)
+        run("conv_dense_1x1_s2", GC.check_conv_dense, 2, 12, 12, 64, 256, 1, 2)
+        run("maxpool", GC.check_maxpool_relu_pool, 2, 16, 16, 64)
+        run("maxpool_odd", GC.check_maxpool_relu_pool, 3, 15, 13, 64)
+        run("engine_r18_fp16", EC.run_parity, "resnet18", 8, 96, 96, dtype="fp16", gemm_impl=a.gemm, verbose=True)
+        run("engine_r50_fp16", EC.run_parity, "resnet50", 8, 96, 96, dtype="fp16", gemm_impl=a.gemm)
+        run("engine_r18_bf16", EC.run_parity, "resnet18", 8, 96, 96, dtype="bf16", gemm_impl=a.gemm)
     if want("engine"):
         run("engine_b0_fp16_%s" % a.gemm, EC.run_parity, "efficientnet_b0", 16, 96, 96, dtype="fp16", gemm_impl=a.gemm, verbose=True)
         run("engine_b0_bf16_%s" % a.gemm, EC.run_parity, "efficientnet_b0", 16, 96, 96, dtype="bf16", gemm_impl=a.gemm)
