@@ -43,10 +43,17 @@ def tap_to_nchw(t):
 
 
 def run_parity(arch, batch, H, W, dtype="bf16", steps=2, gemm_impl="tc", opt_kind="sgd", lr=0.01, smoothing=0.0,
-               soft=False, verbose=False):
+               soft=False, verbose=False, tame=False):
     tdt = torch.bfloat16 if dtype == "bf16" else torch.float16
     spec = get_spec(arch)
     sd0 = synth_state(spec, seed=7)
+    if tame and spec.family == "resnet":
+        # the reference zero-initialises the last BN gamma of every residual block (resnet.py:417-420); the synthetic
+        # weights use gamma ~ 1 everywhere, which makes a ReLU network's gradients chaotic under 16-bit rounding.
+        # Damping the residual branches (both implementations see the same weights) keeps the comparison informative.
+        for b in spec.blocks:
+            k = b.name + (".bn2.weight" if b.kind == "basic" else ".bn3.weight")
+            sd0[k] = sd0[k] * 0.2
     eng = Engine(arch, batch, H, W, dtype=dtype, gemm_impl=gemm_impl)
     eng.load_state_dict(sd0)
     wd = 1e-4

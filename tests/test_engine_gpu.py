@@ -40,6 +40,20 @@ def test_train_step_parity(arch, b, res, dtype, impl):
     assert rep["eval_logits_rel"] < 2e-2, rep["eval_logits_rel"]
 
 
+@pytest.mark.parametrize("arch,dtype", [("resnet18", "fp16"), ("resnet50", "fp16"), ("resnet18", "bf16")])
+def test_resnet_train_step_parity(arch, dtype):
+    """ResNet path (BASELINE configs 1 and 4 architectures). ReLU masks flip under 16-bit rounding, so gradients are only
+    held to the yardstick (oracle 16-bit emulation vs fp32); forward, loss and eval logits are held tightly."""
+    rep = _ec().run_parity(arch, 8, 96, 96, dtype=dtype, steps=1, tame=True)
+    st = rep["steps"][0]
+    em, fp, yd = st["emul"], st["fp32"], st["yard"]
+    assert em["logits_rel"] < (2e-2 if dtype == "fp16" else 6e-2), em
+    assert abs(em["loss_native"] - em["loss_oracle"]) < 5e-3, em
+    assert fp["logits_rel"] < 1.5 * yd["logits_rel"] + 1e-2, (fp, yd)
+    assert fp["grad_rel_total"] < 1.5 * yd["grad_rel_total"] + 3e-2, (fp, yd)
+    assert rep["eval_logits_rel"] < 5e-2, rep["eval_logits_rel"]
+
+
 def test_against_reference_goldens(golden_dir):
     out = _ec().golden_compare("step_efficientnet_b0", golden_dir)
     for i, o in enumerate(out):
