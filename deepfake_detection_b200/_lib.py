@@ -36,11 +36,11 @@ SIGNATURES = {
     "dfd_add_inplace": "pp" "li" "p",
     "dfd_se_fc_fwd": "pppppp" "iii" "p",
     "dfd_se_fc_bwd": "pppppp" "pppppppp" "iii" "p",
-    "dfd_head_fwd": "pppp" "iii" "pp" "ff" "ppp" "p",
+    "dfd_head_fwd": "pppp" "iii" "pp" "ff" "pppp" "p",
     "dfd_head_bwd": "pppppp" "iii" "p",
-    "dfd_sgd_step": "ppp" "l" "fffi" "f" "pp" "i" "p",
-    "dfd_adam_step": "pppp" "l" "fffff" "ii" "f" "pp" "i" "p",
-    "dfd_rmsprop_tf_step": "pppp" "l" "fffff" "f" "pp" "i" "p",
+    "dfd_sgd_step": "ppp" "l" "fffi" "f" "ppp" "i" "p",
+    "dfd_adam_step": "pppp" "l" "fffff" "ii" "f" "ppp" "i" "p",
+    "dfd_rmsprop_tf_step": "pppp" "l" "fffff" "f" "ppp" "i" "p",
     "dfd_cast_arena": "pp" "li" "p",
     "dfd_check_finite": "p" "l" "pp",
     "dfd_update_loss_scale": "ppp" "i" "pp",

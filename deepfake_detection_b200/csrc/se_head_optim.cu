@@ -139,8 +139,9 @@ __global__ void se_fc_wgrad_kernel(const float* __restrict__ d_e, const float* _
 __global__ void head_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ W,
                                 const float* __restrict__ b, float* __restrict__ logits, int F, int K,
                                 const long long* __restrict__ tgt_i, const float* __restrict__ tgt_f, float smoothing,
-                                float inv_n, float loss_scale, float* __restrict__ loss_acc,
-                                float* __restrict__ correct_acc, float* __restrict__ dlogits) {
+                                float inv_n, float loss_scale, const float* __restrict__ loss_scale_dev,
+                                float* __restrict__ loss_acc, float* __restrict__ correct_acc,
+                                float* __restrict__ dlogits) {
     __shared__ float z[32];
     const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const float* p = pooled + (size_t)n * F;
@@ -170,8 +171,9 @@ __global__ void head_fwd_kernel(const float* __restrict__ pooled, const float* _
         int lab = t1 > t0 ? 1 : 0;
         if (pred == lab) atomicAdd(correct_acc, 1.f);
         if (dlogits) {
-            dlogits[n * 2] = -g1 * inv_n * loss_scale;
-            dlogits[n * 2 + 1] = g1 * inv_n * loss_scale;
+            const float ls = loss_scale_dev ? loss_scale * *loss_scale_dev : loss_scale;   // fp16 dynamic loss scaling
+            dlogits[n * 2] = -g1 * inv_n * ls;
+            dlogits[n * 2 + 1] = g1 * inv_n * ls;
         }
     }
 }
@@ -216,8 +218,9 @@ __device__ __forceinline__ void store16(void* p16, size_t i, float v) {
 template <typename T16>
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, size_t n,
                            float lr, float momentum, float wd, int nesterov, float grad_scale,
-                           const int* __restrict__ skip, void* __restrict__ p16) {
+                           const float* __restrict__ gscale_dev, const int* __restrict__ skip, void* __restrict__ p16) {
     if (skip && *skip) return;
+    if (gscale_dev) grad_scale *= *gscale_dev;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         float w = p[i];
@@ -235,8 +238,9 @@ template <typename T16>
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
                             int decoupled, float bc1, float bc2_sqrt, float grad_scale,
-                            const int* __restrict__ skip, void* __restrict__ p16) {
+                            const float* __restrict__ gscale_dev, const int* __restrict__ skip, void* __restrict__ p16) {
     if (skip && *skip) return;
+    if (gscale_dev) grad_scale *= *gscale_dev;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         float w = p[i];
@@ -257,9 +261,10 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 template <typename T16>
 __global__ void rmsprop_tf_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq,
                                   float* __restrict__ mom, size_t n, float lr, float alpha, float eps, float wd,
-                                  float momentum, float grad_scale, const int* __restrict__ skip,
-                                  void* __restrict__ p16) {
+                                  float momentum, float grad_scale, const float* __restrict__ gscale_dev,
+                                  const int* __restrict__ skip, void* __restrict__ p16) {
     if (skip && *skip) return;
+    if (gscale_dev) grad_scale *= *gscale_dev;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         float w = p[i];
@@ -309,6 +314,7 @@ __global__ void update_loss_scale_kernel(int* __restrict__ flag, float* __restri
         *good = g;
     }
     if (inv_scale_out) *inv_scale_out = 1.f / *scale;
+    *flag = 0;        // consumed: the next step starts clean
 }
 
 // transposed 16-bit copies of the 1x1-conv weights for dgrad: src [O, I] -> dst [I, O]
@@ -375,13 +381,13 @@ int dfd_se_fc_bwd(const float* draw, const float* pooled, const float* Wr, const
 }
 
 int dfd_head_fwd(const float* pooled, const float* W, const float* b, float* logits, int N, int F, int K,
-                 const long long* tgt_i, const float* tgt_f, float smoothing, float loss_scale, float* loss_acc,
-                 float* correct_acc, float* dlogits, void* stream) {
+                 const long long* tgt_i, const float* tgt_f, float smoothing, float loss_scale,
+                 const float* loss_scale_dev, float* loss_acc, float* correct_acc, float* dlogits, void* stream) {
     if (N <= 0 || F <= 0 || K <= 0 || K > 32) return dfd_set_error(DFD_ERR_ARG, "dfd_head_fwd: sizes");
     if (loss_acc && K != 2) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_head_fwd: fused sigmoid-BCE needs num_classes == 2");
     if (loss_acc && !tgt_i && !tgt_f) return dfd_set_error(DFD_ERR_ARG, "dfd_head_fwd: loss without target");
     head_fwd_kernel<<<N, 64, 0, (cudaStream_t)stream>>>(pooled, W, b, logits, F, K, tgt_i, tgt_f, smoothing,
-                                                         1.f / (float)N, loss_scale, loss_acc, correct_acc, dlogits);
+                                                         1.f / (float)N, loss_scale, loss_scale_dev, loss_acc, correct_acc, dlogits);
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }
@@ -402,29 +408,29 @@ int dfd_head_bwd(const float* dlogits, const float* pooled, const float* W, floa
     else { typedef bf16 T16; __VA_ARGS__; }
 
 int dfd_sgd_step(float* p, const float* g, float* m, long long n, float lr, float momentum, float wd, int nesterov,
-                 float grad_scale, const int* skip, void* p16, int dt, void* stream) {
+                 float grad_scale, const float* gscale_dev, const int* skip, void* p16, int dt, void* stream) {
     if (n <= 0) return DFD_OK;
-    DISPATCH_16(dt, (sgd_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, (size_t)n, lr, momentum, wd, nesterov, grad_scale, skip, p16)));
+    DISPATCH_16(dt, (sgd_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, (size_t)n, lr, momentum, wd, nesterov, grad_scale, gscale_dev, skip, p16)));
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }
 
 int dfd_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                  float wd, int decoupled, int step, float grad_scale, const int* skip, void* p16, int dt,
-                  void* stream) {
+                  float wd, int decoupled, int step, float grad_scale, const float* gscale_dev, const int* skip, void* p16,
+                  int dt, void* stream) {
     if (n <= 0) return DFD_OK;
     float bc1 = 1.f - powf(b1, (float)step);
     float bc2s = sqrtf(1.f - powf(b2, (float)step));
-    DISPATCH_16(dt, (adam_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (size_t)n, lr, b1, b2, eps, wd, decoupled, bc1, bc2s, grad_scale, skip, p16)));
+    DISPATCH_16(dt, (adam_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (size_t)n, lr, b1, b2, eps, wd, decoupled, bc1, bc2s, grad_scale, gscale_dev, skip, p16)));
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }
 
 int dfd_rmsprop_tf_step(float* p, const float* g, float* sq, float* mom, long long n, float lr, float alpha,
-                        float eps, float wd, float momentum, float grad_scale, const int* skip, void* p16, int dt,
-                        void* stream) {
+                        float eps, float wd, float momentum, float grad_scale, const float* gscale_dev, const int* skip,
+                        void* p16, int dt, void* stream) {
     if (n <= 0) return DFD_OK;
-    DISPATCH_16(dt, (rmsprop_tf_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, sq, mom, (size_t)n, lr, alpha, eps, wd, momentum, grad_scale, skip, p16)));
+    DISPATCH_16(dt, (rmsprop_tf_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, sq, mom, (size_t)n, lr, alpha, eps, wd, momentum, grad_scale, gscale_dev, skip, p16)));
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

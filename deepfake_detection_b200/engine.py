@@ -486,7 +486,7 @@ class Engine:
         self._run(self.fwd_ops, st, training)
         return self.logits
 
-    def head(self, with_loss, smoothing=0.0, loss_scale=1.0, soft=False, stream=None):
+    def head(self, with_loss, smoothing=0.0, loss_scale=1.0, soft=False, stream=None, loss_scale_dev=None):
         """classifier (+ fused sigmoid-BCE loss, top-1 count and dL/dlogits when with_loss)."""
         st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
         spec = self.spec
@@ -495,10 +495,11 @@ class Engine:
         if with_loss:
             _lib.call("dfd_head_fwd", _ptr(self.pooled), pw, pb, _ptr(self.logits), self.N, spec.num_features,
                       spec.num_classes, None if soft else _ptr(self.target_i), _ptr(self.target_f) if soft else None,
-                      float(smoothing), float(loss_scale), _ptr(self.scalars), _ptr(self.scalars, 1), _ptr(self.dlogits), st)
+                      float(smoothing), float(loss_scale), loss_scale_dev, _ptr(self.scalars), _ptr(self.scalars, 1),
+                      _ptr(self.dlogits), st)
         else:
             _lib.call("dfd_head_fwd", _ptr(self.pooled), pw, pb, _ptr(self.logits), self.N, spec.num_features,
-                      spec.num_classes, None, None, 0.0, 1.0, None, None, None, st)
+                      spec.num_classes, None, None, 0.0, 1.0, None, None, None, None, st)
 
     def backward(self, stream=None):
         """Back-propagates self.dlogits; gradients are ACCUMULATED into self.grads32 (zero it per step)."""

@@ -48,6 +48,7 @@ class ArenaOptimizer:
         self.step_count = 0
         self.grad_scale = 1.0          # 1/world (DDP mean) * 1/loss_scale
         self.skip_flag = None          # device int* (fp16 overflow)
+        self.gscale_dev = None         # device float*: 1/loss_scale (fp16 dynamic loss scaling)
         e.n_launch["opt"] = 3
 
     def zero_grad(self, set_to_none=False):
@@ -67,14 +68,14 @@ class ArenaOptimizer:
             a = _ptr(self.state_a, lo)
             if self.kind == "sgd":
                 _lib.call("dfd_sgd_step", p, gr, a, n, g["lr"], g["momentum"], g["weight_decay"], 1, self.grad_scale,
-                          self.skip_flag, p16, e.dt, st)
+                          self.gscale_dev, self.skip_flag, p16, e.dt, st)
             elif self.kind in ("adam", "adamw"):
                 _lib.call("dfd_adam_step", p, gr, a, _ptr(self.state_b, lo), n, g["lr"], g["betas"][0], g["betas"][1],
                           g["eps"], g["weight_decay"], 1 if self.kind == "adamw" else 0, self.step_count,
-                          self.grad_scale, self.skip_flag, p16, e.dt, st)
+                          self.grad_scale, self.gscale_dev, self.skip_flag, p16, e.dt, st)
             else:
                 _lib.call("dfd_rmsprop_tf_step", p, gr, a, _ptr(self.state_b, lo), n, g["lr"], g["alpha"], g["eps"],
-                          g["weight_decay"], g["momentum"], self.grad_scale, self.skip_flag, p16, e.dt, st)
+                          g["weight_decay"], g["momentum"], self.grad_scale, self.gscale_dev, self.skip_flag, p16, e.dt, st)
         e.refresh_weight_layouts(st)
 
     # ---- torch-compatible (de)serialisation so `--resume` works across backends -----------------

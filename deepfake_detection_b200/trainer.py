@@ -20,12 +20,22 @@ from .optim import ArenaOptimizer
 class Trainer:
     def __init__(self, arch, batch, height=None, width=None, dtype="bf16", opt="sgd", lr=0.01, momentum=0.9,
                  weight_decay=1e-4, opt_eps=1e-8, smoothing=0.0, num_classes=2, in_chans=3, bn_momentum=0.1,
-                 bn_eps=1e-5, use_graph=True, gemm_impl="tc", process_group=None, bucket_mb=8.0):
+                 bn_eps=1e-5, use_graph=True, gemm_impl="tc", process_group=None, bucket_mb=8.0, loss_scale=None,
+                 scale_window=2000):
         self.engine = Engine(arch, batch, height, width, num_classes=num_classes, in_chans=in_chans, dtype=dtype,
                              bn_momentum=bn_momentum, bn_eps=bn_eps, gemm_impl=gemm_impl)
         self.optimizer = ArenaOptimizer(self.engine, opt=opt, lr=lr, momentum=momentum, weight_decay=weight_decay,
                                         eps=opt_eps)
         self.smoothing = float(smoothing)
+        # fp16: dynamic loss scaling with skip-on-overflow (apex AMP O1 semantics, train.py:353,632-634), entirely on the
+        # device: scale / 1/scale / overflow flag / clean-step counter live in engine.loss_scale_state and engine.flags
+        self.dynamic_scale = dtype in ("fp16", torch.float16) if loss_scale is None else loss_scale == "dynamic"
+        self.scale_window = int(scale_window)
+        if self.dynamic_scale:
+            e0 = self.engine
+            e0.loss_scale_state.copy_(torch.tensor([65536.0, 1.0 / 65536.0]))
+            self.optimizer.gscale_dev = _ptr(e0.loss_scale_state, 1)
+            self.optimizer.skip_flag = _ptr(e0.flags, 0)
         self.use_graph = bool(use_graph) and self.optimizer.kind in ("sgd", "rmsproptf")
         self._graph = None
         self._graph_key = None
@@ -55,12 +65,18 @@ class Trainer:
         st = torch.cuda.current_stream().cuda_stream
         e.zero_step_scratch(st, grads=True)
         e.forward(training=True, stream=st)
-        e.head(True, smoothing=self.smoothing, soft=soft, stream=st)
+        e.head(True, smoothing=self.smoothing, soft=soft, stream=st,
+               loss_scale_dev=_ptr(e.loss_scale_state, 0) if self.dynamic_scale else None)
         if self.reducer is not None:
             self.reducer.backward_and_reduce()
         else:
             e.backward(stream=st)
+        if self.dynamic_scale:
+            _lib.call("dfd_check_finite", _ptr(e.grads32), e.n_params, _ptr(e.flags, 0), st)
         self.optimizer.step(stream=st)
+        if self.dynamic_scale:
+            _lib.call("dfd_update_loss_scale", _ptr(e.flags, 0), _ptr(e.loss_scale_state, 0), _ptr(e.flags, 1),
+                      self.scale_window, _ptr(e.loss_scale_state, 1), st)
 
     def _graph_signature(self, soft):
         return (soft, self.smoothing, tuple((g["lr"], g["momentum"], g["weight_decay"]) for g in self.optimizer.param_groups),

@@ -125,20 +125,21 @@ int dfd_se_fc_bwd(const float* draw, const float* pooled, const float* Wr, const
  *      (utils.py:170-186).  2-class softmax-CE is computed as sigmoid-BCE on z1 - z0 (exactly equal). ----- */
 int dfd_head_fwd(const float* pooled, const float* W, const float* b, float* logits, int N, int F, int K,
                  const long long* target_i64, const float* target_soft, float smoothing, float loss_scale,
-                 float* loss_acc, float* correct_acc, float* dlogits, void* stream);
+                 const float* loss_scale_dev, float* loss_acc, float* correct_acc, float* dlogits, void* stream);
 int dfd_head_bwd(const float* dlogits, const float* pooled, const float* W, float* dW, float* db, float* dpooled,
                  int N, int F, int K, void* stream);
 
 /* ---- optimizers over the flat fp32 parameter arena: create_optimizer, optim_factory.py:26-100;
  *      RMSpropTF rmsprop_tf.py:57-122; AdamW adamw.py:55-117; apex AMP loss scaling train.py:353,632-634 ---- */
+/* effective gradient scale = grad_scale * (*gscale_dev if non-null): 1/world for the DDP mean, 1/loss_scale on device */
 int dfd_sgd_step(float* p, const float* g, float* m, long long n, float lr, float momentum, float wd, int nesterov,
-                 float grad_scale, const int* skip, void* p16, int dt, void* stream);
+                 float grad_scale, const float* gscale_dev, const int* skip, void* p16, int dt, void* stream);
 int dfd_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                  float wd, int decoupled, int step, float grad_scale, const int* skip, void* p16, int dt,
-                  void* stream);
+                  float wd, int decoupled, int step, float grad_scale, const float* gscale_dev, const int* skip, void* p16,
+                  int dt, void* stream);
 int dfd_rmsprop_tf_step(float* p, const float* g, float* sq, float* mom, long long n, float lr, float alpha,
-                        float eps, float wd, float momentum, float grad_scale, const int* skip, void* p16, int dt,
-                        void* stream);
+                        float eps, float wd, float momentum, float grad_scale, const float* gscale_dev, const int* skip,
+                        void* p16, int dt, void* stream);
 int dfd_cast_arena(const float* p, void* p16, long long n, int dt, void* stream);
 int dfd_check_finite(const float* g, long long n, int* flag, void* stream);
 int dfd_update_loss_scale(int* flag, float* scale, int* good_steps, int interval, float* inv_scale_out,

@@ -296,7 +296,7 @@ def check_head(N, Fdim, smoothing=0.0, soft=False, seed=0):
     dlog = torch.zeros(N, 2, device="cuda")
     acc = torch.zeros(2, device="cuda")
     _lib.call("dfd_head_fwd", P(pooled), P(W), P(b), P(logits), N, Fdim, 2, None if soft else P(y), P(tf) if soft else None,
-              smoothing, 1.0, P(acc), P(acc) + 4, P(dlog), st())
+              smoothing, 1.0, None, P(acc), P(acc) + 4, P(dlog), st())
     pr = pooled.clone().requires_grad_(True)
     z = F.linear(pr, W, b)
     logp = F.log_softmax(z, -1)
@@ -333,12 +333,12 @@ def check_optimizer(kind, n=10007, steps=3, dtype=torch.bfloat16, seed=0):
         gr = torch.randn(n, device="cuda", generator=g)
         OT.optimizer_step(opt, p_ref, {"w": gr.cpu().view(n, 1)})
         if kind == "sgd":
-            _lib.call("dfd_sgd_step", P(p), P(gr), P(a), n, lr, mom, wd, 1, 1.0, None, P(p16), DT[dtype], st())
+            _lib.call("dfd_sgd_step", P(p), P(gr), P(a), n, lr, mom, wd, 1, 1.0, None, None, P(p16), DT[dtype], st())
         elif kind in ("adam", "adamw"):
             _lib.call("dfd_adam_step", P(p), P(gr), P(a), P(b), n, lr, 0.9, 0.999, eps, wd, 1 if kind == "adamw" else 0, s + 1, 1.0,
-                      None, P(p16), DT[dtype], st())
+                      None, None, P(p16), DT[dtype], st())
         else:
-            _lib.call("dfd_rmsprop_tf_step", P(p), P(gr), P(a), P(b), n, lr, 0.9, eps, wd, mom, 1.0, None, P(p16), DT[dtype], st())
+            _lib.call("dfd_rmsprop_tf_step", P(p), P(gr), P(a), P(b), n, lr, 0.9, eps, wd, mom, 1.0, None, None, P(p16), DT[dtype], st())
         torch.cuda.synchronize()
         worst = max(worst, relerr(p.cpu(), p_ref["w"].view(-1)))
     return dict(rel=worst, p16_rel=relerr(p16.float(), p.to(dtype).float()))

@@ -96,3 +96,34 @@ def test_full_size_properties():
     rel = float((e.grads32 - 2 * g1).norm() / (2 * g1).norm())
     assert rel < 2e-2, rel
     assert float((e.logits - l1).abs().max()) == 0.0      # forward is deterministic
+
+
+def test_fp16_dynamic_loss_scaling():
+    """BASELINE config 5 precision mode (fp16 + dynamic loss scale, apex O1 semantics): the scaled backward reproduces the
+    unscaled update; an injected overflow skips the step, halves the scale and leaves the weights untouched."""
+    import torch
+    from deepfake_detection_b200.arch import get_spec
+    from deepfake_detection_b200.trainer import Trainer
+    from oracle.weights import synth_batch, synth_state
+    spec = get_spec("efficientnet_b0")
+    sd = synth_state(spec, seed=7)
+    x, y = synth_batch(8, 3, 96, 96, seed=1)
+    res = {}
+    for mode in ("dynamic", "none"):
+        tr = Trainer("efficientnet_b0", 8, 96, 96, dtype="fp16", lr=0.01, use_graph=False, loss_scale=mode)
+        tr.load_state_dict(sd)
+        tr.train_step(x.cuda(), y.cuda())
+        torch.cuda.synchronize()
+        res[mode] = (tr.engine.params32.clone(), float(tr.engine.loss), tr)
+    a, b = res["dynamic"][0], res["none"][0]
+    assert float((a - b).norm() / b.norm()) < 2e-4          # scaling changes fp16 rounding of small gradients only
+    assert abs(res["dynamic"][1] - res["none"][1]) < 1e-6
+    tr = res["dynamic"][2]
+    e = tr.engine
+    assert float(e.loss_scale_state[0]) == 65536.0 and int(e.flags[1]) == 1
+    before = e.params32.clone()
+    e.loss_scale_state.copy_(torch.tensor([3.0e38, 1.0 / 3.0e38]))     # guarantees inf gradients
+    tr.train_step(x.cuda(), y.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(e.params32, before)                               # step skipped
+    assert float(e.loss_scale_state[0]) == 1.5e38 and int(e.flags[1]) == 0 and int(e.flags[0]) == 0
