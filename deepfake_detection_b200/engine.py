@@ -61,7 +61,7 @@ class Engine:
             if share_from.spec.arch != spec.arch or share_from.dt != self.dt:
                 raise ValueError("share_from: architecture / dtype mismatch")
             for a in ("p_off", "n_decay", "n_params", "param_names", "params32", "grads32", "params16", "b_off", "bn_names",
-                      "buffers32", "nbt", "t_off", "paramsT16", "_ttable", "_ttable_count"):
+                      "buffers32", "nbt", "t_off", "paramsT16", "_ttable", "_ttable_count", "loss_scale_state", "flags"):
                 setattr(self, a, getattr(share_from, a))
         else:
             self._layout_params()
@@ -209,8 +209,9 @@ class Engine:
             co += (c + 3) // 4 * 4
             self.bns[name] = bn
         self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)     # loss_acc, correct_acc, (spare)
-        self.loss_scale_state = torch.ones(2, dtype=torch.float32, device=dev)   # scale, 1/scale
-        self.flags = torch.zeros(2, dtype=torch.int32, device=dev)          # found_inf, good_steps
+        if not hasattr(self, "loss_scale_state"):      # shared between plans over the same weights (share_from)
+            self.loss_scale_state = torch.ones(2, dtype=torch.float32, device=dev)   # scale, 1/scale
+            self.flags = torch.zeros(2, dtype=torch.int32, device=dev)          # found_inf, good_steps
 
 
     def _build(self):

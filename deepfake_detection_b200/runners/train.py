@@ -136,6 +136,14 @@ def _trainer_for(model, engine, optimizer, loss_fn):
         tr.smoothing = float(loss_fn.native_smoothing)
         tr.use_graph = optimizer.kind in ("sgd", "rmsproptf")
         tr._graph = tr._graph_key = None
+        tr.scale_window = 2000
+        tr.dynamic_scale = model.dtype_name in ("fp16", torch.float16)      # apex O1 semantics for half precision
+        if tr.dynamic_scale and optimizer.gscale_dev is None:
+            from ..engine import _ptr
+            e0 = model.engine
+            e0.loss_scale_state.copy_(torch.tensor([65536.0, 1.0 / 65536.0]))
+            optimizer.gscale_dev = _ptr(e0.loss_scale_state, 1)
+            optimizer.skip_flag = _ptr(e0.flags, 0)
         tr.reducer = getattr(model, "_reducer", None)
         cache[key] = tr
     return tr
