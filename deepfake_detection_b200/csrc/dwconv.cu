@@ -19,7 +19,8 @@ namespace {
 
 constexpr int CB = 64;       // channels per CTA
 constexpr int P = 8;         // output columns per strip
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 256;            // k = 3 kernels; k = 5 kernels (50 weight registers per thread) run 128-thread CTAs
+#define NT_FOR_K(K) ((K) == 5 ? 128 : 256)   // so that four of them, not two, share an SM's register file
 constexpr int DW_MAX_SMEM = 200 * 1024;
 
 struct DwGeom {
@@ -49,7 +50,7 @@ __device__ __forceinline__ void stage_input_tile(uint32_t* tile, const T* __rest
     float sc[8], sh[8];
     if (AFFINE) { load_chan_params(scale, cbase, C, sc, 1.f); load_chan_params(shift, cbase, C, sh, 0.f); }
     const int npix = IH * IW;
-    constexpr int PSTEP = NTHREADS / 8;
+    const int PSTEP = blockDim.x / 8;
     for (int base = threadIdx.x >> 3; base < npix; base += PSTEP * UNR) {
         uint4 raw[UNR];
         bool ok[UNR];
@@ -99,7 +100,7 @@ __device__ __forceinline__ void stage_grad_tile(uint32_t* tile, const T* __restr
     float A[8], B[8], Cc[8];
     if (AFFINE) { load_chan_params(cA, cbase, C, A, 1.f); load_chan_params(cB, cbase, C, B, 0.f); load_chan_params(cC, cbase, C, Cc, 0.f); }
     const int npix = IH * IW;
-    constexpr int PSTEP = NTHREADS / 8;
+    const int PSTEP = blockDim.x / 8;
     constexpr int UG = AFFINE ? 2 : 4;     // two tensors are read when the BN backward is folded in
     for (int base = threadIdx.x >> 3; base < npix; base += PSTEP * UG) {
         uint4 graw[UG], yraw[UG];
@@ -201,7 +202,7 @@ __device__ __forceinline__ void reduce_warps_emit(float* sm, float a, float b, F
     if (threadIdx.x < 64) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < NTHREADS / 32; w++) s += sm[w * 64 + threadIdx.x];
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sm[w * 64 + threadIdx.x];
         fn(threadIdx.x, s);
     }
     __syncthreads();
@@ -211,7 +212,7 @@ __device__ __forceinline__ void reduce_warps_emit(float* sm, float a, float b, F
 // forward
 // ---------------------------------------------------------------------------------------------
 template <typename T, int K, int S, int ACT, bool AFFINE>
-__global__ void __launch_bounds__(NTHREADS)
+__global__ void __launch_bounds__(NT_FOR_K(K))
 dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                   const float* __restrict__ wgt, T* __restrict__ out, double* __restrict__ dsum,
                   double* __restrict__ dsq, DwGeom g) {
@@ -238,7 +239,7 @@ dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, cons
     const int strips_x = g.TW / P;
     const int nstrips = g.TH * strips_x;
     T* oimg = out + (size_t)n * g.Ho * g.Wo * g.C;
-    for (int s = warp; s < nstrips; s += NTHREADS / 32) {
+    for (int s = warp; s < nstrips; s += (int)(blockDim.x >> 5)) {
         int sy = s / strips_x, sx = (s - sy * strips_x) * P;
         int oy = oy0 + sy, ox = ox0 + sx;
         if (oy >= g.Ho || ox >= g.Wo) continue;
@@ -274,7 +275,7 @@ dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, cons
 // MODE 1: gu = ga * act'(scale*xin + shift); BN-backward reductions s1 += gu, s2 += gu*xhat
 // ---------------------------------------------------------------------------------------------
 template <typename T, int K, int S, int MODE, bool AFFINE>
-__global__ void __launch_bounds__(NTHREADS)
+__global__ void __launch_bounds__(NT_FOR_K(K))
 dwconv_dgrad_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const float* __restrict__ cA,
                     const float* __restrict__ cB, const float* __restrict__ cC, const float* __restrict__ wgt,
                     const T* __restrict__ xin, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -311,7 +312,7 @@ dwconv_dgrad_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const 
     const int strips_x = g.TW / P;
     const int nstrips = g.TH * strips_x;
     const size_t ioff = (size_t)n * g.H * g.W * g.C;
-    for (int s = warp; s < nstrips; s += NTHREADS / 32) {
+    for (int s = warp; s < nstrips; s += (int)(blockDim.x >> 5)) {
         int sy = s / strips_x, sx = (s - sy * strips_x) * P;
         int iy = y0 + sy, ix = x0 + sx;
         if (iy >= g.H || ix >= g.W) continue;
@@ -370,7 +371,7 @@ dwconv_dgrad_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const 
 // gridDim.z image groups: each CTA loops over images z, z+gridDim.z, ... to bound the number of atomics.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int K, int S, int ACT, bool AFFINE_IN, bool AFFINE_G>
-__global__ void __launch_bounds__(NTHREADS)
+__global__ void __launch_bounds__(NT_FOR_K(K))
 dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                     const T* __restrict__ gy, const T* __restrict__ yout, const float* __restrict__ cA,
                     const float* __restrict__ cB, const float* __restrict__ cC, float* __restrict__ dW, DwGeom g) {
@@ -412,7 +413,7 @@ dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, co
         __syncthreads();    // previous image's tile fully consumed
         stage_input_tile<T, ACT, AFFINE_IN>(tile, img, g.H, g.W, g.C, c0, oy0 * S - g.pad, ox0 * S - g.pad, g.IH, g.IW, scale, shift);
         __syncthreads();
-        for (int s = warp; s < nstrips; s += NTHREADS / 32) {
+        for (int s = warp; s < nstrips; s += (int)(blockDim.x >> 5)) {
             int sy = s / strips_x, sx = (s - sy * strips_x) * P;
             int oy = oy0 + sy, ox = ox0 + sx;
             float dy[P][2];
@@ -428,7 +429,7 @@ dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, co
                 dy[p][0] = ok ? gg.x : 0.f;
                 dy[p][1] = ok ? gg.y : 0.f;
             }
-            if (s + NTHREADS / 32 < nstrips) prefetch(s + NTHREADS / 32);
+            if (s + (int)(blockDim.x >> 5) < nstrips) prefetch(s + (int)(blockDim.x >> 5));
             if (oy >= g.Ho || ox >= g.Wo || !chv) continue;
 #pragma unroll
             for (int kh = 0; kh < K; kh++) {
@@ -509,7 +510,7 @@ static int set_smem(KernelT k, int bytes) {
             attr_done__ = true;                                      \
         }                                                            \
         if (smem > DW_MAX_SMEM) return dfd_set_error(DFD_ERR_UNSUPPORTED, "depthwise tile exceeds shared memory"); \
-        kfn__<<<grid, NTHREADS, smem, st>>>(__VA_ARGS__);            \
+        kfn__<<<grid, NT_FOR_K(K), smem, st>>>(__VA_ARGS__);         \
     } while (0)
 
 extern "C" {
