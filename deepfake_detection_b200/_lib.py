@@ -53,6 +53,9 @@ SIGNATURES = {
     "dfd_maxpool_bwd": "ppp" "iiii" "i" "p",
     "dfd_relu_bwd": "ppp" "li" "p",
     "dfd_pool_bwd": "pp" "ili" "i" "p",
+    "dfd_stem_im2col": "pp" "iiiiiiii" "i" "p",
+    "dfd_pad_weight": "pp" "iii" "i" "p",
+    "dfd_unpad_grad": "pp" "iii" "p",
 }
 
 DT_BF16, DT_FP16 = 0, 1

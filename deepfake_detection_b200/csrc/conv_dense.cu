@@ -219,6 +219,53 @@ __global__ void pool_bwd_kernel(const float* __restrict__ dpooled, T* __restrict
     }
 }
 
+
+// ---- stem as a GEMM: im2col of the NCHW image in (ci, kh, kw) column order (== OIHW flattening), K padded to a multiple of 8
+template <typename T>
+__global__ void stem_im2col_kernel(const T* __restrict__ x, T* __restrict__ cols, int N, int Cin, int H, int W, int k, int s,
+                                   int pad, int Ho, int Wo, int Kp) {
+    const int G = Kp / 8;
+    const int taps = Cin * k * k;
+    const long long total = (long long)N * Ho * Wo * G;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int g = (int)(i % G);
+        long long m = i / G;
+        int ox = (int)(m % Wo);
+        long long t2 = m / Wo;
+        int oy = (int)(t2 % Ho);
+        int n = (int)(t2 / Ho);
+        const T* img = x + (size_t)n * Cin * H * W;
+        T vals[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            int t = g * 8 + j;
+            T v = from_f<T>(0.f);
+            if (t < taps) {
+                int ci = t / (k * k), r = t - ci * k * k;
+                int kh = r / k, kw = r - kh * k;
+                int iy = oy * s - pad + kh, ix = ox * s - pad + kw;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[((size_t)ci * H + iy) * W + ix];
+            }
+            vals[j] = v;
+        }
+        stg16(cols + (size_t)m * Kp + g * 8, *reinterpret_cast<const uint4*>(vals));
+    }
+}
+// 16-bit weight [O][taps] -> [O][Kp] (zero padded), and the inverse for the fp32 gradient (accumulating)
+template <typename T>
+__global__ void pad_weight_kernel(const T* __restrict__ src, T* __restrict__ dst, int O, int taps, int Kp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= O * Kp) return;
+    int o = i / Kp, t = i - o * Kp;
+    dst[i] = t < taps ? src[(size_t)o * taps + t] : from_f<T>(0.f);
+}
+__global__ void unpad_grad_kernel(const float* __restrict__ gp, float* __restrict__ g, int O, int taps, int Kp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= O * taps) return;
+    int o = i / taps, t = i - o * taps;
+    g[i] += gp[(size_t)o * Kp + t];
+}
+
 static int nblocks(long long total) {
     long long b = (total + 255) / 256;
     if (b > 148 * 32) b = 148 * 32;
@@ -300,6 +347,28 @@ int dfd_pool_bwd(const float* dpooled, void* dout, int N, long long hw, int C, i
     if (C % 8 || N <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_pool_bwd: C%8");
     long long total = (long long)N * hw * (C / 8);
     CD_T(dt, (pool_bwd_kernel<T><<<nblocks(total), 256, 0, (cudaStream_t)stream>>>(dpooled, (T*)dout, N, hw, C)));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_stem_im2col(const void* x_nchw, void* cols, int N, int Cin, int H, int W, int k, int stride, int pad, int Kp, int dt,
+                    void* stream) {
+    if (Kp % 8 || Kp < Cin * k * k) return dfd_set_error(DFD_ERR_ARG, "dfd_stem_im2col: Kp");
+    int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    long long total = (long long)N * Ho * Wo * (Kp / 8);
+    CD_T(dt, (stem_im2col_kernel<T><<<nblocks(total), 256, 0, (cudaStream_t)stream>>>((const T*)x_nchw, (T*)cols, N, Cin, H, W, k, stride, pad, Ho, Wo, Kp)));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_pad_weight(const void* src, void* dst, int O, int taps, int Kp, int dt, void* stream) {
+    CD_T(dt, (pad_weight_kernel<T><<<cdiv((long long)O * Kp, 256), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, O, taps, Kp)));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_unpad_grad(const float* gp, float* g, int O, int taps, int Kp, void* stream) {
+    unpad_grad_kernel<<<cdiv((long long)O * taps, 256), 256, 0, (cudaStream_t)stream>>>(gp, g, O, taps, Kp);
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

@@ -13,6 +13,8 @@
 //     held in registers (sliding-window reuse: (P-1)*s+k smem reads feed P*k FMAs per kernel row);
 //   * per-channel BN statistics of the (rounded) outputs are reduced in the epilogue: one fp64 atomic per
 //     channel per CTA.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -20,7 +22,7 @@ namespace {
 constexpr int CB = 64;       // channels per CTA
 constexpr int P = 8;         // output columns per strip
 constexpr int NTHREADS = 256;            // k = 3 kernels; k = 5 kernels (50 weight registers per thread) run 128-thread CTAs
-#define NT_FOR_K(K) ((K) == 5 ? 128 : 256)   // so that four of them, not two, share an SM's register file
+#define NT_FOR_K(K) NT   // so that four of them, not two, share an SM's register file
 constexpr int DW_MAX_SMEM = 200 * 1024;
 
 struct DwGeom {
@@ -211,8 +213,8 @@ __device__ __forceinline__ void reduce_warps_emit(float* sm, float a, float b, F
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <typename T, int K, int S, int ACT, bool AFFINE>
-__global__ void __launch_bounds__(NT_FOR_K(K))
+template <typename T, int K, int S, int ACT, bool AFFINE, int NT>
+__global__ void __launch_bounds__(NT)
 dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                   const float* __restrict__ wgt, T* __restrict__ out, double* __restrict__ dsum,
                   double* __restrict__ dsq, DwGeom g) {
@@ -274,8 +276,8 @@ dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, cons
 // MODE 0: dx = ga (+ add)                                   (DS block: dw conv reads the block input directly)
 // MODE 1: gu = ga * act'(scale*xin + shift); BN-backward reductions s1 += gu, s2 += gu*xhat
 // ---------------------------------------------------------------------------------------------
-template <typename T, int K, int S, int MODE, bool AFFINE>
-__global__ void __launch_bounds__(NT_FOR_K(K))
+template <typename T, int K, int S, int MODE, bool AFFINE, int NT>
+__global__ void __launch_bounds__(NT)
 dwconv_dgrad_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const float* __restrict__ cA,
                     const float* __restrict__ cB, const float* __restrict__ cC, const float* __restrict__ wgt,
                     const T* __restrict__ xin, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -370,8 +372,8 @@ dwconv_dgrad_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const 
 // a = act(scale*x+shift) is re-staged like the forward; dy = A*g + B*y + C is formed per strip.
 // gridDim.z image groups: each CTA loops over images z, z+gridDim.z, ... to bound the number of atomics.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int K, int S, int ACT, bool AFFINE_IN, bool AFFINE_G>
-__global__ void __launch_bounds__(NT_FOR_K(K))
+template <typename T, int K, int S, int ACT, bool AFFINE_IN, bool AFFINE_G, int NT>
+__global__ void __launch_bounds__(NT)
 dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                     const T* __restrict__ gy, const T* __restrict__ yout, const float* __restrict__ cA,
                     const float* __restrict__ cB, const float* __restrict__ cC, float* __restrict__ dW, DwGeom g) {
@@ -488,11 +490,26 @@ static int set_smem(KernelT k, int bytes) {
 
 }  // namespace
 
+// CTA size per kernel size: k = 5 holds 50 weight registers per thread, so 128-thread CTAs let four of them (not two)
+// share an SM's register file; overridable for experiments with DFD_DW_NT3 / DFD_DW_NT5 (128 or 256).
+static int dw_nt(int k) {
+    static int nt3 = 0, nt5 = 0;
+    if (!nt3) {
+        const char* e3 = getenv("DFD_DW_NT3");
+        const char* e5 = getenv("DFD_DW_NT5");
+        nt3 = (e3 && atoi(e3) == 128) ? 128 : 256;
+        nt5 = (e5 && atoi(e5) == 256) ? 256 : 128;
+    }
+    return k == 5 ? nt5 : nt3;
+}
+#define DW_NT(K_, ...)                                                            \
+    if (dw_nt(K_) == 128) { constexpr int NT = 128; __VA_ARGS__; }                \
+    else { constexpr int NT = 256; __VA_ARGS__; }
 #define DW_DISPATCH_KS(K_, S_, ...)                                               \
-    if (K_ == 3 && S_ == 1) { constexpr int K = 3, S = 1; __VA_ARGS__; }          \
-    else if (K_ == 3 && S_ == 2) { constexpr int K = 3, S = 2; __VA_ARGS__; }     \
-    else if (K_ == 5 && S_ == 1) { constexpr int K = 5, S = 1; __VA_ARGS__; }     \
-    else if (K_ == 5 && S_ == 2) { constexpr int K = 5, S = 2; __VA_ARGS__; }     \
+    if (K_ == 3 && S_ == 1) { constexpr int K = 3, S = 1; DW_NT(K_, __VA_ARGS__); }          \
+    else if (K_ == 3 && S_ == 2) { constexpr int K = 3, S = 2; DW_NT(K_, __VA_ARGS__); }     \
+    else if (K_ == 5 && S_ == 1) { constexpr int K = 5, S = 1; DW_NT(K_, __VA_ARGS__); }     \
+    else if (K_ == 5 && S_ == 2) { constexpr int K = 5, S = 2; DW_NT(K_, __VA_ARGS__); }     \
     else return dfd_set_error(DFD_ERR_UNSUPPORTED, "depthwise conv: k in {3,5}, stride in {1,2}");
 
 #define DW_DISPATCH_T(dt, ...)                                           \
@@ -510,7 +527,7 @@ static int set_smem(KernelT k, int bytes) {
             attr_done__ = true;                                      \
         }                                                            \
         if (smem > DW_MAX_SMEM) return dfd_set_error(DFD_ERR_UNSUPPORTED, "depthwise tile exceeds shared memory"); \
-        kfn__<<<grid, NT_FOR_K(K), smem, st>>>(__VA_ARGS__);         \
+        kfn__<<<grid, NT, smem, st>>>(__VA_ARGS__);                  \
     } while (0)
 
 extern "C" {
@@ -527,8 +544,8 @@ int dfd_dwconv_fwd(const void* x, const float* scale, const float* shift, const 
     dim3 grid(g.tiles_x * g.tiles_y, (C + CB - 1) / CB, N);
     cudaStream_t st = (cudaStream_t)stream;
     DW_DISPATCH_T(dt, DW_DISPATCH_KS(k, stride, {
-        if (scale) DW_LAUNCH((dwconv_fwd_kernel<T, K, S, DFD_ACT_SWISH, true>), grid, smem, st, (const T*)x, scale, shift, w, (T*)out, dsum, dsq, g);
-        else DW_LAUNCH((dwconv_fwd_kernel<T, K, S, DFD_ACT_NONE, false>), grid, smem, st, (const T*)x, scale, shift, w, (T*)out, dsum, dsq, g);
+        if (scale) DW_LAUNCH((dwconv_fwd_kernel<T, K, S, DFD_ACT_SWISH, true, NT>), grid, smem, st, (const T*)x, scale, shift, w, (T*)out, dsum, dsq, g);
+        else DW_LAUNCH((dwconv_fwd_kernel<T, K, S, DFD_ACT_NONE, false, NT>), grid, smem, st, (const T*)x, scale, shift, w, (T*)out, dsum, dsq, g);
     }));
     DFD_LAUNCH_CHECK();
     return DFD_OK;
@@ -548,7 +565,7 @@ int dfd_dwconv_dgrad(const void* gy, const void* yout, const float* cA, const fl
     int smem = fill_geom(g, N, H, W, C, k, stride, true);
     dim3 grid(g.tiles_x * g.tiles_y, (C + CB - 1) / CB, N);
     cudaStream_t st = (cudaStream_t)stream;
-#define DG(MODE, AFF) DW_LAUNCH((dwconv_dgrad_kernel<T, K, S, MODE, AFF>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, s1, s2, g)
+#define DG(MODE, AFF) DW_LAUNCH((dwconv_dgrad_kernel<T, K, S, MODE, AFF, NT>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, s1, s2, g)
     DW_DISPATCH_T(dt, DW_DISPATCH_KS(k, stride, {
         if (mode == 1) { if (cA) DG(1, true); else DG(1, false); }
         else { if (cA) DG(0, true); else DG(0, false); }
@@ -571,7 +588,7 @@ int dfd_dwconv_wgrad(const void* x, const float* scale, const float* shift, cons
     if (gz < 1) gz = 1;
     dim3 grid(tiles, cbs, gz);
     cudaStream_t st = (cudaStream_t)stream;
-#define WG(ACT, AIN, AG) DW_LAUNCH((dwconv_wgrad_kernel<T, K, S, ACT, AIN, AG>), grid, smem, st, (const T*)x, scale, shift, (const T*)gy, (const T*)yout, cA, cB, cC, dW, g)
+#define WG(ACT, AIN, AG) DW_LAUNCH((dwconv_wgrad_kernel<T, K, S, ACT, AIN, AG, NT>), grid, smem, st, (const T*)x, scale, shift, (const T*)gy, (const T*)yout, cA, cB, cC, dW, g)
     DW_DISPATCH_T(dt, DW_DISPATCH_KS(k, stride, {
         if (scale) { if (cA) WG(DFD_ACT_SWISH, true, true); else WG(DFD_ACT_SWISH, true, false); }
         else { if (cA) WG(DFD_ACT_NONE, false, true); else WG(DFD_ACT_NONE, false, false); }

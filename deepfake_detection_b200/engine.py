@@ -33,7 +33,7 @@ class _BN:
 
 class Engine:
     def __init__(self, arch, batch, height=None, width=None, num_classes=2, in_chans=3, dtype="bf16",
-                 bn_momentum=0.1, bn_eps=1e-5, device=None, gemm_impl="tc", share_from=None):
+                 bn_momentum=0.1, bn_eps=1e-5, device=None, gemm_impl="tc", share_from=None, stem_impl="gemm"):
         # _plan_only: build the arenas and the call plan on the CPU for host-logic tests; nothing can be executed
         self._plan_only = device == "plan-only"
         if self._plan_only:
@@ -53,8 +53,10 @@ class Engine:
         self.bn_momentum = float(bn_momentum)
         self.bn_eps = float(bn_eps)
         self.gemm_impl = gemm_impl
+        self.stem_impl = stem_impl
         self.training = True
         self.n_launch = {"fwd": 0, "bwd": 0, "opt": 0}
+        self._shared_from = share_from
         if share_from is not None:
             # a second plan (other batch size / resolution, e.g. the validation loader) over the SAME weights,
             # gradients and running statistics
@@ -183,6 +185,23 @@ class Engine:
         _lib.call("dfd_transpose_weights", _ptr(self._ttable), self._ttable_count, self.dt, stream)
         if getattr(self, "_rtable_count", 0):
             _lib.call("dfd_repack_weights", _ptr(self._rtable), self._rtable_count, self.dt, stream)
+        if getattr(self, "_stem_pad", None) is not None:
+            name, O, taps, Kp = self._stem_pad
+            _lib.call("dfd_pad_weight", _ptr(self.params16, self.p_off[name][0]), _ptr(self.stem_wpad), O, taps, Kp, self.dt, stream)
+
+    def _stem_gemm_setup(self, wname, Cout, k, M):
+        """stem convolution as im2col + tcgen05 GEMM (K = Cin*k*k padded to a multiple of 8)"""
+        taps = self.spec.in_chans * k * k
+        Kp = (taps + 7) // 8 * 8
+        self._stem_pad = (wname, Cout, taps, Kp)
+        if self._shared_from is not None and getattr(self._shared_from, "stem_wpad", None) is not None:
+            self.stem_wpad = self._shared_from.stem_wpad      # derived weight layouts are refreshed through the owner
+            self._stem_pad = None
+        else:
+            self.stem_wpad = torch.zeros(Cout * Kp, dtype=self.tdtype, device=self.device)
+        self.stem_gpad = torch.zeros(Cout * Kp, dtype=torch.float32, device=self.device)
+        self.stem_cols = self._alloc16(M, Kp)
+        return taps, Kp
 
     def _alloc_bn(self, bn_specs):
         """per-BN pointers into the parameter / running-stat arenas + the per-step statistic and coefficient arenas"""
@@ -295,8 +314,13 @@ class Engine:
         self.acts["conv_stem"] = y0
         self.acts["stem.out"] = stem_out
         bn = self.bns["bn1"]
-        fwd.append(("dfd_stem_fwd", (_ptr(self.x_in), P32("conv_stem.weight"), _ptr(y0), N, spec.in_chans, self.H, self.W,
-                                     spec.stem, 3, 2, 1, dt, bn.fsum, bn.fsq)))
+        if self.stem_impl == "gemm":
+            taps, Kp = self._stem_gemm_setup("conv_stem.weight", spec.stem, 3, N * Hs * Ws)
+            fwd.append(("dfd_stem_im2col", (_ptr(self.x_in), _ptr(self.stem_cols), N, spec.in_chans, self.H, self.W, 3, 2, 1, Kp, dt)))
+            fwd.append(gemm(_ptr(self.stem_cols), _ptr(self.stem_wpad), _ptr(y0), N * Hs * Ws, spec.stem, Kp, bn))
+        else:
+            fwd.append(("dfd_stem_fwd", (_ptr(self.x_in), P32("conv_stem.weight"), _ptr(y0), N, spec.in_chans, self.H, self.W,
+                                         spec.stem, 3, 2, 1, dt, bn.fsum, bn.fsq)))
         fwd.append(finalize(bn, N * Hs * Ws))
         fwd.append(("dfd_bn_act", (_ptr(y0), bn.scale, bn.shift, None, None, _ptr(stem_out), N, Hs * Ws, spec.stem,
                                    ACT_SWISH, 0, dt)))
@@ -427,8 +451,14 @@ class Engine:
         bwd.append(("dfd_act_bwd", (sm[cur], _ptr(y0), bn.scale, bn.shift, bn.mean, bn.rstd, None, None, mid_a, N, Hs * Ws,
                                     spec.stem, ACT_SWISH, dt, bn.bs1, bn.bs2)))
         bwd.append(bwd_finalize(bn, N * Hs * Ws))
-        bwd.append(("dfd_stem_wgrad", (_ptr(self.x_in), mid_a, _ptr(y0), bn.cA, bn.cB, bn.cC, G32("conv_stem.weight"), N,
-                                       spec.in_chans, self.H, self.W, spec.stem, 3, 2, 1, dt)))
+        if self.stem_impl == "gemm":
+            bwd.append(("dfd_bn_bwd_apply", (mid_a, _ptr(y0), None, bn.cA, bn.cB, bn.cC, mid_b, N, Hs * Ws, spec.stem, dt)))
+            bwd.append(("dfd_memset_async", (_ptr(self.stem_gpad), 0, spec.stem * Kp * 4)))
+            bwd.append(("dfd_gemm_wgrad_mma", (mid_b, _ptr(self.stem_cols), _ptr(self.stem_gpad), N * Hs * Ws, spec.stem, Kp, dt)))
+            bwd.append(("dfd_unpad_grad", (_ptr(self.stem_gpad), G32("conv_stem.weight"), spec.stem, taps, Kp)))
+        else:
+            bwd.append(("dfd_stem_wgrad", (_ptr(self.x_in), mid_a, _ptr(y0), bn.cA, bn.cB, bn.cC, G32("conv_stem.weight"), N,
+                                           spec.in_chans, self.H, self.W, spec.stem, 3, 2, 1, dt)))
         for n, a in fwd + bwd:      # arity / type check of the plan against the ABI table
             codes = _lib.SIGNATURES[n]
             if len(a) != len(codes) - 1:

@@ -33,12 +33,16 @@ def build_resnet(e):
         if len(s) == 4 and s[2] > 1 and not n.startswith("conv1."):
             pk_off[n] = (off, s[0], s[1], s[2])
             off += (k + 7) // 8 * 8
-    e.wpack16 = torch.zeros(max(off, 8), dtype=e.tdtype, device=dev)
-    e.wpackT16 = torch.zeros(max(off, 8), dtype=e.tdtype, device=dev)
-    raw = b"".join(struct.pack("<QQQiiii", _ptr(e.params16, e.p_off[n][0]), _ptr(e.wpack16, o), _ptr(e.wpackT16, o), O, I, k, 0)
-                   for n, (o, O, I, k) in pk_off.items())
-    e._rtable = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
-    e._rtable_count = len(pk_off)
+    if e._shared_from is not None:
+        e.wpack16, e.wpackT16 = e._shared_from.wpack16, e._shared_from.wpackT16     # refreshed through the owner engine
+        e._rtable_count = 0
+    else:
+        e.wpack16 = torch.zeros(max(off, 8), dtype=e.tdtype, device=dev)
+        e.wpackT16 = torch.zeros(max(off, 8), dtype=e.tdtype, device=dev)
+        raw = b"".join(struct.pack("<QQQiiii", _ptr(e.params16, e.p_off[n][0]), _ptr(e.wpack16, o), _ptr(e.wpackT16, o), O, I, k, 0)
+                       for n, (o, O, I, k) in pk_off.items())
+        e._rtable = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        e._rtable_count = len(pk_off)
     e.gperm = torch.zeros(max([O * I * k * k for (_, O, I, k) in pk_off.values()] + [8]), dtype=torch.float32, device=dev)
 
     P32 = lambda n: _ptr(e.params32, e.p_off[n][0])
@@ -105,8 +109,13 @@ def build_resnet(e):
     x0 = e._alloc16(N, H2, W2, 64)
     e.pool_idx = torch.zeros(N * H2 * W2 * 64, dtype=torch.uint8, device=dev)
     bn0 = bns["bn1"]
-    fwd.append(("dfd_stem_fwd", (_ptr(e.x_in), P32("conv1.weight"), _ptr(y0), N, spec.in_chans, e.H, e.W, 64, 7, 2, 3, dt,
-                                 bn0.fsum, bn0.fsq)))
+    if e.stem_impl == "gemm":
+        taps, Kp = e._stem_gemm_setup("conv1.weight", 64, 7, N * H1 * W1)
+        fwd.append(("dfd_stem_im2col", (_ptr(e.x_in), _ptr(e.stem_cols), N, spec.in_chans, e.H, e.W, 7, 2, 3, Kp, dt)))
+        fwd.append(gemm(_ptr(e.stem_cols), _ptr(e.stem_wpad), _ptr(y0), N * H1 * W1, 64, Kp, bn0))
+    else:
+        fwd.append(("dfd_stem_fwd", (_ptr(e.x_in), P32("conv1.weight"), _ptr(y0), N, spec.in_chans, e.H, e.W, 64, 7, 2, 3, dt,
+                                     bn0.fsum, bn0.fsq)))
     fwd.append(finalize(bn0, N * H1 * W1))
     fwd.append(bn_relu(y0, bn0, a0, H1 * W1, 64))
     fwd.append(("dfd_maxpool_fwd", (_ptr(a0), _ptr(x0), _ptr(e.pool_idx), N, H1, W1, 64, dt)))
@@ -263,8 +272,14 @@ def build_resnet(e):
     bwd.append(("dfd_act_bwd", (t1, _ptr(y0), bn0.scale, bn0.shift, bn0.mean, bn0.rstd, None, None, t2, N, H1 * W1, 64,
                                 ACT_RELU, dt, bn0.bs1, bn0.bs2)))
     bwd.append(bwd_finalize(bn0, N * H1 * W1))
-    bwd.append(("dfd_stem_wgrad", (_ptr(e.x_in), t2, _ptr(y0), bn0.cA, bn0.cB, bn0.cC, G32("conv1.weight"), N, spec.in_chans,
-                                   e.H, e.W, 64, 7, 2, 3, dt)))
+    if e.stem_impl == "gemm":
+        bwd.append(("dfd_bn_bwd_apply", (t2, _ptr(y0), None, bn0.cA, bn0.cB, bn0.cC, t1, N, H1 * W1, 64, dt)))
+        bwd.append(("dfd_memset_async", (_ptr(e.stem_gpad), 0, 64 * Kp * 4)))
+        bwd.append(("dfd_gemm_wgrad_mma", (t1, _ptr(e.stem_cols), _ptr(e.stem_gpad), N * H1 * W1, 64, Kp, dt)))
+        bwd.append(("dfd_unpad_grad", (_ptr(e.stem_gpad), G32("conv1.weight"), 64, taps, Kp)))
+    else:
+        bwd.append(("dfd_stem_wgrad", (_ptr(e.x_in), t2, _ptr(y0), bn0.cA, bn0.cB, bn0.cC, G32("conv1.weight"), N, spec.in_chans,
+                                       e.H, e.W, 64, 7, 2, 3, dt)))
 
     for n, a in fwd + bwd:
         codes = _lib.SIGNATURES[n]

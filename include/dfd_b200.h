@@ -73,6 +73,13 @@ int dfd_stem_wgrad(const void* x_nchw, const void* g, const void* y, const float
                    const float* cC, float* dW, int N, int Cin, int H, int W, int Cout, int k, int stride, int pad,
                    int dt, void* stream);
 
+/* stem as a GEMM (round-1 perf path): im2col of the NCHW image, column order (ci,kh,kw) == OIHW flattening, K padded to
+ * Kp % 8 == 0; weights padded to [Cout, Kp]; fp32 gradient un-padded (accumulating) into the OIHW arena */
+int dfd_stem_im2col(const void* x_nchw, void* cols, int N, int Cin, int H, int W, int k, int stride, int pad, int Kp, int dt,
+                    void* stream);
+int dfd_pad_weight(const void* src16, void* dst16, int O, int taps, int Kp, int dt, void* stream);
+int dfd_unpad_grad(const float* g_padded, float* g_accum, int O, int taps, int Kp, void* stream);
+
 /* ---- dense k x k convolution, max-pool, ReLU tail (ResNet: resnet.py:129-136,150-175,195-260,379-382,450-468).
  *      conv = im2col -> dfd_gemm_tn; dgrad = dfd_gemm_tn -> col2im; wgrad = dfd_gemm_wgrad_mma on the im2col matrix.
  *      Column order of the im2col matrix / packed weights: (kh, kw, ci). ------------------------------------------- */
