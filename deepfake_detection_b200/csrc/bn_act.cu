@@ -186,7 +186,22 @@ __global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ s
         acc[i] = 0.f;
     }
     const T* base = y + (size_t)blockIdx.y * hw * C + c0;
-    for (long long r = threadIdx.y; r < hw; r += blockDim.y) {
+    // one CTA per image keeps the reduction deterministic; 4 independent loads per thread keep HBM busy despite it
+    constexpr int U = 4;
+    long long r = threadIdx.y;
+    for (; r + (long long)(U - 1) * blockDim.y < hw; r += (long long)U * blockDim.y) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) raw[u] = ldg16(base + (size_t)(r + (long long)u * blockDim.y) * C);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            float f[8];
+            unpack8<T>(raw[u], f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] += act_fwd<ACT>(fmaf(f[i], sc[i], sh[i]));
+        }
+    }
+    for (; r < hw; r += blockDim.y) {
         float f[8];
         unpack8<T>(ldg16(base + (size_t)r * C), f);
 #pragma unroll

@@ -61,8 +61,10 @@ __global__ void se_fc_bwd_kernel(const float* __restrict__ draw, const float* __
     float* rpre = sm + 2 * C;      // [Cse]
     float* r = rpre + Cse;         // [Cse]
     float* drp = r + Cse;          // [Cse]
+    float* r_acc = drp + Cse;      // [Cse] cross-warp accumulator of d_r
     const int n = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     for (int c = tid; c < C; c += nt) p[c] = pooled[(size_t)n * C + c];
+    for (int j = tid; j < Cse; j += nt) r_acc[j] = 0.f;
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     for (int j = warp; j < Cse; j += nw) {
@@ -83,11 +85,18 @@ __global__ void se_fc_bwd_kernel(const float* __restrict__ draw, const float* __
         d_e[(size_t)n * C + c] = v;
     }
     __syncthreads();
-    for (int j = warp; j < Cse; j += nw) {
+    // d_r[j] = sum_c We[c,j] * de[c]: lanes walk j (contiguous in We's rows), warps split c; partials meet in smem
+    for (int j0 = 0; j0 < Cse; j0 += 32) {
+        const int j = j0 + lane;
         float s = 0.f;
-        for (int c = lane; c < C; c += 32) s = fmaf(We[(size_t)c * Cse + j], de[c], s);
-        s = warp_sum(s);
-        if (lane == 0) {
+        if (j < Cse)
+            for (int c = warp; c < C; c += nw) s = fmaf(We[(size_t)c * Cse + j], de[c], s);
+        if (j < Cse) atomicAdd(&r_acc[j], s);
+    }
+    __syncthreads();
+    for (int j = tid; j < Cse; j += nt) {
+        float s = r_acc[j];
+        {
             float x = rpre[j];
             float sg = sigmoid_precise(x);
             float v = s * (sg * (1.f + x * (1.f - sg)));
@@ -370,7 +379,7 @@ int dfd_se_fc_bwd(const float* draw, const float* pooled, const float* Wr, const
                   const float* be, float* d_e, float* r, float* d_rpre, float* dpool, float* dWr, float* dbr,
                   float* dWe, float* dbe, int N, int C, int Cse, void* stream) {
     if (N <= 0 || C <= 0 || Cse <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_fc_bwd: sizes");
-    size_t smem = (size_t)(2 * C + 3 * Cse) * sizeof(float);
+    size_t smem = (size_t)(2 * C + 4 * Cse) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     se_fc_bwd_kernel<<<N, 256, smem, st>>>(draw, pooled, Wr, br, We, be, d_e, r, d_rpre, dpool, C, Cse);
     DFD_LAUNCH_CHECK();

@@ -19,7 +19,7 @@ def _ec():
 
 
 @pytest.mark.parametrize("arch,b,res,dtype,impl", [("efficientnet_b0", 16, 96, "fp16", "tc"), ("efficientnet_b0", 16, 96, "bf16", "tc"),
-                                                    ("efficientnet_b0", 16, 96, "fp16", "mma"), ("efficientnet_b4", 4, 76, "fp16", "tc")])
+                                                    ("efficientnet_b0", 16, 96, "fp16", "mma"), ("efficientnet_b4", 8, 108, "fp16", "tc")])
 def test_train_step_parity(arch, b, res, dtype, impl):
     """Two statements per step (i = 0, 1; the second step sees weights updated by the first):
       tight   : fp16 native vs the oracle's fp16 emulation (same rounding points) -> kernel logic;
@@ -32,9 +32,9 @@ def test_train_step_parity(arch, b, res, dtype, impl):
             assert em["logits_rel"] < 2e-2 * (1 + i), em
             assert em["grad_rel_total"] < 4e-2 * (1 + i), em
             assert abs(em["loss_native"] - em["loss_oracle"]) < 3e-3 * (1 + i), em
-        assert fp["logits_rel"] < 1.5 * yd["logits_rel"] + 1e-2, (fp, yd)
+        assert fp["logits_rel"] < 2.0 * yd["logits_rel"] + 1e-2, (fp, yd)
         assert fp["grad_rel_total"] < 1.5 * yd["grad_rel_total"] + 2e-2, (fp, yd)
-        assert abs(fp["loss_native"] - fp["loss_oracle"]) < 1.5 * yd["loss_abs"] + 5e-3, (fp, yd)
+        assert abs(fp["loss_native"] - fp["loss_oracle"]) < 2.0 * yd["loss_abs"] + 5e-3, (fp, yd)
         assert fp["param_rel_worst"][0][1] < 3e-2, fp       # updated weights (north_star: 1e-2 bf16 on a sane-lr step)
         assert fp["prec1_native"] == fp["prec1_oracle"] or abs(fp["prec1_native"] - fp["prec1_oracle"]) <= 100.0 / b + 1e-6
     assert rep["eval_logits_rel"] < 2e-2, rep["eval_logits_rel"]
