@@ -58,6 +58,9 @@ int dfd_gemm_wgrad_mma(const void* G, const void* X, float* dW, long long M, int
 /* ---- depthwise k x k convolution: nn.Conv2d(groups=C), efficientnet_blocks.py:152-153,283-285 -------- */
 int dfd_dwconv_fwd(const void* x, const float* scale, const float* shift, const float* w, void* out, int N, int H,
                    int W, int C, int k, int stride, int act_in, int dt, double* dsum, double* dsq, void* stream);
+/* stride-1 forward on tcgen05: per-tap diagonal weight tiles x shifted shared-memory descriptors (csrc/dwconv_tc.cu) */
+int dfd_dwconv_fwd_tc(const void* x, const float* scale, const float* shift, const float* w, void* out, int N, int H,
+                      int W, int C, int k, int stride, int act_in, int dt, double* dsum, double* dsq, void* stream);
 int dfd_dwconv_dgrad(const void* gy, const void* yout, const float* cA, const float* cB, const float* cC,
                      const float* w, const void* xin, const float* scale, const float* shift, const float* mean,
                      const float* rstd, const void* add, void* gx, int N, int H, int W, int C, int k, int stride,

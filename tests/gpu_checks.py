@@ -95,7 +95,7 @@ def _bn_params(C, g):
     return scale, shift
 
 
-def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0):
+def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0, fwd_impl="dfd_dwconv_fwd"):
     """fwd + dgrad (both modes) + wgrad against F.conv2d autograd on the rounded operands."""
     g = torch.Generator(device="cuda").manual_seed(seed)
     pad = (k - 1) // 2
@@ -106,7 +106,7 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0):
     out = torch.full((N, Ho, Wo, C), float("nan"), device="cuda", dtype=dtype)
     s1, s2 = stat_buf(C), stat_buf(C)
     act = 1 if affine else 0
-    _lib.call("dfd_dwconv_fwd", P(x), P(scale) if affine else None, P(shift) if affine else None, P(w), P(out), N, H, W, C,
+    _lib.call(fwd_impl, P(x), P(scale) if affine else None, P(shift) if affine else None, P(w), P(out), N, H, W, C,
               k, s, act, DT[dtype], P(s1), P(s2), st())
     torch.cuda.synchronize()
     # reference (fp32, same rounding points: activated input rounded to `dtype`)

@@ -106,4 +106,5 @@ def test_conv_dense(N, H, W, Cin, Cout, k, s):
 @pytest.mark.parametrize("N,H,W,C", [(2, 16, 16, 64), (3, 15, 13, 64)])
 def test_maxpool_relu_pool(N, H, W, C):
     r = _gc().check_maxpool_relu_pool(N, H, W, C)
-    assert r["fwd_exact"] == 0 and r["bwd_rel"] < 1e-6 and r["relu_mismatch"] == 0 and r["pool_bwd_rel"] < 1e-6, r
+    # bwd: an input that is the arg-max of several windows receives a SUM of gradients, rounded once to 16 bit
+    assert r["fwd_exact"] == 0 and r["bwd_rel"] < 3e-3 and r["relu_mismatch"] == 0 and r["pool_bwd_rel"] < 1e-6, r
