@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
 # algorithmic bytes of one launch of each kernel family (ideal: every operand once, 2 B / element)
 # ---------------------------------------------------------------------------------------------------
 def op_bytes(name, a):
-    if name in ("dfd_gemm_tn",):
+    if name in ("dfd_gemm_tn", "dfd_gemm_tn_rowpack"):
         M, N, K = a[3], a[4], a[5]
         return 2 * (M * K + N * K + M * N)
     if name == "dfd_gemm_tn_mma":

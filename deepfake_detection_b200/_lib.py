@@ -17,6 +17,8 @@ SIGNATURES = {
     "dfd_stat_slots": "",
     "dfd_memset_async": "pilp",
     "dfd_gemm_tn": "ppplii" "i" "ppp",
+    "dfd_gemm_tn_rowpack": "ppplii" "ii" "ppp",
+    "dfd_blockdiag_weights": "piip",
     "dfd_gemm_tn_mma": "pppp" "lii" "i" "ppp",
     "dfd_gemm_wgrad_mma": "ppp" "lii" "i" "p",
     "dfd_dwconv_fwd": "ppppp" "iiiiii" "ii" "ppp",

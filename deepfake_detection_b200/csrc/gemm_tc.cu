@@ -26,13 +26,12 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // 64 x 2 B = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int SLAB = 64;             // epilogue / TMA-store column slab
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 384;      // TMA, MMA, TMEM-alloc, spare warp + two epilogue warpgroups
+constexpr int EPI_THREADS = 128;      // per epilogue warpgroup
 constexpr int TMEM_COLS = 256;         // per CTA; two CTAs share an SM's 512 columns
 constexpr int ACC_STRIDE = 128;      // TMEM column offset between the two accumulator stages
 constexpr int MAX_BLOCK_N = 128;
-constexpr int SMEM_BUDGET = 113 * 1024;   // two CTAs per SM: the epilogue of one overlaps the other's (measured: one
-                                          // epilogue warpgroup per SM leaves output-heavy tiles latency-bound at ~1.5 TB/s)
+constexpr int SMEM_BUDGET = 200 * 1024;   // one CTA per SM (the epilogue holds a whole 128 x 128 fp32 tile in registers)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -132,7 +131,13 @@ __device__ __forceinline__ uint32_t make_idesc(int is_bf16, int n) {
     return d;
 }
 
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void epi_barrier(int wg) { asm volatile("bar.sync %0, %1;" ::"r"(wg + 1), "n"(EPI_THREADS) : "memory"); }
+
+struct BlockDiagDesc {
+    const void* src;
+    void* dst;
+    int N, K, pack, _pad;
+};
 
 struct TcParams {
     int M, N, K;
@@ -142,30 +147,32 @@ struct TcParams {
     int is_bf16;
     double* dsum;         // optional [DFD_STAT_SLOTS][N]
     double* dsq;
-    int dbg;              // debug switches (DFD_DBG env): 1 = skip TMA store, 2 = skip stats pass
+    int stat_n;           // statistics channel of output column c is c % stat_n (== N unless rows are packed)
+    int dbg;              // debug switches (DFD_DBG env): 1 = skip TMA store, 2 = skip stats pass, 4 = skip slabs, 8 = A from L2
+    long long* ts;        // optional trace (DFD_TS env): CTA 0 records clock64 at 8 pipeline points for its first 32 tiles
 };
 
 template <typename T>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // SWIZZLE_128B tiles must sit on 1024-byte boundaries of the shared address space
     uint8_t* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
-    // carve-up (all tile bases 1024-byte aligned): [A stages][B stages][2 C slabs][barriers]
+    // carve-up (all tile bases 1024-byte aligned): [A stages][B stages][2 warpgroups x 2 C slabs][barriers]
     const uint32_t a_bytes = BLOCK_M * BLOCK_K * 2;
     const uint32_t b_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
     const uint32_t b_stride = (b_bytes + 1023) & ~1023u;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem_a + (size_t)p.stages * a_bytes;
     uint8_t* smem_c = smem_b + (size_t)p.stages * b_stride;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * BLOCK_M * SLAB * 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 4 * BLOCK_M * SLAB * 2);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + 8;
     uint64_t* tmem_full = bars + 16;
     uint64_t* tmem_empty = bars + 18;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
-    float* red = reinterpret_cast<float*>(bars + 22);        // [2][2][64]
+    float* red_all = reinterpret_cast<float*>(bars + 22);    // [warpgroup][2][2][64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -191,12 +198,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int lt = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, lt++) {
                 const int m_idx = tile / p.num_n_tiles, n_idx = tile - m_idx * p.num_n_tiles;
                 for (int kb = 0; kb < p.num_k_blocks; kb++) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
+                    if (p.ts && kb == 0 && blockIdx.x == 0 && lt < 32) p.ts[lt * 8 + 0] = clock64();
                     mbar_arrive_expect_tx(full_bar + stage, a_bytes + b_bytes);
-                    tma_load_2d(smem_a + (size_t)stage * a_bytes, &tmap_a, full_bar + stage, kb * BLOCK_K, m_idx * BLOCK_M);
+                    tma_load_2d(smem_a + (size_t)stage * a_bytes, &tmap_a, full_bar + stage, kb * BLOCK_K, (p.dbg & 8) ? 0 : m_idx * BLOCK_M);
                     tma_load_2d(smem_b + (size_t)stage * b_stride, &tmap_b, full_bar + stage, kb * BLOCK_K, n_idx * p.block_n);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -210,13 +219,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int lt = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, lt++) {
                 mbar_wait(tmem_empty + acc, acc_phase ^ 1);
                 tc_fence_after();
+                const bool rec = p.ts && blockIdx.x == 0 && lt < 32;
+                if (rec) p.ts[lt * 8 + 1] = clock64();
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
                 for (int kb = 0; kb < p.num_k_blocks; kb++) {
                     mbar_wait(full_bar + stage, phase);
                     tc_fence_after();
+                    if (rec && kb == 0) p.ts[lt * 8 + 2] = clock64();
                     const uint32_t a_addr = smem_addr(smem_a + (size_t)stage * a_bytes);
                     const uint32_t b_addr = smem_addr(smem_b + (size_t)stage * b_stride);
                     int krem = p.K - kb * BLOCK_K;
@@ -230,62 +243,79 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tmem_full + acc);                // accumulator complete -> epilogue
+                if (rec) p.ts[lt * 8 + 3] = clock64();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
-        // ================= epilogue =================
-        const int et = threadIdx.x - (NUM_THREADS - EPI_THREADS);     // 0..127 == TMEM lane == tile row
-        const int q = warp & 3;                                       // TMEM lane quarter this warp may access
+        // ================= epilogue: two warpgroups, one per accumulator stage =================
+        // The CTA's i-th tile accumulates in TMEM stage i & 1 and is drained by warpgroup i & 1, so two tiles are in the
+        // epilogue at once (measured: one warpgroup needs ~2500 cycles per 128 x 96 tile - TMEM load, pack, staging,
+        // TMA store - which alone caps output-heavy GEMMs at a third of the HBM rate).
+        const int wg = (warp - 4) >> 2;                                // 0 / 1
+        const int et = (threadIdx.x - 128) & 127;                      // 0..127 == TMEM lane == tile row
+        const int q = warp & 3;                                        // TMEM lane quarter this warp may access
         const bool leader = et == 0;
-        int acc = 0;
+        uint8_t* my_c = smem_c + (size_t)wg * (2 * BLOCK_M * SLAB * 2);
+        float* red = red_all + wg * 256;
         uint32_t acc_phase = 0;
         uint32_t slab_count = 0;
         const int nslabs = (p.block_n + SLAB - 1) / SLAB;
         const bool keep = p.num_n_tiles == 1;          // column identity is fixed -> keep sums in registers
-        float ks[4] = {0.f, 0.f, 0.f, 0.f}, kq[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        float ks[2] = {0.f, 0.f}, kq[2] = {0.f, 0.f};
+        const uint32_t t_base = tmem_base + wg * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+        int lt = wg;                                    // index of the tile within this CTA's sequence
+        for (int tile = blockIdx.x + wg * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, lt += 2) {
             const int m_idx = tile / p.num_n_tiles, n_idx = tile - m_idx * p.num_n_tiles;
-            mbar_wait(tmem_full + acc, acc_phase);
+            const bool rec = p.ts && leader && blockIdx.x == 0 && lt < 32;
+            if (rec) p.ts[lt * 8 + 4] = clock64();
+            mbar_wait(tmem_full + wg, acc_phase);
             tc_fence_after();
-            const uint32_t t_base = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-            for (int s = 0; s < nslabs; s++) {
-                uint8_t* cbuf = smem_c + (size_t)(slab_count & 1) * (BLOCK_M * SLAB * 2);
-                // all TMEM loads of the slab are issued back to back (one wait), BEFORE the staging buffer is known to be
-                // free: TMEM latency overlaps the wait for the TMA store that last read this buffer
-                const int ncols = min(SLAB, p.block_n - s * SLAB);
-                uint32_t v[SLAB / 16][16];
+            if (rec) p.ts[lt * 8 + 5] = clock64();
+            uint32_t v[SLAB / 16][16];
 #pragma unroll
-                for (int q4 = 0; q4 < SLAB / 16; q4++)
-                    if (q4 * 16 < ncols) tmem_ld16(t_base + s * SLAB + q4 * 16, v[q4]);
+            for (int q4 = 0; q4 < SLAB / 16; q4++)
+                if (q4 * 16 < p.block_n) tmem_ld16(t_base + q4 * 16, v[q4]);
+#pragma unroll
+            for (int s = 0; s < MAX_BLOCK_N / SLAB; s++) {
+                if (s >= nslabs || (p.dbg & 4)) break;
+                uint8_t* cbuf = my_c + (size_t)(slab_count & 1) * (BLOCK_M * SLAB * 2);
+                const int ncols = min(SLAB, p.block_n - s * SLAB);
                 if (leader) tma_store_wait_read<1>();       // the store that last used this buffer has drained
-                epi_barrier();
                 tmem_ld_wait();
+                epi_barrier(wg);
 #pragma unroll
                 for (int q4 = 0; q4 < SLAB / 16; q4++) {
                     if (q4 * 16 < ncols) {
+                        const uint32_t (&w)[16] = v[q4];
                         uint4 lo, hi;
-                        lo.x = pack2<T>(__uint_as_float(v[q4][0]), __uint_as_float(v[q4][1]));
-                        lo.y = pack2<T>(__uint_as_float(v[q4][2]), __uint_as_float(v[q4][3]));
-                        lo.z = pack2<T>(__uint_as_float(v[q4][4]), __uint_as_float(v[q4][5]));
-                        lo.w = pack2<T>(__uint_as_float(v[q4][6]), __uint_as_float(v[q4][7]));
-                        hi.x = pack2<T>(__uint_as_float(v[q4][8]), __uint_as_float(v[q4][9]));
-                        hi.y = pack2<T>(__uint_as_float(v[q4][10]), __uint_as_float(v[q4][11]));
-                        hi.z = pack2<T>(__uint_as_float(v[q4][12]), __uint_as_float(v[q4][13]));
-                        hi.w = pack2<T>(__uint_as_float(v[q4][14]), __uint_as_float(v[q4][15]));
+                        lo.x = pack2<T>(__uint_as_float(w[0]), __uint_as_float(w[1]));
+                        lo.y = pack2<T>(__uint_as_float(w[2]), __uint_as_float(w[3]));
+                        lo.z = pack2<T>(__uint_as_float(w[4]), __uint_as_float(w[5]));
+                        lo.w = pack2<T>(__uint_as_float(w[6]), __uint_as_float(w[7]));
+                        hi.x = pack2<T>(__uint_as_float(w[8]), __uint_as_float(w[9]));
+                        hi.y = pack2<T>(__uint_as_float(w[10]), __uint_as_float(w[11]));
+                        hi.z = pack2<T>(__uint_as_float(w[12]), __uint_as_float(w[13]));
+                        hi.w = pack2<T>(__uint_as_float(w[14]), __uint_as_float(w[15]));
                         const int j = q4 * 2;            // logical 16-byte chunk index within the 128-byte row
                         uint8_t* row = cbuf + et * 128;
                         *reinterpret_cast<uint4*>(row + ((j ^ (et & 7)) << 4)) = lo;
                         *reinterpret_cast<uint4*>(row + (((j + 1) ^ (et & 7)) << 4)) = hi;
                     }
                 }
-                if (s == nslabs - 1) {
+                if (s + 1 < nslabs) {
+                    // the next slab's TMEM loads fly while this one is fenced, stored and reduced
+#pragma unroll
+                    for (int q4 = 0; q4 < SLAB / 16; q4++)
+                        if ((s + 1) * SLAB + q4 * 16 < p.block_n) tmem_ld16(t_base + (s + 1) * SLAB + q4 * 16, v[q4]);
+                } else {
                     // all TMEM reads of this accumulator are done: hand it back to the MMA warp
                     tc_fence_before();
-                    mbar_arrive(tmem_empty + acc);
+                    mbar_arrive(tmem_empty + wg);
+                    if (rec) p.ts[lt * 8 + 6] = clock64();
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                epi_barrier();
+                epi_barrier(wg);
                 if (leader && !(p.dbg & 1)) {
                     tma_store_2d(&tmap_c, cbuf, n_idx * p.block_n + s * SLAB, m_idx * BLOCK_M);
                     tma_store_commit();
@@ -309,29 +339,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                     red[(0 * 2 + half) * 64 + c] = sum;
                     red[(1 * 2 + half) * 64 + c] = sq;
-                    epi_barrier();
+                    epi_barrier(wg);
                     if (et < 64) {
                         float ts = red[et] + red[64 + et], tq = red[128 + et] + red[192 + et];
                         if (keep) { ks[s] += ts; kq[s] += tq; }
                         else {
                             int gc = n_idx * p.block_n + s * SLAB + et;
                             if (et < ncols && gc < p.N) {
-                                atomicAdd(stat_slot(p.dsum, p.N) + gc, (double)ts);
-                                atomicAdd(stat_slot(p.dsq, p.N) + gc, (double)tq);
+                                atomicAdd(stat_slot(p.dsum, p.stat_n) + gc % p.stat_n, (double)ts);
+                                atomicAdd(stat_slot(p.dsq, p.stat_n) + gc % p.stat_n, (double)tq);
                             }
                         }
                     }
                 }
                 slab_count++;
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (p.dbg & 4) { tmem_ld_wait(); tc_fence_before(); mbar_arrive(tmem_empty + wg); }
+            if (rec) p.ts[lt * 8 + 7] = clock64();
+            acc_phase ^= 1;
         }
         if (p.dsum && keep && et < 64) {
-            for (int s = 0; s < nslabs; s++) {
+#pragma unroll
+            for (int s = 0; s < MAX_BLOCK_N / SLAB; s++) {
                 int gc = s * SLAB + et;
-                if (gc < p.N && gc < p.block_n) {
-                    atomicAdd(stat_slot(p.dsum, p.N) + gc, (double)ks[s]);
-                    atomicAdd(stat_slot(p.dsq, p.N) + gc, (double)kq[s]);
+                if (s < nslabs && gc < p.N && gc < p.block_n) {
+                    atomicAdd(stat_slot(p.dsum, p.stat_n) + gc % p.stat_n, (double)ks[s]);
+                    atomicAdd(stat_slot(p.dsq, p.stat_n) + gc % p.stat_n, (double)kq[s]);
                 }
             }
         }
@@ -378,18 +411,13 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, int cols, 
     return DFD_OK;
 }
 
-}  // namespace
 
-extern "C" {
-
-// C[M,N] = A[M,K] * B[N,K]^T on tcgen05; optional fp64 column statistics of the stored C ([8][N] slots).
-// All pointers must be 16-byte aligned, K % 8 == 0 and N % 8 == 0 (TMA global strides are multiples of 16 B).
-int dfd_gemm_tn(const void* A, const void* B, void* C, long long M, int N, int K, int dt, double* dsum, double* dsq,
-                void* stream) {
-    if (M <= 0 || N <= 0 || K <= 0 || (N % 8) || (K % 8)) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn: N%8, K%8");
-    if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn: dtype");
+// C[M,N] = A[M,K] * B[N,K]^T; statistics of output column c go to channel c % stat_n
+static int launch_gemm_tc(const void* A, const void* B, void* C, long long M, int N, int K, int dt, double* dsum,
+                          double* dsq, int stat_n, void* stream) {
     TcParams p;
     p.M = (int)M; p.N = N; p.K = K;
+    p.stat_n = stat_n;
     p.is_bf16 = dt == DFD_DT_BF16;
     p.block_n = N <= MAX_BLOCK_N ? ((N + 15) / 16) * 16 : MAX_BLOCK_N;
     p.num_m_tiles = cdiv(M, BLOCK_M);
@@ -397,9 +425,13 @@ int dfd_gemm_tn(const void* A, const void* B, void* C, long long M, int N, int K
     p.num_k_blocks = cdiv(K, BLOCK_K);
     p.dsum = dsum; p.dsq = dsq;
     { const char* e = getenv("DFD_DBG"); p.dbg = e ? atoi(e) : 0; }
+    p.ts = nullptr;
+    static long long* ts_buf = nullptr;
+    const bool trace = getenv("DFD_TS") != nullptr;
+    if (trace) { if (!ts_buf) cudaMalloc(&ts_buf, 32 * 8 * sizeof(long long)); cudaMemset(ts_buf, 0, 32 * 8 * sizeof(long long)); p.ts = ts_buf; }
     const int a_bytes = BLOCK_M * BLOCK_K * 2;
     const int b_stride = ((p.block_n * BLOCK_K * 2) + 1023) & ~1023;
-    const int fixed = 2 * BLOCK_M * SLAB * 2 + 22 * 8 + 4 * 64 * 4 + 1024 /* alignment slack */;
+    const int fixed = 4 * BLOCK_M * SLAB * 2 + 22 * 8 + 2 * 4 * 64 * 4 + 1024 /* alignment slack */;
     int stages = (SMEM_BUDGET - fixed) / (a_bytes + b_stride);
     if (stages > 6) stages = 6;
     if (stages < 2) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_gemm_tn: smem");
@@ -416,7 +448,7 @@ int dfd_gemm_tn(const void* A, const void* B, void* C, long long M, int N, int K
     cudaGetDevice(&device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     int grid = p.num_m_tiles * p.num_n_tiles;
-    if (grid > 2 * sms) grid = 2 * sms;
+    if (grid > sms) grid = sms;
     cudaStream_t st = (cudaStream_t)stream;
     if (p.is_bf16) {
         auto kf = gemm_tc_kernel<bf16>;
@@ -429,6 +461,73 @@ int dfd_gemm_tn(const void* A, const void* B, void* C, long long M, int N, int K
         if (!attr) { cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET); attr = true; }
         kf<<<grid, NUM_THREADS, smem, st>>>(ma, mb, mc, p);
     }
+    DFD_LAUNCH_CHECK();
+    if (trace) {
+        // diagnostics only: synchronous dump of CTA 0's pipeline timestamps (cycles relative to its first event)
+        long long h[32 * 8];
+        cudaDeviceSynchronize();
+        cudaMemcpy(h, ts_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        long long t0 = h[0];
+        fprintf(stderr, "gemm_tc trace M=%d N=%d K=%d block_n=%d stages=%d: tile | prod_go mma_acc_free mma_data mma_commit | epi_wait epi_go epi_ld epi_end\n",
+                M, N, K, p.block_n, p.stages);
+        for (int t = 0; t < 32 && h[t * 8 + 1]; t++) {
+            fprintf(stderr, "  %2d |", t);
+            for (int j = 0; j < 8; j++) fprintf(stderr, " %7lld%s", h[t * 8 + j] - t0, j == 3 ? " |" : "");
+            fprintf(stderr, "\n");
+        }
+    }
+    return DFD_OK;
+}
+
+#define DISPATCH_16(dt, ...)                                          \
+    if ((dt) == DFD_DT_FP16) { typedef __half T16; __VA_ARGS__; }     \
+    else { typedef bf16 T16; __VA_ARGS__; }
+
+template <typename T>
+__global__ void blockdiag_kernel(const BlockDiagDesc* __restrict__ table) {
+    const BlockDiagDesc d = table[blockIdx.y];
+    const T* src = (const T*)d.src;
+    T* dst = (T*)d.dst;
+    const int Kp = d.K * d.pack;
+    const long long total = (long long)d.N * d.pack * Kp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % Kp), row = (int)(i / Kp);
+        const int j = row / d.N, n = row - j * d.N, jj = col / d.K, k = col - jj * d.K;
+        dst[i] = j == jj ? src[(size_t)n * d.K + k] : from_f<T>(0.f);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// C[M,N] = A[M,K] * B[N,K]^T on tcgen05; optional fp64 column statistics of the stored C ([8][N] slots).
+// All pointers must be 16-byte aligned, K % 8 == 0 and N % 8 == 0 (TMA global strides are multiples of 16 B).
+int dfd_gemm_tn(const void* A, const void* B, void* C, long long M, int N, int K, int dt, double* dsum, double* dsq,
+                void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0 || (N % 8) || (K % 8)) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn: N%8, K%8");
+    if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn: dtype");
+    return launch_gemm_tc(A, B, C, M, N, K, dt, dsum, dsq, N, stream);
+}
+
+// The same product for SMALL K (a pointwise conv with 16 / 24 / 32 input channels): `pack` consecutive rows of A are
+// read as ONE row of pack*K values and multiplied by the block-diagonal weight Bd[pack*N, pack*K] (dfd_blockdiag_weights),
+// which yields `pack` consecutive rows of C side by side - byte for byte the row-major C[M,N]. TMA fetches a tile row
+// per request, so 32-byte rows (K = 16) leave the load path request-bound at a quarter of the HBM rate; the packed view
+// issues 128-byte rows. The extra MMA work multiplies zeros and is free at these K.
+int dfd_gemm_tn_rowpack(const void* A, const void* Bd, void* C, long long M, int N, int K, int pack, int dt,
+                        double* dsum, double* dsq, void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0 || (N % 8) || (K % 8)) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn_rowpack: N%8, K%8");
+    if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn_rowpack: dtype");
+    if (pack < 1 || pack > 8 || (M % pack)) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn_rowpack: M % pack");
+    return launch_gemm_tc(A, Bd, C, M / pack, N * pack, K * pack, dt, dsum, dsq, N, stream);
+}
+
+// table: device array of {src [N,K], dst [pack*N, pack*K], N, K, pack}; dst(j*N+n, j'*K+k) = (j == j') ? src(n,k) : 0
+int dfd_blockdiag_weights(const void* table, int count, int dt, void* stream) {
+    if (count <= 0) return DFD_OK;
+    dim3 grid(16, count);
+    DISPATCH_16(dt, (blockdiag_kernel<T16><<<grid, 256, 0, (cudaStream_t)stream>>>((const BlockDiagDesc*)table)));
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

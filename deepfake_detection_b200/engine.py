@@ -11,6 +11,7 @@ PyTorch is used for device memory and streams only; there is no PyTorch compute 
 fallback: constructing an Engine without a CUDA device or without libdfd_b200.so raises.
 """
 import ctypes
+import os
 from collections import OrderedDict
 
 import torch
@@ -68,6 +69,10 @@ class Engine:
         else:
             self._layout_params()
         self._build()
+        if share_from is not None and not self._plan_only and getattr(share_from, "_bd_reg", None) and \
+                getattr(share_from, "_bd_table", None) is None:
+            # this plan registered new derived weight layouts with the owner: fill them now (never inside a graph capture)
+            self.refresh_weight_layouts(torch.cuda.current_stream().cuda_stream)
 
     # ------------------------------------------------------------------------------------------
     # parameter / buffer arenas
@@ -180,14 +185,47 @@ class Engine:
         self._keep.append(t)
         return t
 
+    # rows of A fused per TMA row for small-K pointwise convs, measured on B200 at batch 256 (tools/gemm_time2.py): the best
+    # factor makes pack*K a multiple of the 64-element k-block where that keeps pack*N modest
+    _ROW_PACK = {8: 8, 16: 4, 24: 8, 32: 4, 40: 2, 48: 4, 56: 2}
+
+    @classmethod
+    def _row_pack(cls, M, K):
+        """rows of A read as one (dfd_gemm_tn_rowpack): keeps the TMA rows of small-K pointwise convs at >= 128 bytes"""
+        if os.environ.get("DFD_NO_ROWPACK"):
+            return 1
+        pack = cls._ROW_PACK.get(K, 1)
+        while pack > 1 and M % pack:
+            pack //= 2
+        return pack
+
+    def _blockdiag(self, B, Nn, K, pack):
+        """block-diagonal [pack*Nn, pack*K] copy of the weight at B; owned (and refreshed) by the primary engine"""
+        o = self._shared_from if self._shared_from is not None else self
+        reg = o.__dict__.setdefault("_bd_reg", OrderedDict())
+        key = (B, Nn, K, pack)
+        if key not in reg:
+            reg[key] = torch.zeros(pack * Nn * pack * K, dtype=self.tdtype, device=self.device)
+            o._bd_table = None
+        return _ptr(reg[key])
+
     def refresh_weight_layouts(self, stream):
-        """derived 16-bit weight layouts (transposed 1x1, packed k x k) from the 16-bit arena"""
+        """derived 16-bit weight layouts (transposed 1x1, packed k x k, block-diagonal small-K) from the 16-bit arena"""
         _lib.call("dfd_transpose_weights", _ptr(self._ttable), self._ttable_count, self.dt, stream)
+        o = self._shared_from if self._shared_from is not None else self
+        reg = getattr(o, "_bd_reg", None)
+        if reg:
+            if getattr(o, "_bd_table", None) is None:
+                import struct
+                raw = b"".join(struct.pack("<QQiiii", B, _ptr(t), Nn, K, pack, 0) for (B, Nn, K, pack), t in reg.items())
+                o._bd_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
         if getattr(self, "_rtable_count", 0):
             _lib.call("dfd_repack_weights", _ptr(self._rtable), self._rtable_count, self.dt, stream)
         if getattr(self, "_stem_pad", None) is not None:
             name, O, taps, Kp = self._stem_pad
             _lib.call("dfd_pad_weight", _ptr(self.params16, self.p_off[name][0]), _ptr(self.stem_wpad), O, taps, Kp, self.dt, stream)
+        if reg:
+            _lib.call("dfd_blockdiag_weights", _ptr(o._bd_table), len(reg), self.dt, stream)
 
     def _stem_gemm_setup(self, wname, Cout, k, M):
         """stem convolution as im2col + tcgen05 GEMM (K = Cin*k*k padded to a multiple of 8)"""
@@ -276,6 +314,9 @@ class Engine:
         def gemm(A, B, C, M, Nn, K, bn=None):
             fs, fq = (bn.fsum, bn.fsq) if bn is not None else (None, None)
             if self.gemm_impl == "tc":
+                pack = self._row_pack(M, K)
+                if pack > 1:
+                    return ("dfd_gemm_tn_rowpack", (A, self._blockdiag(B, Nn, K, pack), C, M, Nn, K, pack, dt, fs, fq))
                 return ("dfd_gemm_tn", (A, B, C, M, Nn, K, dt, fs, fq))
             return ("dfd_gemm_tn_mma", (A, B, C, None, M, Nn, K, dt, fs, fq))
 
@@ -485,7 +526,8 @@ class Engine:
                 args = tuple((1 if training else 0) if a == "TRAINING" else a for a in args)
                 if not training:
                     args = (None, None) + args[2:]
-            elif not training and name in ("dfd_gemm_tn", "dfd_gemm_tn_mma", "dfd_dwconv_fwd", "dfd_stem_fwd"):
+            elif not training and name in ("dfd_gemm_tn", "dfd_gemm_tn_rowpack", "dfd_gemm_tn_mma", "dfd_dwconv_fwd",
+                                           "dfd_stem_fwd"):
                 args = tuple(args[:-2]) + (None, None)      # eval: no batch statistics
             rc = fn(*args, stream)
             if rc != 0:

@@ -49,6 +49,13 @@ int dfd_memset_async(void* p, int value, long long bytes, void* stream);
  * dsum/dsq (optional): per-column sum / sum of squares of the stored C for the following BatchNorm. */
 int dfd_gemm_tn(const void* A, const void* B, void* C, long long M, int N, int K, int dt, double* dsum, double* dsq,
                 void* stream);
+/* Small-K variant (Cin = 16 / 24 / 32 pointwise convs and their input gradients): `pack` consecutive rows of A are read
+ * as one row of pack*K values against the block-diagonal weight Bd[pack*N, pack*K] built by dfd_blockdiag_weights; the
+ * result is byte-identical row-major C[M,N], statistics are folded back onto the N channels. Requires M % pack == 0. */
+int dfd_gemm_tn_rowpack(const void* A, const void* Bd, void* C, long long M, int N, int K, int pack, int dt,
+                        double* dsum, double* dsq, void* stream);
+/* table: device array of { const void* src; void* dst; int N; int K; int pack; int _pad; } */
+int dfd_blockdiag_weights(const void* table, int count, int dt, void* stream);
 /* same contract on the warp-level mma.sync path (+ optional residual `add` [M,N]); cross-check / fallback */
 int dfd_gemm_tn_mma(const void* A, const void* B, void* C, const void* add, long long M, int N, int K, int dt,
                     double* dsum, double* dsq, void* stream);

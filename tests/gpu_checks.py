@@ -64,6 +64,14 @@ def check_gemm(impl, M, K, N, dtype=torch.bfloat16, with_stats=True, with_add=Fa
     if impl == "tc":
         assert not with_add
         _lib.call("dfd_gemm_tn", P(A), P(B), P(C), M, N, K, DT[dtype], P(s1), P(s2), st())
+    elif impl.startswith("rowpack"):
+        # small-K path: block-diagonal weight built on the device, `pack` rows of A per TMA row
+        import struct
+        pack = int(impl[len("rowpack"):])
+        Bd = torch.full((pack * N, pack * K), float("nan"), device="cuda", dtype=dtype)
+        table = torch.frombuffer(bytearray(struct.pack("<QQiiii", P(B), P(Bd), N, K, pack, 0)), dtype=torch.uint8).cuda()
+        _lib.call("dfd_blockdiag_weights", P(table), 1, DT[dtype], st())
+        _lib.call("dfd_gemm_tn_rowpack", P(A), P(Bd), P(C), M, N, K, pack, DT[dtype], P(s1), P(s2), st())
     else:
         _lib.call("dfd_gemm_tn_mma", P(A), P(B), P(C), P(add), M, N, K, DT[dtype], P(s1), P(s2), st())
     torch.cuda.synchronize()

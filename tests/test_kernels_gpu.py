@@ -25,6 +25,14 @@ def test_gemm_tcgen05(M, K, N):
     assert r["nan"] == 0 and r["out_max"] < OUT16 and r["sum_rel"] < RED and r["sq_rel"] < RED, r
 
 
+@pytest.mark.parametrize("M,K,N,pack", [(1000, 16, 96, 4), (4096 + 38, 24, 144, 2), (50176, 32, 32, 2), (3 * 1001, 16, 32, 3),
+                                        (25088 * 4, 16, 96, 4), (8, 32, 16, 2)])
+def test_gemm_tcgen05_rowpack(M, K, N, pack):
+    """small-K pointwise conv: packed rows against the block-diagonal weight == the plain product, statistics folded"""
+    r = _gc().check_gemm("rowpack%d" % pack, M, K, N)
+    assert r["nan"] == 0 and r["out_max"] < OUT16 and r["sum_rel"] < RED and r["sq_rel"] < RED, r
+
+
 def test_gemm_tcgen05_fp16():
     r = _gc().check_gemm("tc", 3000, 144, 40, dtype=torch.float16)
     assert r["nan"] == 0 and r["out_max"] < 2.0 ** -9 and r["sum_rel"] < RED, r
