@@ -460,6 +460,192 @@ dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused backward of an MBConv depthwise stage: the input gradient of MODE 1 above AND the weight gradient in one pass.
+// Both are sums over the same (input pixel x, tap t) pairs of the staged dy tile:
+//     ga[x] += dy[o(x,t)] * w[t]            dW[t] += dy[o(x,t)] * a[x],   a = swish(scale*xin + shift)
+// so the pass that owns input pixel x (this kernel's tiling) feeds two FMAs from every shared-memory read, the dy
+// operand (two tensors when the BN backward is folded in) is fetched and formed once instead of twice, and the
+// sigmoid of the input pixel serves both a and swish'.  A CTA walks images blockIdx.z, +gridDim.z, ... so that its
+// k*k weight-gradient partials (registers) are reduced and flushed once, not once per image.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int K, bool WG>
+__device__ __forceinline__ void strip_bwd_s2(const uint32_t* __restrict__ tile, int IW, int sy, int sx, int lane,
+                                             const float (&w)[K * K][2], float (&acc)[P][2],
+                                             const float (&av)[P][2], float (&wacc)[K * K][2]) {
+    constexpr int PAD = (K - 1) / 2;
+#pragma unroll
+    for (int kh = 0; kh < K; kh++) {
+        const int q = sy + PAD - kh;
+        if (q & 1) continue;                          // warp-uniform
+        const int row = (q >> 1) + 1;
+        const uint32_t* rp = tile + ((size_t)row * IW + (sx >> 1)) * 32 + lane;
+        float2 vv[P / 2 + 2];
+#pragma unroll
+        for (int j = 0; j < P / 2 + 2; j++) vv[j] = unpack2<T>(rp[j * 32]);
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+#pragma unroll
+            for (int kw = 0; kw < K; kw++) {
+                const int e = p + PAD - kw;
+                if (((e % 2) + 2) % 2 == 0) {
+                    const int col = (e + 2) / 2;
+                    acc[p][0] = fmaf(vv[col].x, w[kh * K + kw][0], acc[p][0]);
+                    acc[p][1] = fmaf(vv[col].y, w[kh * K + kw][1], acc[p][1]);
+                    if (WG) {
+                        wacc[kh * K + kw][0] = fmaf(vv[col].x, av[p][0], wacc[kh * K + kw][0]);
+                        wacc[kh * K + kw][1] = fmaf(vv[col].y, av[p][1], wacc[kh * K + kw][1]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int K>
+__device__ __forceinline__ void strip_bwd_s1(const uint32_t* __restrict__ tile, int IW, int r0, int c0, int lane,
+                                             const float (&w)[K * K][2], float (&acc)[P][2],
+                                             const float (&av)[P][2], float (&wacc)[K * K][2]) {
+#pragma unroll
+    for (int kh = 0; kh < K; kh++) {
+        const uint32_t* row = tile + ((size_t)(r0 + kh) * IW + c0) * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < P - 1 + K; j++) {
+            float2 x = unpack2<T>(row[j * 32]);
+#pragma unroll
+            for (int kw = 0; kw < K; kw++) {
+                const int pj = j - kw;
+                if (pj >= 0 && pj < P) {
+                    acc[pj][0] = fmaf(x.x, w[kh * K + kw][0], acc[pj][0]);
+                    acc[pj][1] = fmaf(x.y, w[kh * K + kw][1], acc[pj][1]);
+                    wacc[kh * K + kw][0] = fmaf(x.x, av[pj][0], wacc[kh * K + kw][0]);
+                    wacc[kh * K + kw][1] = fmaf(x.y, av[pj][1], wacc[kh * K + kw][1]);
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int K, int S, bool AFFINE, int NT>
+__global__ void __launch_bounds__(NT)
+dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const float* __restrict__ cA,
+                  const float* __restrict__ cB, const float* __restrict__ cC, const float* __restrict__ wgt,
+                  const T* __restrict__ xin, const float* __restrict__ scale, const float* __restrict__ shift,
+                  const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ gx,
+                  float* __restrict__ dW, double* __restrict__ ds1, double* __restrict__ ds2, DwGeom g) {
+    extern __shared__ __align__(16) uint32_t tile[];
+    __shared__ float red[NTHREADS / 32 * 64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = NT / 32;
+    const int tx = blockIdx.x % g.tiles_x, ty = blockIdx.x / g.tiles_x;
+    const int c0 = blockIdx.y * CB;
+    const int y0 = ty * g.TH, x0 = tx * g.TW;           // input-space tile origin
+    const int pp = K - 1 - g.pad;
+    const int ch = c0 + lane * 2;
+    const bool chv = ch < g.C;
+    float w[K * K][2], wacc[K * K][2];
+#pragma unroll
+    for (int i = 0; i < K * K; i++) {       // stride 1: flipped taps (correlation form); stride 2: direct taps
+        const int src = S == 1 ? (K * K - 1 - i) : i;
+        w[i][0] = chv ? wgt[(size_t)ch * K * K + src] : 0.f;
+        w[i][1] = chv ? wgt[(size_t)(ch + 1) * K * K + src] : 0.f;
+        wacc[i][0] = 0.f; wacc[i][1] = 0.f;
+    }
+    float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f, mu0 = 0.f, mu1 = 0.f, rs0 = 0.f, rs1 = 0.f;
+    if (chv) {
+        sc0 = scale[ch]; sc1 = scale[ch + 1]; sh0 = shift[ch]; sh1 = shift[ch + 1];
+        mu0 = mean[ch]; mu1 = mean[ch + 1]; rs0 = rstd[ch]; rs1 = rstd[ch + 1];
+    }
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    const int strips_x = g.TW / P;
+    const int nstrips = g.TH * strips_x;
+
+    for (int n = blockIdx.z; n < g.N; n += gridDim.z) {
+        const size_t ooff = (size_t)n * g.Ho * g.Wo * g.C;
+        const size_t ioff = (size_t)n * g.H * g.W * g.C;
+        // the strip's pre-activation inputs are an OPERAND here (a = swish(bn(xin))): fetched one strip ahead, the
+        // first one before the tile is staged, so their latency hides behind staging / the previous strip's FMAs
+        uint32_t pre[P];
+        auto prefetch = [&](int s) {
+            const int sy = s / strips_x, sx = (s - sy * strips_x) * P;
+            const int iy = y0 + sy, ix = x0 + sx;
+            const bool rowok = chv && iy < g.H;
+            const size_t off0 = ioff + ((size_t)iy * g.W + ix) * g.C + ch;
+#pragma unroll
+            for (int p = 0; p < P; p++)
+                pre[p] = (rowok && ix + p < g.W) ? __ldg(reinterpret_cast<const uint32_t*>(xin + off0 + (size_t)p * g.C)) : 0u;
+        };
+        if (warp < nstrips) prefetch(warp);
+        __syncthreads();    // previous image's tile fully consumed
+        stage_grad_tile<T, AFFINE>(tile, gy + ooff, AFFINE ? yout + ooff : nullptr, g.Ho, g.Wo, g.C, c0,
+                                   S == 1 ? y0 - pp : (y0 >> 1) - 1, S == 1 ? x0 - pp : (x0 >> 1) - 1, g.IH, g.IW, cA, cB, cC);
+        __syncthreads();
+        for (int s = warp; s < nstrips; s += NW) {
+            const int sy = s / strips_x, sx = (s - sy * strips_x) * P;
+            const int iy = y0 + sy, ix = x0 + sx;
+            float av[P][2], da[P][2], xh[P][2];
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const bool ok = chv && iy < g.H && ix + p < g.W;
+                const float2 xi = unpack2<T>(pre[p]);
+                const float u0 = fmaf(xi.x, sc0, sh0), u1 = fmaf(xi.y, sc1, sh1);
+                const float g0 = sigmoid_fast(u0), g1 = sigmoid_fast(u1);
+                // the forward staged a = swish(u) as a 16-bit value: the weight gradient sees the same rounding
+                const float2 ar = unpack2<T>(pack2<T>(u0 * g0, u1 * g1));
+                av[p][0] = ok ? ar.x : 0.f;
+                av[p][1] = ok ? ar.y : 0.f;
+                da[p][0] = g0 * (1.0f + u0 * (1.0f - g0));
+                da[p][1] = g1 * (1.0f + u1 * (1.0f - g1));
+                xh[p][0] = (xi.x - mu0) * rs0;
+                xh[p][1] = (xi.y - mu1) * rs1;
+            }
+            if (s + NW < nstrips) prefetch(s + NW);
+            if (iy >= g.H || ix >= g.W) continue;
+            float acc[P][2];
+#pragma unroll
+            for (int p = 0; p < P; p++) { acc[p][0] = 0.f; acc[p][1] = 0.f; }
+            if (S == 1) strip_bwd_s1<T, K>(tile, g.IW, sy, sx, lane, w, acc, av, wacc);
+            else strip_bwd_s2<T, K, true>(tile, g.IW, sy, sx, lane, w, acc, av, wacc);
+            if (chv) {
+                const size_t off0 = ioff + ((size_t)iy * g.W + ix) * g.C + ch;
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    if (ix + p < g.W) {
+                        const uint32_t pk = pack2<T>(acc[p][0] * da[p][0], acc[p][1] * da[p][1]);
+                        *reinterpret_cast<uint32_t*>(gx + off0 + (size_t)p * g.C) = pk;
+                        const float2 r = unpack2<T>(pk);
+                        a0 += r.x; a1 += r.y;
+                        b0 = fmaf(r.x, xh[p][0], b0);
+                        b1 = fmaf(r.y, xh[p][1], b1);
+                    }
+                }
+            }
+        }
+    }
+    double* p1 = stat_slot(ds1, g.C);
+    double* p2 = stat_slot(ds2, g.C);
+    reduce_warps_emit(red, a0, a1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p1 + c0 + c, (double)v); });
+    reduce_warps_emit(red, b0, b1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p2 + c0 + c, (double)v); });
+    // weight-gradient partials: all taps through the (now free) tile memory in one go, [warp][tap][64 channels]
+    float* wr = reinterpret_cast<float*>(tile);
+#pragma unroll
+    for (int i = 0; i < K * K; i++) {
+        wr[(warp * K * K + i) * 64 + lane * 2] = wacc[i][0];
+        wr[(warp * K * K + i) * 64 + lane * 2 + 1] = wacc[i][1];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < K * K * 64; e += NT) {
+        const int i = e >> 6, c = e & 63;
+        if (c0 + c < g.C) {
+            float v = 0.f;
+#pragma unroll
+            for (int q = 0; q < NW; q++) v += wr[(q * K * K + i) * 64 + c];
+            const int tap = S == 1 ? (K * K - 1 - i) : i;
+            atomicAdd(dW + (size_t)(c0 + c) * K * K + tap, v);
+        }
+    }
+}
+
 static int fill_geom(DwGeom& g, int N, int H, int W, int C, int K, int S, bool input_space) {
     // input_space: tiles partition the INPUT pixels (dgrad); the staged tile is then dy: shifted (S=1) or compact (S=2)
     g.N = N; g.H = H; g.W = W; g.C = C; g.pad = (K - 1) / 2;
@@ -594,6 +780,39 @@ int dfd_dwconv_wgrad(const void* x, const float* scale, const float* shift, cons
         else { if (cA) WG(DFD_ACT_NONE, false, true); else WG(DFD_ACT_NONE, false, false); }
     }));
 #undef WG
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+// Fused backward of a depthwise stage whose input is BN + Swish of `xin` (every MBConv block with an expansion):
+// dfd_dwconv_dgrad mode 1 and dfd_dwconv_wgrad in one pass over the dy tile (operands as there; dW accumulated).
+int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const float* cB, const float* cC,
+                   const float* w, const void* xin, const float* scale, const float* shift, const float* mean,
+                   const float* rstd, void* gx, float* dW, int N, int H, int W, int C, int k, int stride, int dt,
+                   double* s1, double* s2, void* stream) {
+    if (C % 8 || N <= 0 || H <= 0 || W <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: sizes");
+    if (!xin || !scale || !shift || !mean || !rstd || !s1 || !s2 || !dW) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: operands");
+    DwGeom g;
+    int smem = fill_geom(g, N, H, W, C, k, stride, true);
+    constexpr int NT = 128;
+    const int red_bytes = (NT / 32) * k * k * 64 * (int)sizeof(float);
+    if (smem < red_bytes) smem = red_bytes;
+    const int tiles = g.tiles_x * g.tiles_y, cbs = (C + CB - 1) / CB;
+    // image groups: enough CTAs for ~6 per SM, each walking N / gz images (gz a divisor of N keeps them balanced)
+    int gz = (148 * 6 + tiles * cbs - 1) / (tiles * cbs);
+    if (gz > N) gz = N;
+    while (gz < N && N % gz) gz++;
+    dim3 grid(tiles, cbs, gz);
+    cudaStream_t st = (cudaStream_t)stream;
+#define BW(K_, S_, AFF) DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, NT>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (T*)gx, dW, s1, s2, g)
+    DW_DISPATCH_T(dt, {
+        if (k == 3 && stride == 1) { if (cA) BW(3, 1, true); else BW(3, 1, false); }
+        else if (k == 3 && stride == 2) { if (cA) BW(3, 2, true); else BW(3, 2, false); }
+        else if (k == 5 && stride == 1) { if (cA) BW(5, 1, true); else BW(5, 1, false); }
+        else if (k == 5 && stride == 2) { if (cA) BW(5, 2, true); else BW(5, 2, false); }
+        else return dfd_set_error(DFD_ERR_UNSUPPORTED, "depthwise conv: k in {3,5}, stride in {1,2}");
+    });
+#undef BW
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

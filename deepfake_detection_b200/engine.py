@@ -469,11 +469,18 @@ class Engine:
             bwd.append(bwd_finalize(bn_mid, M2))
             if b.kind == "ir":
                 y1 = rec["y1"]
-                bwd.append(("dfd_dwconv_dgrad", (mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
-                                                 _ptr(y1), dw_bn.scale, dw_bn.shift, dw_bn.mean, dw_bn.rstd, None, mid_a,
-                                                 N, h, w, b.cmid, b.k, b.stride, 1, dt, dw_bn.bs1, dw_bn.bs2)))
-                bwd.append(("dfd_dwconv_wgrad", (_ptr(y1), dw_bn.scale, dw_bn.shift, mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB,
-                                                 bn_mid.cC, G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt)))
+                if os.environ.get("DFD_DW_SPLIT_BWD"):      # diagnostics: the two-pass form (same results)
+                    bwd.append(("dfd_dwconv_dgrad", (mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
+                                                     _ptr(y1), dw_bn.scale, dw_bn.shift, dw_bn.mean, dw_bn.rstd, None, mid_a,
+                                                     N, h, w, b.cmid, b.k, b.stride, 1, dt, dw_bn.bs1, dw_bn.bs2)))
+                    bwd.append(("dfd_dwconv_wgrad", (_ptr(y1), dw_bn.scale, dw_bn.shift, mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB,
+                                                     bn_mid.cC, G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt)))
+                else:
+                    # input gradient (through bn1 + Swish) and weight gradient in one pass over the dy tile
+                    bwd.append(("dfd_dwconv_bwd", (mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
+                                                   _ptr(y1), dw_bn.scale, dw_bn.shift, dw_bn.mean, dw_bn.rstd, mid_a,
+                                                   G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt,
+                                                   dw_bn.bs1, dw_bn.bs2)))
                 bwd.append(bwd_finalize(dw_bn, M1))
                 bwd.append(("dfd_bn_bwd_apply", (mid_a, _ptr(y1), None, dw_bn.cA, dw_bn.cB, dw_bn.cC, mid_b, N, h * w, b.cmid, dt)))
                 bwd.append(gemm(mid_b, T16(p + ".conv_pw.weight"), t2, M1, b.cin, b.cmid))

@@ -160,6 +160,18 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0, fw
         xhat = (x.double() - mean.double()) * rstd.double()
         res["bs1_rel"] = relerr(b1.sum(0), gxd.sum((0, 1, 2)))
         res["bs2_rel"] = relerr(b2.sum(0), (gxd * xhat).sum((0, 1, 2)))
+        # the fused pass (dgrad mode 1 + wgrad over one staged dy tile) must reproduce both
+        gx2 = torch.full((N, H, W, C), float("nan"), device="cuda", dtype=dtype)
+        dW2 = torch.zeros_like(w)
+        c1, c2 = stat_buf(C), stat_buf(C)
+        _lib.call("dfd_dwconv_bwd", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), P(scale), P(shift), P(mean), P(rstd),
+                  P(gx2), P(dW2), N, H, W, C, k, s, DT[dtype], P(c1), P(c2), st())
+        torch.cuda.synchronize()
+        res["fused_gx_diff"] = float((gx2.float() - gx.float()).abs().max())
+        res["fused_nan"] = int(torch.isnan(gx2.float()).sum())
+        res["fused_wgrad_rel"] = relerr(dW2, wr.grad)
+        res["fused_bs1_rel"] = relerr(c1.sum(0), gxd.sum((0, 1, 2)))
+        res["fused_bs2_rel"] = relerr(c2.sum(0), (gxd * xhat).sum((0, 1, 2)))
     else:
         add = torch.randn(N, H, W, C, device="cuda", generator=g).to(dtype)
         _lib.call("dfd_dwconv_dgrad", P(gy), P(out), P(cA), P(cB), P(cC), P(w), None, None, None, None, None, P(add), P(gx), N, H,

@@ -59,6 +59,9 @@ def test_dwconv(N, H, W, C, k, s, aff):
     assert r["dgrad_rel"] < 8e-3 and r["wgrad_rel"] < RED, r      # tanh.approx sigmoid: 2^-11 relative
     if aff:
         assert r["bs1_rel"] < RED and r["bs2_rel"] < RED, r
+        # fused dgrad + wgrad pass: the same input gradient bit for bit, the same reductions
+        assert r["fused_nan"] == 0 and r["fused_gx_diff"] == 0.0 and r["fused_wgrad_rel"] < RED, r
+        assert r["fused_bs1_rel"] < RED and r["fused_bs2_rel"] < RED, r
 
 
 def test_dwconv_fp16():
