@@ -25,6 +25,7 @@ constexpr int NTHREADS = 256;            // k = 3 kernels; k = 5 kernels (50 wei
 #define NT_FOR_K(K) NT   // so that four of them, not two, share an SM's register file
 constexpr int DW_MAX_SMEM = 200 * 1024;
 
+
 struct DwGeom {
     int N, H, W, C, Ho, Wo, pad;
     int TH, TW;              // output tile (TW multiple of 8)
@@ -91,7 +92,7 @@ __device__ __forceinline__ void stage_input_tile(uint32_t* tile, const T* __rest
 // Stage the output gradient dy = A*g + B*y + C (BN backward folded into the load): tile pixel (r, c) <-> dy[oy0 + r,
 // ox0 + c], zero outside [0,Ho) x [0,Wo).  (Compact: the stride-2 input-gradient kernel indexes it by parity, nothing is
 // zero-upsampled.)
-template <typename T, bool AFFINE>
+template <typename T, bool AFFINE, int UG_ = 0>
 __device__ __forceinline__ void stage_grad_tile(uint32_t* tile, const T* __restrict__ g, const T* __restrict__ y,
                                                 int Ho, int Wo, int C, int c0, int oy0, int ox0, int IH, int IW,
                                                 const float* __restrict__ cA, const float* __restrict__ cB,
@@ -103,7 +104,7 @@ __device__ __forceinline__ void stage_grad_tile(uint32_t* tile, const T* __restr
     if (AFFINE) { load_chan_params(cA, cbase, C, A, 1.f); load_chan_params(cB, cbase, C, B, 0.f); load_chan_params(cC, cbase, C, Cc, 0.f); }
     const int npix = IH * IW;
     const int PSTEP = blockDim.x / 8;
-    constexpr int UG = AFFINE ? 2 : 4;     // two tensors are read when the BN backward is folded in
+    constexpr int UG = UG_ ? UG_ : (AFFINE ? 2 : 4);     // two tensors are read when the BN backward is folded in
     for (int base = threadIdx.x >> 3; base < npix; base += PSTEP * UG) {
         uint4 graw[UG], yraw[UG];
         bool ok[UG];
@@ -577,7 +578,9 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
         };
         if (warp < nstrips) prefetch(warp);
         __syncthreads();    // previous image's tile fully consumed
-        stage_grad_tile<T, AFFINE>(tile, gy + ooff, AFFINE ? yout + ooff : nullptr, g.Ho, g.Wo, g.C, c0,
+        // staging batch (16-byte loads in flight per thread and tensor): 4 for k = 5 (two CTAs per SM either way, measured
+        // -8 %), 2 for k = 3 where the deeper batch costs the third resident CTA (measured +3..16 %)
+        stage_grad_tile<T, AFFINE, (K == 5 ? 4 : 2)>(tile, gy + ooff, AFFINE ? yout + ooff : nullptr, g.Ho, g.Wo, g.C, c0,
                                    S == 1 ? y0 - pp : (y0 >> 1) - 1, S == 1 ? x0 - pp : (x0 >> 1) - 1, g.IH, g.IW, cA, cB, cC);
         __syncthreads();
         for (int s = warp; s < nstrips; s += NW) {
