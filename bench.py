@@ -258,8 +258,22 @@ def run_native(args):
     top = max(fam.items(), key=lambda kv: kv[1]["ms"])
     top_name, tf = top
     ach = tf["bytes"] / (tf["ms"] / 1e3) / 1e9 if tf["ms"] > 0 else 0.0
+    # measured DRAM bytes per launch of that kernel (dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu
+    # launch list, same workload: profiles/r01_ncu_launches.md), valid for the default workload only
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tpath) and arch == "efficientnet_b0" and B == 256 and args.dtype == "bf16":
+        try:
+            with open(tpath) as f:
+                tj = json.load(f)
+            ent = tj.get(top_name[len("dfd_"):] + "_kernel")
+            if ent and ent["launches"] == tf["launches"]:
+                traffic, traffic_src = ent["dram_bytes_per_launch"], "profiles/r01_ncu_traffic.json"
+        except Exception:  # noqa: BLE001
+            pass
     roofline = dict(bound="hbm", kernel=top_name, achieved=round(ach, 1), peak=peaks["hbm_gbs"], unit="GB/s",
-                    frac=round(ach / peaks["hbm_gbs"], 4), traffic=None, peak_source=peaks["source"],
+                    frac=round(ach / peaks["hbm_gbs"], 4), traffic=traffic, traffic_source=traffic_src,
+                    algorithmic_bytes_per_launch=int(tf["bytes"] / max(tf["launches"], 1)), peak_source=peaks["source"],
                     kernel_share_of_step=round(tf["ms"] / tot_ms, 4), launches=tf["launches"],
                     step_frac_of_ideal_fusion_roofline=round(img_s / world * w["act_mb"] * 1e6 / (peaks["hbm_gbs"] * 1e9), 4),
                     step_frac_of_tensor_roofline=round(img_s / world * w["gflop"] * 1e9 / (peaks["tf_sustained"] * 1e12), 4),
