@@ -146,26 +146,42 @@ __global__ void bn_act_kernel(const T* __restrict__ y, const float* __restrict__
     long long r1 = r0 + rows_per_block;
     if (r1 > hw) r1 = hw;
     const size_t img = (size_t)blockIdx.y * hw * C + c0;
-    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-        size_t off = img + (size_t)r * C;
-        float f[8];
-        unpack8<T>(ldg16(y + off), f);
+    // U rows per trip, all loads issued before any math: a thread with one 16-byte load in flight cannot keep HBM
+    // busy at the occupancy these register counts allow (Little: ~44 KB in flight per SM for 6.5 TB/s)
+    constexpr int U = RES ? 2 : 4;
+    for (long long r = r0 + threadIdx.y; r < r1; r += (long long)U * blockDim.y) {
+        uint4 raw[U], rraw[U];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            float u = fmaf(f[i], sc[i], sh[i]);
-            f[i] = act_fwd<ACT>(u);
-            if (GATE) f[i] *= gt[i];
-        }
-        if (RES) {
-            float g[8];
-            unpack8<T>(ldg16(res + off), g);
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                f[i] += g[i];
-                if (RES == 2) f[i] = fmaxf(f[i], 0.f);
+        for (int u = 0; u < U; u++) {
+            const long long rr = r + (long long)u * blockDim.y;
+            if (rr < r1) {
+                raw[u] = ldg16(y + img + (size_t)rr * C);
+                if (RES) rraw[u] = ldg16(res + img + (size_t)rr * C);
             }
         }
-        stg16(out + off, pack8<T>(f));
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long long rr = r + (long long)u * blockDim.y;
+            if (rr >= r1) break;
+            float f[8];
+            unpack8<T>(raw[u], f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float uu = fmaf(f[i], sc[i], sh[i]);
+                f[i] = act_fwd<ACT>(uu);
+                if (GATE) f[i] *= gt[i];
+            }
+            if (RES) {
+                float g[8];
+                unpack8<T>(rraw[u], g);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    f[i] += g[i];
+                    if (RES == 2) f[i] = fmaxf(f[i], 0.f);
+                }
+            }
+            stg16(out + img + (size_t)rr * C, pack8<T>(f));
+        }
     }
 }
 
@@ -290,20 +306,36 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict
     long long r1 = r0 + rows_per_block;
     if (r1 > hw) r1 = hw;
     const size_t img = (size_t)blockIdx.y * hw * C + c0;
-    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-        size_t off = img + (size_t)r * C;
-        float gg[8], yy[8];
-        unpack8<T>(ldg16(g + off), gg);
-        unpack8<T>(ldg16(y + off), yy);
-        if (RELU_MASK) {
-            float oo[8];
-            unpack8<T>(ldg16(out + off), oo);
+    constexpr int U = 2;                   // 4-6 independent 16-byte loads in flight per thread (see bn_act_kernel)
+    for (long long r = r0 + threadIdx.y; r < r1; r += (long long)U * blockDim.y) {
+        uint4 graw[U], yraw[U], oraw[U];
 #pragma unroll
-            for (int i = 0; i < 8; i++) gg[i] = oo[i] > 0.f ? gg[i] : 0.f;
+        for (int u = 0; u < U; u++) {
+            const long long rr = r + (long long)u * blockDim.y;
+            if (rr < r1) {
+                const size_t off = img + (size_t)rr * C;
+                graw[u] = ldg16(g + off);
+                yraw[u] = ldg16(y + off);
+                if (RELU_MASK) oraw[u] = ldg16(out + off);
+            }
         }
 #pragma unroll
-        for (int i = 0; i < 8; i++) gg[i] = fmaf(A[i], gg[i], fmaf(B[i], yy[i], Cc[i]));
-        stg16(dy + off, pack8<T>(gg));
+        for (int u = 0; u < U; u++) {
+            const long long rr = r + (long long)u * blockDim.y;
+            if (rr >= r1) break;
+            float gg[8], yy[8];
+            unpack8<T>(graw[u], gg);
+            unpack8<T>(yraw[u], yy);
+            if (RELU_MASK) {
+                float oo[8];
+                unpack8<T>(oraw[u], oo);
+#pragma unroll
+                for (int i = 0; i < 8; i++) gg[i] = oo[i] > 0.f ? gg[i] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) gg[i] = fmaf(A[i], gg[i], fmaf(B[i], yy[i], Cc[i]));
+            stg16(dy + img + (size_t)rr * C, pack8<T>(gg));
+        }
     }
 }
 
@@ -359,23 +391,38 @@ __global__ void act_bwd_kernel(const T* __restrict__ da, const T* __restrict__ y
     long long r1 = r0 + rows_per_block;
     if (r1 > hw) r1 = hw;
     const size_t img = (size_t)blockIdx.y * hw * C + c0;
-    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-        size_t off = img + (size_t)r * C;
-        float d[8], f[8];
-        if (HAS_DA) unpack8<T>(ldg16(da + off), d);
-        unpack8<T>(ldg16(y + off), f);
+    constexpr int U = 2;                   // 4 independent 16-byte loads in flight per thread (see bn_act_kernel)
+    for (long long r = r0 + threadIdx.y; r < r1; r += (long long)U * blockDim.y) {
+        uint4 draw_[U], yraw[U];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            float u = fmaf(f[i], sc[i], sh[i]);
-            float gin = HAS_DA ? fmaf(d[i], gt[i], dp[i]) : dp[i];
-            float o = gin * act_bwd<ACT>(u);
-            // the stored (rounded) value is what the consumers see: reduce the rounded value
-            o = round_t<T>(o);
-            d[i] = o;
-            a1[i] += o;
-            a2[i] = fmaf(o, (f[i] - mu[i]) * rs[i], a2[i]);
+        for (int u = 0; u < U; u++) {
+            const long long rr = r + (long long)u * blockDim.y;
+            if (rr < r1) {
+                const size_t off = img + (size_t)rr * C;
+                if (HAS_DA) draw_[u] = ldg16(da + off);
+                yraw[u] = ldg16(y + off);
+            }
         }
-        stg16(gu + off, pack8<T>(d));
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long long rr = r + (long long)u * blockDim.y;
+            if (rr >= r1) break;
+            float d[8], f[8];
+            if (HAS_DA) unpack8<T>(draw_[u], d);
+            unpack8<T>(yraw[u], f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                float uu = fmaf(f[i], sc[i], sh[i]);
+                float gin = HAS_DA ? fmaf(d[i], gt[i], dp[i]) : dp[i];
+                float o = gin * act_bwd<ACT>(uu);
+                // the stored (rounded) value is what the consumers see: reduce the rounded value
+                o = round_t<T>(o);
+                d[i] = o;
+                a1[i] += o;
+                a2[i] = fmaf(o, (f[i] - mu[i]) * rs[i], a2[i]);
+            }
+            stg16(gu + img + (size_t)rr * C, pack8<T>(d));
+        }
     }
     double* p1 = stat_slot(s1, C);
     double* p2 = stat_slot(s2, C);
