@@ -247,21 +247,36 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restric
     long long r1 = r0 + rows_per_block;
     if (r1 > hw) r1 = hw;
     const size_t img = (size_t)blockIdx.y * hw * C + c0;
-    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-        size_t off = img + (size_t)r * C;
-        float gg[8], yy[8];
-        unpack8<T>(ldg16(g + off), gg);
-        unpack8<T>(ldg16(y + off), yy);
-        if (RELU_MASK) {
-            float oo[8];
-            unpack8<T>(ldg16(out + off), oo);
+    constexpr int U = 2;
+    for (long long r = r0 + threadIdx.y; r < r1; r += (long long)U * blockDim.y) {
+        uint4 graw[U], yraw[U], oraw[U];
 #pragma unroll
-            for (int i = 0; i < 8; i++) gg[i] = oo[i] > 0.f ? gg[i] : 0.f;
+        for (int u = 0; u < U; u++) {
+            const long long rr = r + (long long)u * blockDim.y;
+            if (rr < r1) {
+                const size_t off = img + (size_t)rr * C;
+                graw[u] = ldg16(g + off);
+                yraw[u] = ldg16(y + off);
+                if (RELU_MASK) oraw[u] = ldg16(out + off);
+            }
         }
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            a1[i] += gg[i];
-            a2[i] = fmaf(gg[i], (yy[i] - mu[i]) * rs[i], a2[i]);
+        for (int u = 0; u < U; u++) {
+            if (r + (long long)u * blockDim.y >= r1) break;
+            float gg[8], yy[8];
+            unpack8<T>(graw[u], gg);
+            unpack8<T>(yraw[u], yy);
+            if (RELU_MASK) {
+                float oo[8];
+                unpack8<T>(oraw[u], oo);
+#pragma unroll
+                for (int i = 0; i < 8; i++) gg[i] = oo[i] > 0.f ? gg[i] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                a1[i] += gg[i];
+                a2[i] = fmaf(gg[i], (yy[i] - mu[i]) * rs[i], a2[i]);
+            }
         }
     }
     double* p1 = stat_slot(s1, C);
@@ -306,7 +321,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict
     long long r1 = r0 + rows_per_block;
     if (r1 > hw) r1 = hw;
     const size_t img = (size_t)blockIdx.y * hw * C + c0;
-    constexpr int U = 2;                   // 4-6 independent 16-byte loads in flight per thread (see bn_act_kernel)
+    constexpr int U = RELU_MASK ? 2 : 4;   // 6-8 independent 16-byte loads in flight per thread (see bn_act_kernel)
     for (long long r = r0 + threadIdx.y; r < r1; r += (long long)U * blockDim.y) {
         uint4 graw[U], yraw[U], oraw[U];
 #pragma unroll
@@ -353,13 +368,23 @@ __global__ void se_bwd_reduce_kernel(const T* __restrict__ da, const T* __restri
 #pragma unroll
     for (int i = 0; i < 8; i++) { sc[i] = scale[c0 + i]; sh[i] = shift[c0 + i]; acc[i] = 0.f; }
     const size_t img = (size_t)blockIdx.y * hw * C + c0;
-    for (long long r = threadIdx.y; r < hw; r += blockDim.y) {
-        size_t off = img + (size_t)r * C;
-        float d[8], f[8];
-        unpack8<T>(ldg16(da + off), d);
-        unpack8<T>(ldg16(y + off), f);
+    constexpr int U = 1;                   // one CTA per image: deeper batching measured slower here
+    for (long long r = threadIdx.y; r < hw; r += (long long)U * blockDim.y) {
+        uint4 draw_[U], yraw[U];
 #pragma unroll
-        for (int i = 0; i < 8; i++) acc[i] = fmaf(d[i], act_fwd<ACT>(fmaf(f[i], sc[i], sh[i])), acc[i]);
+        for (int u = 0; u < U; u++) {
+            const long long rr = r + (long long)u * blockDim.y;
+            if (rr < hw) { draw_[u] = ldg16(da + img + (size_t)rr * C); yraw[u] = ldg16(y + img + (size_t)rr * C); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (r + (long long)u * blockDim.y >= hw) break;
+            float d[8], f[8];
+            unpack8<T>(draw_[u], d);
+            unpack8<T>(yraw[u], f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = fmaf(d[i], act_fwd<ACT>(fmaf(f[i], sc[i], sh[i])), acc[i]);
+        }
     }
     float* dst = draw + (size_t)blockIdx.y * C;
     reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v; });
