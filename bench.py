@@ -99,9 +99,9 @@ def op_bytes(name, a):
         return 2 * N * C * ((2 * o if a[2] else o) + (2 if mode == 1 else 1) * H * W + (H * W if a[11] else 0))
     if name == "dfd_dwconv_bwd":
         # dy operand(s) once, pre-activation input once, input gradient once (the k*k weight gradient is negligible)
-        N, H, W, C, k, s = a[13:19]
+        N, H, W, C, k, s = a[14:20]
         o = ((H + s - 1) // s) * ((W + s - 1) // s)
-        return 2 * N * C * ((2 * o if a[2] else o) + 2 * H * W)
+        return 2 * N * C * ((2 * o if a[2] else o) + 2 * H * W + (H * W if a[11] else 0))
     if name == "dfd_dwconv_wgrad":
         N, H, W, C, k, s = a[9:15]
         o = ((H + s - 1) // s) * ((W + s - 1) // s)

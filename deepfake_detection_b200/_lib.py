@@ -25,7 +25,7 @@ SIGNATURES = {
     "dfd_dwconv_fwd_tc": "ppppp" "iiiiii" "ii" "ppp",
     "dfd_dwconv_dgrad": "ppppp" "pppppp" "pp" "iiiiii" "ii" "ppp",
     "dfd_dwconv_wgrad": "ppppp" "pppp" "iiiiii" "i" "p",
-    "dfd_dwconv_bwd": "ppppp" "pppppp" "pp" "iiiiii" "i" "ppp",
+    "dfd_dwconv_bwd": "ppppp" "pppppp" "ppp" "iiiiii" "i" "ppp",
     "dfd_stem_fwd": "ppp" "iiiiiiii" "i" "ppp",
     "dfd_stem_wgrad": "ppppppp" "iiiiiiii" "i" "p",
     "dfd_colstats": "p" "ili" "i" "ppp",

@@ -220,35 +220,46 @@ __global__ void pool_bwd_kernel(const float* __restrict__ dpooled, T* __restrict
 }
 
 
-// ---- stem as a GEMM: im2col of the NCHW image in (ci, kh, kw) column order (== OIHW flattening), K padded to a multiple of 8
+// ---- stem as a GEMM: im2col of the NCHW image in (ci, kh, kw) column order (== OIHW flattening), K padded to a multiple of 8.
+// One CTA per output row: the Cin x k input rows it needs are staged (zero-padded) in shared memory with coalesced reads,
+// then every thread assembles 16-byte column groups from it (a per-thread 2-byte gather from global ran at 0.6 TB/s).
 template <typename T>
 __global__ void stem_im2col_kernel(const T* __restrict__ x, T* __restrict__ cols, int N, int Cin, int H, int W, int k, int s,
                                    int pad, int Ho, int Wo, int Kp) {
-    const int G = Kp / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int WP = W + 2 * pad;                      // padded row
     const int taps = Cin * k * k;
-    const long long total = (long long)N * Ho * Wo * G;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int g = (int)(i % G);
-        long long m = i / G;
-        int ox = (int)(m % Wo);
-        long long t2 = m / Wo;
-        int oy = (int)(t2 % Ho);
-        int n = (int)(t2 / Ho);
-        const T* img = x + (size_t)n * Cin * H * W;
+    T* rows = reinterpret_cast<T*>(smem_raw);        // [Cin][k][WP]
+    int* offs = reinterpret_cast<int*>(smem_raw + (((size_t)Cin * k * WP * sizeof(T) + 15) & ~(size_t)15));   // [Kp]
+    const int oy = blockIdx.x % Ho, n = blockIdx.x / Ho;
+    const T* img = x + (size_t)n * Cin * H * W;
+    for (int i = threadIdx.x; i < Cin * k * WP; i += blockDim.x) {
+        const int px = i % WP, r = i / WP;           // r = ci * k + kh
+        const int kh = r % k, ci = r / k;
+        const int iy = oy * s - pad + kh, ix = px - pad;
+        rows[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? img[((size_t)ci * H + iy) * W + ix] : from_f<T>(0.f);
+    }
+    for (int t = threadIdx.x; t < Kp; t += blockDim.x) {
+        int o = -1;
+        if (t < taps) {
+            const int ci = t / (k * k), r = t - ci * k * k;
+            const int kh = r / k, kw = r - kh * k;
+            o = (ci * k + kh) * WP + kw;
+        }
+        offs[t] = o;
+    }
+    __syncthreads();
+    const int G = Kp / 8;
+    T* out = cols + ((size_t)n * Ho + oy) * Wo * Kp;
+    for (int i = threadIdx.x; i < Wo * G; i += blockDim.x) {
+        const int g = i % G, ox = i / G;
         T vals[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            int t = g * 8 + j;
-            T v = from_f<T>(0.f);
-            if (t < taps) {
-                int ci = t / (k * k), r = t - ci * k * k;
-                int kh = r / k, kw = r - kh * k;
-                int iy = oy * s - pad + kh, ix = ox * s - pad + kw;
-                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[((size_t)ci * H + iy) * W + ix];
-            }
-            vals[j] = v;
+            const int o = offs[g * 8 + j];
+            vals[j] = o >= 0 ? rows[o + ox * s] : from_f<T>(0.f);
         }
-        stg16(cols + (size_t)m * Kp + g * 8, *reinterpret_cast<const uint4*>(vals));
+        stg16(out + (size_t)ox * Kp + g * 8, *reinterpret_cast<const uint4*>(vals));
     }
 }
 // 16-bit weight [O][taps] -> [O][Kp] (zero padded), and the inverse for the fp32 gradient (accumulating)
@@ -355,8 +366,9 @@ int dfd_stem_im2col(const void* x_nchw, void* cols, int N, int Cin, int H, int W
                     void* stream) {
     if (Kp % 8 || Kp < Cin * k * k) return dfd_set_error(DFD_ERR_ARG, "dfd_stem_im2col: Kp");
     int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-    long long total = (long long)N * Ho * Wo * (Kp / 8);
-    CD_T(dt, (stem_im2col_kernel<T><<<nblocks(total), 256, 0, (cudaStream_t)stream>>>((const T*)x_nchw, (T*)cols, N, Cin, H, W, k, stride, pad, Ho, Wo, Kp)));
+    size_t smem = (((size_t)Cin * k * (W + 2 * pad) * 2 + 15) & ~(size_t)15) + (size_t)Kp * sizeof(int);
+    if (smem > 48 * 1024) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_stem_im2col: input rows exceed shared memory");
+    CD_T(dt, (stem_im2col_kernel<T><<<N * Ho, 256, smem, (cudaStream_t)stream>>>((const T*)x_nchw, (T*)cols, N, Cin, H, W, k, stride, pad, Ho, Wo, Kp)));
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

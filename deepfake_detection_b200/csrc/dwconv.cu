@@ -527,12 +527,15 @@ __device__ __forceinline__ void strip_bwd_s1(const uint32_t* __restrict__ tile, 
     }
 }
 
-template <typename T, int K, int S, bool AFFINE, int NT>
+// MODE 1: xin is the pre-BN expand output (a = swish(scale*xin + shift), gx = ga * swish', BN-backward sums);
+// MODE 0: xin is the block input itself (DS block): a = xin, gx = ga (+ add).
+template <typename T, int K, int S, bool AFFINE, int MODE, int NT>
 __global__ void __launch_bounds__(NT)
 dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const float* __restrict__ cA,
                   const float* __restrict__ cB, const float* __restrict__ cC, const float* __restrict__ wgt,
                   const T* __restrict__ xin, const float* __restrict__ scale, const float* __restrict__ shift,
-                  const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ gx,
+                  const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ add,
+                  T* __restrict__ gx,
                   float* __restrict__ dW, double* __restrict__ ds1, double* __restrict__ ds2, DwGeom g) {
     extern __shared__ __align__(16) uint32_t tile[];
     __shared__ float red[NTHREADS / 32 * 64];
@@ -553,7 +556,7 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
         wacc[i][0] = 0.f; wacc[i][1] = 0.f;
     }
     float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f, mu0 = 0.f, mu1 = 0.f, rs0 = 0.f, rs1 = 0.f;
-    if (chv) {
+    if (MODE == 1 && chv) {
         sc0 = scale[ch]; sc1 = scale[ch + 1]; sh0 = shift[ch]; sh1 = shift[ch + 1];
         mu0 = mean[ch]; mu1 = mean[ch + 1]; rs0 = rstd[ch]; rs1 = rstd[ch + 1];
     }
@@ -591,16 +594,23 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
             for (int p = 0; p < P; p++) {
                 const bool ok = chv && iy < g.H && ix + p < g.W;
                 const float2 xi = unpack2<T>(pre[p]);
-                const float u0 = fmaf(xi.x, sc0, sh0), u1 = fmaf(xi.y, sc1, sh1);
-                const float g0 = sigmoid_fast(u0), g1 = sigmoid_fast(u1);
-                // the forward staged a = swish(u) as a 16-bit value: the weight gradient sees the same rounding
-                const float2 ar = unpack2<T>(pack2<T>(u0 * g0, u1 * g1));
-                av[p][0] = ok ? ar.x : 0.f;
-                av[p][1] = ok ? ar.y : 0.f;
-                da[p][0] = g0 * (1.0f + u0 * (1.0f - g0));
-                da[p][1] = g1 * (1.0f + u1 * (1.0f - g1));
-                xh[p][0] = (xi.x - mu0) * rs0;
-                xh[p][1] = (xi.y - mu1) * rs1;
+                if (MODE == 1) {
+                    const float u0 = fmaf(xi.x, sc0, sh0), u1 = fmaf(xi.y, sc1, sh1);
+                    const float g0 = sigmoid_fast(u0), g1 = sigmoid_fast(u1);
+                    // the forward staged a = swish(u) as a 16-bit value: the weight gradient sees the same rounding
+                    const float2 ar = unpack2<T>(pack2<T>(u0 * g0, u1 * g1));
+                    av[p][0] = ok ? ar.x : 0.f;
+                    av[p][1] = ok ? ar.y : 0.f;
+                    da[p][0] = g0 * (1.0f + u0 * (1.0f - g0));
+                    da[p][1] = g1 * (1.0f + u1 * (1.0f - g1));
+                    xh[p][0] = (xi.x - mu0) * rs0;
+                    xh[p][1] = (xi.y - mu1) * rs1;
+                } else {
+                    av[p][0] = ok ? xi.x : 0.f;      // pre[] is zero outside the image already; ok also covers !chv
+                    av[p][1] = ok ? xi.y : 0.f;
+                    da[p][0] = da[p][1] = 1.f;
+                    xh[p][0] = xh[p][1] = 0.f;
+                }
             }
             if (s + NW < nstrips) prefetch(s + NW);
             if (iy >= g.H || ix >= g.W) continue;
@@ -614,21 +624,33 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
 #pragma unroll
                 for (int p = 0; p < P; p++) {
                     if (ix + p < g.W) {
-                        const uint32_t pk = pack2<T>(acc[p][0] * da[p][0], acc[p][1] * da[p][1]);
-                        *reinterpret_cast<uint32_t*>(gx + off0 + (size_t)p * g.C) = pk;
-                        const float2 r = unpack2<T>(pk);
-                        a0 += r.x; a1 += r.y;
-                        b0 = fmaf(r.x, xh[p][0], b0);
-                        b1 = fmaf(r.y, xh[p][1], b1);
+                        if (MODE == 1) {
+                            const uint32_t pk = pack2<T>(acc[p][0] * da[p][0], acc[p][1] * da[p][1]);
+                            *reinterpret_cast<uint32_t*>(gx + off0 + (size_t)p * g.C) = pk;
+                            const float2 r = unpack2<T>(pk);
+                            a0 += r.x; a1 += r.y;
+                            b0 = fmaf(r.x, xh[p][0], b0);
+                            b1 = fmaf(r.y, xh[p][1], b1);
+                        } else {
+                            float v0 = acc[p][0], v1 = acc[p][1];
+                            if (add) {
+                                const float2 ad = unpack2<T>(__ldg(reinterpret_cast<const uint32_t*>(add + off0 + (size_t)p * g.C)));
+                                v0 += ad.x; v1 += ad.y;
+                            }
+                            *reinterpret_cast<uint32_t*>(gx + off0 + (size_t)p * g.C) = pack2<T>(v0, v1);
+                        }
                     }
                 }
             }
         }
     }
-    double* p1 = stat_slot(ds1, g.C);
-    double* p2 = stat_slot(ds2, g.C);
-    reduce_warps_emit(red, a0, a1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p1 + c0 + c, (double)v); });
-    reduce_warps_emit(red, b0, b1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p2 + c0 + c, (double)v); });
+    if (MODE == 1) {
+        double* p1 = stat_slot(ds1, g.C);
+        double* p2 = stat_slot(ds2, g.C);
+        reduce_warps_emit(red, a0, a1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p1 + c0 + c, (double)v); });
+        reduce_warps_emit(red, b0, b1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p2 + c0 + c, (double)v); });
+    }
+    __syncthreads();      // every warp is done with the dy tile before it is reused
     // weight-gradient partials: all taps through the (now free) tile memory in one go, [warp][tap][64 channels]
     float* wr = reinterpret_cast<float*>(tile);
 #pragma unroll
@@ -787,14 +809,16 @@ int dfd_dwconv_wgrad(const void* x, const float* scale, const float* shift, cons
     return DFD_OK;
 }
 
-// Fused backward of a depthwise stage whose input is BN + Swish of `xin` (every MBConv block with an expansion):
-// dfd_dwconv_dgrad mode 1 and dfd_dwconv_wgrad in one pass over the dy tile (operands as there; dW accumulated).
+// Fused backward of a depthwise stage: dfd_dwconv_dgrad and dfd_dwconv_wgrad in one pass over the dy tile (operands as
+// there; dW accumulated). scale != NULL: the stage input is BN + Swish of `xin` (mode 1: every MBConv block with an
+// expansion, `add` unused); scale == NULL: `xin` is consumed as is (mode 0: DS block), gx = dgrad (+ add).
 int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const float* cB, const float* cC,
                    const float* w, const void* xin, const float* scale, const float* shift, const float* mean,
-                   const float* rstd, void* gx, float* dW, int N, int H, int W, int C, int k, int stride, int dt,
-                   double* s1, double* s2, void* stream) {
+                   const float* rstd, const void* add, void* gx, float* dW, int N, int H, int W, int C, int k,
+                   int stride, int dt, double* s1, double* s2, void* stream) {
     if (C % 8 || N <= 0 || H <= 0 || W <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: sizes");
-    if (!xin || !scale || !shift || !mean || !rstd || !s1 || !s2 || !dW) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: operands");
+    if (!xin || !dW) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: operands");
+    if (scale && (!shift || !mean || !rstd || !s1 || !s2)) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: mode 1 operands");
     DwGeom g;
     int smem = fill_geom(g, N, H, W, C, k, stride, true);
     constexpr int NT = 128;
@@ -807,15 +831,17 @@ int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const floa
     while (gz < N && N % gz) gz++;
     dim3 grid(tiles, cbs, gz);
     cudaStream_t st = (cudaStream_t)stream;
-#define BW(K_, S_, AFF) DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, NT>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (T*)gx, dW, s1, s2, g)
+#define BW1(K_, S_, AFF, MODE_) DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, dW, s1, s2, g)
+#define BW(K_, S_) do { if (scale) { if (cA) BW1(K_, S_, true, 1); else BW1(K_, S_, false, 1); } else { if (cA) BW1(K_, S_, true, 0); else BW1(K_, S_, false, 0); } } while (0)
     DW_DISPATCH_T(dt, {
-        if (k == 3 && stride == 1) { if (cA) BW(3, 1, true); else BW(3, 1, false); }
-        else if (k == 3 && stride == 2) { if (cA) BW(3, 2, true); else BW(3, 2, false); }
-        else if (k == 5 && stride == 1) { if (cA) BW(5, 1, true); else BW(5, 1, false); }
-        else if (k == 5 && stride == 2) { if (cA) BW(5, 2, true); else BW(5, 2, false); }
+        if (k == 3 && stride == 1) BW(3, 1);
+        else if (k == 3 && stride == 2) BW(3, 2);
+        else if (k == 5 && stride == 1) BW(5, 1);
+        else if (k == 5 && stride == 2) BW(5, 2);
         else return dfd_set_error(DFD_ERR_UNSUPPORTED, "depthwise conv: k in {3,5}, stride in {1,2}");
     });
 #undef BW
+#undef BW1
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

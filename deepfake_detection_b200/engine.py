@@ -478,7 +478,7 @@ class Engine:
                 else:
                     # input gradient (through bn1 + Swish) and weight gradient in one pass over the dy tile
                     bwd.append(("dfd_dwconv_bwd", (mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
-                                                   _ptr(y1), dw_bn.scale, dw_bn.shift, dw_bn.mean, dw_bn.rstd, mid_a,
+                                                   _ptr(y1), dw_bn.scale, dw_bn.shift, dw_bn.mean, dw_bn.rstd, None, mid_a,
                                                    G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt,
                                                    dw_bn.bs1, dw_bn.bs2)))
                 bwd.append(bwd_finalize(dw_bn, M1))
@@ -487,12 +487,17 @@ class Engine:
                 if b.has_residual:
                     bwd.append(("dfd_add_inplace", (t2, dout, M1 * b.cin, dt)))
                 bwd.append(("dfd_gemm_wgrad_mma", (mid_b, _ptr(xin), G32(p + ".conv_pw.weight"), M1, b.cmid, b.cin, dt)))
-            else:
+            elif os.environ.get("DFD_DW_SPLIT_BWD"):
                 bwd.append(("dfd_dwconv_dgrad", (mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
                                                  None, None, None, None, None, dout if b.has_residual else None, t2,
                                                  N, h, w, b.cmid, b.k, b.stride, 0, dt, None, None)))
                 bwd.append(("dfd_dwconv_wgrad", (_ptr(xin), None, None, mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC,
                                                  G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt)))
+            else:
+                # DS block: the depthwise conv reads the block input as is (mode 0 of the fused pass)
+                bwd.append(("dfd_dwconv_bwd", (mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
+                                               _ptr(xin), None, None, None, None, dout if b.has_residual else None, t2,
+                                               G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt, None, None)))
             cur = (cur + 2) % 3
         # stem
         bn = self.bns["bn1"]

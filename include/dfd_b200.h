@@ -75,12 +75,13 @@ int dfd_dwconv_dgrad(const void* gy, const void* yout, const float* cA, const fl
 int dfd_dwconv_wgrad(const void* x, const float* scale, const float* shift, const void* gy, const void* yout,
                      const float* cA, const float* cB, const float* cC, float* dW, int N, int H, int W, int C, int k,
                      int stride, int dt, void* stream);
-/* dfd_dwconv_dgrad (mode 1) + dfd_dwconv_wgrad of one MBConv depthwise stage in a single pass over dy: the autograd
- * backward of conv_dw + bn1/act1 behind it (efficientnet_blocks.py:283-285, 277-281), dW accumulated into `dW` */
+/* dfd_dwconv_dgrad + dfd_dwconv_wgrad of one depthwise stage in a single pass over dy: the autograd backward of conv_dw
+ * (+ bn1/act1 behind it when scale != NULL, efficientnet_blocks.py:283-285, 277-281; scale == NULL: DS block,
+ * efficientnet_blocks.py:152-153, gx = dgrad (+ add)), dW accumulated into `dW` */
 int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const float* cB, const float* cC,
                    const float* w, const void* xin, const float* scale, const float* shift, const float* mean,
-                   const float* rstd, void* gx, float* dW, int N, int H, int W, int C, int k, int stride, int dt,
-                   double* s1, double* s2, void* stream);
+                   const float* rstd, const void* add, void* gx, float* dW, int N, int H, int W, int C, int k,
+                   int stride, int dt, double* s1, double* s2, void* stream);
 
 /* ---- stem convolution: conv_stem 3x3 s2 (efficientnet.py:275,321) / conv1 7x7 s2 (resnet.py:379,451) ---- */
 int dfd_stem_fwd(const void* x_nchw, const float* w, void* out_nhwc, int N, int Cin, int H, int W, int Cout, int k,

@@ -164,7 +164,7 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0, fw
         gx2 = torch.full((N, H, W, C), float("nan"), device="cuda", dtype=dtype)
         dW2 = torch.zeros_like(w)
         c1, c2 = stat_buf(C), stat_buf(C)
-        _lib.call("dfd_dwconv_bwd", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), P(scale), P(shift), P(mean), P(rstd),
+        _lib.call("dfd_dwconv_bwd", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), P(scale), P(shift), P(mean), P(rstd), None,
                   P(gx2), P(dW2), N, H, W, C, k, s, DT[dtype], P(c1), P(c2), st())
         torch.cuda.synchronize()
         res["fused_gx_diff"] = float((gx2.float() - gx.float()).abs().max())
@@ -180,8 +180,32 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0, fw
         ref_gx = xr.grad + nchw(add.float())
         res["dgrad_max"] = maxerr_scaled(nchw(gx.float()), ref_gx)
         res["dgrad_rel"] = relerr(nchw(gx.float()), ref_gx)
+        # fused pass, mode 0 (input consumed as is, residual gradient added)
+        gx2 = torch.full((N, H, W, C), float("nan"), device="cuda", dtype=dtype)
+        dW2 = torch.zeros_like(w)
+        _lib.call("dfd_dwconv_bwd", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), None, None, None, None, P(add), P(gx2), P(dW2),
+                  N, H, W, C, k, s, DT[dtype], None, None, st())
+        torch.cuda.synchronize()
+        res["fused_gx_diff"] = float((gx2.float() - gx.float()).abs().max())
+        res["fused_nan"] = int(torch.isnan(gx2.float()).sum())
+        res["fused_wgrad_rel"] = relerr(dW2, wr.grad)
     res["nan_b"] = int(torch.isnan(gx.float()).sum())
     return res
+
+
+def check_stem_im2col(N, Cin, H, W, k, s, pad, dtype=torch.bfloat16, seed=0):
+    """im2col rows of the NCHW image in (ci, kh, kw) order, K zero-padded to a multiple of 8: exact against F.unfold"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g).to(dtype)
+    taps = Cin * k * k
+    Kp = (taps + 7) // 8 * 8
+    Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    cols = torch.full((N * Ho * Wo, Kp), float("nan"), device="cuda", dtype=dtype)
+    _lib.call("dfd_stem_im2col", P(x), P(cols), N, Cin, H, W, k, s, pad, Kp, DT[dtype], st())
+    torch.cuda.synchronize()
+    ref = F.unfold(x.float(), k, padding=pad, stride=s).transpose(1, 2).reshape(N * Ho * Wo, taps)
+    return dict(diff=float((cols[:, :taps].float() - ref).abs().max()), pad_max=float(cols[:, taps:].float().abs().max()) if Kp > taps else 0.0,
+                nan=int(torch.isnan(cols.float()).sum()))
 
 
 def check_stem(N, Cin, H, W, Cout, k, dtype=torch.bfloat16, seed=0):

@@ -57,10 +57,10 @@ def test_dwconv(N, H, W, C, k, s, aff):
     assert r["nan"] == 0 and r["nan_b"] == 0, r
     assert r["fwd_max"] < OUT16 and r["sum_rel"] < RED and r["sq_rel"] < RED, r
     assert r["dgrad_rel"] < 8e-3 and r["wgrad_rel"] < RED, r      # tanh.approx sigmoid: 2^-11 relative
+    # fused dgrad + wgrad pass: the same input gradient bit for bit, the same reductions
+    assert r["fused_nan"] == 0 and r["fused_gx_diff"] == 0.0 and r["fused_wgrad_rel"] < RED, r
     if aff:
         assert r["bs1_rel"] < RED and r["bs2_rel"] < RED, r
-        # fused dgrad + wgrad pass: the same input gradient bit for bit, the same reductions
-        assert r["fused_nan"] == 0 and r["fused_gx_diff"] == 0.0 and r["fused_wgrad_rel"] < RED, r
         assert r["fused_bs1_rel"] < RED and r["fused_bs2_rel"] < RED, r
 
 
@@ -73,6 +73,12 @@ def test_dwconv_fp16():
 def test_stem(N, Cin, H, Cout, k):
     r = _gc().check_stem(N, Cin, H, H, Cout, k)
     assert r["nan"] == 0 and r["fwd_max"] < OUT16 and r["sum_rel"] < RED and r["sq_rel"] < RED and r["wgrad_rel"] < 1e-4, r
+
+
+@pytest.mark.parametrize("N,Cin,H,W,k,s,pad", [(2, 3, 32, 32, 3, 2, 1), (3, 3, 37, 45, 3, 2, 1), (2, 3, 64, 64, 7, 2, 3), (1, 4, 19, 23, 3, 1, 1)])
+def test_stem_im2col(N, Cin, H, W, k, s, pad):
+    r = _gc().check_stem_im2col(N, Cin, H, W, k, s, pad)
+    assert r["nan"] == 0 and r["diff"] == 0.0 and r["pad_max"] == 0.0, r
 
 
 @pytest.mark.parametrize("N,HW,C", [(3, 64, 32), (2, 49, 1152), (4, 200, 144), (2, 1000, 16)])

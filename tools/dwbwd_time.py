@@ -13,7 +13,7 @@ def t(N, H, W, C, k, s, reps=10):
     s1 = torch.zeros(8, C, dtype=torch.float64, device="cuda"); s2 = torch.zeros_like(s1)
     st = torch.cuda.current_stream().cuda_stream
     f = lambda: _lib.call("dfd_dwconv_bwd", gy.data_ptr(), y.data_ptr(), v[0].data_ptr(), v[1].data_ptr(), v[2].data_ptr(), w.data_ptr(),
-                          x.data_ptr(), v[3].data_ptr(), v[4].data_ptr(), v[5].data_ptr(), v[6].data_ptr(), gx.data_ptr(), dW.data_ptr(),
+                          x.data_ptr(), v[3].data_ptr(), v[4].data_ptr(), v[5].data_ptr(), v[6].data_ptr(), None, gx.data_ptr(), dW.data_ptr(),
                           N, H, W, C, k, s, 0, s1.data_ptr(), s2.data_ptr(), st)
     for _ in range(3): f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
