@@ -31,6 +31,7 @@ struct DwGeom {
     int TH, TW;              // output tile (TW multiple of 8)
     int IH, IW;              // staged input tile
     int tiles_x, tiles_y;
+    int dbg;                 // diagnostics (DFD_DW_DBG): 1 = skip the strip math, 2 = skip tile staging (fused backward only)
 };
 
 __device__ __forceinline__ void load_chan_params(const float* p, int cbase, int C, float* out, float dflt) {
@@ -54,16 +55,21 @@ __device__ __forceinline__ void stage_input_tile(uint32_t* tile, const T* __rest
     if (AFFINE) { load_chan_params(scale, cbase, C, sc, 1.f); load_chan_params(shift, cbase, C, sh, 0.f); }
     const int npix = IH * IW;
     const int PSTEP = blockDim.x / 8;
+    // (row, col) of the visited pixels advance by PSTEP each: kept incrementally (an integer division per pixel cost
+    // more issue slots than the activation it feeds)
+    const int dq = PSTEP / IW, dr = PSTEP - dq * IW;
+    int r = (threadIdx.x >> 3) / IW, c = (threadIdx.x >> 3) - r * IW;
     for (int base = threadIdx.x >> 3; base < npix; base += PSTEP * UNR) {
         uint4 raw[UNR];
         bool ok[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
-            int pix = base + u * PSTEP;
-            int r = pix / IW, c = pix - r * IW;
-            int iy = iy0 + r, ix = ix0 + c;
+            const int pix = base + u * PSTEP;
+            const int iy = iy0 + r, ix = ix0 + c;
             ok[u] = pix < npix && cvalid && iy >= 0 && iy < H && ix >= 0 && ix < W;
-            if (ok[u]) raw[u] = ldg16(img + ((size_t)iy * W + ix) * C + cbase);
+            if (ok[u]) raw[u] = ldg16(img + (uint32_t)((iy * W + ix) * C + cbase));      // in-image offsets fit 32 bits
+            r += dq; c += dr;
+            if (c >= IW) { c -= IW; r++; }
         }
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
@@ -84,7 +90,7 @@ __device__ __forceinline__ void stage_input_tile(uint32_t* tile, const T* __rest
                     o = raw[u];
                 }
             }
-            *reinterpret_cast<uint4*>(tile + (size_t)pix * 32 + v * 4) = o;
+            *reinterpret_cast<uint4*>(tile + pix * 32 + v * 4) = o;
         }
     }
 }
@@ -105,20 +111,23 @@ __device__ __forceinline__ void stage_grad_tile(uint32_t* tile, const T* __restr
     const int npix = IH * IW;
     const int PSTEP = blockDim.x / 8;
     constexpr int UG = UG_ ? UG_ : (AFFINE ? 2 : 4);     // two tensors are read when the BN backward is folded in
+    const int dq = PSTEP / IW, dr = PSTEP - dq * IW;          // incremental (row, col), see stage_input_tile
+    int r = (threadIdx.x >> 3) / IW, c = (threadIdx.x >> 3) - r * IW;
     for (int base = threadIdx.x >> 3; base < npix; base += PSTEP * UG) {
         uint4 graw[UG], yraw[UG];
         bool ok[UG];
 #pragma unroll
         for (int u = 0; u < UG; u++) {
-            int pix = base + u * PSTEP;
-            int r = pix / IW, c = pix - r * IW;
-            int oy = oy0 + r, ox = ox0 + c;
+            const int pix = base + u * PSTEP;
+            const int oy = oy0 + r, ox = ox0 + c;
             ok[u] = pix < npix && cvalid && oy >= 0 && oy < Ho && ox >= 0 && ox < Wo;
             if (ok[u]) {
-                size_t off = ((size_t)oy * Wo + ox) * C + cbase;
+                const uint32_t off = (uint32_t)((oy * Wo + ox) * C + cbase);
                 graw[u] = ldg16(g + off);
                 if (AFFINE) yraw[u] = ldg16(y + off);
             }
+            r += dq; c += dr;
+            if (c >= IW) { c -= IW; r++; }
         }
 #pragma unroll
         for (int u = 0; u < UG; u++) {
@@ -137,7 +146,7 @@ __device__ __forceinline__ void stage_grad_tile(uint32_t* tile, const T* __restr
                     o = graw[u];
                 }
             }
-            *reinterpret_cast<uint4*>(tile + (size_t)pix * 32 + v * 4) = o;
+            *reinterpret_cast<uint4*>(tile + pix * 32 + v * 4) = o;
         }
     }
 }
@@ -154,7 +163,7 @@ __device__ __forceinline__ void strip_dgrad_s2(const uint32_t* __restrict__ tile
         const int q = sy + PAD - kh;
         if (q & 1) continue;                          // warp-uniform
         const int row = (q >> 1) + 1;
-        const uint32_t* rp = tile + ((size_t)row * IW + (sx >> 1)) * 32 + lane;
+        const uint32_t* rp = tile + (row * IW + (sx >> 1)) * 32 + lane;
         float2 vv[P / 2 + 2];
 #pragma unroll
         for (int j = 0; j < P / 2 + 2; j++) vv[j] = unpack2<T>(rp[j * 32]);
@@ -179,7 +188,7 @@ __device__ __forceinline__ void strip_conv(const uint32_t* __restrict__ tile, in
                                            const float (&w)[K * K][2], float (&acc)[P][2]) {
 #pragma unroll
     for (int kh = 0; kh < K; kh++) {
-        const uint32_t* row = tile + ((size_t)(r0 + kh) * IW + c0) * 32 + lane;
+        const uint32_t* row = tile + ((r0 + kh) * IW + c0) * 32 + lane;
 #pragma unroll
         for (int j = 0; j < (P - 1) * S + K; j++) {
             float2 x = unpack2<T>(row[j * 32]);
@@ -239,11 +248,12 @@ dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, cons
     __syncthreads();
 
     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-    const int strips_x = g.TW / P;
+    const int strips_x = g.TW / P;              // TW in {8,16,32}, P in {4,8}: a power of two
+    const int xsh = 31 - __clz(strips_x);
     const int nstrips = g.TH * strips_x;
     T* oimg = out + (size_t)n * g.Ho * g.Wo * g.C;
     for (int s = warp; s < nstrips; s += (int)(blockDim.x >> 5)) {
-        int sy = s / strips_x, sx = (s - sy * strips_x) * P;
+        const int sy = s >> xsh, sx = (s & (strips_x - 1)) * P;
         int oy = oy0 + sy, ox = ox0 + sx;
         if (oy >= g.Ho || ox >= g.Wo) continue;
         float acc[P][2];
@@ -255,7 +265,7 @@ dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, cons
             for (int p = 0; p < P; p++) {
                 if (ox + p < g.Wo) {
                     uint32_t pk = pack2<T>(acc[p][0], acc[p][1]);
-                    *reinterpret_cast<uint32_t*>(oimg + ((size_t)oy * g.Wo + ox + p) * g.C + ch) = pk;
+                    *reinterpret_cast<uint32_t*>(oimg + (uint32_t)((oy * g.Wo + ox + p) * g.C + ch)) = pk;
                     float2 r = unpack2<T>(pk);
                     s0 += r.x; s1 += r.y;
                     q0 = fmaf(r.x, r.x, q0); q1 = fmaf(r.y, r.y, q1);
@@ -312,11 +322,12 @@ dwconv_dgrad_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const 
     __syncthreads();
 
     float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-    const int strips_x = g.TW / P;
+    const int strips_x = g.TW / P;              // TW in {8,16,32}, P in {4,8}: a power of two
+    const int xsh = 31 - __clz(strips_x);
     const int nstrips = g.TH * strips_x;
     const size_t ioff = (size_t)n * g.H * g.W * g.C;
     for (int s = warp; s < nstrips; s += (int)(blockDim.x >> 5)) {
-        int sy = s / strips_x, sx = (s - sy * strips_x) * P;
+        const int sy = s >> xsh, sx = (s & (strips_x - 1)) * P;
         int iy = y0 + sy, ix = x0 + sx;
         if (iy >= g.H || ix >= g.W) continue;
         // issue the strip's global reads (pre-activation input / residual gradient) BEFORE the conv math so that
@@ -391,7 +402,8 @@ dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, co
     float wacc[K * K][2];
 #pragma unroll
     for (int i = 0; i < K * K; i++) { wacc[i][0] = 0.f; wacc[i][1] = 0.f; }
-    const int strips_x = g.TW / P;
+    const int strips_x = g.TW / P;              // TW in {8,16,32}, P in {4,8}: a power of two
+    const int xsh = 31 - __clz(strips_x);
     const int nstrips = g.TH * strips_x;
 
     for (int n = blockIdx.z; n < g.N; n += gridDim.z) {
@@ -401,7 +413,7 @@ dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, co
         // the tile is staged) so that their global latency overlaps staging / the previous strip's FMAs
         uint32_t gq[P], yq[P];
         auto prefetch = [&](int s) {
-            int sy = s / strips_x, sx = (s - sy * strips_x) * P;
+            const int sy = s >> xsh, sx = (s & (strips_x - 1)) * P;
             int oy = oy0 + sy, ox = ox0 + sx;
             const bool rowok = chv && oy < g.Ho;
             const size_t off0 = ooff + ((size_t)oy * g.Wo + ox) * g.C + ch;
@@ -417,7 +429,7 @@ dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, co
         stage_input_tile<T, ACT, AFFINE_IN>(tile, img, g.H, g.W, g.C, c0, oy0 * S - g.pad, ox0 * S - g.pad, g.IH, g.IW, scale, shift);
         __syncthreads();
         for (int s = warp; s < nstrips; s += (int)(blockDim.x >> 5)) {
-            int sy = s / strips_x, sx = (s - sy * strips_x) * P;
+            const int sy = s >> xsh, sx = (s & (strips_x - 1)) * P;
             int oy = oy0 + sy, ox = ox0 + sx;
             float dy[P][2];
 #pragma unroll
@@ -436,7 +448,7 @@ dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, co
             if (oy >= g.Ho || ox >= g.Wo || !chv) continue;
 #pragma unroll
             for (int kh = 0; kh < K; kh++) {
-                const uint32_t* row = tile + ((size_t)(sy * S + kh) * g.IW + sx * S) * 32 + lane;
+                const uint32_t* row = tile + ((sy * S + kh) * g.IW + sx * S) * 32 + lane;
 #pragma unroll
                 for (int j = 0; j < (P - 1) * S + K; j++) {
                     float2 a = unpack2<T>(row[j * 32]);
@@ -470,7 +482,7 @@ dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, co
 // sigmoid of the input pixel serves both a and swish'.  A CTA walks images blockIdx.z, +gridDim.z, ... so that its
 // k*k weight-gradient partials (registers) are reduced and flushed once, not once per image.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int K, bool WG>
+template <typename T, int K, bool WG, int P>
 __device__ __forceinline__ void strip_bwd_s2(const uint32_t* __restrict__ tile, int IW, int sy, int sx, int lane,
                                              const float (&w)[K * K][2], float (&acc)[P][2],
                                              const float (&av)[P][2], float (&wacc)[K * K][2]) {
@@ -480,7 +492,7 @@ __device__ __forceinline__ void strip_bwd_s2(const uint32_t* __restrict__ tile, 
         const int q = sy + PAD - kh;
         if (q & 1) continue;                          // warp-uniform
         const int row = (q >> 1) + 1;
-        const uint32_t* rp = tile + ((size_t)row * IW + (sx >> 1)) * 32 + lane;
+        const uint32_t* rp = tile + (row * IW + (sx >> 1)) * 32 + lane;
         float2 vv[P / 2 + 2];
 #pragma unroll
         for (int j = 0; j < P / 2 + 2; j++) vv[j] = unpack2<T>(rp[j * 32]);
@@ -503,13 +515,13 @@ __device__ __forceinline__ void strip_bwd_s2(const uint32_t* __restrict__ tile, 
     }
 }
 
-template <typename T, int K>
+template <typename T, int K, int P>
 __device__ __forceinline__ void strip_bwd_s1(const uint32_t* __restrict__ tile, int IW, int r0, int c0, int lane,
                                              const float (&w)[K * K][2], float (&acc)[P][2],
                                              const float (&av)[P][2], float (&wacc)[K * K][2]) {
 #pragma unroll
     for (int kh = 0; kh < K; kh++) {
-        const uint32_t* row = tile + ((size_t)(r0 + kh) * IW + c0) * 32 + lane;
+        const uint32_t* row = tile + ((r0 + kh) * IW + c0) * 32 + lane;
 #pragma unroll
         for (int j = 0; j < P - 1 + K; j++) {
             float2 x = unpack2<T>(row[j * 32]);
@@ -529,8 +541,8 @@ __device__ __forceinline__ void strip_bwd_s1(const uint32_t* __restrict__ tile, 
 
 // MODE 1: xin is the pre-BN expand output (a = swish(scale*xin + shift), gx = ga * swish', BN-backward sums);
 // MODE 0: xin is the block input itself (DS block): a = xin, gx = ga (+ add).
-template <typename T, int K, int S, bool AFFINE, int MODE, int NT>
-__global__ void __launch_bounds__(NT)
+template <typename T, int K, int S, bool AFFINE, int MODE, int NT, int P>
+__global__ void __launch_bounds__(NT, K == 3 ? (P == 4 ? 4 : 3) : 2)
 dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const float* __restrict__ cA,
                   const float* __restrict__ cB, const float* __restrict__ cC, const float* __restrict__ wgt,
                   const T* __restrict__ xin, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -561,33 +573,38 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
         mu0 = mean[ch]; mu1 = mean[ch + 1]; rs0 = rstd[ch]; rs1 = rstd[ch + 1];
     }
     float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-    const int strips_x = g.TW / P;
+    const int strips_x = g.TW / P;              // TW in {8,16,32}, P in {4,8}: a power of two
+    const int xsh = 31 - __clz(strips_x);
     const int nstrips = g.TH * strips_x;
 
     for (int n = blockIdx.z; n < g.N; n += gridDim.z) {
         const size_t ooff = (size_t)n * g.Ho * g.Wo * g.C;
         const size_t ioff = (size_t)n * g.H * g.W * g.C;
+        const T* xin_n = xin + ioff;        // per-image bases: offsets inside an image fit 32 bits
+        T* gx_n = gx + ioff;
         // the strip's pre-activation inputs are an OPERAND here (a = swish(bn(xin))): fetched one strip ahead, the
         // first one before the tile is staged, so their latency hides behind staging / the previous strip's FMAs
         uint32_t pre[P];
         auto prefetch = [&](int s) {
-            const int sy = s / strips_x, sx = (s - sy * strips_x) * P;
+            const int sy = s >> xsh, sx = (s & (strips_x - 1)) * P;
             const int iy = y0 + sy, ix = x0 + sx;
             const bool rowok = chv && iy < g.H;
-            const size_t off0 = ioff + ((size_t)iy * g.W + ix) * g.C + ch;
+            const uint32_t off0 = (uint32_t)((iy * g.W + ix) * g.C + ch);
 #pragma unroll
             for (int p = 0; p < P; p++)
-                pre[p] = (rowok && ix + p < g.W) ? __ldg(reinterpret_cast<const uint32_t*>(xin + off0 + (size_t)p * g.C)) : 0u;
+                pre[p] = (rowok && ix + p < g.W) ? __ldg(reinterpret_cast<const uint32_t*>(xin_n + off0 + (uint32_t)(p * g.C))) : 0u;
         };
         if (warp < nstrips) prefetch(warp);
         __syncthreads();    // previous image's tile fully consumed
         // staging batch (16-byte loads in flight per thread and tensor): 4 for k = 5 (two CTAs per SM either way, measured
         // -8 %), 2 for k = 3 where the deeper batch costs the third resident CTA (measured +3..16 %)
-        stage_grad_tile<T, AFFINE, (K == 5 ? 4 : 2)>(tile, gy + ooff, AFFINE ? yout + ooff : nullptr, g.Ho, g.Wo, g.C, c0,
+        if (!(g.dbg & 2))
+            stage_grad_tile<T, AFFINE, (K == 5 ? 4 : 2)>(tile, gy + ooff, AFFINE ? yout + ooff : nullptr, g.Ho, g.Wo, g.C, c0,
                                    S == 1 ? y0 - pp : (y0 >> 1) - 1, S == 1 ? x0 - pp : (x0 >> 1) - 1, g.IH, g.IW, cA, cB, cC);
         __syncthreads();
+        if (!(g.dbg & 1))
         for (int s = warp; s < nstrips; s += NW) {
-            const int sy = s / strips_x, sx = (s - sy * strips_x) * P;
+            const int sy = s >> xsh, sx = (s & (strips_x - 1)) * P;
             const int iy = y0 + sy, ix = x0 + sx;
             float av[P][2], da[P][2], xh[P][2];
 #pragma unroll
@@ -617,16 +634,16 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
             float acc[P][2];
 #pragma unroll
             for (int p = 0; p < P; p++) { acc[p][0] = 0.f; acc[p][1] = 0.f; }
-            if (S == 1) strip_bwd_s1<T, K>(tile, g.IW, sy, sx, lane, w, acc, av, wacc);
-            else strip_bwd_s2<T, K, true>(tile, g.IW, sy, sx, lane, w, acc, av, wacc);
+            if (S == 1) strip_bwd_s1<T, K, P>(tile, g.IW, sy, sx, lane, w, acc, av, wacc);
+            else strip_bwd_s2<T, K, true, P>(tile, g.IW, sy, sx, lane, w, acc, av, wacc);
             if (chv) {
-                const size_t off0 = ioff + ((size_t)iy * g.W + ix) * g.C + ch;
+                const uint32_t off0 = (uint32_t)((iy * g.W + ix) * g.C + ch);
 #pragma unroll
                 for (int p = 0; p < P; p++) {
                     if (ix + p < g.W) {
                         if (MODE == 1) {
                             const uint32_t pk = pack2<T>(acc[p][0] * da[p][0], acc[p][1] * da[p][1]);
-                            *reinterpret_cast<uint32_t*>(gx + off0 + (size_t)p * g.C) = pk;
+                            *reinterpret_cast<uint32_t*>(gx_n + off0 + (uint32_t)(p * g.C)) = pk;
                             const float2 r = unpack2<T>(pk);
                             a0 += r.x; a1 += r.y;
                             b0 = fmaf(r.x, xh[p][0], b0);
@@ -634,10 +651,10 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
                         } else {
                             float v0 = acc[p][0], v1 = acc[p][1];
                             if (add) {
-                                const float2 ad = unpack2<T>(__ldg(reinterpret_cast<const uint32_t*>(add + off0 + (size_t)p * g.C)));
+                                const float2 ad = unpack2<T>(__ldg(reinterpret_cast<const uint32_t*>(add + ioff + off0 + (uint32_t)(p * g.C))));
                                 v0 += ad.x; v1 += ad.y;
                             }
-                            *reinterpret_cast<uint32_t*>(gx + off0 + (size_t)p * g.C) = pack2<T>(v0, v1);
+                            *reinterpret_cast<uint32_t*>(gx_n + off0 + (uint32_t)(p * g.C)) = pack2<T>(v0, v1);
                         }
                     }
                 }
@@ -689,6 +706,7 @@ static int fill_geom(DwGeom& g, int N, int H, int W, int C, int K, int S, bool i
     }
     g.tiles_x = (tw_dim + g.TW - 1) / g.TW;
     g.tiles_y = (th_dim + g.TH - 1) / g.TH;
+    { const char* e = getenv("DFD_DW_DBG"); g.dbg = e ? atoi(e) : 0; }
     return g.IH * g.IW * 32 * (int)sizeof(uint32_t);
 }
 
@@ -831,7 +849,10 @@ int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const floa
     while (gz < N && N % gz) gz++;
     dim3 grid(tiles, cbs, gz);
     cudaStream_t st = (cudaStream_t)stream;
-#define BW1(K_, S_, AFF, MODE_) DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, dW, s1, s2, g)
+    static int pb3 = 0, pb5 = 0;       // strip width per kernel size: 4 for k = 3 (four CTAs per SM, measured -1..-14 %), 8 for k = 5 (4 measured slower); DFD_DW_PB3 / DFD_DW_PB5 override
+    if (!pb3) { const char* e3 = getenv("DFD_DW_PB3"); const char* e5 = getenv("DFD_DW_PB5"); pb3 = (e3 && atoi(e3) == 8) ? 8 : 4; pb5 = (e5 && atoi(e5) == 4) ? 4 : 8; }
+    const int pb = k == 3 ? pb3 : pb5;
+#define BW1(K_, S_, AFF, MODE_) if (pb == 4) DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT, 4>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, dW, s1, s2, g); else DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT, 8>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, dW, s1, s2, g)
 #define BW(K_, S_) do { if (scale) { if (cA) BW1(K_, S_, true, 1); else BW1(K_, S_, false, 1); } else { if (cA) BW1(K_, S_, true, 0); else BW1(K_, S_, false, 0); } } while (0)
     DW_DISPATCH_T(dt, {
         if (k == 3 && stride == 1) BW(3, 1);
