@@ -107,7 +107,7 @@ template <int ACT> __device__ __forceinline__ float act_fwd(float u) {
 template <int ACT> __device__ __forceinline__ float act_bwd(float u) {
     if (ACT == DFD_ACT_SWISH) {
         float s = sigmoid_fast(u);
-        return s * (1.0f + u * (1.0f - s));
+        return fmaf(s, fmaf(-u, s, u), s);      // s * (1 + u * (1 - s)) in two FMAs
     }
     if (ACT == DFD_ACT_RELU) return u > 0.0f ? 1.0f : 0.0f;
     return 1.0f;

@@ -572,6 +572,7 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
         sc0 = scale[ch]; sc1 = scale[ch + 1]; sh0 = shift[ch]; sh1 = shift[ch + 1];
         mu0 = mean[ch]; mu1 = mean[ch + 1]; rs0 = rstd[ch]; rs1 = rstd[ch + 1];
     }
+    const float nm0 = -mu0 * rs0, nm1 = -mu1 * rs1;
     float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
     const int strips_x = g.TW / P;              // TW in {8,16,32}, P in {4,8}: a power of two
     const int xsh = 31 - __clz(strips_x);
@@ -607,26 +608,36 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
             const int sy = s >> xsh, sx = (s & (strips_x - 1)) * P;
             const int iy = y0 + sy, ix = x0 + sx;
             float av[P][2], da[P][2], xh[P][2];
+            // interior strips (warp-uniform) need no per-pixel masking: lanes beyond C compute garbage that is never
+            // stored, reduced or flushed
+            const bool interior = iy < g.H && ix + P <= g.W;
 #pragma unroll
             for (int p = 0; p < P; p++) {
-                const bool ok = chv && iy < g.H && ix + p < g.W;
                 const float2 xi = unpack2<T>(pre[p]);
                 if (MODE == 1) {
                     const float u0 = fmaf(xi.x, sc0, sh0), u1 = fmaf(xi.y, sc1, sh1);
                     const float g0 = sigmoid_fast(u0), g1 = sigmoid_fast(u1);
                     // the forward staged a = swish(u) as a 16-bit value: the weight gradient sees the same rounding
                     const float2 ar = unpack2<T>(pack2<T>(u0 * g0, u1 * g1));
-                    av[p][0] = ok ? ar.x : 0.f;
-                    av[p][1] = ok ? ar.y : 0.f;
-                    da[p][0] = g0 * (1.0f + u0 * (1.0f - g0));
-                    da[p][1] = g1 * (1.0f + u1 * (1.0f - g1));
-                    xh[p][0] = (xi.x - mu0) * rs0;
-                    xh[p][1] = (xi.y - mu1) * rs1;
+                    av[p][0] = ar.x;
+                    av[p][1] = ar.y;
+                    da[p][0] = fmaf(g0, fmaf(-u0, g0, u0), g0);       // == act_bwd<SWISH>(u)
+                    da[p][1] = fmaf(g1, fmaf(-u1, g1, u1), g1);
+                    xh[p][0] = fmaf(xi.x, rs0, nm0);                  // (x - mean) * rstd
+                    xh[p][1] = fmaf(xi.y, rs1, nm1);
                 } else {
-                    av[p][0] = ok ? xi.x : 0.f;      // pre[] is zero outside the image already; ok also covers !chv
-                    av[p][1] = ok ? xi.y : 0.f;
+                    av[p][0] = xi.x;                 // pre[] is zero outside the image and beyond C already
+                    av[p][1] = xi.y;
                     da[p][0] = da[p][1] = 1.f;
                     xh[p][0] = xh[p][1] = 0.f;
+                }
+            }
+            if (MODE == 1 && !interior) {
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    const bool ok = iy < g.H && ix + p < g.W;
+                    av[p][0] = ok ? av[p][0] : 0.f;
+                    av[p][1] = ok ? av[p][1] : 0.f;
                 }
             }
             if (s + NW < nstrips) prefetch(s + NW);
