@@ -87,7 +87,7 @@ def op_bytes(name, a):
     if name == "dfd_gemm_tn_mma":
         M, N, K = a[4], a[5], a[6]
         return 2 * (M * K + N * K + M * N)
-    if name == "dfd_gemm_wgrad_mma":
+    if name in ("dfd_gemm_wgrad_mma", "dfd_gemm_wgrad"):
         M, Nw, Kw = a[3], a[4], a[5]
         return 2 * M * (Nw + Kw) + 4 * Nw * Kw
     if name == "dfd_dwconv_fwd":

@@ -21,6 +21,7 @@ SIGNATURES = {
     "dfd_blockdiag_weights": "piip",
     "dfd_gemm_tn_mma": "pppp" "lii" "i" "ppp",
     "dfd_gemm_wgrad_mma": "ppp" "lii" "i" "p",
+    "dfd_gemm_wgrad": "ppp" "lii" "i" "p",
     "dfd_dwconv_fwd": "ppppp" "iiiiii" "ii" "ppp",
     "dfd_dwconv_fwd_tc": "ppppp" "iiiiii" "ii" "ppp",
     "dfd_dwconv_dgrad": "ppppp" "pppppp" "pp" "iiiiii" "ii" "ppp",

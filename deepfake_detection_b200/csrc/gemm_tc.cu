@@ -376,6 +376,138 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// =============================================================================================
+// 1x1 conv weight gradient on tcgen05: dW[Nw,Kw] (fp32, accumulated) += G[M,Nw]^T * X[M,Kw].
+// The contraction runs over the NHWC rows, so BOTH operands are MN-major for the MMA: a TMA box of {64 channels, 64 rows}
+// with 128-byte swizzle is already the canonical MN-major SW128 atom sequence (64 contiguous MN elements per K row, 8-row
+// groups 1024 B apart = SBO; 64-channel column blocks one box apart = LBO), so the tiles go from NHWC memory to the tensor
+// core without any transpose. One CTA = one (128 x block_n) tile of dW and one contiguous range of 64-row blocks (split-K);
+// the fp32 accumulator lives in TMEM for the whole range and is flushed once with red.global.add.
+// =============================================================================================
+constexpr int WG_KP = 64;                      // rows (pixels) per pipeline stage
+constexpr int WG_BOX_BYTES = WG_KP * 128;      // one {64 ch, 64 rows} box
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // LBO: next 64-element block along M / N
+    d |= (uint64_t)(1024 >> 4) << 32;                     // SBO: next 8-row group along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+    return d;
+}
+
+struct WgParams {
+    long long M;
+    int Nw, Kw;
+    int block_n;            // dW columns per tile: multiple of 16, <= 128
+    long long kblocks;      // ceil(M / 64)
+    long long kb_per_split;
+    int stages;
+    int is_bf16;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                float* __restrict__ dW, const WgParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
+    const int nbox_b = p.block_n > 64 ? 2 : 1;
+    const uint32_t a_bytes = 2 * WG_BOX_BYTES, b_bytes = (uint32_t)nbox_b * WG_BOX_BYTES;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem_a + (size_t)p.stages * a_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + 8;
+    uint64_t* tmem_full = bars + 16;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * p.block_n;
+    const long long kb0 = (long long)blockIdx.z * p.kb_per_split;
+    long long kb1 = kb0 + p.kb_per_split;
+    if (kb1 > p.kblocks) kb1 = p.kblocks;
+    if (kb0 >= kb1) return;                                   // uniform per CTA
+    const bool a_box1 = m0 + 64 < p.Nw;                       // second 64-channel block of the tile exists
+    const bool b_box1 = nbox_b == 2 && n0 + 64 < p.Kw;
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_x); }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.stages; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx = (a_box1 ? 2u : 1u) * WG_BOX_BYTES + (b_box1 ? 2u : 1u) * WG_BOX_BYTES;
+            for (long long kb = kb0; kb < kb1; kb++) {
+                mbar_wait(empty_bar + stage, phase ^ 1);
+                mbar_arrive_expect_tx(full_bar + stage, tx);
+                uint8_t* a = smem_a + (size_t)stage * a_bytes;
+                uint8_t* b = smem_b + (size_t)stage * b_bytes;
+                const int row = (int)(kb * WG_KP);
+                tma_load_2d(a, &tmap_g, full_bar + stage, m0, row);
+                if (a_box1) tma_load_2d(a + WG_BOX_BYTES, &tmap_g, full_bar + stage, m0 + 64, row);
+                tma_load_2d(b, &tmap_x, full_bar + stage, n0, row);
+                if (b_box1) tma_load_2d(b + WG_BOX_BYTES, &tmap_x, full_bar + stage, n0 + 64, row);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: fp32 accumulate, 16-bit inputs, A and B MN-major (bits 15 / 16), N, M = 128
+            uint32_t idesc = make_idesc(p.is_bf16, p.block_n) | (1u << 15) | (1u << 16);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long kb = kb0; kb < kb1; kb++) {
+                mbar_wait(full_bar + stage, phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_addr(smem_a + (size_t)stage * a_bytes);
+                const uint32_t b_addr = smem_addr(smem_b + (size_t)stage * b_bytes);
+#pragma unroll
+                for (int k = 0; k < WG_KP / UMMA_K; k++) {
+                    // 16 rows of K = two 8-row groups = 2048 bytes further into every box
+                    const uint64_t adesc = make_mnmajor_sw128_desc(a_addr + k * (UMMA_K * 128), WG_BOX_BYTES);
+                    const uint64_t bdesc = make_mnmajor_sw128_desc(b_addr + k * (UMMA_K * 128), WG_BOX_BYTES);
+                    umma_f16(tmem_base, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty_bar + stage);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tmem_full);
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int row = m0 + q * 32 + lane;                  // dW row (output channel) of this TMEM lane
+        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c = 0; c < p.block_n; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_base + c, v);
+            tmem_ld_wait();
+            if (row < p.Nw) {
+                float* dst = dW + (size_t)row * p.Kw + n0 + c;
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (n0 + c + j < p.Kw) atomicAdd(dst + j, __uint_as_float(v[j]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 128);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -528,6 +660,56 @@ int dfd_blockdiag_weights(const void* table, int count, int dt, void* stream) {
     if (count <= 0) return DFD_OK;
     dim3 grid(16, count);
     DISPATCH_16(dt, (blockdiag_kernel<T16><<<grid, 256, 0, (cudaStream_t)stream>>>((const BlockDiagDesc*)table)));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+// dW[Nw,Kw] (fp32, accumulated) += G[M,Nw]^T * X[M,Kw] on tcgen05 (MN-major operands straight from NHWC, split over M)
+int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* stream) {
+    if (M <= 0 || Nw <= 0 || Kw <= 0 || (Nw % 8) || (Kw % 8)) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_wgrad: Nw%8, Kw%8");
+    if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_wgrad: dtype");
+    WgParams p;
+    p.M = M; p.Nw = Nw; p.Kw = Kw;
+    p.is_bf16 = dt == DFD_DT_BF16;
+    p.block_n = Kw >= 128 ? 128 : ((Kw + 15) / 16) * 16;
+    p.kblocks = (M + WG_KP - 1) / WG_KP;
+    const int tm = cdiv(Nw, 128), tn = cdiv(Kw, p.block_n);
+    int device = 0, sms = 148;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    long long splits = (2LL * sms + tm * tn - 1) / (tm * tn);
+    long long max_splits = (p.kblocks + 3) / 4;              // at least 4 row blocks per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    p.kb_per_split = (p.kblocks + splits - 1) / splits;
+    splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
+    const int nbox_b = p.block_n > 64 ? 2 : 1;
+    const int stage_bytes = (2 + nbox_b) * WG_BOX_BYTES;
+    const int fixed = 18 * 8 + 64 + 1024;
+    // ~100 KB per CTA: two CTAs (128 TMEM columns each) share an SM, so 2 x SMs splits run as one wave
+    int stages = (100 * 1024 - fixed) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    size_t smem = (size_t)stages * stage_bytes + fixed;
+    CUtensorMap mg, mx;
+    int rc;
+    if ((rc = make_map(&mg, G, M, Nw, WG_KP, p.is_bf16))) return rc;
+    if ((rc = make_map(&mx, X, M, Kw, WG_KP, p.is_bf16))) return rc;
+    dim3 grid(tm, tn, (unsigned)splits);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.is_bf16) {
+        auto kf = wgrad_tc_kernel<bf16>;
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+        kf<<<grid, 256, smem, st>>>(mg, mx, dW, p);
+    } else {
+        auto kf = wgrad_tc_kernel<__half>;
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+        kf<<<grid, 256, smem, st>>>(mg, mx, dW, p);
+    }
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

@@ -54,6 +54,8 @@ class Engine:
         self.bn_momentum = float(bn_momentum)
         self.bn_eps = float(bn_eps)
         self.gemm_impl = gemm_impl
+        # 1x1 weight gradient: tcgen05 with MN-major operands, or the mma.sync cross-check path
+        self._wgrad_name = "dfd_gemm_wgrad" if gemm_impl == "tc" and not os.environ.get("DFD_WGRAD_MMA") else "dfd_gemm_wgrad_mma"
         self.stem_impl = stem_impl
         self.training = True
         self.n_launch = {"fwd": 0, "bwd": 0, "opt": 0}
@@ -439,7 +441,7 @@ class Engine:
         bwd.append(("dfd_bn_bwd_apply", (mid_a, _ptr(yh), None, bnh.cA, bnh.cB, bnh.cC, mid_b, N, Hf * Wf, F, dt)))
         cur = 0
         bwd.append(gemm(mid_b, T16("conv_head.weight"), sm[cur], Mf, spec.head_in, F))
-        bwd.append(("dfd_gemm_wgrad_mma", (mid_b, _ptr(self._head_in), G32("conv_head.weight"), Mf, F, spec.head_in, dt)))
+        bwd.append((self._wgrad_name, (mid_b, _ptr(self._head_in), G32("conv_head.weight"), Mf, F, spec.head_in, dt)))
         for rec in reversed(recs):
             b, h, w, ho, wo, xin = rec["b"], rec["h"], rec["w"], rec["ho"], rec["wo"], rec["x"]
             p = b.name
@@ -453,7 +455,7 @@ class Engine:
             bwd.append(bwd_finalize(bn_out, M2))
             bwd.append(("dfd_bn_bwd_apply", (dout, _ptr(y3), None, bn_out.cA, bn_out.cB, bn_out.cC, t1, N, ho * wo, b.cout, dt)))
             bwd.append(gemm(t1, T16(p + pw_name + ".weight"), mid_a, M2, b.cmid, b.cout))
-            bwd.append(("dfd_gemm_wgrad_mma", (t1, _ptr(a2), G32(p + pw_name + ".weight"), M2, b.cout, b.cmid, dt)))
+            bwd.append((self._wgrad_name, (t1, _ptr(a2), G32(p + pw_name + ".weight"), M2, b.cout, b.cmid, dt)))
             gate_ptr = dpool_ptr = None
             if b.cse:
                 gate_ptr, dpool_ptr = _ptr(rec["gate"]), se_dpool
@@ -486,7 +488,7 @@ class Engine:
                 bwd.append(gemm(mid_b, T16(p + ".conv_pw.weight"), t2, M1, b.cin, b.cmid))
                 if b.has_residual:
                     bwd.append(("dfd_add_inplace", (t2, dout, M1 * b.cin, dt)))
-                bwd.append(("dfd_gemm_wgrad_mma", (mid_b, _ptr(xin), G32(p + ".conv_pw.weight"), M1, b.cmid, b.cin, dt)))
+                bwd.append((self._wgrad_name, (mid_b, _ptr(xin), G32(p + ".conv_pw.weight"), M1, b.cmid, b.cin, dt)))
             elif os.environ.get("DFD_DW_SPLIT_BWD"):
                 bwd.append(("dfd_dwconv_dgrad", (mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
                                                  None, None, None, None, None, dout if b.has_residual else None, t2,
@@ -507,7 +509,7 @@ class Engine:
         if self.stem_impl == "gemm":
             bwd.append(("dfd_bn_bwd_apply", (mid_a, _ptr(y0), None, bn.cA, bn.cB, bn.cC, mid_b, N, Hs * Ws, spec.stem, dt)))
             bwd.append(("dfd_memset_async", (_ptr(self.stem_gpad), 0, spec.stem * Kp * 4)))
-            bwd.append(("dfd_gemm_wgrad_mma", (mid_b, _ptr(self.stem_cols), _ptr(self.stem_gpad), N * Hs * Ws, spec.stem, Kp, dt)))
+            bwd.append((self._wgrad_name, (mid_b, _ptr(self.stem_cols), _ptr(self.stem_gpad), N * Hs * Ws, spec.stem, Kp, dt)))
             bwd.append(("dfd_unpad_grad", (_ptr(self.stem_gpad), G32("conv_stem.weight"), spec.stem, taps, Kp)))
         else:
             bwd.append(("dfd_stem_wgrad", (_ptr(self.x_in), mid_a, _ptr(y0), bn.cA, bn.cB, bn.cC, G32("conv_stem.weight"), N,

@@ -61,6 +61,9 @@ int dfd_gemm_tn_mma(const void* A, const void* B, void* C, const void* add, long
                     double* dsum, double* dsq, void* stream);
 /* weight gradient dW[Nw,Kw] (fp32, accumulated) += G[M,Nw]^T * X[M,Kw]  (autograd of the conv, train.py:634) */
 int dfd_gemm_wgrad_mma(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* stream);
+/* the same contract on tcgen05: both operands MN-major straight from NHWC memory (TMA 128-byte swizzle boxes), fp32
+ * accumulator in TMEM over a contiguous range of rows per CTA, one red.global.add flush */
+int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* stream);
 
 /* ---- depthwise k x k convolution: nn.Conv2d(groups=C), efficientnet_blocks.py:152-153,283-285 -------- */
 int dfd_dwconv_fwd(const void* x, const float* scale, const float* shift, const float* w, void* out, int N, int H,

@@ -86,12 +86,12 @@ def check_gemm(impl, M, K, N, dtype=torch.bfloat16, with_stats=True, with_add=Fa
     return out
 
 
-def check_wgrad(M, Nw, Kw, dtype=torch.bfloat16, seed=0):
+def check_wgrad(M, Nw, Kw, dtype=torch.bfloat16, seed=0, impl="dfd_gemm_wgrad_mma"):
     g = torch.Generator(device="cuda").manual_seed(seed)
     G = (torch.randn(M, Nw, device="cuda", generator=g) * 0.3).to(dtype)
     X = (torch.randn(M, Kw, device="cuda", generator=g)).to(dtype)
     dW = torch.zeros(Nw, Kw, device="cuda")
-    _lib.call("dfd_gemm_wgrad_mma", P(G), P(X), P(dW), M, Nw, Kw, DT[dtype], st())
+    _lib.call(impl, P(G), P(X), P(dW), M, Nw, Kw, DT[dtype], st())
     torch.cuda.synchronize()
     ref = G.double().t() @ X.double()
     return dict(rel=relerr(dW, ref))

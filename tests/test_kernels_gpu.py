@@ -49,6 +49,17 @@ def test_wgrad(M, Nw, Kw):
     assert _gc().check_wgrad(M, Nw, Kw)["rel"] < 1e-4
 
 
+@pytest.mark.parametrize("M,Nw,Kw", [(5000, 96, 16), (12345, 144, 24), (3000, 1152, 192), (777, 320, 1280), (64, 24, 144),
+                                     (50176, 672, 112), (130, 40, 240), (4096, 128, 128), (70, 8, 8)])
+def test_wgrad_tcgen05(M, Nw, Kw):
+    """MN-major tcgen05 weight gradient (operands straight from NHWC rows) against fp64"""
+    assert _gc().check_wgrad(M, Nw, Kw, impl="dfd_gemm_wgrad")["rel"] < 1e-4
+
+
+def test_wgrad_tcgen05_fp16():
+    assert _gc().check_wgrad(3000, 144, 40, dtype=torch.float16, impl="dfd_gemm_wgrad")["rel"] < 1e-4
+
+
 @pytest.mark.parametrize("N,H,W,C,k,s,aff", [(2, 16, 16, 32, 3, 1, True), (2, 17, 19, 96, 3, 2, True), (2, 14, 14, 144, 5, 1, True),
                                               (2, 15, 15, 240, 5, 2, True), (3, 7, 7, 1152, 5, 1, True), (2, 40, 40, 32, 3, 1, False),
                                               (1, 33, 33, 24, 3, 1, False), (2, 56, 56, 144, 5, 2, True)])
