@@ -496,10 +496,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constan
             tmem_ld16(t_base + c, v);
             tmem_ld_wait();
             if (row < p.Nw) {
+                // 16-byte vector reductions (Kw % 8 == 0 keeps every group of 4 columns aligned and all-or-nothing): the
+                // small-M layers are bound by the NUMBER of L2 reduction ops, not by their bytes
                 float* dst = dW + (size_t)row * p.Kw + n0 + c;
 #pragma unroll
-                for (int j = 0; j < 16; j++)
-                    if (n0 + c + j < p.Kw) atomicAdd(dst + j, __uint_as_float(v[j]));
+                for (int j = 0; j < 16; j += 4)
+                    if (n0 + c + j < p.Kw)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                                     "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                     : "memory");
             }
         }
     }
