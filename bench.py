@@ -177,8 +177,8 @@ def run_native(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from deepfake_detection_b200.trainer import Trainer
-    from oracle.weights import synth_state
     from deepfake_detection_b200.arch import get_spec
+    from deepfake_detection_b200.models import init_state_dict
     arch, B = args.arch, args.batch
     res = args.res or WORK[arch]["res"]
     lr = 0.0001 * B * world          # args.lr = batch * world * basic_lr (train.py:814), basic_lr small for stability
@@ -186,7 +186,7 @@ def run_native(args):
                  use_graph=not args.no_graph, gemm_impl=args.gemm)
     spec = get_spec(arch)
     torch.manual_seed(42)
-    tr.load_state_dict({k: v for k, v in synth_state(spec, seed=42).items()})
+    tr.load_state_dict(init_state_dict(spec, seed=42))        # random init with the reference's initialisers
     if tr.reducer is not None:
         tr.reducer.broadcast_parameters()
     e = tr.engine

@@ -46,6 +46,32 @@ class _NativeForward(torch.autograd.Function):
         return None, None, None, None
 
 
+def init_state_dict(spec, seed=None):
+    """Random-init state in the reference's key order with the reference's initialisers:
+    efficientnet_builder.py:537-575 (`_init_weight_goog`), resnet.py:411-420."""
+    import math
+    g = torch.Generator(device="cpu").manual_seed((torch.initial_seed() if seed is None else seed) % (2 ** 31))
+    sd = OrderedDict()
+    for name, shape, role in state_entries(spec):
+        if role in ("conv_w", "dw_w", "se_w"):
+            fan_out = shape[0] * shape[2] * shape[3]
+            if role == "dw_w":
+                fan_out = shape[2] * shape[3]           # fan_out //= groups
+            sd[name] = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_out)
+        elif role == "bn_w":
+            sd[name] = torch.ones(shape)
+        elif role in ("bn_b", "se_b", "fc_b", "bn_rm"):
+            sd[name] = torch.zeros(shape)
+        elif role == "bn_rv":
+            sd[name] = torch.ones(shape)
+        elif role == "bn_nbt":
+            sd[name] = torch.zeros((), dtype=torch.int64)
+        elif role == "fc_w":
+            r = 1.0 / math.sqrt(shape[0])               # fan_out of the Linear, _init_weight_goog
+            sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * r
+    return sd
+
+
 class NativeModel(nn.Module):
     def __init__(self, arch, num_classes=2, in_chans=3, dtype="bf16", bn_momentum=None, bn_eps=None, bn_tf=False,
                  drop_rate=0.0, drop_path_rate=0.0, gemm_impl="tc", **unused):
@@ -99,28 +125,7 @@ class NativeModel(nn.Module):
         return self._primary
 
     def _init_weights(self, e):
-        """Reference initialisers: efficientnet_builder.py:537-575 (`_init_weight_goog`), resnet.py:411-420."""
-        import math
-        g = torch.Generator(device="cpu").manual_seed(torch.initial_seed() % (2 ** 31))
-        sd = OrderedDict()
-        for name, shape, role in state_entries(self.spec):
-            if role in ("conv_w", "dw_w", "se_w"):
-                fan_out = shape[0] * shape[2] * shape[3]
-                if role == "dw_w":
-                    fan_out = shape[2] * shape[3]           # fan_out //= groups
-                sd[name] = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_out)
-            elif role == "bn_w":
-                sd[name] = torch.ones(shape)
-            elif role in ("bn_b", "se_b", "fc_b", "bn_rm"):
-                sd[name] = torch.zeros(shape)
-            elif role == "bn_rv":
-                sd[name] = torch.ones(shape)
-            elif role == "bn_nbt":
-                sd[name] = torch.zeros((), dtype=torch.int64)
-            elif role == "fc_w":
-                r = 1.0 / math.sqrt(shape[0])               # fan_out of the Linear, _init_weight_goog
-                sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * r
-        e.load_state_dict(sd)
+        e.load_state_dict(init_state_dict(self.spec))
 
     # ---- nn.Module protocol ---------------------------------------------------------------------------
     def forward(self, x):

@@ -10,13 +10,13 @@ import torch  # noqa: E402
 
 from deepfake_detection_b200.arch import get_spec  # noqa: E402
 from deepfake_detection_b200.trainer import Trainer  # noqa: E402
-from oracle.weights import synth_state  # noqa: E402
+from deepfake_detection_b200.models import init_state_dict  # noqa: E402
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 arch = sys.argv[2] if len(sys.argv) > 2 else "efficientnet_b0"
 res = int(sys.argv[3]) if len(sys.argv) > 3 else 224
 tr = Trainer(arch, batch, res, res, dtype="bf16", use_graph=False)
-tr.load_state_dict(synth_state(get_spec(arch), seed=42))
+tr.load_state_dict(init_state_dict(get_spec(arch), seed=42))
 g = torch.Generator(device="cuda").manual_seed(0)
 x = torch.randn(batch, 3, res, res, device="cuda", generator=g)
 y = torch.randint(0, 2, (batch,), device="cuda", generator=g)
