@@ -32,7 +32,7 @@ SIGNATURES = {
     "dfd_colstats": "p" "ili" "i" "ppp",
     "dfd_bn_finalize": "ppd" "ppppp" "ffii" "ppppp",
     "dfd_bn_act": "pppppp" "ili" "iii" "p",
-    "dfd_pool": "pppp" "ili" "ii" "p",
+    "dfd_pool": "pppp" "ili" "ii" "pi" "p",
     "dfd_bn_bwd_reduce": "ppppp" "ili" "i" "ppp",
     "dfd_bn_bwd_finalize": "ppd" "pppppppp" "i" "p",
     "dfd_bn_bwd_apply": "ppppppp" "ili" "i" "p",

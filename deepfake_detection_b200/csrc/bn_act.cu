@@ -190,7 +190,8 @@ __global__ void bn_act_kernel(const T* __restrict__ y, const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 template <typename T, int ACT>
 __global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ scale,
-                            const float* __restrict__ shift, float* __restrict__ pooled, long long hw) {
+                            const float* __restrict__ shift, float* __restrict__ pooled, float* __restrict__ partial,
+                            long long hw, long long rows_per_block) {
     extern __shared__ float sm[];
     const int V = blockDim.x, C = V * 8;
     const int c0 = threadIdx.x * 8;
@@ -202,10 +203,15 @@ __global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ s
         acc[i] = 0.f;
     }
     const T* base = y + (size_t)blockIdx.y * hw * C + c0;
-    // one CTA per image keeps the reduction deterministic; 4 independent loads per thread keep HBM busy despite it
+    // gridDim.x row chunks per image: one (the usual case: the batch alone fills the GPU) stores the mean directly; several
+    // write their partial sums to `partial` [chunk][image][C] for pool_finish_kernel, which adds them in chunk order -
+    // the forward stays bit-reproducible (no float atomics). 4 independent loads per thread keep HBM busy.
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > hw) r1 = hw;
     constexpr int U = 4;
-    long long r = threadIdx.y;
-    for (; r + (long long)(U - 1) * blockDim.y < hw; r += (long long)U * blockDim.y) {
+    long long r = r0 + threadIdx.y;
+    for (; r + (long long)(U - 1) * blockDim.y < r1; r += (long long)U * blockDim.y) {
         uint4 raw[U];
 #pragma unroll
         for (int u = 0; u < U; u++) raw[u] = ldg16(base + (size_t)(r + (long long)u * blockDim.y) * C);
@@ -217,15 +223,29 @@ __global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ s
             for (int i = 0; i < 8; i++) acc[i] += act_fwd<ACT>(fmaf(f[i], sc[i], sh[i]));
         }
     }
-    for (; r < hw; r += blockDim.y) {
+    for (; r < r1; r += blockDim.y) {
         float f[8];
         unpack8<T>(ldg16(base + (size_t)r * C), f);
 #pragma unroll
         for (int i = 0; i < 8; i++) acc[i] += act_fwd<ACT>(fmaf(f[i], sc[i], sh[i]));
     }
-    const float inv = 1.f / (float)hw;
-    float* dst = pooled + (size_t)blockIdx.y * C;
-    reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v * inv; });
+    if (gridDim.x == 1) {
+        const float inv = 1.f / (float)hw;
+        float* dst = pooled + (size_t)blockIdx.y * C;
+        reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v * inv; });
+    } else {
+        float* dst = partial + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * C;
+        reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v; });
+    }
+}
+
+__global__ void pool_finish_kernel(const float* __restrict__ partial, float* __restrict__ pooled, int chunks, long long nc,
+                                   float inv) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    float s = 0.f;
+    for (int k = 0; k < chunks; k++) s += partial[(size_t)k * nc + i];      // fixed order: deterministic
+    pooled[i] = s * inv;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -360,7 +380,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict
 template <typename T, int ACT>
 __global__ void se_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
-                                     float* __restrict__ draw, long long hw) {
+                                     float* __restrict__ draw, long long hw, long long rows_per_block) {
     extern __shared__ float sm[];
     const int V = blockDim.x, C = V * 8;
     const int c0 = threadIdx.x * 8;
@@ -368,26 +388,22 @@ __global__ void se_bwd_reduce_kernel(const T* __restrict__ da, const T* __restri
 #pragma unroll
     for (int i = 0; i < 8; i++) { sc[i] = scale[c0 + i]; sh[i] = shift[c0 + i]; acc[i] = 0.f; }
     const size_t img = (size_t)blockIdx.y * hw * C + c0;
-    constexpr int U = 1;                   // one CTA per image: deeper batching measured slower here
-    for (long long r = threadIdx.y; r < hw; r += (long long)U * blockDim.y) {
-        uint4 draw_[U], yraw[U];
+    // gridDim.x chunks per image (several when the batch alone cannot fill the SMs): partial sums meet in fp32 atomics on
+    // the pre-zeroed output; a single chunk stores directly
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > hw) r1 = hw;
+    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+        size_t off = img + (size_t)r * C;
+        float d[8], f[8];
+        unpack8<T>(ldg16(da + off), d);
+        unpack8<T>(ldg16(y + off), f);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const long long rr = r + (long long)u * blockDim.y;
-            if (rr < hw) { draw_[u] = ldg16(da + img + (size_t)rr * C); yraw[u] = ldg16(y + img + (size_t)rr * C); }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (r + (long long)u * blockDim.y >= hw) break;
-            float d[8], f[8];
-            unpack8<T>(draw_[u], d);
-            unpack8<T>(yraw[u], f);
-#pragma unroll
-            for (int i = 0; i < 8; i++) acc[i] = fmaf(d[i], act_fwd<ACT>(fmaf(f[i], sc[i], sh[i])), acc[i]);
-        }
+        for (int i = 0; i < 8; i++) acc[i] = fmaf(d[i], act_fwd<ACT>(fmaf(f[i], sc[i], sh[i])), acc[i]);
     }
     float* dst = draw + (size_t)blockIdx.y * C;
-    reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v; });
+    if (gridDim.x == 1) reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v; });
+    else reduce_rows_and_emit(sm, acc, [&](int c, float v) { atomicAdd(dst + c, v); });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -531,17 +547,30 @@ int dfd_bn_act(const void* y, const float* scale, const float* shift, const floa
 }
 
 int dfd_pool(const void* y, const float* scale, const float* shift, float* pooled, int n, long long hw, int C,
-             int act, int dt, void* stream) {
+             int act, int dt, float* partial, int max_chunks, void* stream) {
     if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_pool: C%8, sizes");
-    RowGeom g = make_geom(C, hw, n, 1);
-    g.grid = dim3(1, n, 1);
+    // one CTA per image while the batch fills the GPU; otherwise up to max_chunks row chunks per image through `partial`
+    RowGeom g = make_geom(C, hw, n, (partial && max_chunks > 1 && n < 296) ? 592 : 1);
+    if (!(partial && max_chunks > 1 && n < 296)) { g.grid = dim3(1, n, 1); g.rows_per_block = (int)hw; }
+    if ((int)g.grid.x > max_chunks && g.grid.x > 1) {
+        long long rpb = (hw + max_chunks - 1) / max_chunks;
+        rpb = ((rpb + g.block.y - 1) / g.block.y) * g.block.y;
+        g.rows_per_block = (int)rpb;
+        g.grid.x = (unsigned)((hw + rpb - 1) / rpb);
+    }
     cudaStream_t st = (cudaStream_t)stream;
+    const long long rpb = g.rows_per_block;
     DISPATCH_T(dt, {
-        if (act == DFD_ACT_SWISH) pool_kernel<T, 1><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)y, scale, shift, pooled, hw);
-        else if (act == DFD_ACT_RELU) pool_kernel<T, 2><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)y, scale, shift, pooled, hw);
-        else pool_kernel<T, 0><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)y, scale, shift, pooled, hw);
+        if (act == DFD_ACT_SWISH) pool_kernel<T, 1><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)y, scale, shift, pooled, partial, hw, rpb);
+        else if (act == DFD_ACT_RELU) pool_kernel<T, 2><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)y, scale, shift, pooled, partial, hw, rpb);
+        else pool_kernel<T, 0><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)y, scale, shift, pooled, partial, hw, rpb);
     });
     DFD_LAUNCH_CHECK();
+    if (g.grid.x > 1) {
+        const long long nc = (long long)n * C;
+        pool_finish_kernel<<<cdiv(nc, 256), 256, 0, st>>>(partial, pooled, (int)g.grid.x, nc, 1.f / (float)hw);
+        DFD_LAUNCH_CHECK();
+    }
     return DFD_OK;
 }
 
@@ -584,10 +613,15 @@ int dfd_bn_bwd_apply(const void* g_, const void* y, const void* out, const float
 int dfd_se_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift, float* draw, int n,
                       long long hw, int C, int dt, void* stream) {
     if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_bwd_reduce: C%8, sizes");
-    RowGeom g = make_geom(C, hw, n, 1);
-    g.grid = dim3(1, n, 1);
+    // one CTA per image while the batch fills the GPU (>= 2 CTAs per SM); otherwise several row chunks per image
+    RowGeom g = make_geom(C, hw, n, n >= 296 ? 1 : 592);
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH_T(dt, (se_bwd_reduce_kernel<T, 1><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)da, (const T*)y, scale, shift, draw, hw)));
+    if (g.grid.x > 1) {
+        cudaError_t e = cudaMemsetAsync(draw, 0, (size_t)n * C * sizeof(float), st);
+        if (e != cudaSuccess) return dfd_set_cuda_error(e, __FILE__, __LINE__);
+    }
+    DISPATCH_T(dt, (se_bwd_reduce_kernel<T, 1><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)da, (const T*)y, scale, shift, draw, hw,
+                                                                                         (long long)g.rows_per_block)));
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

@@ -20,6 +20,7 @@ from . import _lib
 from .arch import get_spec, is_no_decay, param_entries, state_entries
 
 ACT_NONE, ACT_SWISH, ACT_RELU = _lib.ACT_NONE, _lib.ACT_SWISH, _lib.ACT_RELU
+POOL_CHUNKS = 8          # row chunks per image of the pooling kernels when the batch alone cannot fill the GPU
 
 
 def _ptr(t, off_elems=0):
@@ -345,6 +346,7 @@ class Engine:
         se_max_r = max([b.cse for b in spec.blocks if b.cse] + [8])
         self.se_tmp = torch.zeros(3 * N * se_max_c + 2 * N * se_max_r, dtype=torch.float32, device=dev)
         se_draw = _ptr(self.se_tmp)
+        self.pool_partial = torch.zeros(POOL_CHUNKS * N * max(se_max_c, spec.num_features), dtype=torch.float32, device=dev)
         se_de = _ptr(self.se_tmp, N * se_max_c)
         se_dpool = _ptr(self.se_tmp, 2 * N * se_max_c)
         se_r = _ptr(self.se_tmp, 3 * N * se_max_c)
@@ -395,7 +397,8 @@ class Engine:
                 gate = torch.zeros(N, b.cmid, dtype=torch.float32, device=dev)
                 self._keep += [pooled, gate]
                 rec.update(pooled=pooled, gate=gate)
-                fwd.append(("dfd_pool", (_ptr(y2), bn_mid.scale, bn_mid.shift, _ptr(pooled), N, ho * wo, b.cmid, ACT_SWISH, dt)))
+                fwd.append(("dfd_pool", (_ptr(y2), bn_mid.scale, bn_mid.shift, _ptr(pooled), N, ho * wo, b.cmid, ACT_SWISH, dt,
+                                         _ptr(self.pool_partial), POOL_CHUNKS)))
                 fwd.append(("dfd_se_fc_fwd", (_ptr(pooled), P32(p + ".se.conv_reduce.weight"), P32(p + ".se.conv_reduce.bias"),
                                               P32(p + ".se.conv_expand.weight"), P32(p + ".se.conv_expand.bias"),
                                               _ptr(gate), N, b.cmid, b.cse)))
@@ -423,7 +426,8 @@ class Engine:
         fwd.append(gemm(_ptr(x), P16("conv_head.weight"), _ptr(yh), Mf, F, spec.head_in, bnh))
         fwd.append(finalize(bnh, Mf))
         self.pooled = torch.zeros(N, F, dtype=torch.float32, device=dev)
-        fwd.append(("dfd_pool", (_ptr(yh), bnh.scale, bnh.shift, _ptr(self.pooled), N, Hf * Wf, F, ACT_SWISH, dt)))
+        fwd.append(("dfd_pool", (_ptr(yh), bnh.scale, bnh.shift, _ptr(self.pooled), N, Hf * Wf, F, ACT_SWISH, dt,
+                             _ptr(self.pool_partial), POOL_CHUNKS)))
         K = spec.num_classes
         self.logits = torch.zeros(N, K, dtype=torch.float32, device=dev)
         self.dlogits = torch.zeros(N, K, dtype=torch.float32, device=dev)

@@ -181,7 +181,8 @@ def build_resnet(e):
         x = out
     F, K = spec.num_features, spec.num_classes
     e.pooled = torch.zeros(N, F, dtype=torch.float32, device=dev)
-    fwd.append(("dfd_pool", (_ptr(x), None, None, _ptr(e.pooled), N, Hf * Wf, F, ACT_NONE, dt)))
+    e.pool_partial = torch.zeros(8 * N * F, dtype=torch.float32, device=dev)
+    fwd.append(("dfd_pool", (_ptr(x), None, None, _ptr(e.pooled), N, Hf * Wf, F, ACT_NONE, dt, _ptr(e.pool_partial), 8)))
     e.logits = torch.zeros(N, K, dtype=torch.float32, device=dev)
     e.dlogits = torch.zeros(N, K, dtype=torch.float32, device=dev)
     e.dpooled = torch.zeros(N, F, dtype=torch.float32, device=dev)

@@ -124,8 +124,11 @@ int dfd_bn_finalize(const double* dsum, const double* dsq, double count, const f
                     void* stream);
 int dfd_bn_act(const void* y, const float* scale, const float* shift, const float* gate, const void* res, void* out,
                int n, long long hw, int C, int act, int res_mode, int dt, void* stream);
+/* pooled[n,c] = mean_hw act(scale*y + shift). `partial` (optional, max_chunks * n * C floats): when the batch alone cannot
+ * fill the GPU, every image is reduced by up to max_chunks CTAs whose partial sums are added in a fixed order (the
+ * forward stays bit-reproducible); NULL / max_chunks <= 1: one CTA per image */
 int dfd_pool(const void* y, const float* scale, const float* shift, float* pooled, int n, long long hw, int C,
-             int act, int dt, void* stream);
+             int act, int dt, float* partial, int max_chunks, void* stream);
 int dfd_bn_bwd_reduce(const void* g, const void* y, const void* out, const float* mean, const float* rstd, int n,
                       long long hw, int C, int dt, double* s1, double* s2, void* stream);
 int dfd_bn_bwd_finalize(const double* s1, const double* s2, double count, const float* gamma, const float* mean,

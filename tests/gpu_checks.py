@@ -261,7 +261,12 @@ def check_bn_chain(N, HW, C, dtype=torch.bfloat16, seed=0):
     o_res = torch.full((N, HW, C), float("nan"), device="cuda", dtype=dtype)
     _lib.call("dfd_bn_act", P(y), P(scale), P(shift), None, P(res_t), P(o_res), N, HW, C, 0, 1, d, st())
     pooled = torch.zeros(N, C, device="cuda")
-    _lib.call("dfd_pool", P(y), P(scale), P(shift), P(pooled), N, HW, C, 1, d, st())
+    _lib.call("dfd_pool", P(y), P(scale), P(shift), P(pooled), N, HW, C, 1, d, None, 0, st())
+    # chunked variant (several CTAs per image, partial sums added in a fixed order): same means, bit-reproducible
+    pooled_c = [torch.full((N, C), float("nan"), device="cuda") for _ in range(2)]
+    partial = torch.full((8 * N * C,), float("nan"), device="cuda")
+    for pc in pooled_c:
+        _lib.call("dfd_pool", P(y), P(scale), P(shift), P(pc), N, HW, C, 1, d, P(partial), 8, st())
     torch.cuda.synchronize()
     # reference
     yr = y.float().permute(0, 2, 1).reshape(N, C, HW, 1).requires_grad_(True)
@@ -273,7 +278,8 @@ def check_bn_chain(N, HW, C, dtype=torch.bfloat16, seed=0):
         rm_rel=relerr(rm, rm_ref), rv_rel=relerr(rv, rv_ref), nbt=int(nbt.item()),
         gate_max=maxerr_scaled(a2.float().permute(0, 2, 1), (sw.squeeze(-1) * gate.unsqueeze(-1)).detach()),
         res_max=maxerr_scaled(o_res.float().permute(0, 2, 1), (u.squeeze(-1) + res_t.float().permute(0, 2, 1)).detach()),
-        pool_rel=relerr(pooled, sw.mean((2, 3)).detach()))
+        pool_rel=relerr(pooled, sw.mean((2, 3)).detach()), pool_chunk_rel=relerr(pooled_c[0], sw.mean((2, 3)).detach()),
+        pool_chunk_repro=float((pooled_c[0] - pooled_c[1]).abs().max()))
     # backward: gu = (da*gate + dpool/HW) * swish'(u); then BN backward
     da = (torch.randn(N, HW, C, device="cuda", generator=g) * 0.1).to(dtype)
     dpool = torch.randn(N, C, device="cuda", generator=g) * 0.1
