@@ -708,6 +708,8 @@ static int fill_geom(DwGeom& g, int N, int H, int W, int C, int K, int S, bool i
     int eff_s = input_space ? 1 : S;
     g.TW = tw_dim <= 8 ? 8 : ((tw_dim <= 16 || eff_s == 2) ? 16 : 32);   // stride-2 tiles stage 2x the columns
     g.TH = th_dim < 8 ? th_dim : 8;
+    // forward k = 5 stride 2: an 8-row tile stages 19 x 35 pixels (85 KB) and leaves two 4-warp CTAs per SM; 4 rows double that
+    if (!input_space && S == 2 && K == 5 && th_dim >= 8 && !getenv("DFD_DW_TH8")) g.TH = 4;
     if (input_space && S == 2) {
         g.IW = g.TW / 2 + 2;
         g.IH = (g.TH + 1) / 2 + 2;
