@@ -21,8 +21,7 @@ namespace {
 
 constexpr int CB = 64;       // channels per CTA
 constexpr int P = 8;         // output columns per strip
-constexpr int NTHREADS = 256;            // k = 3 kernels; k = 5 kernels (50 weight registers per thread) run 128-thread CTAs
-#define NT_FOR_K(K) NT   // so that four of them, not two, share an SM's register file
+constexpr int NTHREADS = 256;            // largest CTA (sizes the static reduction buffer); see dw_nt() for the per-k choice
 constexpr int DW_MAX_SMEM = 200 * 1024;
 
 
