@@ -92,7 +92,8 @@ __global__ void colstats_kernel(const T* __restrict__ y, long long hw, int rows_
 // ---------------------------------------------------------------------------------------------
 // BN finalise: batch statistics -> (scale, shift, mean, rstd) + running-stat EMA (unbiased var)
 // ---------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const double* __restrict__ dsum, const double* __restrict__ dsq, double count,
+__global__ void bn_finalize_kernel(const double* __restrict__ dsum, const double* __restrict__ dsq, double inv_count,
+                                   double unbias,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ nbt, float momentum, float eps, int training, int C,
@@ -103,12 +104,14 @@ __global__ void bn_finalize_kernel(const double* __restrict__ dsum, const double
     if (c >= C) return;
     float mean, var;
     if (training) {
-        double m = stat_total(dsum, C, c) / count;
-        double v = stat_total(dsq, C, c) / count - m * m;
+        // reciprocals come from the host: fp64 divisions are long dependent sequences on this part and these one-block
+        // kernels sit on the critical path of every layer
+        double m = stat_total(dsum, C, c) * inv_count;
+        double v = stat_total(dsq, C, c) * inv_count - m * m;
         if (v < 0) v = 0;
         mean = (float)m;
         var = (float)v;
-        double unb = count > 1 ? v * count / (count - 1) : v;
+        double unb = v * unbias;                 // count / (count - 1)
         running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
     } else {
@@ -308,7 +311,7 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restric
 // BN backward, phase 2 (per channel): parameter gradients and the affine coefficients of
 //   dy = A*g + B*y + C  with A = gamma*rstd, B = -gamma*rstd^2*m2, C = -A*m1 - B*mean,
 //   m1 = s1/count, m2 = s2/count.
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ s1, const double* __restrict__ s2, double count,
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ s1, const double* __restrict__ s2, double inv_count,
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                        const float* __restrict__ rstd, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ cA, float* __restrict__ cB,
@@ -318,7 +321,7 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ s1, const doub
     double sum_g = stat_total(s1, C, c), sum_gx = stat_total(s2, C, c);
     dgamma[c] += (float)sum_gx;
     dbeta[c] += (float)sum_g;
-    float m1 = (float)(sum_g / count), m2 = (float)(sum_gx / count);
+    float m1 = (float)(sum_g * inv_count), m2 = (float)(sum_gx * inv_count);
     float A = gamma[c] * rstd[c];
     float B = -A * rstd[c] * m2;
     cA[c] = A;
@@ -513,7 +516,7 @@ int dfd_bn_finalize(const double* dsum, const double* dsq, double count, const f
                     float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
                     int training, int C, float* scale, float* shift, float* mean, float* rstd, void* stream) {
     if (C <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_bn_finalize: C");
-    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(dsum, dsq, count, gamma, beta, running_mean,
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(dsum, dsq, 1.0 / count, count > 1 ? count / (count - 1) : 1.0, gamma, beta, running_mean,
                                                                          running_var, nbt, momentum, eps, training, C,
                                                                          scale, shift, mean, rstd);
     DFD_LAUNCH_CHECK();
@@ -591,7 +594,7 @@ int dfd_bn_bwd_finalize(const double* s1, const double* s2, double count, const 
                         const float* rstd, float* dgamma, float* dbeta, float* cA, float* cB, float* cC, int C,
                         void* stream) {
     if (C <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_bn_bwd_finalize: C");
-    bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(s1, s2, count, gamma, mean, rstd, dgamma,
+    bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(s1, s2, 1.0 / count, gamma, mean, rstd, dgamma,
                                                                              dbeta, cA, cB, cC, C);
     DFD_LAUNCH_CHECK();
     return DFD_OK;
