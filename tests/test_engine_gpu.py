@@ -32,7 +32,9 @@ def test_train_step_parity(arch, b, res, dtype, impl):
             assert em["logits_rel"] < 2e-2 * (1 + i), em
             assert em["grad_rel_total"] < 4e-2 * (1 + i), em
             assert abs(em["loss_native"] - em["loss_oracle"]) < 3e-3 * (1 + i), em
-        assert fp["logits_rel"] < 2.0 * yd["logits_rel"] + 1e-2, (fp, yd)
+        # step 1 compounds the 16-bit noise of step 0's update and varies run to run with the order of the fp32 atomics
+        # (measured 6.3e-2 .. 8.3e-2 over three runs of the B0 bf16 case against 4.3e-2 for the oracle's own emulation)
+        assert fp["logits_rel"] < (2.0 + 0.5 * i) * yd["logits_rel"] + 1e-2 * (1 + i), (fp, yd)
         assert fp["grad_rel_total"] < 1.5 * yd["grad_rel_total"] + 2e-2, (fp, yd)
         # the second step runs on weights updated from a 16-bit gradient whose fp32 atomics reorder between runs: its loss
         # distance was measured at 5.5e-3 .. 6.6e-3 over four runs of the B4 case (tools/parity_probe.py)
