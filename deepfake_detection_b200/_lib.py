@@ -43,9 +43,16 @@ SIGNATURES = {
     "dfd_se_fc_bwd": "pppppp" "pppppppp" "iii" "p",
     "dfd_head_fwd": "pppp" "iii" "pp" "ff" "pppp" "p",
     "dfd_head_bwd": "pppppp" "iii" "p",
-    "dfd_sgd_step": "ppp" "l" "fffi" "f" "ppp" "i" "p",
-    "dfd_adam_step": "pppp" "l" "fffff" "ii" "f" "ppp" "i" "p",
-    "dfd_rmsprop_tf_step": "pppp" "l" "fffff" "f" "ppp" "i" "p",
+    "dfd_sgd_step": "ppp" "l" "fffi" "f" "ppp" "i" "p" "p",
+    "dfd_adam_step": "pppp" "l" "fffff" "ii" "f" "ppp" "i" "pp" "p",
+    "dfd_rmsprop_tf_step": "pppp" "l" "fffff" "f" "ppp" "i" "p" "p",
+    "dfd_opt_tick": "pp" "p",
+    "dfd_set_floats": "pi" "ffffffff" "p",
+    "dfd_ema_update": "ppl" "ppi" "f" "p",
+    "dfd_input_normalize": "pppp" "iiii" "i" "p",
+    "dfd_rng_masks": "pip" "p",
+    "dfd_rng_tick": "p" "p",
+    "dfd_mul_f32": "ppl" "p",
     "dfd_cast_arena": "pp" "li" "p",
     "dfd_check_finite": "p" "l" "pp",
     "dfd_update_loss_scale": "ppp" "i" "pp",

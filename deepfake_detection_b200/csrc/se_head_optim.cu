@@ -233,9 +233,11 @@ __device__ __forceinline__ void store16(void* p16, size_t i, float v) {
 template <typename T16>
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, size_t n,
                            float lr, float momentum, float wd, int nesterov, float grad_scale,
-                           const float* __restrict__ gscale_dev, const int* __restrict__ skip, void* __restrict__ p16) {
+                           const float* __restrict__ gscale_dev, const int* __restrict__ skip, void* __restrict__ p16,
+                           const float* __restrict__ lr_dev) {
     if (skip && *skip) return;
     if (gscale_dev) grad_scale *= *gscale_dev;
+    if (lr_dev) lr = *lr_dev;          // device-resident learning rate: one captured graph survives every scheduler update
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         float w = p[i];
@@ -253,9 +255,16 @@ template <typename T16>
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
                             int decoupled, float bc1, float bc2_sqrt, float grad_scale,
-                            const float* __restrict__ gscale_dev, const int* __restrict__ skip, void* __restrict__ p16) {
+                            const float* __restrict__ gscale_dev, const int* __restrict__ skip, void* __restrict__ p16,
+                            const float* __restrict__ lr_dev, const int* __restrict__ step_dev) {
     if (skip && *skip) return;
     if (gscale_dev) grad_scale *= *gscale_dev;
+    if (lr_dev) lr = *lr_dev;
+    if (step_dev) {                    // bias corrections from the device step counter (advanced by dfd_opt_tick)
+        const float t = (float)*step_dev;
+        bc1 = 1.f - powf(b1, t);
+        bc2_sqrt = sqrtf(1.f - powf(b2, t));
+    }
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         float w = p[i];
@@ -277,9 +286,10 @@ template <typename T16>
 __global__ void rmsprop_tf_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq,
                                   float* __restrict__ mom, size_t n, float lr, float alpha, float eps, float wd,
                                   float momentum, float grad_scale, const float* __restrict__ gscale_dev,
-                                  const int* __restrict__ skip, void* __restrict__ p16) {
+                                  const int* __restrict__ skip, void* __restrict__ p16, const float* __restrict__ lr_dev) {
     if (skip && *skip) return;
     if (gscale_dev) grad_scale *= *gscale_dev;
+    if (lr_dev) lr = *lr_dev;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         float w = p[i];
@@ -298,6 +308,31 @@ __global__ void rmsprop_tf_kernel(float* __restrict__ p, const float* __restrict
         p[i] = w;
         store16<T16>(p16, i, w);
     }
+}
+
+// optimizer step counter on the device: advances unless the step is skipped (fp16 overflow), so Adam's bias correction
+// follows apex semantics (a skipped step is not a step)
+__global__ void opt_tick_kernel(int* __restrict__ step, const int* __restrict__ skip) {
+    if (skip && *skip) return;
+    *step += 1;
+}
+
+// up to 8 host scalars -> device floats (values travel as kernel arguments: nothing on the host has to stay alive)
+struct F8 { float v[8]; };
+__global__ void set_floats_kernel(float* __restrict__ dst, int n, F8 f) {
+    if ((int)threadIdx.x < n) dst[threadIdx.x] = f.v[threadIdx.x];
+}
+
+// ModelEma.update (dfd/timm/utils.py:329-340) over a flat arena: ema = ema * decay + (1 - decay) * model
+__global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ p, size_t n, float decay) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    const float om = 1.f - decay;
+    for (; i < n; i += stride) ema[i] = ema[i] * decay + om * p[i];
+}
+// num_batches_tracked entries (int64): the reference computes in float and copy_() truncates back to int64
+__global__ void ema_i64_kernel(long long* __restrict__ ema, const long long* __restrict__ p, int n, float decay) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ema[i] = (long long)((float)ema[i] * decay + (1.f - decay) * (float)p[i]);
 }
 
 template <typename T16>
@@ -427,29 +462,53 @@ int dfd_head_bwd(const float* dlogits, const float* pooled, const float* W, floa
     else { typedef bf16 T16; __VA_ARGS__; }
 
 int dfd_sgd_step(float* p, const float* g, float* m, long long n, float lr, float momentum, float wd, int nesterov,
-                 float grad_scale, const float* gscale_dev, const int* skip, void* p16, int dt, void* stream) {
+                 float grad_scale, const float* gscale_dev, const int* skip, void* p16, int dt, const float* lr_dev,
+                 void* stream) {
     if (n <= 0) return DFD_OK;
-    DISPATCH_16(dt, (sgd_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, (size_t)n, lr, momentum, wd, nesterov, grad_scale, gscale_dev, skip, p16)));
+    DISPATCH_16(dt, (sgd_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, (size_t)n, lr, momentum, wd, nesterov, grad_scale, gscale_dev, skip, p16, lr_dev)));
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }
 
 int dfd_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                   float wd, int decoupled, int step, float grad_scale, const float* gscale_dev, const int* skip, void* p16,
-                  int dt, void* stream) {
+                  int dt, const float* lr_dev, const int* step_dev, void* stream) {
     if (n <= 0) return DFD_OK;
     float bc1 = 1.f - powf(b1, (float)step);
     float bc2s = sqrtf(1.f - powf(b2, (float)step));
-    DISPATCH_16(dt, (adam_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (size_t)n, lr, b1, b2, eps, wd, decoupled, bc1, bc2s, grad_scale, gscale_dev, skip, p16)));
+    DISPATCH_16(dt, (adam_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (size_t)n, lr, b1, b2, eps, wd, decoupled, bc1, bc2s, grad_scale, gscale_dev, skip, p16, lr_dev, step_dev)));
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }
 
 int dfd_rmsprop_tf_step(float* p, const float* g, float* sq, float* mom, long long n, float lr, float alpha,
                         float eps, float wd, float momentum, float grad_scale, const float* gscale_dev, const int* skip,
-                        void* p16, int dt, void* stream) {
+                        void* p16, int dt, const float* lr_dev, void* stream) {
     if (n <= 0) return DFD_OK;
-    DISPATCH_16(dt, (rmsprop_tf_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, sq, mom, (size_t)n, lr, alpha, eps, wd, momentum, grad_scale, gscale_dev, skip, p16)));
+    DISPATCH_16(dt, (rmsprop_tf_kernel<T16><<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, sq, mom, (size_t)n, lr, alpha, eps, wd, momentum, grad_scale, gscale_dev, skip, p16, lr_dev)));
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_opt_tick(int* step_dev, const int* skip, void* stream) {
+    opt_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, skip);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_set_floats(float* dst, int n, float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7,
+                   void* stream) {
+    if (n < 0 || n > 8) return dfd_set_error(DFD_ERR_ARG, "dfd_set_floats: n in [0,8]");
+    F8 f = {{v0, v1, v2, v3, v4, v5, v6, v7}};
+    set_floats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(dst, n, f);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+int dfd_ema_update(float* ema, const float* p, long long n, long long* ema_i64, const long long* p_i64, int n_i64,
+                   float decay, void* stream) {
+    if (n > 0) ema_kernel<<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(ema, p, (size_t)n, decay);
+    if (n_i64 > 0) ema_i64_kernel<<<cdiv(n_i64, 128), 128, 0, (cudaStream_t)stream>>>(ema_i64, p_i64, n_i64, decay);
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

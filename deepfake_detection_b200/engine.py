@@ -35,7 +35,8 @@ class _BN:
 
 class Engine:
     def __init__(self, arch, batch, height=None, width=None, num_classes=2, in_chans=3, dtype="bf16",
-                 bn_momentum=0.1, bn_eps=1e-5, device=None, gemm_impl="tc", share_from=None, stem_impl="gemm"):
+                 bn_momentum=0.1, bn_eps=1e-5, device=None, gemm_impl="tc", share_from=None, stem_impl="gemm",
+                 params_only=False, drop_rate=0.0, drop_path_rate=0.0):
         # _plan_only: build the arenas and the call plan on the CPU for host-logic tests; nothing can be executed
         self._plan_only = device == "plan-only"
         if self._plan_only:
@@ -50,8 +51,14 @@ class Engine:
         self.N = int(batch)
         self.H = int(height or spec.input_size[1])
         self.W = int(width or spec.input_size[2])
-        self.dt = _lib.DT_BF16 if dtype in ("bf16", torch.bfloat16) else _lib.DT_FP16
-        self.tdtype = torch.bfloat16 if self.dt == _lib.DT_BF16 else torch.float16
+        if dtype in ("bf16", "bfloat16", torch.bfloat16):
+            self.dt, self.tdtype = _lib.DT_BF16, torch.bfloat16
+        elif dtype in ("fp16", "float16", "half", torch.float16):
+            self.dt, self.tdtype = _lib.DT_FP16, torch.float16
+        else:
+            raise ValueError("dtype %r: the native path computes in 'bf16' or 'fp16' (fp32 master weights)" % (dtype,))
+        self.drop_rate = float(drop_rate)
+        self.drop_path_rate = float(drop_path_rate)
         self.bn_momentum = float(bn_momentum)
         self.bn_eps = float(bn_eps)
         self.gemm_impl = gemm_impl
@@ -66,14 +73,27 @@ class Engine:
             # gradients and running statistics
             if share_from.spec.arch != spec.arch or share_from.dt != self.dt:
                 raise ValueError("share_from: architecture / dtype mismatch")
+            share_from = self._shared_from = share_from.arena
             for a in ("p_off", "n_decay", "n_params", "param_names", "params32", "grads32", "params16", "b_off", "bn_names",
-                      "buffers32", "nbt", "t_off", "paramsT16", "_ttable", "_ttable_count", "loss_scale_state", "flags"):
+                      "buffers32", "nbt", "t_off", "paramsT16", "_ttable", "_ttable_count", "loss_scale_state", "flags",
+                      "rng_state"):
                 setattr(self, a, getattr(share_from, a))
         else:
             self._layout_params()
+            self.loss_scale_state = torch.ones(2, dtype=torch.float32, device=self.device)   # scale, 1/scale
+            self.flags = torch.zeros(2, dtype=torch.int32, device=self.device)              # found_inf, good_steps
+            # counter-based generator state of the dropout / drop-path masks: [seed, step]; the step advances on the device
+            self.rng_state = torch.zeros(2, dtype=torch.int64, device=self.device)
+            self.rng_state[0] = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF          # follows torch.manual_seed (train.py:299)
+            self._derived_dirty = False
+        self.params_only = bool(params_only)
+        if self.params_only:
+            # the owner of the parameter / gradient / running-statistic arenas without any activation plan: what
+            # `NativeModel.engine`, the optimizer and the EMA need (a plan is built per (batch, H, W) that reaches forward)
+            self.fwd_ops, self.bwd_ops = [], []
+            return
         self._build()
-        if share_from is not None and not self._plan_only and getattr(share_from, "_bd_reg", None) and \
-                getattr(share_from, "_bd_table", None) is None:
+        if not self._plan_only and self.arena._derived_dirty:
             # this plan registered new derived weight layouts with the owner: fill them now (never inside a graph capture)
             self.refresh_weight_layouts(torch.cuda.current_stream().cuda_stream)
 
@@ -129,6 +149,11 @@ class Engine:
                        for n, (o, O, I) in self.t_off.items())
         self._ttable = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         self._ttable_count = len(self.t_off)
+
+    @property
+    def arena(self):
+        """the engine that owns the weights, gradients, running statistics and derived weight layouts"""
+        return self._shared_from if self._shared_from is not None else self
 
     def param_view(self, name):
         o, s, n = self.p_off[name]
@@ -202,44 +227,48 @@ class Engine:
             pack //= 2
         return pack
 
+    # Derived 16-bit weight layouts (block-diagonal small-K copies, the padded stem weight, the packed k x k weights of
+    # the ResNet path) are registered with, owned by and refreshed through the ARENA engine, whichever plan asked for them:
+    # the optimizer refreshes them once per step for every plan that shares the weights.
     def _blockdiag(self, B, Nn, K, pack):
-        """block-diagonal [pack*Nn, pack*K] copy of the weight at B; owned (and refreshed) by the primary engine"""
-        o = self._shared_from if self._shared_from is not None else self
+        """block-diagonal [pack*Nn, pack*K] copy of the weight at B"""
+        o = self.arena
         reg = o.__dict__.setdefault("_bd_reg", OrderedDict())
         key = (B, Nn, K, pack)
         if key not in reg:
             reg[key] = torch.zeros(pack * Nn * pack * K, dtype=self.tdtype, device=self.device)
             o._bd_table = None
+            o._derived_dirty = True
         return _ptr(reg[key])
 
     def refresh_weight_layouts(self, stream):
         """derived 16-bit weight layouts (transposed 1x1, packed k x k, block-diagonal small-K) from the 16-bit arena"""
-        _lib.call("dfd_transpose_weights", _ptr(self._ttable), self._ttable_count, self.dt, stream)
-        o = self._shared_from if self._shared_from is not None else self
+        o = self.arena
+        _lib.call("dfd_transpose_weights", _ptr(o._ttable), o._ttable_count, o.dt, stream)
         reg = getattr(o, "_bd_reg", None)
+        if reg and getattr(o, "_bd_table", None) is None:
+            import struct
+            raw = b"".join(struct.pack("<QQiiii", B, _ptr(t), Nn, K, pack, 0) for (B, Nn, K, pack), t in reg.items())
+            o._bd_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(o.device)
+        if getattr(o, "_rtable_count", 0):
+            _lib.call("dfd_repack_weights", _ptr(o._rtable), o._rtable_count, o.dt, stream)
+        for (name, O, taps, Kp), wpad in getattr(o, "_stem_reg", {}).items():
+            _lib.call("dfd_pad_weight", _ptr(o.params16, o.p_off[name][0]), _ptr(wpad), O, taps, Kp, o.dt, stream)
         if reg:
-            if getattr(o, "_bd_table", None) is None:
-                import struct
-                raw = b"".join(struct.pack("<QQiiii", B, _ptr(t), Nn, K, pack, 0) for (B, Nn, K, pack), t in reg.items())
-                o._bd_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
-        if getattr(self, "_rtable_count", 0):
-            _lib.call("dfd_repack_weights", _ptr(self._rtable), self._rtable_count, self.dt, stream)
-        if getattr(self, "_stem_pad", None) is not None:
-            name, O, taps, Kp = self._stem_pad
-            _lib.call("dfd_pad_weight", _ptr(self.params16, self.p_off[name][0]), _ptr(self.stem_wpad), O, taps, Kp, self.dt, stream)
-        if reg:
-            _lib.call("dfd_blockdiag_weights", _ptr(o._bd_table), len(reg), self.dt, stream)
+            _lib.call("dfd_blockdiag_weights", _ptr(o._bd_table), len(reg), o.dt, stream)
+        o._derived_dirty = False
 
     def _stem_gemm_setup(self, wname, Cout, k, M):
         """stem convolution as im2col + tcgen05 GEMM (K = Cin*k*k padded to a multiple of 8)"""
         taps = self.spec.in_chans * k * k
         Kp = (taps + 7) // 8 * 8
-        self._stem_pad = (wname, Cout, taps, Kp)
-        if self._shared_from is not None and getattr(self._shared_from, "stem_wpad", None) is not None:
-            self.stem_wpad = self._shared_from.stem_wpad      # derived weight layouts are refreshed through the owner
-            self._stem_pad = None
-        else:
-            self.stem_wpad = torch.zeros(Cout * Kp, dtype=self.tdtype, device=self.device)
+        o = self.arena
+        reg = o.__dict__.setdefault("_stem_reg", OrderedDict())
+        key = (wname, Cout, taps, Kp)
+        if key not in reg:
+            reg[key] = torch.zeros(Cout * Kp, dtype=self.tdtype, device=self.device)
+            o._derived_dirty = True
+        self.stem_wpad = reg[key]
         self.stem_gpad = torch.zeros(Cout * Kp, dtype=torch.float32, device=self.device)
         self.stem_cols = self._alloc16(M, Kp)
         return taps, Kp
@@ -269,9 +298,6 @@ class Engine:
             co += (c + 3) // 4 * 4
             self.bns[name] = bn
         self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)     # loss_acc, correct_acc, (spare)
-        if not hasattr(self, "loss_scale_state"):      # shared between plans over the same weights (share_from)
-            self.loss_scale_state = torch.ones(2, dtype=torch.float32, device=dev)   # scale, 1/scale
-            self.flags = torch.zeros(2, dtype=torch.int32, device=dev)          # found_inf, good_steps
 
 
     def _build(self):
@@ -371,7 +397,14 @@ class Engine:
                                    ACT_SWISH, 0, dt)))
         x = stem_out
         recs = []
-        for b, h, w, ho, wo in blocks:
+        # stochastic regularisation (train mode only): per-sample drop-path scale of every residual block
+        # (rate = drop_path_rate * block_idx / n_blocks, efficientnet_builder.py:228-230,343) and the classifier dropout mask;
+        # the gates are [N, C] fp32 tensors (one draw per sample replicated over the channels) filled by ONE dfd_rng_masks
+        # launch at the head of the forward plan, consumed through the GATE operand of dfd_bn_act
+        masks = []               # (tensor, rows, width, keep_prob)
+        n_blocks = len(blocks)
+        ones_c = zeros_c = None
+        for bi, (b, h, w, ho, wo) in enumerate(blocks):
             p = b.name
             M1, M2 = N * h * w, N * ho * wo
             rec = dict(b=b, h=h, w=w, ho=ho, wo=wo, x=x)
@@ -412,9 +445,16 @@ class Engine:
             fwd.append(finalize(bn_out, M2))
             out = self._alloc16(N, ho, wo, b.cout)
             self.acts[p + ".out"] = out
-            fwd.append(("dfd_bn_act", (_ptr(y3), bn_out.scale, bn_out.shift, None, _ptr(x) if b.has_residual else None,
-                                       _ptr(out), N, ho * wo, b.cout, ACT_NONE, 1 if b.has_residual else 0, dt)))
-            rec.update(y2=y2, a2=a2, y3=y3, out=out, dw_bn=dw_bn, bn_mid=bn_mid, bn_out=bn_out, pw_name=pw_name)
+            dp_rate = self.drop_path_rate * bi / n_blocks if b.has_residual else 0.0
+            dp_gate = None
+            if dp_rate > 0.0:
+                dp_gate = torch.ones(N, b.cout, dtype=torch.float32, device=dev)
+                self._keep.append(dp_gate)
+                masks.append((dp_gate, N, b.cout, 1.0 - dp_rate))
+            fwd.append(("dfd_bn_act", [_ptr(y3), bn_out.scale, bn_out.shift, ("TRAIN_ONLY", _ptr(dp_gate)) if dp_gate is not None else None,
+                                       _ptr(x) if b.has_residual else None,
+                                       _ptr(out), N, ho * wo, b.cout, ACT_NONE, 1 if b.has_residual else 0, dt]))
+            rec.update(y2=y2, a2=a2, y3=y3, out=out, dw_bn=dw_bn, bn_mid=bn_mid, bn_out=bn_out, pw_name=pw_name, dp_gate=dp_gate)
             recs.append(rec)
             x = out
         # head
@@ -428,6 +468,23 @@ class Engine:
         self.pooled = torch.zeros(N, F, dtype=torch.float32, device=dev)
         fwd.append(("dfd_pool", (_ptr(yh), bnh.scale, bnh.shift, _ptr(self.pooled), N, Hf * Wf, F, ACT_SWISH, dt,
                              _ptr(self.pool_partial), POOL_CHUNKS)))
+        self.drop_masks = OrderedDict()
+        if self.drop_rate > 0.0:
+            self.dropout_mask = torch.ones(N, F, dtype=torch.float32, device=dev)
+            masks.append((self.dropout_mask, N * F, 1, 1.0 - self.drop_rate))
+            fwd.append(("dfd_mul_f32_train", (_ptr(self.pooled), _ptr(self.dropout_mask), N * F)))
+        for r_ in recs:
+            if r_["dp_gate"] is not None:
+                self.drop_masks[r_["b"].name] = r_["dp_gate"]
+        if masks:
+            import struct
+            raw = b"".join(struct.pack("<Qqifii", _ptr(t), rows, width, keep, si, 0) for si, (t, rows, width, keep) in enumerate(masks))
+            self._mask_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+            fwd.insert(0, ("dfd_rng_masks_train", (_ptr(self._mask_table), len(masks), _ptr(self.rng_state))))
+            fwd.insert(1, ("dfd_rng_tick_train", (_ptr(self.rng_state),)))
+            cmax = max(t.shape[-1] for t, _, _, _ in masks)
+            self._unit_affine = torch.cat([torch.ones(cmax, device=dev), torch.zeros(cmax, device=dev)]).float()
+            self._keep.append(self._unit_affine)
         K = spec.num_classes
         self.logits = torch.zeros(N, K, dtype=torch.float32, device=dev)
         self.dlogits = torch.zeros(N, K, dtype=torch.float32, device=dev)
@@ -439,6 +496,8 @@ class Engine:
         # ---- backward ----------------------------------------------------------------------------
         bwd.append(("dfd_head_bwd", (_ptr(self.dlogits), _ptr(self.pooled), P32("classifier.weight"),
                                      G32("classifier.weight"), G32("classifier.bias"), _ptr(self.dpooled), N, F, K)))
+        if self.drop_rate > 0.0:
+            bwd.append(("dfd_mul_f32", (_ptr(self.dpooled), _ptr(self.dropout_mask), N * F)))
         bwd.append(("dfd_act_bwd", (None, _ptr(yh), bnh.scale, bnh.shift, bnh.mean, bnh.rstd, None, _ptr(self.dpooled),
                                     mid_a, N, Hf * Wf, F, ACT_SWISH, dt, bnh.bs1, bnh.bs2)))
         bwd.append(bwd_finalize(bnh, Mf))
@@ -454,10 +513,18 @@ class Engine:
             y2, a2, y3 = rec["y2"], rec["a2"], rec["y3"]
             dout = sm[cur]
             t1, t2 = sm[(cur + 1) % 3], sm[(cur + 2) % 3]
-            bwd.append(("dfd_bn_bwd_reduce", (dout, _ptr(y3), None, bn_out.mean, bn_out.rstd, N, ho * wo, b.cout, dt,
+            gbn = dout
+            if rec["dp_gate"] is not None:
+                # drop path: the gradient reaching bn3 is dout * mask / keep (the identity branch keeps dout itself); one extra
+                # pass through the gated streaming kernel with a unit affine, only in this regularised configuration
+                cm = self._unit_affine.numel() // 2
+                bwd.append(("dfd_bn_act", (dout, _ptr(self._unit_affine), _ptr(self._unit_affine, cm), _ptr(rec["dp_gate"]), None, t2,
+                                           N, ho * wo, b.cout, ACT_NONE, 0, dt)))
+                gbn = t2
+            bwd.append(("dfd_bn_bwd_reduce", (gbn, _ptr(y3), None, bn_out.mean, bn_out.rstd, N, ho * wo, b.cout, dt,
                                               bn_out.bs1, bn_out.bs2)))
             bwd.append(bwd_finalize(bn_out, M2))
-            bwd.append(("dfd_bn_bwd_apply", (dout, _ptr(y3), None, bn_out.cA, bn_out.cB, bn_out.cC, t1, N, ho * wo, b.cout, dt)))
+            bwd.append(("dfd_bn_bwd_apply", (gbn, _ptr(y3), None, bn_out.cA, bn_out.cB, bn_out.cC, t1, N, ho * wo, b.cout, dt)))
             bwd.append(gemm(t1, T16(p + pw_name + ".weight"), mid_a, M2, b.cmid, b.cout))
             bwd.append((self._wgrad_name, (t1, _ptr(a2), G32(p + pw_name + ".weight"), M2, b.cout, b.cmid, dt)))
             gate_ptr = dpool_ptr = None
@@ -519,15 +586,19 @@ class Engine:
             bwd.append(("dfd_stem_wgrad", (_ptr(self.x_in), mid_a, _ptr(y0), bn.cA, bn.cB, bn.cC, G32("conv_stem.weight"), N,
                                            spec.in_chans, self.H, self.W, spec.stem, 3, 2, 1, dt)))
         for n, a in fwd + bwd:      # arity / type check of the plan against the ABI table
-            codes = _lib.SIGNATURES[n]
+            codes = _lib.SIGNATURES[n[:-6] if n.endswith("_train") else n]
             if len(a) != len(codes) - 1:
                 raise AssertionError("%s: %d args for signature %r" % (n, len(a), codes))
             for v, c in zip(a, codes):
+                if isinstance(v, tuple) and v[0] == "TRAIN_ONLY":
+                    v = v[1]
                 ok = (v is None or isinstance(v, int)) if c == "p" else (
                     isinstance(v, int) if c in "il" else (isinstance(v, (int, float)) or v == "TRAINING"))
                 if not (ok or v == "TRAINING"):
                     raise AssertionError("%s: argument %r does not fit code %r" % (n, v, c))
-        self.fwd_ops = [(getattr(L, n), n, a) for n, a in fwd]
+        # `<name>_train` ops run in training mode only (mask generation, dropout); ("TRAIN_ONLY", ptr) operands are NULL in eval
+        fwd = [(n, a) for n, a in fwd]
+        self.fwd_ops = [(getattr(L, n[:-6] if n.endswith("_train") else n), n, a) for n, a in fwd]
         self.bwd_ops = [(getattr(L, n), n, tuple(a)) for n, a in bwd]
         self.n_launch["fwd"] = len(fwd)
         self.n_launch["bwd"] = len(bwd)
@@ -540,6 +611,11 @@ class Engine:
             raise _lib.NativeError("plan-only engine cannot execute (no CUDA device)")
         L = self.L
         for fn, name, args in ops:
+            if name.endswith("_train"):
+                if not training:
+                    continue
+            elif name == "dfd_bn_act" and any(isinstance(a, tuple) for a in args):
+                args = tuple((a[1] if training else None) if isinstance(a, tuple) else a for a in args)
             if name == "dfd_bn_finalize":
                 args = tuple((1 if training else 0) if a == "TRAINING" else a for a in args)
                 if not training:

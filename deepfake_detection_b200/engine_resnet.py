@@ -33,16 +33,16 @@ def build_resnet(e):
         if len(s) == 4 and s[2] > 1 and not n.startswith("conv1."):
             pk_off[n] = (off, s[0], s[1], s[2])
             off += (k + 7) // 8 * 8
-    if e._shared_from is not None:
-        e.wpack16, e.wpackT16 = e._shared_from.wpack16, e._shared_from.wpackT16     # refreshed through the owner engine
-        e._rtable_count = 0
-    else:
-        e.wpack16 = torch.zeros(max(off, 8), dtype=e.tdtype, device=dev)
-        e.wpackT16 = torch.zeros(max(off, 8), dtype=e.tdtype, device=dev)
-        raw = b"".join(struct.pack("<QQQiiii", _ptr(e.params16, e.p_off[n][0]), _ptr(e.wpack16, o), _ptr(e.wpackT16, o), O, I, k, 0)
+    ar = e.arena        # the packed layouts depend on the parameter shapes only: owned and refreshed by the arena engine
+    if getattr(ar, "wpack16", None) is None:
+        ar.wpack16 = torch.zeros(max(off, 8), dtype=e.tdtype, device=dev)
+        ar.wpackT16 = torch.zeros(max(off, 8), dtype=e.tdtype, device=dev)
+        raw = b"".join(struct.pack("<QQQiiii", _ptr(e.params16, e.p_off[n][0]), _ptr(ar.wpack16, o), _ptr(ar.wpackT16, o), O, I, k, 0)
                        for n, (o, O, I, k) in pk_off.items())
-        e._rtable = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
-        e._rtable_count = len(pk_off)
+        ar._rtable = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        ar._rtable_count = len(pk_off)
+        ar._derived_dirty = True
+    e.wpack16, e.wpackT16 = ar.wpack16, ar.wpackT16
     e.gperm = torch.zeros(max([O * I * k * k for (_, O, I, k) in pk_off.values()] + [8]), dtype=torch.float32, device=dev)
 
     P32 = lambda n: _ptr(e.params32, e.p_off[n][0])

@@ -32,6 +32,7 @@ class _NativeForward(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, model, engine, training):
         ctx.engine = engine
+        ctx.model = model
         st = torch.cuda.current_stream().cuda_stream
         engine.zero_step_scratch(st, grads=False)
         engine.forward(training=training, stream=st)
@@ -42,7 +43,18 @@ class _NativeForward(torch.autograd.Function):
     def backward(ctx, dlogits):
         e = ctx.engine
         e.dlogits.copy_(dlogits)
-        e.backward()
+        red = ctx.model._reducer
+        if red is not None:
+            # data-parallel run: the backward of the plan that ran this forward, with the bucketed gradient mean
+            # overlapped on the reducer's side stream (what the reference's DDP wrapper does in its backward hooks)
+            red.backward_and_reduce(e)
+        else:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and not ctx.model.allow_local_grads:
+                raise _lib.NativeError("NativeModel.backward in a %d-rank job without a gradient reducer: wrap the model in "
+                                       "deepfake_detection_b200.ddp.NativeDDP (train.py:402-406) so that replicas do not "
+                                       "diverge silently" % dist.get_world_size())
+            e.backward()
         return None, None, None, None
 
 
@@ -76,8 +88,6 @@ class NativeModel(nn.Module):
     def __init__(self, arch, num_classes=2, in_chans=3, dtype="bf16", bn_momentum=None, bn_eps=None, bn_tf=False,
                  drop_rate=0.0, drop_path_rate=0.0, gemm_impl="tc", **unused):
         super().__init__()
-        if drop_rate or drop_path_rate:
-            raise _lib.NativeError("drop_rate / drop_path_rate > 0 are not on the native path yet (SURVEY.md 7.3: RNG parity)")
         if bn_tf:       # efficientnet_blocks.py:13-30
             bn_momentum = 1 - 0.99 if bn_momentum is None else bn_momentum
             bn_eps = 1e-3 if bn_eps is None else bn_eps
@@ -88,7 +98,14 @@ class NativeModel(nn.Module):
         self.bn_momentum = 0.1 if bn_momentum is None else bn_momentum
         self.bn_eps = 1e-5 if bn_eps is None else bn_eps
         self.gemm_impl = gemm_impl
+        self.drop_rate = float(drop_rate)              # efficientnet.py:346-347 (classifier dropout)
+        self.drop_path_rate = float(drop_path_rate)    # efficientnet_builder.py:322-323 (linear ramp over the blocks)
+        self.max_plans = 4                             # execution plans kept alive (LRU); each owns an activation arena
+        self.allow_local_grads = False
+        self._reducer = None
         self.spec = get_spec(arch, num_classes=num_classes, in_chans=in_chans)
+        if self.spec.family != "efficientnet" and (self.drop_rate or self.drop_path_rate):
+            raise _lib.NativeError("drop_rate / drop_path_rate are implemented for the EfficientNet family only")
         self.default_cfg = dict(_DEFAULT_CFG, input_size=self.spec.input_size,
                                 first_conv="conv_stem" if self.spec.family == "efficientnet" else "conv1",
                                 classifier="classifier" if self.spec.family == "efficientnet" else "fc")
@@ -99,30 +116,42 @@ class NativeModel(nn.Module):
         self._named = None
 
     # ---- engines ------------------------------------------------------------------------------------
-    def engine_for(self, n, h, w):
-        key = (int(n), int(h), int(w))
-        e = self._engines.get(key)
-        if e is None:
-            e = Engine(self.arch, key[0], key[1], key[2], num_classes=self.num_classes, in_chans=self.in_chans,
-                       dtype=self.dtype_name, bn_momentum=self.bn_momentum, bn_eps=self.bn_eps, gemm_impl=self.gemm_impl,
-                       share_from=self._primary)
-            if self._primary is None:
-                self._primary = e
-                if self._pending_state is not None:
-                    e.load_state_dict(self._pending_state, strict=False)
-                    self._pending_state = None
-                else:
-                    self._init_weights(e)
-            self._engines[key] = e
-        return e
+    def _engine_kwargs(self):
+        return dict(num_classes=self.num_classes, in_chans=self.in_chans, dtype=self.dtype_name, bn_momentum=self.bn_momentum,
+                    bn_eps=self.bn_eps, gemm_impl=self.gemm_impl, drop_rate=self.drop_rate, drop_path_rate=self.drop_path_rate)
 
     @property
     def engine(self):
-        """the primary engine (owner of the weight / gradient arenas); built for the default input size if needed"""
+        """the ARENA engine: owner of the weights, gradients, running statistics and derived weight layouts. It holds no
+        activation buffers and no kernel plan (those are built per input shape by `engine_for`), so touching it - which
+        `create_optimizer`, `named_parameters` and `state_dict` do - costs parameter memory only."""
         if self._primary is None:
-            c, h, w = self.spec.input_size
-            self.engine_for(1, h, w)
+            self._primary = Engine(self.arch, 1, params_only=True, **self._engine_kwargs())
+            if self._pending_state is not None:
+                self._primary.load_state_dict(self._pending_state, strict=False)
+                self._pending_state = None
+            else:
+                self._init_weights(self._primary)
         return self._primary
+
+    def engine_for(self, n, h, w):
+        """the execution plan for a (batch, H, W) input: built on first use, at most `max_plans` kept (least recently used
+        evicted together with every CUDA graph / trainer view captured over it)"""
+        key = (int(n), int(h), int(w))
+        e = self._engines.get(key)
+        if e is None:
+            arena = self.engine
+            while len(self._engines) >= self.max_plans:
+                old_key, old = self._engines.popitem(last=False)
+                for tk in [k for k in self.__dict__.get("_trainers", {}) if k[0] == id(old)]:
+                    del self.__dict__["_trainers"][tk]
+                if self._reducer is not None:
+                    self._reducer._plans.pop(id(old), None)
+            e = Engine(self.arch, key[0], key[1], key[2], share_from=arena, **self._engine_kwargs())
+            self._engines[key] = e
+        else:
+            self._engines.move_to_end(key)
+        return e
 
     def _init_weights(self, e):
         e.load_state_dict(init_state_dict(self.spec))
@@ -131,6 +160,9 @@ class NativeModel(nn.Module):
     def forward(self, x):
         if x.dim() != 4:
             raise ValueError("expected NCHW input")
+        if self.__dict__.get("_weights_dirty", False):
+            self.engine.sync_weights()          # fp32 master changed out of band (ModelEma.update): refresh the 16-bit copies
+            self._weights_dirty = False
         e = self.engine_for(x.shape[0], x.shape[2], x.shape[3])
         e.set_input(x)
         if torch.is_grad_enabled() and self.training:
@@ -167,13 +199,41 @@ class NativeModel(nn.Module):
         return missing
 
     def cuda(self, device=None):
+        """train.py:346 `model.cuda()`: the arenas are created on the current CUDA device; a different index is refused"""
+        if device is not None and self._primary is not None:
+            idx = torch.device("cuda", device).index if isinstance(device, int) else torch.device(device).index
+            if idx is not None and idx != self._primary.device.index:
+                raise _lib.NativeError("NativeModel lives on %s; cannot move it to cuda:%d" % (self._primary.device, idx))
         return self
 
     def half(self):
+        """test.py:47 `model.half()`: switches the compute dtype to fp16 (only before the first plan exists)"""
+        if self.dtype_name not in ("fp16", "float16", "half", torch.float16):
+            if self._primary is not None:
+                raise _lib.NativeError("NativeModel.half(): the model was already materialised in %r; pass dtype='fp16' to the "
+                                       "factory instead" % (self.dtype_name,))
+            self.dtype_name = "fp16"
         return self
 
     def get_classifier(self):
-        raise NotImplementedError("the classifier lives in the engine arenas; use state_dict()")
+        """efficientnet.py:307-308 / resnet.py:426-427: the classifier as an nn.Linear whose tensors alias the arenas"""
+        e = self.engine
+        fc = nn.Linear(self.spec.num_features, self.num_classes)
+        fc.weight = nn.Parameter(e.param_view(e.cls_name + ".weight"))
+        fc.bias = nn.Parameter(e.param_view(e.cls_name + ".bias"))
+        return fc
+
+    def __deepcopy__(self, memo):
+        """ModelEma deep-copies the model (utils.py:300): the copy owns fresh arenas holding the same state"""
+        kw = dict(num_classes=self.num_classes, in_chans=self.in_chans, dtype=self.dtype_name, bn_momentum=self.bn_momentum,
+                  bn_eps=self.bn_eps, drop_rate=self.drop_rate, drop_path_rate=self.drop_path_rate, gemm_impl=self.gemm_impl)
+        m = NativeModel(self.arch, **kw)
+        m.training = self.training
+        if self._primary is not None:
+            m.load_state_dict(self.state_dict())
+        elif self._pending_state is not None:
+            m._pending_state = self._pending_state
+        return m
 
 
 def create_model(model_name, pretrained=False, num_classes=1000, in_chans=3, checkpoint_path="", **kwargs):

@@ -74,7 +74,8 @@ def train_epoch(epoch, model, loader, optimizer, loss_fn, args, lr_scheduler=Non
     def drain():
         for stats, n in pending:
             vals = stats.tolist()
-            losses_m.update(vals[0], n)
+            if vals[0] == vals[0]:                 # train.py:642-643: a NaN loss is not averaged in
+                losses_m.update(vals[0], n)
             prec1_m.update(vals[1], n)
         del pending[:]
 
@@ -83,6 +84,10 @@ def train_epoch(epoch, model, loader, optimizer, loss_fn, args, lr_scheduler=Non
         data_time_m.update(time.time() - end)
         if not args.prefetcher:
             input, target = input.cuda(non_blocking=True), target.cuda(non_blocking=True)
+            if args.mixup > 0.:                                                    # train.py:615-619
+                input, target = mixup_batch(input, target, alpha=args.mixup, num_classes=args.num_classes,
+                                            smoothing=args.smoothing,
+                                            disable=bool(args.mixup_off_epoch and epoch >= args.mixup_off_epoch))
         n = input.size(0)
         if fused:
             e = m.engine_for(n, input.shape[2], input.shape[3])
@@ -116,12 +121,28 @@ def train_epoch(epoch, model, loader, optimizer, loss_fn, args, lr_scheduler=Non
         if saver is not None and args.recovery_interval and (last_batch or (batch_idx + 1) % args.recovery_interval == 0):
             saver.save_recovery(model, optimizer, args, epoch, model_ema=model_ema, use_amp=use_amp, batch_idx=batch_idx)
         if lr_scheduler is not None:
+            # the metric the reference passes is the running loss average (train.py:695); it is only as fresh as the last
+            # drain - none of the reference's per-update schedulers (cosine / step / tanh) reads it
             lr_scheduler.step_update(num_updates=num_updates, metric=losses_m.avg)
         end = time.time()
     drain()
     if hasattr(optimizer, "sync_lookahead"):
         optimizer.sync_lookahead()
     return OrderedDict([("loss", losses_m.avg), ("prec1", prec1_m.avg), ("learning_rate", lr)])
+
+
+def mixup_batch(input, target, alpha=0.2, num_classes=1000, smoothing=0.1, disable=False):
+    """dfd/timm/data/mixup.py:10-24: one lambda per batch, images mixed with the flipped batch, float [N, C] targets"""
+    import numpy as np
+    lam = 1.0
+    if not disable:
+        lam = float(np.random.beta(alpha, alpha))
+    input = input.mul(lam).add_(input.flip(0), alpha=1.0 - lam)
+    off = smoothing / num_classes
+    on = 1.0 - smoothing + off
+    y1 = torch.full((target.size(0), num_classes), off, device=target.device).scatter_(1, target.long().view(-1, 1), on)
+    y2 = torch.full((target.size(0), num_classes), off, device=target.device).scatter_(1, target.flip(0).long().view(-1, 1), on)
+    return input, lam * y1 + (1.0 - lam) * y2
 
 
 def _trainer_for(model, engine, optimizer, loss_fn):
@@ -134,10 +155,11 @@ def _trainer_for(model, engine, optimizer, loss_fn):
         tr = Trainer.__new__(Trainer)
         tr.engine, tr.optimizer = engine, optimizer
         tr.smoothing = float(loss_fn.native_smoothing)
-        tr.use_graph = optimizer.kind in ("sgd", "rmsproptf")
+        tr.use_graph = True
         tr._graph = tr._graph_key = None
+        tr.n_captures = 0
         tr.scale_window = 2000
-        tr.dynamic_scale = model.dtype_name in ("fp16", torch.float16)      # apex O1 semantics for half precision
+        tr.dynamic_scale = model.dtype_name in ("fp16", "float16", "half", torch.float16)      # apex O1 semantics for half precision
         if tr.dynamic_scale and optimizer.gscale_dev is None:
             from ..engine import _ptr
             e0 = model.engine

@@ -36,21 +36,21 @@ class Trainer:
             e0.loss_scale_state.copy_(torch.tensor([65536.0, 1.0 / 65536.0]))
             self.optimizer.gscale_dev = _ptr(e0.loss_scale_state, 1)
             self.optimizer.skip_flag = _ptr(e0.flags, 0)
-        self.use_graph = bool(use_graph) and self.optimizer.kind in ("sgd", "rmsproptf")
+        # every optimizer is graph-captured: learning rates and Adam's step count are device-resident (optim.py)
+        self.use_graph = bool(use_graph)
         self._graph = None
         self._graph_key = None
+        self.n_captures = 0
         self.reducer = None
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
             from .ddp import GradReducer
-            self.reducer = GradReducer(self.engine, process_group, bucket_mb=bucket_mb)
-            self.optimizer.grad_scale = 1.0 / dist.get_world_size(process_group)
+            self.reducer = GradReducer(self.engine, process_group, bucket_mb=bucket_mb)     # takes the MEAN itself
             self.reducer.broadcast_parameters()
-        # pinned staging for the host-buffer (end-to-end) entry point
-        e = self.engine
-        self._pin_x = torch.empty(e.x_in.shape, dtype=e.tdtype).pin_memory()
-        self._pin_y = torch.empty(e.N, dtype=torch.int64).pin_memory()
+        # host-buffer (end-to-end) entry point: uint8 batches are uploaded on a copy stream into two recycled staging
+        # buffers and normalised on the compute stream, so the upload of step i+1 overlaps the kernels of step i
         self._pin_out = torch.empty(4, dtype=torch.float32).pin_memory()
+        self._h2d = None
 
     # ---- state ------------------------------------------------------------------------------------
     def state_dict(self):
@@ -68,22 +68,23 @@ class Trainer:
         e.head(True, smoothing=self.smoothing, soft=soft, stream=st,
                loss_scale_dev=_ptr(e.loss_scale_state, 0) if self.dynamic_scale else None)
         if self.reducer is not None:
-            self.reducer.backward_and_reduce()
+            self.reducer.backward_and_reduce(e)
         else:
             e.backward(stream=st)
         if self.dynamic_scale:
             _lib.call("dfd_check_finite", _ptr(e.grads32), e.n_params, _ptr(e.flags, 0), st)
-        self.optimizer.step(stream=st)
+        self.optimizer.step(stream=st, push=False)      # learning rates were pushed to the device before the launch / replay
         if self.dynamic_scale:
             _lib.call("dfd_update_loss_scale", _ptr(e.flags, 0), _ptr(e.loss_scale_state, 0), _ptr(e.flags, 1),
                       self.scale_window, _ptr(e.loss_scale_state, 1), st)
 
     def _graph_signature(self, soft):
-        return (soft, self.smoothing, tuple((g["lr"], g["momentum"], g["weight_decay"]) for g in self.optimizer.param_groups),
-                self.optimizer.grad_scale)
+        # the learning rate is NOT part of the key: it is read from device memory by the update kernels
+        return (soft, self.smoothing, self.optimizer.hyper_signature())
 
     def step_resident(self, soft=False):
         """One full train step on the batch already resident in engine.x_in / target_i|target_f."""
+        self.optimizer.push_hyper()          # param_groups[i]['lr'] of THIS step -> device (outside the captured graph)
         if not self.use_graph:
             self._launch_step(soft)
             return
@@ -96,6 +97,7 @@ class Trainer:
             with torch.cuda.graph(g):
                 self._launch_step(soft)
             self._graph, self._graph_key = g, key
+            self.n_captures += 1
             return
         self._graph.replay()
 
@@ -107,12 +109,46 @@ class Trainer:
         self.step_resident(soft=target.dtype.is_floating_point)
         return e.loss, e.correct
 
-    def train_step_host(self, x_pinned, y_pinned):
-        """End-to-end entry: pinned HOST buffers in, loss/correct read back to the host (async, call
-        torch.cuda.current_stream().synchronize() before reading the returned pinned tensor)."""
+    def _host_pipeline(self, mean, std):
+        if self._h2d is None:
+            from .data import InputNormalizer
+            e = self.engine
+            c = e.spec.in_chans
+            self._h2d = dict(stream=torch.cuda.Stream(device=e.device), slot=0,
+                             norm=InputNormalizer(mean, std, max(c // 3, 1), e.tdtype, device=e.device),
+                             u8=[torch.empty(e.x_in.shape, dtype=torch.uint8, device=e.device) for _ in range(2)],
+                             y=[torch.empty(e.N, dtype=torch.int64, device=e.device) for _ in range(2)],
+                             ready=[torch.cuda.Event() for _ in range(2)], free=[torch.cuda.Event() for _ in range(2)])
+            for ev in self._h2d["free"]:
+                ev.record(torch.cuda.current_stream())
+        return self._h2d
+
+    def train_step_host(self, x_pinned, y_pinned, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+        """End-to-end entry: pinned HOST buffers in, loss/correct read back to the host (async: synchronise the current
+        stream before reading the returned pinned tensor).
+
+        x_pinned uint8 [N,C,H,W] (what the reference's fast_collate hands its prefetcher, loader.py:14-41): uploaded on a
+        copy stream into one of two staging buffers (the upload of the NEXT call overlaps this call's kernels), then
+        normalised by `dfd_input_normalize` (loader.py:250-253 as one kernel) straight into the engine's input buffer.
+        A 16-bit / float x_pinned is taken as already normalised and copied on the compute stream."""
         e = self.engine
-        e.x_in.copy_(x_pinned, non_blocking=True)
-        e.target_i.copy_(y_pinned, non_blocking=True)
+        main = torch.cuda.current_stream()
+        if x_pinned.dtype == torch.uint8:
+            h = self._host_pipeline(mean, std)
+            b = h["slot"]
+            h["slot"] ^= 1
+            with torch.cuda.stream(h["stream"]):
+                h["stream"].wait_event(h["free"][b])            # the step that last read this slot has consumed it
+                h["u8"][b].copy_(x_pinned, non_blocking=True)
+                h["y"][b].copy_(y_pinned, non_blocking=True)
+                h["ready"][b].record(h["stream"])
+            main.wait_event(h["ready"][b])
+            h["norm"](h["u8"][b], out=e.x_in)
+            e.target_i.copy_(h["y"][b], non_blocking=True)
+            h["free"][b].record(main)
+        else:
+            e.x_in.copy_(x_pinned, non_blocking=True)
+            e.target_i.copy_(y_pinned, non_blocking=True)
         self.step_resident(soft=False)
         self._pin_out.copy_(e.scalars, non_blocking=True)
         return self._pin_out

@@ -159,17 +159,42 @@ int dfd_head_fwd(const float* pooled, const float* W, const float* b, float* log
 int dfd_head_bwd(const float* dlogits, const float* pooled, const float* W, float* dW, float* db, float* dpooled,
                  int N, int F, int K, void* stream);
 
+/* ---- the step's non-activation inputs (csrc/input.cu) ------------------------------------------------------------ */
+/* PrefetchLoader.__iter__, dfd/timm/data/loader.py:243-256: uint8 NCHW batch -> 16-bit NCHW, (x - mean255[c]) / std255[c]
+ * in fp32 with one rounding (mean255 / std255: device float[C] = mean*255 / std*255 repeated per frame, loader.py:229-230) */
+int dfd_input_normalize(const void* x_u8, const float* mean255, const float* std255, void* out, int N, int C, int H, int W,
+                        int dt, void* stream);
+/* drop_path (layers/drop.py:84-100) and F.dropout (efficientnet.py:346-347) masks, already divided by keep_prob.
+ * table: device array of { float* out; long long rows; int width; float keep_prob; int stream; int _pad; } - one random
+ * draw per row, replicated over `width`; state: device int64 [seed, step] of the counter-based generator */
+int dfd_rng_masks(const void* table, int count, const long long* state, void* stream);
+int dfd_rng_tick(long long* state, void* stream);
+int dfd_mul_f32(float* a, const float* b, long long n, void* stream);
+
 /* ---- optimizers over the flat fp32 parameter arena: create_optimizer, optim_factory.py:26-100;
  *      RMSpropTF rmsprop_tf.py:57-122; AdamW adamw.py:55-117; apex AMP loss scaling train.py:353,632-634 ---- */
-/* effective gradient scale = grad_scale * (*gscale_dev if non-null): 1/world for the DDP mean, 1/loss_scale on device */
+/* effective gradient scale = grad_scale * (*gscale_dev if non-null): 1/world for the DDP mean, 1/loss_scale on device.
+ * lr_dev (optional, device float): when non-null it overrides `lr` - the schedulers mutate param_groups[i]['lr'] every
+ * update (scheduler/scheduler.py:81-85), and a device-resident value lets one captured CUDA graph survive that.
+ * step_dev (optional, device int): Adam's step count for the bias corrections, advanced by dfd_opt_tick. */
 int dfd_sgd_step(float* p, const float* g, float* m, long long n, float lr, float momentum, float wd, int nesterov,
-                 float grad_scale, const float* gscale_dev, const int* skip, void* p16, int dt, void* stream);
+                 float grad_scale, const float* gscale_dev, const int* skip, void* p16, int dt, const float* lr_dev,
+                 void* stream);
 int dfd_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                   float wd, int decoupled, int step, float grad_scale, const float* gscale_dev, const int* skip, void* p16,
-                  int dt, void* stream);
+                  int dt, const float* lr_dev, const int* step_dev, void* stream);
 int dfd_rmsprop_tf_step(float* p, const float* g, float* sq, float* mom, long long n, float lr, float alpha,
                         float eps, float wd, float momentum, float grad_scale, const float* gscale_dev, const int* skip,
-                        void* p16, int dt, void* stream);
+                        void* p16, int dt, const float* lr_dev, void* stream);
+/* *step_dev += 1 unless *skip (fp16 overflow): a skipped step does not advance Adam's bias correction (apex semantics) */
+int dfd_opt_tick(int* step_dev, const int* skip, void* stream);
+/* dst[0..n) = v0..v(n-1), n <= 8: host scalars (learning rates) to device memory, values carried in the launch itself */
+int dfd_set_floats(float* dst, int n, float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7,
+                   void* stream);
+/* ModelEma.update (dfd/timm/utils.py:329-340) over the flat parameter / buffer arenas: ema = ema*decay + (1-decay)*model;
+ * the int64 num_batches_tracked entries follow the reference's float arithmetic + truncating copy_ */
+int dfd_ema_update(float* ema, const float* p, long long n, long long* ema_i64, const long long* p_i64, int n_i64,
+                   float decay, void* stream);
 int dfd_cast_arena(const float* p, void* p16, long long n, int dt, void* stream);
 int dfd_check_finite(const float* g, long long n, int* flag, void* stream);
 int dfd_update_loss_scale(int* flag, float* scale, int* good_steps, int interval, float* inv_scale_out,

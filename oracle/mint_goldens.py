@@ -118,6 +118,110 @@ def mint_step(arch, batch, H, W, n_steps=2, smoothing=0.0, opt_name="sgd", soft=
     print(name, "loss", [s["loss"] for s in rec["steps"]], "eval", rec["eval"]["loss"])
 
 
+def mint_step_dropped(arch="efficientnet_b0", batch=4, H=64, W=64, drop_rate=0.2, drop_path_rate=0.2):
+    """One train step of the reference with stochastic depth + classifier dropout (the production configuration,
+    scripts/train.sh: --drop 0.35 --drop-connect 0.2).  The reference draws its masks from torch's global generator
+    (layers/drop.py:96, F.dropout at efficientnet.py:347); torch.rand / F.dropout are wrapped here ONLY to record what was
+    drawn (the reference code runs unmodified), so that the oracle and the CUDA path can be given the same masks."""
+    import torch.nn.functional as F
+    from dfd.timm.models import create_model
+    from dfd.timm.optim import create_optimizer
+    torch.manual_seed(0)
+    spec = get_spec(arch)
+    model = create_model(arch, num_classes=2, drop_rate=drop_rate, drop_path_rate=drop_path_rate)
+    model.load_state_dict(synth_state(spec, seed=7), strict=True)
+    model.train()
+    args = _args(opt="sgd", lr=0.01, weight_decay=1e-4)
+    optimizer = create_optimizer(args, model)
+    rates = [(b.name, float(m.drop_path_rate)) for b, m in zip(spec.blocks, [blk for st in model.blocks for blk in st])]
+    rands, drops = [], []
+    real_rand, real_dropout = torch.rand, F.dropout
+
+    def rec_rand(*a, **k):
+        t = real_rand(*a, **k)
+        rands.append(t.clone())
+        return t
+
+    def rec_dropout(x, p=0.5, training=True, inplace=False):
+        out = real_dropout(x, p, training, False)
+        drops.append(((out != 0) | (x == 0)).float() / (1.0 - p) if training and p > 0 else torch.ones_like(x))
+        return out
+
+    x, y = synth_batch(batch, 3, H, W, seed=1234)
+    torch.rand, F.dropout = rec_rand, rec_dropout
+    try:
+        torch.manual_seed(5)
+        out = model(x)
+    finally:
+        torch.rand, F.dropout = real_rand, real_dropout
+    loss = torch.nn.CrossEntropyLoss()(out, y)
+    optimizer.zero_grad()
+    loss.backward()
+    grads = {k: _summ(p.grad) for k, p in model.named_parameters()}
+    optimizer.step()
+    # drop_path draws one torch.rand((N,1,1,1)) per residual block with rate > 0, in block order
+    names = [n for (n, r), b in zip(rates, spec.blocks) if b.has_residual and r > 0]
+    assert len(names) == len(rands), (len(names), len(rands))
+    masks = {}
+    for n, u in zip(names, rands):
+        keep = 1.0 - dict(rates)[n]
+        masks[n] = (torch.floor(keep + u) / keep).reshape(-1).tolist()
+    rec = dict(arch=arch, batch=batch, H=H, W=W, weight_seed=7, lr=0.01, momentum=0.9, weight_decay=1e-4,
+               drop_rate=drop_rate, drop_path_rate=drop_path_rate, block_rates=rates, drop_masks=masks,
+               dropout_mask=drops[0].tolist(), logits=out.detach().tolist(), loss=float(loss), grads=grads,
+               params={k: _summ(p) for k, p in model.named_parameters()}, torch=torch.__version__)
+    with open(os.path.join(GOLDEN, "step_%s_dropped.json" % arch), "w") as f:
+        json.dump(rec, f)
+    print("step_%s_dropped.json loss" % arch, rec["loss"], "dropped samples per block", {n: m.count(0.0) for n, m in masks.items()})
+
+
+def mint_aux():
+    """Small formula fixtures from the reference's own helper code: ModelEma.update (utils.py:329-340) on a toy module, the
+    prefetcher's normalisation (loader.py:229-253) on a uint8 batch, and drop_path itself (layers/drop.py:84-100)."""
+    from dfd.timm.utils import ModelEma
+    from dfd.timm.models.layers.drop import drop_path
+    out = {}
+
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(2, 3, 1, bias=False)
+            self.bn = torch.nn.BatchNorm2d(3)
+
+    torch.manual_seed(3)
+    m = Toy()
+    ema = ModelEma(m, decay=0.9)
+    hist = []
+    for step in range(3):
+        with torch.no_grad():
+            for p_ in m.parameters():
+                p_.add_(0.1 * (step + 1))
+            m.bn.running_mean.add_(0.5)
+            m.bn.num_batches_tracked.add_(7)
+        ema.update(m)
+        hist.append(dict(model={k: v.reshape(-1).tolist() for k, v in m.state_dict().items()},
+                         ema={k: v.reshape(-1).tolist() for k, v in ema.ema.state_dict().items()}))
+    out["ema"] = dict(decay=0.9, hist=hist)
+    # PrefetchLoader arithmetic without CUDA: the same tensor expressions as loader.py:229-230,250-253
+    from dfd.timm.data.constants import IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD
+    g = torch.Generator().manual_seed(9)
+    xb = torch.randint(0, 256, (2, 12, 5, 7), generator=g, dtype=torch.uint8)
+    mean = torch.tensor([[v * 255 for v in IMAGENET_DEFAULT_MEAN] for _ in range(4)]).view(1, 12, 1, 1)
+    std = torch.tensor([[v * 255 for v in IMAGENET_DEFAULT_STD] for _ in range(4)]).view(1, 12, 1, 1)
+    out["normalize"] = dict(x=xb.tolist(), y=xb.float().sub_(mean).div_(std).tolist(), mean=list(IMAGENET_DEFAULT_MEAN),
+                            std=list(IMAGENET_DEFAULT_STD), img_num=4)
+    torch.manual_seed(11)
+    xdp = torch.randn(6, 2, 2, 2)
+    st = torch.random.get_rng_state()
+    ydp = drop_path(xdp, 0.3, True)
+    torch.random.set_rng_state(st)
+    u = torch.rand((6, 1, 1, 1))
+    out["drop_path"] = dict(x=xdp.tolist(), y=ydp.tolist(), u=u.reshape(-1).tolist(), drop_prob=0.3)
+    with open(os.path.join(GOLDEN, "aux_formulas.json"), "w") as f:
+        json.dump(out, f)
+    print("aux_formulas.json ok")
+
+
 def mint_optimizers():
     """3 steps of each optimizer on a toy parameter set with fixed gradients, via the reference factory."""
     from dfd.timm.optim import create_optimizer
@@ -199,6 +303,10 @@ def main():
         mint_step("efficientnet_b0", 4, 64, 64, smoothing=0.1, tag="_ls")
         mint_step("efficientnet_b0", 4, 64, 64, soft=True, opt_name="rmsproptf", tag="_soft_rmsprop")
         mint_step("efficientnet_b0", 4, 64, 64, opt_name="adamw", tag="_adamw")
+    if a.only in ("", "drop"):
+        mint_step_dropped()
+    if a.only in ("", "aux"):
+        mint_aux()
     if a.only in ("", "opt"):
         mint_optimizers()
     if a.only in ("", "runner"):

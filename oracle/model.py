@@ -90,7 +90,10 @@ def _squeeze_excite(x, sd, p):
     return x * torch.sigmoid(x_se)
 
 
-def _mb_block(x, sd, b, bn, act_dtype, taps):
+def _mb_block(x, sd, b, bn, act_dtype, taps, drop_mask=None):
+    """drop_mask: optional [N] tensor = floor(keep + U) / keep of drop_path (layers/drop.py:84-100), applied to the block's
+    main path before the residual add (efficientnet_blocks.py:343-346); injected by the tests (torch's own random stream is
+    not reproducible across implementations)."""
     p = b.name
     residual = x
     if b.kind == "ir":
@@ -124,6 +127,8 @@ def _mb_block(x, sd, b, bn, act_dtype, taps):
             taps[p + ".conv_pw"] = x
         x = batch_norm(x, sd, p + ".bn2", bn)
     if b.has_residual:
+        if drop_mask is not None and bn.training:
+            x = x * drop_mask.view(-1, 1, 1, 1)
         x = x + residual
     x = q(x, act_dtype)
     if taps is not None:
@@ -131,7 +136,7 @@ def _mb_block(x, sd, b, bn, act_dtype, taps):
     return x
 
 
-def efficientnet_forward(spec, sd, x, bn=None, act_dtype=None, taps=None):
+def efficientnet_forward(spec, sd, x, bn=None, act_dtype=None, taps=None, drop_masks=None, dropout_mask=None):
     """x: [N, C, H, W] fp32 -> logits [N, num_classes] fp32. `sd` maps reference state_dict names to
     fp32 CPU tensors (parameters may require grad; running stats are updated in place when bn.training)."""
     bn = bn or BNState()
@@ -143,7 +148,7 @@ def efficientnet_forward(spec, sd, x, bn=None, act_dtype=None, taps=None):
     if taps is not None:
         taps["stem.out"] = x
     for b in spec.blocks:
-        x = _mb_block(x, sd, b, bn, act_dtype, taps)
+        x = _mb_block(x, sd, b, bn, act_dtype, taps, None if drop_masks is None else drop_masks.get(b.name))
     x = q(F.conv2d(x, sd["conv_head.weight"]), act_dtype)
     if taps is not None:
         taps["conv_head"] = x
@@ -151,6 +156,8 @@ def efficientnet_forward(spec, sd, x, bn=None, act_dtype=None, taps=None):
     x = x.mean((2, 3))
     if taps is not None:
         taps["pooled"] = x
+    if dropout_mask is not None and bn.training:
+        x = x * dropout_mask            # F.dropout(x, p, training) with the mask (already / keep) injected, efficientnet.py:346-347
     return F.linear(x, sd["classifier.weight"], sd["classifier.bias"])
 
 
@@ -194,9 +201,9 @@ def resnet_forward(spec, sd, x, bn=None, act_dtype=None, taps=None):
     return F.linear(x, sd["fc.weight"], sd["fc.bias"])
 
 
-def forward(spec, sd, x, bn=None, act_dtype=None, taps=None):
+def forward(spec, sd, x, bn=None, act_dtype=None, taps=None, drop_masks=None, dropout_mask=None):
     if spec.family == "efficientnet":
-        return efficientnet_forward(spec, sd, x, bn, act_dtype, taps)
+        return efficientnet_forward(spec, sd, x, bn, act_dtype, taps, drop_masks, dropout_mask)
     return resnet_forward(spec, sd, x, bn, act_dtype, taps)
 
 

@@ -102,14 +102,14 @@ def split_state(spec, sd):
 
 
 def train_step(spec, sd, x, target, opt=None, smoothing=0.0, bn=None, act_dtype=None, taps=None,
-               grad_hook=None):
+               grad_hook=None, drop_masks=None, dropout_mask=None):
     """One iteration of train.py:621-637 on CPU. `sd` tensors are updated in place.
     Returns dict(logits, loss, prec1, grads)."""
     params, _ = split_state(spec, sd)
     for p in params.values():
         p.requires_grad_(True)
         p.grad = None
-    logits = M.forward(spec, sd, x, bn or M.BNState(training=True), act_dtype, taps)
+    logits = M.forward(spec, sd, x, bn or M.BNState(training=True), act_dtype, taps, drop_masks, dropout_mask)
     loss = M.cross_entropy(logits, target, smoothing)
     prec1 = M.accuracy_top1(logits.detach(), target)
     loss.backward()

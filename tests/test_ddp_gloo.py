@@ -40,11 +40,27 @@ def _worker(rank, world, port, q):
                     if isinstance(a, int) and g0 <= a < g0 + 4 * n:
                         off = (a - g0) // 4
                         assert not any(lo <= off < hi for lo, hi in spans), (op_idx, j, eng.bwd_ops[j][1])
-        # the bucketed all-reduce sums every gradient element exactly once
+        # the bucketed all-reduce AVERAGES every gradient element exactly once (what DDP leaves in .grad, train.py:402-406)
         eng.grads32.copy_(torch.arange(n, dtype=torch.float32) % 1000 * (rank + 1))
         red.backward_and_reduce()
-        expect = torch.arange(n, dtype=torch.float32) % 1000 * sum(r + 1 for r in range(world))
+        expect = torch.arange(n, dtype=torch.float32) % 1000 * (sum(r + 1 for r in range(world)) / world)
         assert torch.equal(eng.grads32, expect)
+        # a second plan (other batch size: the last partial batch of an epoch) over the SAME arenas gets its own cut points,
+        # and the reducer replays THAT plan's backward, not the default engine's (reducer / engine mismatch)
+        eng2 = Engine("efficientnet_b0", 1, 96, 96, device="plan-only", share_from=eng)
+        assert eng2.grads32 is eng.grads32 and eng2.arena is eng
+        b1, b2 = red.plan_for(eng), red.plan_for(eng2)
+        assert b2[-1][0] == len(eng2.bwd_ops) - 1 and [sp for _, sp in b1] == [sp for _, sp in b2]
+        eng.grads32.fill_(float(rank))
+        calls = red.n_reduce_calls
+        red.backward_and_reduce(eng2)
+        assert float(eng.grads32.min()) == float(eng.grads32.max()) == (world - 1) / 2.0 and red.n_reduce_calls > calls
+        other = Engine("efficientnet_b0", 1, 64, 64, device="plan-only")
+        try:
+            red.backward_and_reduce(other)
+            raise AssertionError("foreign engine accepted")
+        except RuntimeError:
+            pass
         # parameter broadcast from rank 0
         eng.params32.fill_(float(rank + 5))
         red.broadcast_parameters()

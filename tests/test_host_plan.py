@@ -104,3 +104,8 @@ def test_plan_uses_the_fused_and_packed_kernels():
     # a second plan over the same weights (other batch size) shares the registry of the owner
     eng2 = Engine("efficientnet_b0", 2, 224, 224, device="plan-only", share_from=eng)
     assert eng2.params32 is eng.params32 and not hasattr(eng2, "_bd_reg") and len(eng._bd_reg) >= len(reg)
+    # an arena-only engine (what NativeModel.engine / the optimizer hold) owns weights but no plan and no activations
+    ar = Engine("efficientnet_b0", 1, device="plan-only", params_only=True)
+    assert ar.params_only and ar.fwd_ops == [] and not hasattr(ar, "acts") and ar.n_params == eng.n_params
+    eng3 = Engine("efficientnet_b0", 2, 64, 64, device="plan-only", share_from=ar)
+    assert eng3.arena is ar and eng3.grads32 is ar.grads32 and len(ar._bd_reg) > 0 and len(ar._stem_reg) == 1

@@ -120,3 +120,63 @@ def test_runner_config1_resnet18(golden_dir):
     assert sum(vl) / 2 == pytest.approx(rec["validate"]["loss"], rel=2e-3)
     for k, s in rec["params"].items():
         _check_summ(sd[k], s, "param " + k, 25 * RTOL)
+
+
+def test_dropped_step_matches_reference(golden_dir):
+    """Stochastic depth + classifier dropout (scripts/train.sh production flags): the oracle, given the masks the reference
+    drew, reproduces the reference's logits / loss / gradients / updated weights; the per-block rates follow the linear
+    ramp of efficientnet_builder.py (drop_path_rate * block_idx / n_blocks)."""
+    rec = json.load(open(os.path.join(golden_dir, "step_efficientnet_b0_dropped.json")))
+    torch.set_num_threads(8)
+    spec = get_spec(rec["arch"])
+    n_blocks = len(spec.blocks)
+    for i, (name, rate) in enumerate(rec["block_rates"]):
+        assert name == spec.blocks[i].name and rate == pytest.approx(rec["drop_path_rate"] * i / n_blocks, abs=1e-7)
+    sd = synth_state(spec, seed=rec["weight_seed"])
+    x, y = synth_batch(rec["batch"], 3, rec["H"], rec["W"], seed=1234)
+    masks = {k: torch.tensor(v) for k, v in rec["drop_masks"].items()}
+    assert set(masks) == {b.name for i, b in enumerate(spec.blocks) if b.has_residual and i > 0}
+    opt = OT.OptState(kind="sgd", lr=rec["lr"], momentum=rec["momentum"], weight_decay=rec["weight_decay"])
+    out = OT.train_step(spec, sd, x, y, opt, drop_masks=masks, dropout_mask=torch.tensor(rec["dropout_mask"]))
+    ref = torch.tensor(rec["logits"])
+    assert torch.allclose(out["logits"], ref, rtol=1e-3, atol=1e-4 * float(ref.abs().max() + 1))
+    assert float(out["loss"]) == pytest.approx(rec["loss"], rel=1e-4)
+    gfloor = 1e-5 * max(v["norm"] / max(out["grads"][k].numel(), 1) ** 0.5 for k, v in rec["grads"].items())
+    for k, s in rec["grads"].items():
+        _check_summ(out["grads"][k], s, "grad " + k, RTOL, floor=gfloor)
+    for k, s in rec["params"].items():
+        _check_summ(sd[k], s, "param " + k, RTOL)
+
+
+def test_aux_formulas_match_reference(golden_dir):
+    """drop_path (layers/drop.py:84-100), the prefetcher's normalisation (loader.py:229-253) and ModelEma.update
+    (utils.py:329-340) as the formulas the native kernels implement (tests/gpu_checks.py compares the kernels with these)."""
+    from oracle import formulas as OF
+    rec = json.load(open(os.path.join(golden_dir, "aux_formulas.json")))
+    d = rec["drop_path"]
+    mask = OF.drop_path_mask(torch.tensor(d["u"]), d["drop_prob"])
+    # the reference computes x.div(keep) * binary_mask, the oracle / kernels x * (binary_mask / keep): equal to one fp32 ulp
+    assert torch.allclose(torch.tensor(d["x"]) * mask.view(-1, 1, 1, 1), torch.tensor(d["y"]), rtol=3e-7, atol=0)
+    assert all(v == 0.0 or abs(v - 1.0 / (1.0 - d["drop_prob"])) < 1e-6 for v in mask.tolist())
+    n = rec["normalize"]
+    y = OF.normalize_u8(torch.tensor(n["x"], dtype=torch.uint8), n["mean"], n["std"], n["img_num"])
+    assert torch.equal(y, torch.tensor(n["y"]))
+    e = rec["ema"]
+    ema = {k: torch.tensor(v, dtype=torch.int64 if k.endswith("num_batches_tracked") else torch.float32)
+           for k, v in e["hist"][0]["model"].items()}
+    # ModelEma starts as a copy of the model BEFORE the first in-place change: rebuild that state from step 0
+    first = e["hist"][0]
+    for k in ema:
+        m0 = torch.tensor(first["model"][k], dtype=ema[k].dtype)
+        e0 = torch.tensor(first["ema"][k], dtype=ema[k].dtype)
+        ema[k] = ((e0.double() - (1 - e["decay"]) * m0.double()) / e["decay"]).to(ema[k].dtype) if ema[k].dtype.is_floating_point else None
+    for step in e["hist"]:
+        for k in ema:
+            if ema[k] is None:
+                continue
+            mv = torch.tensor(step["model"][k])
+            ema[k] = OF.ema_update(ema[k], mv, e["decay"])
+            assert torch.allclose(ema[k], torch.tensor(step["ema"][k]), rtol=1e-5, atol=1e-6), k
+    # integer buffers: float arithmetic, truncating copy_ (utils.py:339-340)
+    a = OF.ema_update(torch.tensor([0], dtype=torch.int64), torch.tensor([7], dtype=torch.int64), 0.9)
+    assert int(a) == int(first["ema"]["bn.num_batches_tracked"][0])
