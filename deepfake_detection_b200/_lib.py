@@ -21,12 +21,14 @@ SIGNATURES = {
     "dfd_blockdiag_weights": "piip",
     "dfd_gemm_tn_mma": "pppp" "lii" "i" "ppp",
     "dfd_gemm_wgrad_mma": "ppp" "lii" "i" "p",
-    "dfd_gemm_wgrad": "ppp" "lii" "i" "p",
+    "dfd_gemm_wgrad": "ppp" "lii" "i" "pl" "p",
+    "dfd_gemm_wgrad_workspace_kib": "lii",
     "dfd_dwconv_fwd": "ppppp" "iiiiii" "ii" "ppp",
     "dfd_dwconv_fwd_tc": "ppppp" "iiiiii" "ii" "ppp",
     "dfd_dwconv_dgrad": "ppppp" "pppppp" "pp" "iiiiii" "ii" "ppp",
     "dfd_dwconv_wgrad": "ppppp" "pppp" "iiiiii" "i" "p",
-    "dfd_dwconv_bwd": "ppppp" "pppppp" "ppp" "iiiiii" "i" "ppp",
+    "dfd_dwconv_bwd": "ppppp" "pppppp" "ppp" "iiiiii" "i" "pp" "pl" "p",
+    "dfd_dwconv_bwd_workspace_kib": "iiiiii",
     "dfd_stem_fwd": "ppp" "iiiiiiii" "i" "ppp",
     "dfd_stem_wgrad": "ppppppp" "iiiiiiii" "i" "p",
     "dfd_colstats": "p" "ili" "i" "ppp",

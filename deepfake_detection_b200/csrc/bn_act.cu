@@ -380,6 +380,12 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict
 // ---------------------------------------------------------------------------------------------
 // SE backward reduce: draw[n,c] = sum_hw da[n,hw,c] * act(scale*y + shift)
 // ---------------------------------------------------------------------------------------------
+// scratch of the chunked per-image reductions (library-owned, zero at load; tickets self-reset)
+constexpr long long ROWRED_WS_FLOATS = 4LL << 20;
+constexpr int ROWRED_TICKETS = 65536;
+__device__ float g_rowred_ws[ROWRED_WS_FLOATS];
+__device__ int g_rowred_tk[ROWRED_TICKETS];
+
 template <typename T, int ACT>
 __global__ void se_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
@@ -405,8 +411,28 @@ __global__ void se_bwd_reduce_kernel(const T* __restrict__ da, const T* __restri
         for (int i = 0; i < 8; i++) acc[i] = fmaf(d[i], act_fwd<ACT>(fmaf(f[i], sc[i], sh[i])), acc[i]);
     }
     float* dst = draw + (size_t)blockIdx.y * C;
-    if (gridDim.x == 1) reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v; });
-    else reduce_rows_and_emit(sm, acc, [&](int c, float v) { atomicAdd(dst + c, v); });
+    if (gridDim.x == 1) { reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v; }); return; }
+    // several chunks per image: fixed-slot partials [chunk][image][C] in the library scratch; the last chunk of an image to
+    // arrive (ticket) adds them in chunk order - no fp32 atomics, the result does not depend on CTA arrival order
+    float* part = g_rowred_ws + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * C;
+    reduce_rows_and_emit(sm, acc, [&](int c, float v) { part[c] = v; });
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const int t = atomicAdd(g_rowred_tk + blockIdx.y, 1);
+        s_last = (t == (int)gridDim.x - 1);
+        if (s_last) g_rowred_tk[blockIdx.y] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int c = tid; c < C; c += blockDim.x * blockDim.y) {
+        float v = 0.f;
+        for (int k = 0; k < (int)gridDim.x; k++) v += __ldcg(g_rowred_ws + ((size_t)k * gridDim.y + blockIdx.y) * C + c);
+        dst[c] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -618,11 +644,8 @@ int dfd_se_bwd_reduce(const void* da, const void* y, const float* scale, const f
     if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_bwd_reduce: C%8, sizes");
     // one CTA per image while the batch fills the GPU (>= 2 CTAs per SM); otherwise several row chunks per image
     RowGeom g = make_geom(C, hw, n, n >= 296 ? 1 : 592);
+    if ((long long)g.grid.x * n * C > ROWRED_WS_FLOATS || n > ROWRED_TICKETS) g = make_geom(C, hw, n, 1);   // one chunk per image
     cudaStream_t st = (cudaStream_t)stream;
-    if (g.grid.x > 1) {
-        cudaError_t e = cudaMemsetAsync(draw, 0, (size_t)n * C * sizeof(float), st);
-        if (e != cudaSuccess) return dfd_set_cuda_error(e, __FILE__, __LINE__);
-    }
     DISPATCH_T(dt, (se_bwd_reduce_kernel<T, 1><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)da, (const T*)y, scale, shift, draw, hw,
                                                                                          (long long)g.rows_per_block)));
     DFD_LAUNCH_CHECK();

@@ -31,7 +31,29 @@ struct DwGeom {
     int IH, IW;              // staged input tile
     int tiles_x, tiles_y;
     int dbg;                 // diagnostics (DFD_DW_DBG): 1 = skip the strip math, 2 = skip tile staging (fused backward only)
+    // order-deterministic weight-gradient flush of the fused backward (ws1 != NULL), see dwconv_bwd_kernel
+    float* ws1;              // [cbs][tiles][gz][k*k*64]  per-CTA partials
+    float* ws2;              // [cbs][tiles][k*k*64]      per-tile sums (over the image groups, in group order)
+    int* tk1;                // [cbs][tiles] ticket counters, zero at rest
+    int* tk2;                // [cbs]
 };
+
+// Every thread of the CTA calls this after the CTA's partial result has been stored: true (in every thread) for the LAST
+// CTA of the group of `total` to arrive; the counter returns to zero for the next launch.
+__device__ __forceinline__ bool ticket_last(int* counter, int total) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(counter, 1);
+        s_last = (t == total - 1);
+        if (s_last) *counter = 0;
+    }
+    __syncthreads();
+    const bool last = s_last != 0;
+    if (last) __threadfence();
+    return last;
+}
 
 __device__ __forceinline__ void load_chan_params(const float* p, int cbase, int C, float* out, float dflt) {
 #pragma unroll
@@ -686,14 +708,48 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
         wr[(warp * K * K + i) * 64 + lane * 2 + 1] = wacc[i][1];
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < K * K * 64; e += NT) {
+    if (!g.ws1) {
+        for (int e = threadIdx.x; e < K * K * 64; e += NT) {
+            const int i = e >> 6, c = e & 63;
+            if (c0 + c < g.C) {
+                float v = 0.f;
+#pragma unroll
+                for (int q = 0; q < NW; q++) v += wr[(q * K * K + i) * 64 + c];
+                const int tap = S == 1 ? (K * K - 1 - i) : i;
+                atomicAdd(dW + (size_t)(c0 + c) * K * K + tap, v);
+            }
+        }
+        return;
+    }
+    // ---- order-deterministic flush: fixed-slot partials, two ordered levels (image groups of a tile, then tiles) ----
+    constexpr int KK64 = K * K * 64;
+    const int tiles = gridDim.x;
+    const int grp = blockIdx.y * tiles + blockIdx.x;
+    float* slot = g.ws1 + ((size_t)grp * gridDim.z + blockIdx.z) * KK64;
+    for (int e = threadIdx.x; e < KK64; e += NT) {
+        const int i = e >> 6, c = e & 63;
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < NW; q++) v += wr[(q * K * K + i) * 64 + c];
+        slot[e] = v;
+    }
+    if (!ticket_last(g.tk1 + grp, gridDim.z)) return;
+    const float* zs = g.ws1 + (size_t)grp * gridDim.z * KK64;
+    float* tsum = g.ws2 + (size_t)grp * KK64;
+    for (int e = threadIdx.x; e < KK64; e += NT) {
+        float v = 0.f;
+        for (int z = 0; z < (int)gridDim.z; z++) v += __ldcg(zs + (size_t)z * KK64 + e);
+        tsum[e] = v;
+    }
+    if (!ticket_last(g.tk2 + blockIdx.y, tiles)) return;
+    const float* ts = g.ws2 + (size_t)blockIdx.y * tiles * KK64;
+    for (int e = threadIdx.x; e < KK64; e += NT) {
         const int i = e >> 6, c = e & 63;
         if (c0 + c < g.C) {
             float v = 0.f;
-#pragma unroll
-            for (int q = 0; q < NW; q++) v += wr[(q * K * K + i) * 64 + c];
+            for (int t = 0; t < tiles; t++) v += __ldcg(ts + (size_t)t * KK64 + e);
             const int tap = S == 1 ? (K * K - 1 - i) : i;
-            atomicAdd(dW + (size_t)(c0 + c) * K * K + tap, v);
+            dW[(size_t)(c0 + c) * K * K + tap] += v;
         }
     }
 }
@@ -719,6 +775,7 @@ static int fill_geom(DwGeom& g, int N, int H, int W, int C, int K, int S, bool i
     g.tiles_x = (tw_dim + g.TW - 1) / g.TW;
     g.tiles_y = (th_dim + g.TH - 1) / g.TH;
     { const char* e = getenv("DFD_DW_DBG"); g.dbg = e ? atoi(e) : 0; }
+    g.ws1 = g.ws2 = nullptr; g.tk1 = g.tk2 = nullptr;
     return g.IH * g.IW * 32 * (int)sizeof(uint32_t);
 }
 
@@ -844,10 +901,38 @@ int dfd_dwconv_wgrad(const void* x, const float* scale, const float* shift, cons
 // Fused backward of a depthwise stage: dfd_dwconv_dgrad and dfd_dwconv_wgrad in one pass over the dy tile (operands as
 // there; dW accumulated). scale != NULL: the stage input is BN + Swish of `xin` (mode 1: every MBConv block with an
 // expansion, `add` unused); scale == NULL: `xin` is consumed as is (mode 0: DS block), gx = dgrad (+ add).
+// grid of the fused backward: (tiles, 64-channel blocks, image groups); enough CTAs for ~6 per SM, each walking N / gz images
+// (gz a divisor of N keeps them balanced)
+static void dw_bwd_grid(const DwGeom& g, int N, int C, int& tiles, int& cbs, int& gz) {
+    tiles = g.tiles_x * g.tiles_y;
+    cbs = (C + CB - 1) / CB;
+    gz = (148 * 6 + tiles * cbs - 1) / (tiles * cbs);
+    if (gz > N) gz = N;
+    while (gz < N && N % gz) gz++;
+}
+static long long dw_bwd_ws_layout(int tiles, int cbs, int gz, int k, long long& off_ws2, long long& off_ws1) {
+    const long long kk64 = (long long)k * k * 64 * 4;
+    long long tk = ((long long)(tiles * cbs + cbs) * 4 + 4095) / 4096 * 4096;
+    off_ws2 = tk;
+    off_ws1 = tk + (long long)tiles * cbs * kk64;
+    return off_ws1 + (long long)tiles * cbs * gz * kk64;
+}
+
+// KiB of workspace that make the weight-gradient flush of dfd_dwconv_bwd order-deterministic for this shape
+int dfd_dwconv_bwd_workspace_kib(int N, int H, int W, int C, int k, int stride) {
+    if (C % 8 || N <= 0 || H <= 0 || W <= 0 || (k != 3 && k != 5) || (stride != 1 && stride != 2)) return 0;
+    DwGeom g;
+    fill_geom(g, N, H, W, C, k, stride, true);
+    int tiles, cbs, gz;
+    dw_bwd_grid(g, N, C, tiles, cbs, gz);
+    long long a, b;
+    return (int)((dw_bwd_ws_layout(tiles, cbs, gz, k, a, b) + 1023) / 1024);
+}
+
 int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const float* cB, const float* cC,
                    const float* w, const void* xin, const float* scale, const float* shift, const float* mean,
                    const float* rstd, const void* add, void* gx, float* dW, int N, int H, int W, int C, int k,
-                   int stride, int dt, double* s1, double* s2, void* stream) {
+                   int stride, int dt, double* s1, double* s2, void* ws, long long ws_bytes, void* stream) {
     if (C % 8 || N <= 0 || H <= 0 || W <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: sizes");
     if (!xin || !dW) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: operands");
     if (scale && (!shift || !mean || !rstd || !s1 || !s2)) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: mode 1 operands");
@@ -856,11 +941,17 @@ int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const floa
     constexpr int NT = 128;
     const int red_bytes = (NT / 32) * k * k * 64 * (int)sizeof(float);
     if (smem < red_bytes) smem = red_bytes;
-    const int tiles = g.tiles_x * g.tiles_y, cbs = (C + CB - 1) / CB;
-    // image groups: enough CTAs for ~6 per SM, each walking N / gz images (gz a divisor of N keeps them balanced)
-    int gz = (148 * 6 + tiles * cbs - 1) / (tiles * cbs);
-    if (gz > N) gz = N;
-    while (gz < N && N % gz) gz++;
+    int tiles, cbs, gz;
+    dw_bwd_grid(g, N, C, tiles, cbs, gz);
+    if (ws) {
+        long long o2, o1;
+        if (dw_bwd_ws_layout(tiles, cbs, gz, k, o2, o1) > ws_bytes)
+            return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: workspace too small (dfd_dwconv_bwd_workspace_kib)");
+        g.tk1 = (int*)ws;
+        g.tk2 = g.tk1 + tiles * cbs;
+        g.ws2 = (float*)((char*)ws + o2);
+        g.ws1 = (float*)((char*)ws + o1);
+    }
     dim3 grid(tiles, cbs, gz);
     cudaStream_t st = (cudaStream_t)stream;
     static int pb3 = 0, pb5 = 0;       // strip width per kernel size: 4 for k = 3 (four CTAs per SM, measured -1..-14 %), 8 for k = 5 (4 measured slower); DFD_DW_PB3 / DFD_DW_PB5 override

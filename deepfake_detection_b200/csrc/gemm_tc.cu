@@ -405,6 +405,12 @@ struct WgParams {
     long long kb_per_split;
     int stages;
     int is_bf16;
+    // order-deterministic flush (ws != NULL): split z stores its fp32 partial tile at part[z][Nw][Kw]; the LAST split of a
+    // tile to arrive (ticket counter per tile, self-resetting) adds the partials in split order 0..splits-1 into dW.
+    // ws == NULL: red.global.add from every split (the order of fp32 additions then varies run to run).
+    float* part;
+    int* tickets;           // [tiles_m * tiles_n], zero at rest
+    int splits;
 };
 
 template <typename T>
@@ -491,6 +497,50 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constan
         tc_fence_after();
         const int row = m0 + q * 32 + lane;                  // dW row (output channel) of this TMEM lane
         const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (p.part) {
+            // ---- deterministic path: plain stores of this split's partial tile, then the ticket ----
+            float* mine = p.part + (size_t)blockIdx.z * p.Nw * p.Kw;
+            for (int c = 0; c < p.block_n; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_base + c, v);
+                tmem_ld_wait();
+                if (row < p.Nw) {
+                    float* dst = mine + (size_t)row * p.Kw + n0 + c;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        if (n0 + c + j < p.Kw)
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                }
+            }
+            __shared__ int s_last;
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int et = threadIdx.x - 128;
+            if (et == 0) {
+                int* tk = p.tickets + blockIdx.y * gridDim.x + blockIdx.x;
+                const int t = atomicAdd(tk, 1);
+                s_last = (t == p.splits - 1);
+                if (s_last) *tk = 0;                           // at rest again for the next launch on this stream
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (s_last) {
+                __threadfence();
+                // 128 threads sweep the tile in float4 columns: coalesced reads of every split's partial, fixed order z = 0..
+                const int ncol4 = (min(p.block_n, p.Kw - n0) + 3) >> 2;
+                const int nrow = min(128, p.Nw - m0);
+                for (int e = et; e < nrow * ncol4; e += 128) {
+                    const int r = e / ncol4, c4 = e - r * ncol4;
+                    const size_t off = (size_t)(m0 + r) * p.Kw + n0 + c4 * 4;
+                    float4 acc = *reinterpret_cast<const float4*>(dW + off);
+                    for (int z = 0; z < p.splits; z++) {
+                        const float4 a = __ldcg(reinterpret_cast<const float4*>(p.part + (size_t)z * p.Nw * p.Kw + off));
+                        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+                    }
+                    *reinterpret_cast<float4*>(dW + off) = acc;
+                }
+            }
+        } else
         for (int c = 0; c < p.block_n; c += 16) {
             uint32_t v[16];
             tmem_ld16(t_base + c, v);
@@ -670,7 +720,22 @@ int dfd_blockdiag_weights(const void* table, int count, int dt, void* stream) {
 }
 
 // dW[Nw,Kw] (fp32, accumulated) += G[M,Nw]^T * X[M,Kw] on tcgen05 (MN-major operands straight from NHWC, split over M)
-int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* stream) {
+// KiB of workspace that make dfd_gemm_wgrad order-deterministic for this shape (tickets + the split partials)
+int dfd_gemm_wgrad_workspace_kib(long long M, int Nw, int Kw) {
+    if (M <= 0 || Nw <= 0 || Kw <= 0) return 0;
+    const int block_n = Kw >= 128 ? 128 : ((Kw + 15) / 16) * 16;
+    const long long kblocks = (M + WG_KP - 1) / WG_KP;
+    const int tm = cdiv(Nw, 128), tn = cdiv(Kw, block_n);
+    long long splits = (2LL * 148 + tm * tn - 1) / (tm * tn);
+    long long max_splits = (kblocks + 3) / 4;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    const long long bytes = ((long long)tm * tn * 4 + 4095) / 4096 * 4096 + splits * Nw * (long long)Kw * 4;
+    return (int)((bytes + 1023) / 1024);
+}
+
+int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* ws, long long ws_bytes,
+                   void* stream) {
     if (M <= 0 || Nw <= 0 || Kw <= 0 || (Nw % 8) || (Kw % 8)) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_wgrad: Nw%8, Kw%8");
     if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_wgrad: dtype");
     WgParams p;
@@ -687,8 +752,20 @@ int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw,
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     if (splits > 65535) splits = 65535;
+    p.part = nullptr; p.tickets = nullptr;
+    if (ws) {
+        // tickets first (one int per tile, rounded up to 4 KiB), then `splits` partial matrices; fewer splits if they do not fit
+        const long long tk_bytes = ((long long)tm * tn * 4 + 4095) / 4096 * 4096;
+        const long long per = (long long)Nw * Kw * 4;
+        long long fit = (ws_bytes - tk_bytes) / per;
+        if (fit < 1) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_wgrad: workspace too small (dfd_gemm_wgrad_workspace_kib)");
+        if (splits > fit) splits = fit;
+        p.tickets = (int*)ws;
+        p.part = (float*)((char*)ws + tk_bytes);
+    }
     p.kb_per_split = (p.kblocks + splits - 1) / splits;
     splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
+    p.splits = (int)splits;
     const int nbox_b = p.block_n > 64 ? 2 : 1;
     const int stage_bytes = (2 + nbox_b) * WG_BOX_BYTES;
     const int fixed = 18 * 8 + 64 + 1024;

@@ -13,6 +13,29 @@
 
 namespace {
 
+// Scratch of the small batch-reduction kernels below (SE / classifier parameter gradients, the loss): split partial sums
+// land in fixed slots and the last CTA of a group to arrive (ticket) adds them in slot order, so the results do not depend
+// on CTA arrival order. Library-owned (zero at load, tickets self-reset); the kernels of one process run on one stream.
+constexpr int SMALL_WS_FLOATS = 1 << 20;
+constexpr int SMALL_TICKETS = 8192;
+__device__ float g_small_ws[SMALL_WS_FLOATS];
+__device__ int g_small_tk[SMALL_TICKETS];
+
+__device__ __forceinline__ bool ticket_last(int* counter, int total) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(counter, 1);
+        s_last = (t == total - 1);
+        if (s_last) *counter = 0;
+    }
+    __syncthreads();
+    const bool last = s_last != 0;
+    if (last) __threadfence();
+    return last;
+}
+
 __device__ __forceinline__ float swish_precise(float x) { return x * sigmoid_precise(x); }
 __device__ __forceinline__ float softplus_precise(float x) {
     // log(1 + exp(x)), stable
@@ -63,10 +86,9 @@ __global__ void se_fc_bwd_kernel(const float* __restrict__ draw, const float* __
     float* rpre = sm + 2 * C;      // [Cse]
     float* r = rpre + Cse;         // [Cse]
     float* drp = r + Cse;          // [Cse]
-    float* r_acc = drp + Cse;      // [Cse] cross-warp accumulator of d_r
+    float* r_part = drp + Cse;     // [warps][Cse] per-warp partials of d_r, summed in warp order
     const int n = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     for (int c = tid; c < C; c += nt) p[c] = pooled[(size_t)n * C + c];
-    for (int j = tid; j < Cse; j += nt) r_acc[j] = 0.f;
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     for (int j = warp; j < Cse; j += nw) {
@@ -93,11 +115,12 @@ __global__ void se_fc_bwd_kernel(const float* __restrict__ draw, const float* __
         float s = 0.f;
         if (j < Cse)
             for (int c = warp; c < C; c += nw) s = fmaf(We[(size_t)c * Cse + j], de[c], s);
-        if (j < Cse) atomicAdd(&r_acc[j], s);
+        if (j < Cse) r_part[warp * Cse + j] = s;
     }
     __syncthreads();
     for (int j = tid; j < Cse; j += nt) {
-        float s = r_acc[j];
+        float s = 0.f;
+        for (int w = 0; w < nw; w++) s += r_part[w * Cse + j];
         {
             float x = rpre[j];
             float sg = sigmoid_precise(x);
@@ -120,26 +143,39 @@ __global__ void se_fc_wgrad_kernel(const float* __restrict__ d_e, const float* _
                                    const float* __restrict__ d_rpre, const float* __restrict__ pooled,
                                    float* __restrict__ dWr, float* __restrict__ dbr, float* __restrict__ dWe,
                                    float* __restrict__ dbe, int N, int C, int Cse) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= C * Cse) return;
-    int c = idx / Cse, j = idx - c * Cse;
-    // blockIdx.y splits the images so that the serial chain per thread stays short; partial sums meet in fp32 atomics
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < C * Cse;
+    const int c = valid ? idx / Cse : 0, j = valid ? idx - c * Cse : 0;
+    // blockIdx.y splits the images so that the serial chain per thread stays short; the split partials go to fixed slots
+    // [split][block][4][128] and are added in split order by the last block of this column group (ticket)
     const int per = (N + gridDim.y - 1) / gridDim.y;
     const int n0 = blockIdx.y * per, n1 = min(N, n0 + per);
     float awe = 0.f, awr = 0.f, abe = 0.f, abr = 0.f;
+    if (valid) {
 #pragma unroll 4
-    for (int n = n0; n < n1; n++) {
-        float de = d_e[(size_t)n * C + c], rr = r[(size_t)n * Cse + j];
-        float dr = d_rpre[(size_t)n * Cse + j], pp = pooled[(size_t)n * C + c];
-        awe = fmaf(de, rr, awe);
-        awr = fmaf(dr, pp, awr);
-        abe += de;
-        abr += dr;
+        for (int n = n0; n < n1; n++) {
+            float de = d_e[(size_t)n * C + c], rr = r[(size_t)n * Cse + j];
+            float dr = d_rpre[(size_t)n * Cse + j], pp = pooled[(size_t)n * C + c];
+            awe = fmaf(de, rr, awe);
+            awr = fmaf(dr, pp, awr);
+            abe += de;
+            abr += dr;
+        }
     }
-    atomicAdd(dWe + (size_t)c * Cse + j, awe);
-    atomicAdd(dWr + (size_t)j * C + c, awr);
-    if (j == 0) atomicAdd(dbe + c, abe);
-    if (c == 0) atomicAdd(dbr + j, abr);
+    float* slot = g_small_ws + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 512;
+    slot[threadIdx.x] = awe; slot[128 + threadIdx.x] = awr; slot[256 + threadIdx.x] = abe; slot[384 + threadIdx.x] = abr;
+    if (!ticket_last(g_small_tk + blockIdx.x, gridDim.y)) return;
+    if (!valid) return;
+    awe = awr = abe = abr = 0.f;
+    for (int y = 0; y < (int)gridDim.y; y++) {
+        const float* sl = g_small_ws + ((size_t)y * gridDim.x + blockIdx.x) * 512;
+        awe += __ldcg(sl + threadIdx.x); awr += __ldcg(sl + 128 + threadIdx.x);
+        abe += __ldcg(sl + 256 + threadIdx.x); abr += __ldcg(sl + 384 + threadIdx.x);
+    }
+    dWe[(size_t)c * Cse + j] += awe;
+    dWr[(size_t)j * C + c] += awr;
+    if (j == 0) dbe[c] += abe;
+    if (c == 0) dbr[j] += abr;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -177,15 +213,24 @@ __global__ void head_fwd_kernel(const float* __restrict__ pooled, const float* _
         float loss = t0 * softplus_precise(d) + t1 * softplus_precise(-d);
         float sg = sigmoid_precise(d);
         float g1 = (t0 + t1) * sg - t1;
-        atomicAdd(loss_acc, loss * inv_n);
         int pred = z[1] > z[0] ? 1 : 0;      // topk(1) returns the first index on ties
         int lab = t1 > t0 ? 1 : 0;
-        if (pred == lab) atomicAdd(correct_acc, 1.f);
+        // per-image loss / hit in fixed slots; the last image's CTA adds them in image order (below)
+        g_small_ws[n] = loss * inv_n;
+        g_small_ws[gridDim.x + n] = pred == lab ? 1.f : 0.f;
         if (dlogits) {
             const float ls = loss_scale_dev ? loss_scale * *loss_scale_dev : loss_scale;   // fp16 dynamic loss scaling
             dlogits[n * 2] = -g1 * inv_n * ls;
             dlogits[n * 2 + 1] = g1 * inv_n * ls;
         }
+    }
+    if (K != 2) return;
+    if (!ticket_last(g_small_tk, gridDim.x)) return;
+    if (threadIdx.x == 0) {
+        float l = 0.f, c = 0.f;
+        for (int i = 0; i < (int)gridDim.x; i++) { l += __ldcg(g_small_ws + i); c += __ldcg(g_small_ws + gridDim.x + i); }
+        *loss_acc += l;
+        *correct_acc += c;
     }
 }
 
@@ -203,20 +248,32 @@ __global__ void head_dgrad_kernel(const float* __restrict__ dlogits, const float
 // (a single thread walking all N images serialises N dependent L2 round trips: measured 100 us at N = 256)
 __global__ void head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ pooled,
                                   float* __restrict__ dW, float* __restrict__ db, int N, int F, int K) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= K * F) return;
-    int k = idx / F, f = idx - k * F;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < K * F;
+    const int k = valid ? idx / F : 0, f = valid ? idx - k * F : 0;
     const int per = (N + gridDim.y - 1) / gridDim.y;
     const int n0 = blockIdx.y * per, n1 = min(N, n0 + per);
     float s = 0.f, sb = 0.f;
+    if (valid) {
 #pragma unroll 4
-    for (int n = n0; n < n1; n++) {
-        float d = dlogits[(size_t)n * K + k];
-        s = fmaf(d, pooled[(size_t)n * F + f], s);
-        sb += d;
+        for (int n = n0; n < n1; n++) {
+            float d = dlogits[(size_t)n * K + k];
+            s = fmaf(d, pooled[(size_t)n * F + f], s);
+            sb += d;
+        }
     }
-    atomicAdd(dW + idx, s);
-    if (f == 0) atomicAdd(db + k, sb);
+    // fixed-slot split partials, added in split order by the last block of the column group (no atomics)
+    float* slot = g_small_ws + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 256;
+    slot[threadIdx.x] = s; slot[128 + threadIdx.x] = sb;
+    if (!ticket_last(g_small_tk + blockIdx.x, gridDim.y)) return;
+    if (!valid) return;
+    s = sb = 0.f;
+    for (int y = 0; y < (int)gridDim.y; y++) {
+        const float* sl = g_small_ws + ((size_t)y * gridDim.x + blockIdx.x) * 256;
+        s += __ldcg(sl + threadIdx.x); sb += __ldcg(sl + 128 + threadIdx.x);
+    }
+    dW[idx] += s;
+    if (f == 0) db[k] += sb;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -424,12 +481,24 @@ int dfd_se_fc_bwd(const float* draw, const float* pooled, const float* Wr, const
                   const float* be, float* d_e, float* r, float* d_rpre, float* dpool, float* dWr, float* dbr,
                   float* dWe, float* dbe, int N, int C, int Cse, void* stream) {
     if (N <= 0 || C <= 0 || Cse <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_fc_bwd: sizes");
-    size_t smem = (size_t)(2 * C + 4 * Cse) * sizeof(float);
+    const int nthr = se_threads(C);
+    size_t smem = (size_t)(2 * C + 3 * Cse + (nthr / 32) * Cse) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-    se_fc_bwd_kernel<<<N, se_threads(C), smem, st>>>(draw, pooled, Wr, br, We, be, d_e, r, d_rpre, dpool, C, Cse);
+    if (smem > 48 * 1024) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(se_fc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+        if (smem > 160 * 1024) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_se_fc_bwd: channel count exceeds shared memory");
+    }
+    se_fc_bwd_kernel<<<N, nthr, smem, st>>>(draw, pooled, Wr, br, We, be, d_e, r, d_rpre, dpool, C, Cse);
     DFD_LAUNCH_CHECK();
+    // image splits: only as many as it takes to fill the GPU (the split partials are summed in order by the last block of
+    // every column group: fixed slots in the library scratch, no atomics)
+    const int bx = cdiv((long long)C * Cse, 128);
     int nsplit = N >= 64 ? 16 : (N >= 8 ? 4 : 1);
-    se_fc_wgrad_kernel<<<dim3(cdiv((long long)C * Cse, 128), nsplit), 128, 0, st>>>(d_e, r, d_rpre, pooled, dWr, dbr, dWe, dbe, N, C, Cse);
+    while (nsplit > 1 && ((long long)bx * nsplit > 2368 || (long long)nsplit * bx * 128 * 4 > SMALL_WS_FLOATS)) nsplit >>= 1;
+    if (bx > SMALL_TICKETS || (long long)nsplit * bx * 128 * 4 > SMALL_WS_FLOATS)
+        return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_se_fc_bwd: C * Cse exceeds the reduction scratch");
+    se_fc_wgrad_kernel<<<dim3(bx, nsplit), 128, 0, st>>>(d_e, r, d_rpre, pooled, dWr, dbr, dWe, dbe, N, C, Cse);
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }
@@ -440,6 +509,7 @@ int dfd_head_fwd(const float* pooled, const float* W, const float* b, float* log
     if (N <= 0 || F <= 0 || K <= 0 || K > 32) return dfd_set_error(DFD_ERR_ARG, "dfd_head_fwd: sizes");
     if (loss_acc && K != 2) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_head_fwd: fused sigmoid-BCE needs num_classes == 2");
     if (loss_acc && !tgt_i && !tgt_f) return dfd_set_error(DFD_ERR_ARG, "dfd_head_fwd: loss without target");
+    if (loss_acc && 2 * (long long)N > SMALL_WS_FLOATS) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_head_fwd: batch exceeds the reduction scratch");
     head_fwd_kernel<<<N, 64, 0, (cudaStream_t)stream>>>(pooled, W, b, logits, F, K, tgt_i, tgt_f, smoothing,
                                                          1.f / (float)N, loss_scale, loss_scale_dev, loss_acc, correct_acc, dlogits);
     DFD_LAUNCH_CHECK();

@@ -207,6 +207,33 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # plan construction
     # ------------------------------------------------------------------------------------------
+    # ---- order-deterministic weight gradients ------------------------------------------------------------------
+    # The tcgen05 weight gradient and the fused depthwise backward flush their split partial sums through ONE shared
+    # workspace (fixed slots + ticketed ordered adds, see include/dfd_b200.h) instead of fp32 atomics, so the gradients -
+    # and with them every later step - do not depend on the arrival order of CTAs. The ops are emitted with placeholders
+    # and patched once the largest requirement of the plan is known (kernels of one plan run back to back on one stream).
+    def _wgrad(self, G, X, dW, M, Nw, Kw):
+        if self._wgrad_name != "dfd_gemm_wgrad":
+            return (self._wgrad_name, (G, X, dW, M, Nw, Kw, self.dt))
+        self._ws_kib = max(getattr(self, "_ws_kib", 0), self.L.cdll.dfd_gemm_wgrad_workspace_kib(M, Nw, Kw))
+        return ("dfd_gemm_wgrad", [G, X, dW, M, Nw, Kw, self.dt, "WS", "WSB"])
+
+    def _dw_bwd(self, args, N, H, W, C, k, stride):
+        self._ws_kib = max(getattr(self, "_ws_kib", 0), self.L.cdll.dfd_dwconv_bwd_workspace_kib(N, H, W, C, k, stride))
+        return ("dfd_dwconv_bwd", list(args) + ["WS", "WSB"])
+
+    def _patch_workspace(self, ops):
+        det = not os.environ.get("DFD_NONDET")
+        kib = getattr(self, "_ws_kib", 0)
+        if det and kib:
+            self.det_ws = torch.zeros(kib * 256, dtype=torch.int32, device=self.device)      # tickets must start at zero
+        out = []
+        for n, a in ops:
+            if isinstance(a, list) and "WS" in a:
+                a = [(_ptr(self.det_ws) if det else None) if v == "WS" else ((kib * 1024 if det else 0) if v == "WSB" else v) for v in a]
+            out.append((n, a))
+        return out
+
     def _alloc16(self, *shape):
         # the plan holds RAW pointers: every buffer must stay referenced for the engine's lifetime
         t = torch.empty(shape, dtype=self.tdtype, device=self.device)
@@ -504,7 +531,7 @@ class Engine:
         bwd.append(("dfd_bn_bwd_apply", (mid_a, _ptr(yh), None, bnh.cA, bnh.cB, bnh.cC, mid_b, N, Hf * Wf, F, dt)))
         cur = 0
         bwd.append(gemm(mid_b, T16("conv_head.weight"), sm[cur], Mf, spec.head_in, F))
-        bwd.append((self._wgrad_name, (mid_b, _ptr(self._head_in), G32("conv_head.weight"), Mf, F, spec.head_in, dt)))
+        bwd.append(self._wgrad(mid_b, _ptr(self._head_in), G32("conv_head.weight"), Mf, F, spec.head_in))
         for rec in reversed(recs):
             b, h, w, ho, wo, xin = rec["b"], rec["h"], rec["w"], rec["ho"], rec["wo"], rec["x"]
             p = b.name
@@ -526,7 +553,7 @@ class Engine:
             bwd.append(bwd_finalize(bn_out, M2))
             bwd.append(("dfd_bn_bwd_apply", (gbn, _ptr(y3), None, bn_out.cA, bn_out.cB, bn_out.cC, t1, N, ho * wo, b.cout, dt)))
             bwd.append(gemm(t1, T16(p + pw_name + ".weight"), mid_a, M2, b.cmid, b.cout))
-            bwd.append((self._wgrad_name, (t1, _ptr(a2), G32(p + pw_name + ".weight"), M2, b.cout, b.cmid, dt)))
+            bwd.append(self._wgrad(t1, _ptr(a2), G32(p + pw_name + ".weight"), M2, b.cout, b.cmid))
             gate_ptr = dpool_ptr = None
             if b.cse:
                 gate_ptr, dpool_ptr = _ptr(rec["gate"]), se_dpool
@@ -550,16 +577,16 @@ class Engine:
                                                      bn_mid.cC, G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt)))
                 else:
                     # input gradient (through bn1 + Swish) and weight gradient in one pass over the dy tile
-                    bwd.append(("dfd_dwconv_bwd", (mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
-                                                   _ptr(y1), dw_bn.scale, dw_bn.shift, dw_bn.mean, dw_bn.rstd, None, mid_a,
-                                                   G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt,
-                                                   dw_bn.bs1, dw_bn.bs2)))
+                    bwd.append(self._dw_bwd((mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
+                                             _ptr(y1), dw_bn.scale, dw_bn.shift, dw_bn.mean, dw_bn.rstd, None, mid_a,
+                                             G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt,
+                                             dw_bn.bs1, dw_bn.bs2), N, h, w, b.cmid, b.k, b.stride))
                 bwd.append(bwd_finalize(dw_bn, M1))
                 bwd.append(("dfd_bn_bwd_apply", (mid_a, _ptr(y1), None, dw_bn.cA, dw_bn.cB, dw_bn.cC, mid_b, N, h * w, b.cmid, dt)))
                 bwd.append(gemm(mid_b, T16(p + ".conv_pw.weight"), t2, M1, b.cin, b.cmid))
                 if b.has_residual:
                     bwd.append(("dfd_add_inplace", (t2, dout, M1 * b.cin, dt)))
-                bwd.append((self._wgrad_name, (mid_b, _ptr(xin), G32(p + ".conv_pw.weight"), M1, b.cmid, b.cin, dt)))
+                bwd.append(self._wgrad(mid_b, _ptr(xin), G32(p + ".conv_pw.weight"), M1, b.cmid, b.cin))
             elif os.environ.get("DFD_DW_SPLIT_BWD"):
                 bwd.append(("dfd_dwconv_dgrad", (mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
                                                  None, None, None, None, None, dout if b.has_residual else None, t2,
@@ -568,9 +595,10 @@ class Engine:
                                                  G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt)))
             else:
                 # DS block: the depthwise conv reads the block input as is (mode 0 of the fused pass)
-                bwd.append(("dfd_dwconv_bwd", (mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
-                                               _ptr(xin), None, None, None, None, dout if b.has_residual else None, t2,
-                                               G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt, None, None)))
+                bwd.append(self._dw_bwd((mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
+                                         _ptr(xin), None, None, None, None, dout if b.has_residual else None, t2,
+                                         G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt, None, None),
+                                        N, h, w, b.cmid, b.k, b.stride))
             cur = (cur + 2) % 3
         # stem
         bn = self.bns["bn1"]
@@ -580,11 +608,12 @@ class Engine:
         if self.stem_impl == "gemm":
             bwd.append(("dfd_bn_bwd_apply", (mid_a, _ptr(y0), None, bn.cA, bn.cB, bn.cC, mid_b, N, Hs * Ws, spec.stem, dt)))
             bwd.append(("dfd_memset_async", (_ptr(self.stem_gpad), 0, spec.stem * Kp * 4)))
-            bwd.append((self._wgrad_name, (mid_b, _ptr(self.stem_cols), _ptr(self.stem_gpad), N * Hs * Ws, spec.stem, Kp, dt)))
+            bwd.append(self._wgrad(mid_b, _ptr(self.stem_cols), _ptr(self.stem_gpad), N * Hs * Ws, spec.stem, Kp))
             bwd.append(("dfd_unpad_grad", (_ptr(self.stem_gpad), G32("conv_stem.weight"), spec.stem, taps, Kp)))
         else:
             bwd.append(("dfd_stem_wgrad", (_ptr(self.x_in), mid_a, _ptr(y0), bn.cA, bn.cB, bn.cC, G32("conv_stem.weight"), N,
                                            spec.in_chans, self.H, self.W, spec.stem, 3, 2, 1, dt)))
+        bwd = self._patch_workspace(bwd)
         for n, a in fwd + bwd:      # arity / type check of the plan against the ABI table
             codes = _lib.SIGNATURES[n[:-6] if n.endswith("_train") else n]
             if len(a) != len(codes) - 1:

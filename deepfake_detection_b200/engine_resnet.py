@@ -199,7 +199,7 @@ def build_resnet(e):
                ("dfd_col2im", (COLS, dx_add, dx_out, N, n_h, n_w, Cin, 3, stride, 1, dt)),
                ("dfd_im2col", (_ptr(xin_t), COLS, N, n_h, n_w, Cin, 3, stride, 1, dt)),
                zero_gperm(Cout * 9 * Cin),
-               (e._wgrad_name, (dy, COLS, _ptr(e.gperm), M_out, Cout, 9 * Cin, dt)),
+               e._wgrad(dy, COLS, _ptr(e.gperm), M_out, Cout, 9 * Cin),
                ("dfd_unpack_grad", (_ptr(e.gperm), G32(name), Cout, Cin, 3))]
         return ops
 
@@ -232,7 +232,7 @@ def build_resnet(e):
             bn1, bn2 = bns[p + ".bn1"], bns[p + ".bn2"]
             # conv3 (1x1): dy3 = t1 -> da2 = t2
             bwd.append(gemm(t1, T16(p + ".conv3.weight"), t2, M2, b.planes, b.cout))
-            bwd.append((e._wgrad_name, (t1, _ptr(rec["a2"]), G32(p + ".conv3.weight"), M2, b.cout, b.planes, dt)))
+            bwd.append(e._wgrad(t1, _ptr(rec["a2"]), G32(p + ".conv3.weight"), M2, b.cout, b.planes))
             bwd.append(("dfd_act_bwd", (t2, _ptr(rec["y2"]), bn2.scale, bn2.shift, bn2.mean, bn2.rstd, None, None, t1, N,
                                         ho * wo, b.planes, ACT_RELU, dt, bn2.bs1, bn2.bs2)))
             bwd.append(bwd_finalize(bn2, M2))
@@ -245,7 +245,7 @@ def build_resnet(e):
             bwd.append(("dfd_bn_bwd_apply", (t2, _ptr(rec["y1"]), None, bn1.cA, bn1.cB, bn1.cC, t1, N, h * w, b.planes, dt)))
             # conv1 (1x1): dy1 = t1 -> dx = t3 [M1, cin]
             bwd.append(gemm(t1, T16(p + ".conv1.weight"), t3, M1, b.cin, b.planes))
-            bwd.append((e._wgrad_name, (t1, _ptr(xin), G32(p + ".conv1.weight"), M1, b.planes, b.cin, dt)))
+            bwd.append(e._wgrad(t1, _ptr(xin), G32(p + ".conv1.weight"), M1, b.planes, b.cin))
         # identity / downsample path: gradient gm flows to the block input too
         if b.downsample:
             bnd = rec["bnd"]
@@ -253,7 +253,7 @@ def build_resnet(e):
             bwd.append(bwd_finalize(bnd, M2))
             bwd.append(("dfd_bn_bwd_apply", (gm, _ptr(rec["yd"]), None, bnd.cA, bnd.cB, bnd.cC, t1, N, ho * wo, b.cout, dt)))
             bwd.append(gemm(t1, T16(p + ".downsample.0.weight"), t2, M2, b.cin, b.cout))
-            bwd.append((e._wgrad_name, (t1, _ptr(rec["xs"]), G32(p + ".downsample.0.weight"), M2, b.cout, b.cin, dt)))
+            bwd.append(e._wgrad(t1, _ptr(rec["xs"]), G32(p + ".downsample.0.weight"), M2, b.cout, b.cin))
             if b.stride == 1:
                 bwd.append(("dfd_add_inplace", (t3, t2, M1 * b.cin, dt)))
                 new_dout = t3
@@ -276,12 +276,13 @@ def build_resnet(e):
     if e.stem_impl == "gemm":
         bwd.append(("dfd_bn_bwd_apply", (t2, _ptr(y0), None, bn0.cA, bn0.cB, bn0.cC, t1, N, H1 * W1, 64, dt)))
         bwd.append(("dfd_memset_async", (_ptr(e.stem_gpad), 0, 64 * Kp * 4)))
-        bwd.append((e._wgrad_name, (t1, _ptr(e.stem_cols), _ptr(e.stem_gpad), N * H1 * W1, 64, Kp, dt)))
+        bwd.append(e._wgrad(t1, _ptr(e.stem_cols), _ptr(e.stem_gpad), N * H1 * W1, 64, Kp))
         bwd.append(("dfd_unpad_grad", (_ptr(e.stem_gpad), G32("conv1.weight"), 64, taps, Kp)))
     else:
         bwd.append(("dfd_stem_wgrad", (_ptr(e.x_in), t2, _ptr(y0), bn0.cA, bn0.cB, bn0.cC, G32("conv1.weight"), N, spec.in_chans,
                                        e.H, e.W, 64, 7, 2, 3, dt)))
 
+    bwd = e._patch_workspace(bwd)
     for n, a in fwd + bwd:
         codes = _lib.SIGNATURES[n]
         if len(a) != len(codes) - 1:

@@ -60,11 +60,26 @@ class _NativeForward(torch.autograd.Function):
 
 def init_state_dict(spec, seed=None):
     """Random-init state in the reference's key order with the reference's initialisers:
-    efficientnet_builder.py:537-575 (`_init_weight_goog`), resnet.py:411-420."""
+    EfficientNet: efficientnet_builder.py:537-575 (`_init_weight_goog`: conv N(0, 2/fan_out), depthwise fan_out / groups,
+    Linear U(+-1/sqrt(fan_out)), BN 1 / 0);
+    ResNet: resnet.py:410-420 (conv kaiming_normal fan_out, BN 1 / 0, the LAST BN gamma of every residual block ZERO -
+    `zero_init_last_bn=True` is the constructor default, :353 - and nn.Linear's default U(+-1/sqrt(fan_in)) for fc)."""
     import math
     g = torch.Generator(device="cpu").manual_seed((torch.initial_seed() if seed is None else seed) % (2 ** 31))
     sd = OrderedDict()
+    resnet = spec.family == "resnet"
+    last_bn = set()
+    if resnet:
+        for b in spec.blocks:
+            last_bn.add(b.name + (".bn2.weight" if b.kind == "basic" else ".bn3.weight"))       # resnet.py:147-148,212-213
     for name, shape, role in state_entries(spec):
+        if resnet and role in ("fc_w", "fc_b"):
+            r = 1.0 / math.sqrt(spec.num_features)
+            sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * r
+            continue
+        if name in last_bn:
+            sd[name] = torch.zeros(shape)
+            continue
         if role in ("conv_w", "dw_w", "se_w"):
             fan_out = shape[0] * shape[2] * shape[3]
             if role == "dw_w":

@@ -63,7 +63,12 @@ int dfd_gemm_tn_mma(const void* A, const void* B, void* C, const void* add, long
 int dfd_gemm_wgrad_mma(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* stream);
 /* the same contract on tcgen05: both operands MN-major straight from NHWC memory (TMA 128-byte swizzle boxes), fp32
  * accumulator in TMEM over a contiguous range of rows per CTA, one red.global.add flush */
-int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* stream);
+int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* ws, long long ws_bytes,
+                   void* stream);
+/* ws (optional, zero-initialised once by the caller, >= dfd_gemm_wgrad_workspace_kib KiB): makes the flush ORDER-DETERMINISTIC -
+ * every split stores its fp32 partial tile and the last split of a tile to arrive adds them in split order (per-tile ticket
+ * counters, self-resetting), instead of red.global.add from every split in arrival order. NULL: the atomic flush. */
+int dfd_gemm_wgrad_workspace_kib(long long M, int Nw, int Kw);
 
 /* ---- depthwise k x k convolution: nn.Conv2d(groups=C), efficientnet_blocks.py:152-153,283-285 -------- */
 int dfd_dwconv_fwd(const void* x, const float* scale, const float* shift, const float* w, void* out, int N, int H,
@@ -84,7 +89,11 @@ int dfd_dwconv_wgrad(const void* x, const float* scale, const float* shift, cons
 int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const float* cB, const float* cC,
                    const float* w, const void* xin, const float* scale, const float* shift, const float* mean,
                    const float* rstd, const void* add, void* gx, float* dW, int N, int H, int W, int C, int k,
-                   int stride, int dt, double* s1, double* s2, void* stream);
+                   int stride, int dt, double* s1, double* s2, void* ws, long long ws_bytes, void* stream);
+/* ws (optional, zero-initialised once by the caller, >= dfd_dwconv_bwd_workspace_kib KiB): order-deterministic dW - every CTA
+ * stores its k*k x 64 partial in a fixed slot; the last CTA of a tile's image groups adds them in group order, the last tile
+ * of a channel block adds the tile sums in tile order into dW (ticket counters, self-resetting). NULL: fp32 atomics. */
+int dfd_dwconv_bwd_workspace_kib(int N, int H, int W, int C, int k, int stride);
 
 /* ---- stem convolution: conv_stem 3x3 s2 (efficientnet.py:275,321) / conv1 7x7 s2 (resnet.py:379,451) ---- */
 int dfd_stem_fwd(const void* x_nchw, const float* w, void* out_nhwc, int N, int Cin, int H, int W, int Cout, int k,

@@ -86,15 +86,36 @@ def check_gemm(impl, M, K, N, dtype=torch.bfloat16, with_stats=True, with_add=Fa
     return out
 
 
-def check_wgrad(M, Nw, Kw, dtype=torch.bfloat16, seed=0, impl="dfd_gemm_wgrad_mma"):
+def check_wgrad(M, Nw, Kw, dtype=torch.bfloat16, seed=0, impl="dfd_gemm_wgrad_mma", det=False):
+    """det: the order-deterministic flush of dfd_gemm_wgrad (workspace given): also returns whether two launches agree bit
+    for bit and the distance to the atomic flush"""
     g = torch.Generator(device="cuda").manual_seed(seed)
     G = (torch.randn(M, Nw, device="cuda", generator=g) * 0.3).to(dtype)
     X = (torch.randn(M, Kw, device="cuda", generator=g)).to(dtype)
     dW = torch.zeros(Nw, Kw, device="cuda")
-    _lib.call(impl, P(G), P(X), P(dW), M, Nw, Kw, DT[dtype], st())
+    out = {}
+    if impl == "dfd_gemm_wgrad":
+        ws, wsb = None, 0
+        if det:
+            kib = _lib.lib().cdll.dfd_gemm_wgrad_workspace_kib(M, Nw, Kw)
+            ws = torch.zeros(kib * 256, dtype=torch.int32, device="cuda")
+            wsb = kib * 1024
+        _lib.call(impl, P(G), P(X), P(dW), M, Nw, Kw, DT[dtype], P(ws), wsb, st())
+        if det:
+            again = torch.zeros(Nw, Kw, device="cuda")
+            _lib.call(impl, P(G), P(X), P(again), M, Nw, Kw, DT[dtype], P(ws), wsb, st())
+            atomic = torch.zeros(Nw, Kw, device="cuda")
+            _lib.call(impl, P(G), P(X), P(atomic), M, Nw, Kw, DT[dtype], None, 0, st())
+            torch.cuda.synchronize()
+            out["bitwise"] = bool(torch.equal(dW, again))
+            out["vs_atomic"] = relerr(dW, atomic)
+            out["tickets_at_rest"] = int(ws[:1024].abs().sum()) == 0
+    else:
+        _lib.call(impl, P(G), P(X), P(dW), M, Nw, Kw, DT[dtype], st())
     torch.cuda.synchronize()
     ref = G.double().t() @ X.double()
-    return dict(rel=relerr(dW, ref))
+    out["rel"] = relerr(dW, ref)
+    return out
 
 
 def _bn_params(C, g):
@@ -165,8 +186,18 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0, fw
         dW2 = torch.zeros_like(w)
         c1, c2 = stat_buf(C), stat_buf(C)
         _lib.call("dfd_dwconv_bwd", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), P(scale), P(shift), P(mean), P(rstd), None,
-                  P(gx2), P(dW2), N, H, W, C, k, s, DT[dtype], P(c1), P(c2), st())
+                  P(gx2), P(dW2), N, H, W, C, k, s, DT[dtype], P(c1), P(c2), None, 0, st())
+        # the order-deterministic flush: two launches agree bit for bit, and with the atomic flush to fp32 round-off
+        kib = _lib.lib().cdll.dfd_dwconv_bwd_workspace_kib(N, H, W, C, k, s)
+        ws = torch.zeros(kib * 256, dtype=torch.int32, device="cuda")
+        dW3 = [torch.zeros_like(w), torch.zeros_like(w)]
+        for t in dW3:
+            c3, c4 = stat_buf(C), stat_buf(C)
+            _lib.call("dfd_dwconv_bwd", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), P(scale), P(shift), P(mean), P(rstd), None,
+                      P(gx2), P(t), N, H, W, C, k, s, DT[dtype], P(c3), P(c4), P(ws), kib * 1024, st())
         torch.cuda.synchronize()
+        res["det_bitwise"] = bool(torch.equal(dW3[0], dW3[1]))
+        res["det_vs_atomic"] = relerr(dW3[0], dW2)
         res["fused_gx_diff"] = float((gx2.float() - gx.float()).abs().max())
         res["fused_nan"] = int(torch.isnan(gx2.float()).sum())
         res["fused_wgrad_rel"] = relerr(dW2, wr.grad)
@@ -184,7 +215,7 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0, fw
         gx2 = torch.full((N, H, W, C), float("nan"), device="cuda", dtype=dtype)
         dW2 = torch.zeros_like(w)
         _lib.call("dfd_dwconv_bwd", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), None, None, None, None, P(add), P(gx2), P(dW2),
-                  N, H, W, C, k, s, DT[dtype], None, None, st())
+                  N, H, W, C, k, s, DT[dtype], None, None, None, 0, st())
         torch.cuda.synchronize()
         res["fused_gx_diff"] = float((gx2.float() - gx.float()).abs().max())
         res["fused_nan"] = int(torch.isnan(gx2.float()).sum())

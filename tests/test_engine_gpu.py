@@ -131,3 +131,28 @@ def test_fp16_dynamic_loss_scaling():
     torch.cuda.synchronize()
     assert torch.equal(e.params32, before)                               # step skipped
     assert abs(float(e.loss_scale_state[0]) / 1.5e38 - 1.0) < 1e-6 and int(e.flags[1]) == 0 and int(e.flags[0]) == 0
+
+
+def test_train_step_is_run_to_run_deterministic():
+    """Two independent engines, same weights and batch: bit-identical logits, loss AND gradients.  Weight gradients are
+    flushed through fixed-slot partials added in a fixed order (tcgen05 wgrad, fused depthwise backward, SE / classifier
+    parameter gradients, the loss), never through fp32 atomics.  The one order-dependent accumulation left is the fp64 BN
+    statistic (8 interleaved slots): its order effect is 2^-53 relative, i.e. a different fp32 mean / rstd with probability
+    ~2^-29 per channel - about 5e-5 per step for this network (documented in DESIGN.md section 4)."""
+    import torch
+    from deepfake_detection_b200.arch import get_spec
+    from deepfake_detection_b200.engine import Engine
+    from oracle.weights import synth_batch, synth_state
+    import engine_checks as EC
+    spec = get_spec("efficientnet_b0")
+    sd = synth_state(spec, seed=7)
+    x, y = synth_batch(32, 3, 128, 128, seed=5)
+    runs = []
+    for _ in range(2):
+        eng = Engine("efficientnet_b0", 32, 128, 128, dtype="bf16")
+        eng.load_state_dict(sd)
+        EC.engine_step(eng, None, x.cuda(), y.cuda())
+        runs.append((eng.logits.clone(), float(eng.loss), eng.grads32.clone()))
+        del eng
+    assert torch.equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1]
+    assert torch.equal(runs[0][2], runs[1][2]), float((runs[0][2] - runs[1][2]).abs().max())

@@ -56,6 +56,15 @@ def test_wgrad_tcgen05(M, Nw, Kw):
     assert _gc().check_wgrad(M, Nw, Kw, impl="dfd_gemm_wgrad")["rel"] < 1e-4
 
 
+@pytest.mark.parametrize("M,Nw,Kw", [(50176, 672, 112), (12544, 1280, 320), (3211264 // 8, 96, 16), (130, 40, 240), (70, 8, 8),
+                                     (12544, 512, 4608)])
+def test_wgrad_tcgen05_deterministic(M, Nw, Kw):
+    """order-deterministic flush (split partials in fixed slots, last split of a tile adds them in split order): two launches
+    agree bit for bit, the result matches fp64 and the atomic flush, the ticket counters return to zero"""
+    r = _gc().check_wgrad(M, Nw, Kw, impl="dfd_gemm_wgrad", det=True)
+    assert r["bitwise"] and r["tickets_at_rest"] and r["rel"] < 1e-4 and r["vs_atomic"] < 1e-5, r
+
+
 def test_wgrad_tcgen05_fp16():
     assert _gc().check_wgrad(3000, 144, 40, dtype=torch.float16, impl="dfd_gemm_wgrad")["rel"] < 1e-4
 

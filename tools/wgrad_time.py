@@ -6,7 +6,13 @@ def t(impl, M, Nw, Kw, reps=10):
     G = torch.randn(M, Nw, device="cuda").bfloat16(); X = torch.randn(M, Kw, device="cuda").bfloat16()
     dW = torch.zeros(Nw, Kw, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    f = lambda: _lib.call(impl, G.data_ptr(), X.data_ptr(), dW.data_ptr(), M, Nw, Kw, 0, st)
+    name = impl.replace("+det", "")
+    extra = ()
+    if name == "dfd_gemm_wgrad":
+        kib = _lib.lib().cdll.dfd_gemm_wgrad_workspace_kib(M, Nw, Kw)
+        ws = torch.zeros(kib * 256, dtype=torch.int32, device="cuda")
+        extra = (ws.data_ptr(), kib * 1024) if impl.endswith("+det") else (None, 0)
+    f = lambda: _lib.call(name, G.data_ptr(), X.data_ptr(), dW.data_ptr(), M, Nw, Kw, 0, *extra, st)
     for _ in range(3): f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -17,7 +23,7 @@ def t(impl, M, Nw, Kw, reps=10):
     rel = float((dW.double() - ref).norm() / ref.norm())
     print("%-20s M=%d Nw=%d Kw=%d ms=%.3f GB/s=%.0f rel=%.1e" % (impl, M, Nw, Kw, ms, 2 * M * (Nw + Kw) / ms / 1e6, rel), flush=True)
     return ms
-tot = {"dfd_gemm_wgrad_mma": 0.0, "dfd_gemm_wgrad": 0.0}
+tot = {"dfd_gemm_wgrad_mma": 0.0, "dfd_gemm_wgrad": 0.0, "dfd_gemm_wgrad+det": 0.0}
 for shp in [(3211264, 96, 16), (3211264, 32, 32), (3211264, 16, 32), (802816, 144, 24), (802816, 24, 144), (802816, 24, 96), (200704, 240, 40),
             (200704, 40, 240), (50176, 672, 112), (50176, 112, 672), (50176, 480, 80), (50176, 80, 480), (12544, 1152, 192), (12544, 192, 1152),
             (12544, 1280, 320), (12544, 320, 1152)]:
