@@ -4,6 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--arch efficientnet_b0] [--batch 256]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...        # the reference's arithmetic (oracle port) on the host cores
+    python bench.py --impl library ...          # the same module graph under stock PyTorch eager (autocast, channels_last,
+                                                # cuDNN / cuBLAS, torch DDP over NCCL): the bar SURVEY.md 8(d) names
 
 One "step" = one full train iteration of the reference's hot loop (dfd/runners/train.py:621-637) on a synthetic
 batch: forward, 2-class CE (sigmoid-BCE) loss + top-1, zero_grad, backward, [gradient all-reduce], SGD-nesterov
@@ -28,6 +30,20 @@ WORK = {
     "resnet50": dict(gflop=24.287, act_mb=108.44, bound="tensor", res=224),
     "resnet18": dict(gflop=10.645, act_mb=23.03, bound="tensor", res=224),
 }
+
+
+BASELINE_CFG = {("efficientnet_b0", 256, "bf16"): "BASELINE configs[1]/[2]", ("resnet50", 256, "bf16"): "BASELINE configs[3]",
+                ("efficientnet_b4", 128, "fp16"): "BASELINE configs[4]"}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def load_peaks():
@@ -182,7 +198,7 @@ def run_native(args):
     arch, B = args.arch, args.batch
     res = args.res or WORK[arch]["res"]
     lr = 0.0001 * B * world          # args.lr = batch * world * basic_lr (train.py:814), basic_lr small for stability
-    tr = Trainer(arch, B, res, res, dtype=args.dtype, opt="sgd", lr=lr, momentum=0.9, weight_decay=1e-4,
+    tr = Trainer(arch, B, res, res, dtype=args.dtype, opt=args.opt, lr=lr, momentum=0.9, weight_decay=1e-4,
                  use_graph=not args.no_graph, gemm_impl=args.gemm)
     spec = get_spec(arch)
     torch.manual_seed(42)
@@ -222,8 +238,10 @@ def run_native(args):
         ms = float(t)
 
     # ---- end to end through the public API with HOST buffers (H2D of the batch + D2H of the loss every step) ----
-    xh = torch.empty(B, spec.in_chans, res, res, dtype=e.tdtype).pin_memory()
-    xh.copy_(x.to(e.tdtype))
+    # the batch is what the reference's fast_collate hands its prefetcher: uint8 NCHW in pinned host memory
+    # (loader.py:14-41); Trainer.train_step_host uploads it on a copy stream (double-buffered) and normalises it on the device
+    xh = torch.empty(B, spec.in_chans, res, res, dtype=torch.uint8).pin_memory()
+    xh.copy_((x * 58.0 + 120.0).clamp_(0, 255).to(torch.uint8))
     yh = torch.empty(B, dtype=torch.int64).pin_memory()
     yh.copy_(y)
     for _ in range(3):
@@ -261,14 +279,14 @@ def run_native(args):
     # measured DRAM bytes per launch of that kernel (dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu
     # launch list, same workload: profiles/r01_ncu_launches.md), valid for the default workload only
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     if os.path.exists(tpath) and arch == "efficientnet_b0" and B == 256 and args.dtype == "bf16":
         try:
             with open(tpath) as f:
                 tj = json.load(f)
             ent = tj.get(top_name[len("dfd_"):] + "_kernel")
             if ent and ent["launches"] == tf["launches"]:
-                traffic, traffic_src = ent["dram_bytes_per_launch"], "profiles/r01_ncu_traffic.json"
+                traffic, traffic_src = ent["dram_bytes_per_launch"], "profiles/r02_ncu_traffic.json (ncu capture of this build, see its 'build' field)"
         except Exception:  # noqa: BLE001
             pass
     roofline = dict(bound="hbm", kernel=top_name, achieved=round(ach, 1), peak=peaks["hbm_gbs"], unit="GB/s",
@@ -280,19 +298,27 @@ def run_native(args):
                     families={k: dict(ms=round(v["ms"], 3), gbs=round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1), n=v["launches"])
                               for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:8]})
     cpu = cpu_baseline(arch, sample_steps=args.cpu_steps) if world == 1 and not args.no_cpu else None
-    n_launch = e.n_launch["fwd"] + e.n_launch["bwd"] + 3 + 4   # + head, optimizer groups, transposes, memsets
+    # C-ABI calls of ONE step, counted (not derived): an eager step with the call counter of the binding read before / after
+    from deepfake_detection_b200 import _lib as _L
+    c0 = _L.N_CALLS[0]
+    tr.optimizer.push_hyper()
+    tr._launch_step(False)
+    torch.cuda.synchronize()
+    n_launch = _L.N_CALLS[0] - c0
     line = dict(metric="images/sec (device-timed, max over ranks) %s 3x%dx%d train step" % (arch, res, res),
                 value=round(img_s, 1), unit="images/sec", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=round(ms / args.steps, 4), higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype=args.dtype, data="synthetic",
-                config=dict(workload="%s bf16 train step, synthetic 3x%dx%d, per-GPU batch %d (BASELINE configs[1]%s)" % (
-                    arch, res, res, B, "; DDP weak scaling" if world > 1 else ""), global_batch=B * world,
-                    optimizer="sgd-nesterov", l2_policy="working set (activations ~6 GB/step) far exceeds the 126 MB L2",
+                config=dict(workload="%s %s train step, synthetic 3x%dx%d, per-GPU batch %d (%s%s)" % (
+                    arch, args.dtype, res, res, B, BASELINE_CFG.get((arch, B, args.dtype), "not a BASELINE.json configuration"),
+                    "; DDP weak scaling" if world > 1 else ""), global_batch=B * world,
+                    optimizer=args.opt, l2_policy="working set (activations ~6 GB/step) far exceeds the 126 MB L2",
                     cuda_graph=tr._graph is not None, gemm=args.gemm, loss_final=loss_final),
                 roofline=roofline, cpu_baseline=cpu,
                 e2e=dict(value=round(e2e_img_s, 1), unit="images/sec",
-                         h2d_bytes_per_step=int(xh.numel() * xh.element_size() + yh.numel() * 8), d2h_bytes_per_step=16),
-                gpu_launches=n_launch * args.steps, clocks=clocks)
+                         h2d_bytes_per_step=int(xh.numel() * xh.element_size() + yh.numel() * 8), d2h_bytes_per_step=16,
+                         input="uint8 NCHW pinned host batch, uploaded on a copy stream (2 staging slots) and normalised on the device"),
+                gpu_launches=n_launch * args.steps, gpu_launches_per_step=n_launch, clocks=clocks)
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
@@ -333,10 +359,117 @@ def cpu_baseline(arch, sample_steps=4, batch=None, world=1):
         OT.train_step(spec, sd, x, y, opt)
         done += 1
     dt = time.perf_counter() - t0
-    return dict(value=round(b * done / dt, 2), unit="images/sec", cores=best_t, host_cpus=avail, kind="port",
+    return dict(value=round(b * done / dt, 2), unit="images/sec", cores=best_t, host_cpus=avail, cpu_model=cpu_model(), kind="port",
                 sample="%d train steps of %s fp32, batch %d, 3x%dx%d, torch CPU ops (oracle port of the reference's dfd.timm "
                        "modules + SGD), %d intra-op threads (fastest of a probe over pool sizes)" % (done, arch, b, res, res, best_t),
                 ms_per_step=round(dt / done * 1e3, 1))
+
+
+def run_library(args):
+    """Stock PyTorch eager on the same B200: the reference's module graph as torch.nn modules (baseline/library_model.py),
+    autocast to the benchmark dtype, channels_last, SGD-nesterov, torch DDP over NCCL when launched under torchrun.
+    No kernel, plan or engine of this repository is on this path."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from baseline.library_model import build
+    from deepfake_detection_b200.arch import get_spec
+    arch, B = args.arch, args.batch
+    res = args.res or WORK[arch]["res"]
+    spec = get_spec(arch)
+    torch.manual_seed(42)
+    torch.backends.cudnn.benchmark = True
+    model = build(spec).cuda().to(memory_format=torch.channels_last)
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
+    decay = [p for n, p in model.named_parameters() if p.dim() > 1 and not n.endswith(".bias")]
+    no_decay = [p for n, p in model.named_parameters() if not (p.dim() > 1 and not n.endswith(".bias"))]
+    opt = torch.optim.SGD([dict(params=no_decay, weight_decay=0.0), dict(params=decay, weight_decay=1e-4)],
+                          lr=0.0001 * B * world, momentum=0.9, nesterov=True)
+    adt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    scaler = torch.amp.GradScaler("cuda", enabled=adt == torch.float16)
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    x = torch.randn(B, spec.in_chans, res, res, device="cuda", generator=g).to(memory_format=torch.channels_last)
+    y = torch.randint(0, 2, (B,), device="cuda", generator=g)
+    loss_fn = torch.nn.CrossEntropyLoss()
+
+    def step(xb, yb):
+        with torch.autocast("cuda", dtype=adt):
+            out = model(xb)
+            loss = loss_fn(out.float(), yb)
+        opt.zero_grad(set_to_none=True)
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(x, y)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        loss = step(x, y)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    # end to end: uint8 pinned host batch, uploaded and normalised with the reference's own prefetcher expressions
+    xh = (x * 58.0 + 120.0).clamp_(0, 255).to(torch.uint8).contiguous(memory_format=torch.contiguous_format).cpu().pin_memory()
+    yh = y.cpu().pin_memory()
+    mean = torch.tensor([v * 255 for v in (0.485, 0.456, 0.406)], device="cuda").view(1, 3, 1, 1)
+    std = torch.tensor([v * 255 for v in (0.229, 0.224, 0.225)], device="cuda").view(1, 3, 1, 1)
+    pin_out = torch.empty(1).pin_memory()
+
+    def host_step():
+        xb = xh.cuda(non_blocking=True).float().sub_(mean).div_(std).contiguous(memory_format=torch.channels_last)
+        yb = yh.cuda(non_blocking=True)
+        pin_out.copy_(step(xb, yb).detach().float().reshape(1), non_blocking=True)
+
+    for _ in range(3):
+        host_step()
+    barrier()
+    e2e_steps = max(3, args.steps // 2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        host_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        torch.cuda.synchronize()
+    if rank != 0:
+        sys.stdout.flush()
+        os._exit(0)
+    img_s = B * world * args.steps / (ms / 1e3)
+    line = dict(impl="library", metric="images/sec (device-timed, max over ranks) %s 3x%dx%d train step" % (arch, res, res),
+                value=round(img_s, 1), unit="images/sec", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=round(ms / args.steps, 4), higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype,
+                data="synthetic",
+                config=dict(workload="%s %s train step, synthetic 3x%dx%d, per-GPU batch %d, stock PyTorch %s eager: autocast, "
+                                     "channels_last, cudnn.benchmark, SGD-nesterov%s" % (arch, args.dtype, res, res, B, torch.__version__,
+                                                                                         ", torch DDP/NCCL" if world > 1 else ""),
+                            global_batch=B * world, loss_final=float(loss)),
+                e2e=dict(value=round(B * world * e2e_steps / (e2e_ms / 1e3), 1), unit="images/sec",
+                         h2d_bytes_per_step=int(xh.numel() + yh.numel() * 8), d2h_bytes_per_step=4), gpu_launches=0)
+    print(json.dumps(line))
+    sys.stdout.flush()
+    if world > 1:
+        os._exit(0)
 
 
 def run_reference(args):
@@ -366,12 +499,15 @@ def main():
     ap.add_argument("--res", type=int, default=0)
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--gemm", default="tc")
+    ap.add_argument("--opt", default="sgd")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=4)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "library":
+        run_library(args)
     else:
         run_native(args)
 

@@ -22,13 +22,14 @@ SIGNATURES = {
     "dfd_gemm_tn_mma": "pppp" "lii" "i" "ppp",
     "dfd_gemm_wgrad_mma": "ppp" "lii" "i" "p",
     "dfd_gemm_wgrad": "ppp" "lii" "i" "pl" "p",
-    "dfd_gemm_wgrad_workspace_kib": "lii",
+    "dfd_gemm_wgrad_splits": "lii",
+    "dfd_ordered_reduce": "pi" "pl" "p",
     "dfd_dwconv_fwd": "ppppp" "iiiiii" "ii" "ppp",
     "dfd_dwconv_fwd_tc": "ppppp" "iiiiii" "ii" "ppp",
     "dfd_dwconv_dgrad": "ppppp" "pppppp" "pp" "iiiiii" "ii" "ppp",
     "dfd_dwconv_wgrad": "ppppp" "pppp" "iiiiii" "i" "p",
     "dfd_dwconv_bwd": "ppppp" "pppppp" "ppp" "iiiiii" "i" "pp" "pl" "p",
-    "dfd_dwconv_bwd_workspace_kib": "iiiiii",
+    "dfd_dwconv_bwd_parts": "iiiiii",
     "dfd_stem_fwd": "ppp" "iiiiiiii" "i" "ppp",
     "dfd_stem_wgrad": "ppppppp" "iiiiiiii" "i" "p",
     "dfd_colstats": "p" "ili" "i" "ppp",
@@ -107,6 +108,7 @@ class _Lib:
 
 
 _lib = None
+N_CALLS = [0]       # C-ABI calls issued by this process (bench.py reports the count of one step as `gpu_launches`)
 
 
 def lib():
@@ -119,6 +121,7 @@ def lib():
 def call(name, *args):
     """Call an entry point, raising NativeError on a non-zero status."""
     L = lib()
+    N_CALLS[0] += 1
     rc = getattr(L, name)(*args)
     if rc != 0:
         raise NativeError("%s failed (%d): %s" % (name, rc, L.last_error()))

@@ -564,6 +564,8 @@ int dfd_bn_act(const void* y, const float* scale, const float* shift, const floa
             case 0: LAUNCH(0, false, 0); break;
             case 1: LAUNCH(0, false, 1); break;
             case 2: LAUNCH(0, false, 2); break;
+            case 10: LAUNCH(0, true, 0); break;        // drop-path scaling of a gradient (unit affine, per-sample gate)
+            case 11: LAUNCH(0, true, 1); break;        // block tail with drop path: (scale*y + shift) * gate[n] + residual
             case 100: LAUNCH(1, false, 0); break;
             case 110: LAUNCH(1, true, 0); break;
             case 200: LAUNCH(2, false, 0); break;

@@ -31,29 +31,11 @@ struct DwGeom {
     int IH, IW;              // staged input tile
     int tiles_x, tiles_y;
     int dbg;                 // diagnostics (DFD_DW_DBG): 1 = skip the strip math, 2 = skip tile staging (fused backward only)
-    // order-deterministic weight-gradient flush of the fused backward (ws1 != NULL), see dwconv_bwd_kernel
-    float* ws1;              // [cbs][tiles][gz][k*k*64]  per-CTA partials
-    float* ws2;              // [cbs][tiles][k*k*64]      per-tile sums (over the image groups, in group order)
-    int* tk1;                // [cbs][tiles] ticket counters, zero at rest
-    int* tk2;                // [cbs]
+    // order-deterministic weight gradient of the fused backward (part != NULL): CTA (tile x, block y, group z) stores its
+    // k*k x 64 partial at part[y][x * gz + z][64 * k*k] in dW's own (channel, tap) order with plain stores and leaves dW alone;
+    // dfd_ordered_reduce adds the partials of every channel block in slot order later. NULL: fp32 atomics into dW.
+    float* part;
 };
-
-// Every thread of the CTA calls this after the CTA's partial result has been stored: true (in every thread) for the LAST
-// CTA of the group of `total` to arrive; the counter returns to zero for the next launch.
-__device__ __forceinline__ bool ticket_last(int* counter, int total) {
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int t = atomicAdd(counter, 1);
-        s_last = (t == total - 1);
-        if (s_last) *counter = 0;
-    }
-    __syncthreads();
-    const bool last = s_last != 0;
-    if (last) __threadfence();
-    return last;
-}
 
 __device__ __forceinline__ void load_chan_params(const float* p, int cbase, int C, float* out, float dflt) {
 #pragma unroll
@@ -708,7 +690,7 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
         wr[(warp * K * K + i) * 64 + lane * 2 + 1] = wacc[i][1];
     }
     __syncthreads();
-    if (!g.ws1) {
+    if (!g.part) {
         for (int e = threadIdx.x; e < K * K * 64; e += NT) {
             const int i = e >> 6, c = e & 63;
             if (c0 + c < g.C) {
@@ -721,36 +703,16 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
         }
         return;
     }
-    // ---- order-deterministic flush: fixed-slot partials, two ordered levels (image groups of a tile, then tiles) ----
+    // ---- order-deterministic mode: this CTA's partial goes to its fixed slot, laid out like dW[c0 .. c0+64) x taps ----
     constexpr int KK64 = K * K * 64;
-    const int tiles = gridDim.x;
-    const int grp = blockIdx.y * tiles + blockIdx.x;
-    float* slot = g.ws1 + ((size_t)grp * gridDim.z + blockIdx.z) * KK64;
+    float* slot = g.part + ((size_t)blockIdx.y * gridDim.x * gridDim.z + (size_t)blockIdx.x * gridDim.z + blockIdx.z) * KK64;
     for (int e = threadIdx.x; e < KK64; e += NT) {
-        const int i = e >> 6, c = e & 63;
+        const int c = e / (K * K), tap = e - c * (K * K);            // consecutive threads -> consecutive slot words
+        const int i = S == 1 ? (K * K - 1 - tap) : tap;
         float v = 0.f;
 #pragma unroll
         for (int q = 0; q < NW; q++) v += wr[(q * K * K + i) * 64 + c];
         slot[e] = v;
-    }
-    if (!ticket_last(g.tk1 + grp, gridDim.z)) return;
-    const float* zs = g.ws1 + (size_t)grp * gridDim.z * KK64;
-    float* tsum = g.ws2 + (size_t)grp * KK64;
-    for (int e = threadIdx.x; e < KK64; e += NT) {
-        float v = 0.f;
-        for (int z = 0; z < (int)gridDim.z; z++) v += __ldcg(zs + (size_t)z * KK64 + e);
-        tsum[e] = v;
-    }
-    if (!ticket_last(g.tk2 + blockIdx.y, tiles)) return;
-    const float* ts = g.ws2 + (size_t)blockIdx.y * tiles * KK64;
-    for (int e = threadIdx.x; e < KK64; e += NT) {
-        const int i = e >> 6, c = e & 63;
-        if (c0 + c < g.C) {
-            float v = 0.f;
-            for (int t = 0; t < tiles; t++) v += __ldcg(ts + (size_t)t * KK64 + e);
-            const int tap = S == 1 ? (K * K - 1 - i) : i;
-            dW[(size_t)(c0 + c) * K * K + tap] += v;
-        }
     }
 }
 
@@ -775,7 +737,7 @@ static int fill_geom(DwGeom& g, int N, int H, int W, int C, int K, int S, bool i
     g.tiles_x = (tw_dim + g.TW - 1) / g.TW;
     g.tiles_y = (th_dim + g.TH - 1) / g.TH;
     { const char* e = getenv("DFD_DW_DBG"); g.dbg = e ? atoi(e) : 0; }
-    g.ws1 = g.ws2 = nullptr; g.tk1 = g.tk2 = nullptr;
+    g.part = nullptr;
     return g.IH * g.IW * 32 * (int)sizeof(uint32_t);
 }
 
@@ -910,23 +872,15 @@ static void dw_bwd_grid(const DwGeom& g, int N, int C, int& tiles, int& cbs, int
     if (gz > N) gz = N;
     while (gz < N && N % gz) gz++;
 }
-static long long dw_bwd_ws_layout(int tiles, int cbs, int gz, int k, long long& off_ws2, long long& off_ws1) {
-    const long long kk64 = (long long)k * k * 64 * 4;
-    long long tk = ((long long)(tiles * cbs + cbs) * 4 + 4095) / 4096 * 4096;
-    off_ws2 = tk;
-    off_ws1 = tk + (long long)tiles * cbs * kk64;
-    return off_ws1 + (long long)tiles * cbs * gz * kk64;
-}
-
-// KiB of workspace that make the weight-gradient flush of dfd_dwconv_bwd order-deterministic for this shape
-int dfd_dwconv_bwd_workspace_kib(int N, int H, int W, int C, int k, int stride) {
+// partial slots per 64-channel block that the order-deterministic mode of dfd_dwconv_bwd writes (tiles x image groups); the
+// workspace holds ceil(C/64) x that x 64*k*k floats
+int dfd_dwconv_bwd_parts(int N, int H, int W, int C, int k, int stride) {
     if (C % 8 || N <= 0 || H <= 0 || W <= 0 || (k != 3 && k != 5) || (stride != 1 && stride != 2)) return 0;
     DwGeom g;
     fill_geom(g, N, H, W, C, k, stride, true);
     int tiles, cbs, gz;
     dw_bwd_grid(g, N, C, tiles, cbs, gz);
-    long long a, b;
-    return (int)((dw_bwd_ws_layout(tiles, cbs, gz, k, a, b) + 1023) / 1024);
+    return tiles * gz;
 }
 
 int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const float* cB, const float* cC,
@@ -944,13 +898,9 @@ int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const floa
     int tiles, cbs, gz;
     dw_bwd_grid(g, N, C, tiles, cbs, gz);
     if (ws) {
-        long long o2, o1;
-        if (dw_bwd_ws_layout(tiles, cbs, gz, k, o2, o1) > ws_bytes)
-            return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: workspace too small (dfd_dwconv_bwd_workspace_kib)");
-        g.tk1 = (int*)ws;
-        g.tk2 = g.tk1 + tiles * cbs;
-        g.ws2 = (float*)((char*)ws + o2);
-        g.ws1 = (float*)((char*)ws + o1);
+        if ((long long)cbs * tiles * gz * k * k * 64 * 4 > ws_bytes)
+            return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: workspace too small (ceil(C/64) x dfd_dwconv_bwd_parts x 64*k*k floats)");
+        g.part = (float*)ws;
     }
     dim3 grid(tiles, cbs, gz);
     cudaStream_t st = (cudaStream_t)stream;

@@ -405,11 +405,10 @@ struct WgParams {
     long long kb_per_split;
     int stages;
     int is_bf16;
-    // order-deterministic flush (ws != NULL): split z stores its fp32 partial tile at part[z][Nw][Kw]; the LAST split of a
-    // tile to arrive (ticket counter per tile, self-resetting) adds the partials in split order 0..splits-1 into dW.
-    // ws == NULL: red.global.add from every split (the order of fp32 additions then varies run to run).
+    // order-deterministic mode (part != NULL): split z stores its fp32 partial tile at part[z][Nw][Kw] with plain stores and
+    // dW is left alone; dfd_ordered_reduce adds the partials in split order later. part == NULL: red.global.add from every
+    // split straight into dW (the order of the fp32 additions then varies run to run).
     float* part;
-    int* tickets;           // [tiles_m * tiles_n], zero at rest
     int splits;
 };
 
@@ -498,7 +497,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constan
         const int row = m0 + q * 32 + lane;                  // dW row (output channel) of this TMEM lane
         const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16);
         if (p.part) {
-            // ---- deterministic path: plain stores of this split's partial tile, then the ticket ----
+            // ---- deterministic path: plain stores of this split's partial tile (summed later in split order) ----
             float* mine = p.part + (size_t)blockIdx.z * p.Nw * p.Kw;
             for (int c = 0; c < p.block_n; c += 16) {
                 uint32_t v[16];
@@ -511,33 +510,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constan
                         if (n0 + c + j < p.Kw)
                             *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                }
-            }
-            __shared__ int s_last;
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int et = threadIdx.x - 128;
-            if (et == 0) {
-                int* tk = p.tickets + blockIdx.y * gridDim.x + blockIdx.x;
-                const int t = atomicAdd(tk, 1);
-                s_last = (t == p.splits - 1);
-                if (s_last) *tk = 0;                           // at rest again for the next launch on this stream
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (s_last) {
-                __threadfence();
-                // 128 threads sweep the tile in float4 columns: coalesced reads of every split's partial, fixed order z = 0..
-                const int ncol4 = (min(p.block_n, p.Kw - n0) + 3) >> 2;
-                const int nrow = min(128, p.Nw - m0);
-                for (int e = et; e < nrow * ncol4; e += 128) {
-                    const int r = e / ncol4, c4 = e - r * ncol4;
-                    const size_t off = (size_t)(m0 + r) * p.Kw + n0 + c4 * 4;
-                    float4 acc = *reinterpret_cast<const float4*>(dW + off);
-                    for (int z = 0; z < p.splits; z++) {
-                        const float4 a = __ldcg(reinterpret_cast<const float4*>(p.part + (size_t)z * p.Nw * p.Kw + off));
-                        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-                    }
-                    *reinterpret_cast<float4*>(dW + off) = acc;
                 }
             }
         } else
@@ -720,18 +692,26 @@ int dfd_blockdiag_weights(const void* table, int count, int dt, void* stream) {
 }
 
 // dW[Nw,Kw] (fp32, accumulated) += G[M,Nw]^T * X[M,Kw] on tcgen05 (MN-major operands straight from NHWC, split over M)
-// KiB of workspace that make dfd_gemm_wgrad order-deterministic for this shape (tickets + the split partials)
-int dfd_gemm_wgrad_workspace_kib(long long M, int Nw, int Kw) {
-    if (M <= 0 || Nw <= 0 || Kw <= 0) return 0;
+// split count of the workspace (order-deterministic) mode: as many row ranges as fill the GPU once, but no more than keep
+// the partial-sum traffic (one write + one read of splits x Nw x Kw floats) under half of the operand traffic
+static long long wgrad_ws_splits(long long M, int Nw, int Kw, int sms) {
     const int block_n = Kw >= 128 ? 128 : ((Kw + 15) / 16) * 16;
     const long long kblocks = (M + WG_KP - 1) / WG_KP;
     const int tm = cdiv(Nw, 128), tn = cdiv(Kw, block_n);
-    long long splits = (2LL * 148 + tm * tn - 1) / (tm * tn);
-    long long max_splits = (kblocks + 3) / 4;
+    long long splits = (2LL * sms + tm * tn - 1) / (tm * tn);
+    const long long max_splits = (kblocks + 3) / 4;
     if (splits > max_splits) splits = max_splits;
+    const long long cap = (2 * M * ((long long)Nw + Kw)) / (2LL * 2 * 4 * Nw * Kw);
+    if (splits > cap) splits = cap;
     if (splits < 1) splits = 1;
-    const long long bytes = ((long long)tm * tn * 4 + 4095) / 4096 * 4096 + splits * Nw * (long long)Kw * 4;
-    return (int)((bytes + 1023) / 1024);
+    const long long kb_per = (kblocks + splits - 1) / splits;
+    return (kblocks + kb_per - 1) / kb_per;
+}
+
+// number of partial matrices [Nw, Kw] dfd_gemm_wgrad writes into its workspace for this shape (workspace bytes = that x Nw x Kw x 4)
+int dfd_gemm_wgrad_splits(long long M, int Nw, int Kw) {
+    if (M <= 0 || Nw <= 0 || Kw <= 0) return 0;
+    return (int)wgrad_ws_splits(M, Nw, Kw, 148);
 }
 
 int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* ws, long long ws_bytes,
@@ -752,20 +732,15 @@ int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw,
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     if (splits > 65535) splits = 65535;
-    p.part = nullptr; p.tickets = nullptr;
+    p.part = nullptr;
     if (ws) {
-        // tickets first (one int per tile, rounded up to 4 KiB), then `splits` partial matrices; fewer splits if they do not fit
-        const long long tk_bytes = ((long long)tm * tn * 4 + 4095) / 4096 * 4096;
-        const long long per = (long long)Nw * Kw * 4;
-        long long fit = (ws_bytes - tk_bytes) / per;
-        if (fit < 1) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_wgrad: workspace too small (dfd_gemm_wgrad_workspace_kib)");
-        if (splits > fit) splits = fit;
-        p.tickets = (int*)ws;
-        p.part = (float*)((char*)ws + tk_bytes);
+        splits = wgrad_ws_splits(M, Nw, Kw, 148);
+        if (splits * (long long)Nw * Kw * 4 > ws_bytes)
+            return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_wgrad: workspace too small (dfd_gemm_wgrad_splits x Nw x Kw floats)");
+        p.part = (float*)ws;
     }
     p.kb_per_split = (p.kblocks + splits - 1) / splits;
     splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
-    p.splits = (int)splits;
     const int nbox_b = p.block_n > 64 ? 2 : 1;
     const int stage_bytes = (2 + nbox_b) * WG_BOX_BYTES;
     const int fixed = 18 * 8 + 64 + 1024;

@@ -162,16 +162,18 @@ __global__ void se_fc_wgrad_kernel(const float* __restrict__ d_e, const float* _
             abr += dr;
         }
     }
-    float* slot = g_small_ws + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 512;
-    slot[threadIdx.x] = awe; slot[128 + threadIdx.x] = awr; slot[256 + threadIdx.x] = abe; slot[384 + threadIdx.x] = abr;
-    if (!ticket_last(g_small_tk + blockIdx.x, gridDim.y)) return;
-    if (!valid) return;
-    awe = awr = abe = abr = 0.f;
-    for (int y = 0; y < (int)gridDim.y; y++) {
-        const float* sl = g_small_ws + ((size_t)y * gridDim.x + blockIdx.x) * 512;
-        awe += __ldcg(sl + threadIdx.x); awr += __ldcg(sl + 128 + threadIdx.x);
-        abe += __ldcg(sl + 256 + threadIdx.x); abr += __ldcg(sl + 384 + threadIdx.x);
+    if (gridDim.y > 1) {
+        float* slot = g_small_ws + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 512;
+        slot[threadIdx.x] = awe; slot[128 + threadIdx.x] = awr; slot[256 + threadIdx.x] = abe; slot[384 + threadIdx.x] = abr;
+        if (!ticket_last(g_small_tk + blockIdx.x, gridDim.y)) return;
+        awe = awr = abe = abr = 0.f;
+        for (int y = 0; y < (int)gridDim.y; y++) {
+            const float* sl = g_small_ws + ((size_t)y * gridDim.x + blockIdx.x) * 512;
+            awe += __ldcg(sl + threadIdx.x); awr += __ldcg(sl + 128 + threadIdx.x);
+            abe += __ldcg(sl + 256 + threadIdx.x); abr += __ldcg(sl + 384 + threadIdx.x);
+        }
     }
+    if (!valid) return;
     dWe[(size_t)c * Cse + j] += awe;
     dWr[(size_t)j * C + c] += awr;
     if (j == 0) dbe[c] += abe;
@@ -496,8 +498,7 @@ int dfd_se_fc_bwd(const float* draw, const float* pooled, const float* Wr, const
     const int bx = cdiv((long long)C * Cse, 128);
     int nsplit = N >= 64 ? 16 : (N >= 8 ? 4 : 1);
     while (nsplit > 1 && ((long long)bx * nsplit > 2368 || (long long)nsplit * bx * 128 * 4 > SMALL_WS_FLOATS)) nsplit >>= 1;
-    if (bx > SMALL_TICKETS || (long long)nsplit * bx * 128 * 4 > SMALL_WS_FLOATS)
-        return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_se_fc_bwd: C * Cse exceeds the reduction scratch");
+    if (nsplit > 1 && bx > SMALL_TICKETS) nsplit = 1;          // a single split needs no scratch at all
     se_fc_wgrad_kernel<<<dim3(bx, nsplit), 128, 0, st>>>(d_e, r, d_rpre, pooled, dWr, dbr, dWe, dbe, N, C, Cse);
     DFD_LAUNCH_CHECK();
     return DFD_OK;

@@ -39,6 +39,7 @@ def distribute_bn(model, world_size, reduce=False, group=None):
         engine.buffers32 /= float(world_size)
     else:
         dist.broadcast(engine.buffers32, 0, group=group)
+    engine.arena.state_version += 1          # eval plans re-derive their BN scale / shift from the new running statistics
 
 
 def plan_buckets(spans, bucket_elems):
@@ -175,6 +176,7 @@ class GradReducer:
         a = self.arena
         dist.broadcast(a.params32, 0, group=self.group)
         dist.broadcast(a.buffers32, 0, group=self.group)
+        a.state_version += 1
         if not a._plan_only:
             a.sync_weights()
 

@@ -50,4 +50,5 @@ class ModelEma:
                   int(src.nbt.numel()), float(self.decay), st)
         _lib.call("dfd_ema_update", _ptr(dst.buffers32), _ptr(src.buffers32), int(src.buffers32.numel()), None, None, 0,
                   float(self.decay), st)
+        dst.state_version += 1
         self.ema._weights_dirty = True        # the 16-bit kernel copies are refreshed lazily, when the EMA model is evaluated

@@ -86,7 +86,12 @@ class Engine:
             self.rng_state = torch.zeros(2, dtype=torch.int64, device=self.device)
             self.rng_state[0] = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF          # follows torch.manual_seed (train.py:299)
             self._derived_dirty = False
+            # bumped whenever weights or BN running statistics change (load, a training forward, EMA / distribute_bn): an
+            # eval-mode plan recomputes its per-channel scale / shift vectors only when this moved (see forward)
+            self.state_version = 0
+        self._eval_version = -1
         self.params_only = bool(params_only)
+        self._red_pending, self._ws_bytes = [], 0
         if self.params_only:
             # the owner of the parameter / gradient / running-statistic arenas without any activation plan: what
             # `NativeModel.engine`, the optimizer and the EMA need (a plan is built per (batch, H, W) that reaches forward)
@@ -200,6 +205,7 @@ class Engine:
 
     def sync_weights(self):
         """fp32 master -> 16-bit kernel copies (call after any out-of-band weight change)."""
+        self.arena.state_version += 1
         st = torch.cuda.current_stream().cuda_stream
         _lib.call("dfd_cast_arena", _ptr(self.params32), _ptr(self.params16), self.n_params, self.dt, st)
         self.refresh_weight_layouts(st)
@@ -208,29 +214,65 @@ class Engine:
     # plan construction
     # ------------------------------------------------------------------------------------------
     # ---- order-deterministic weight gradients ------------------------------------------------------------------
-    # The tcgen05 weight gradient and the fused depthwise backward flush their split partial sums through ONE shared
-    # workspace (fixed slots + ticketed ordered adds, see include/dfd_b200.h) instead of fp32 atomics, so the gradients -
-    # and with them every later step - do not depend on the arrival order of CTAs. The ops are emitted with placeholders
-    # and patched once the largest requirement of the plan is known (kernels of one plan run back to back on one stream).
+    # The tcgen05 weight gradient and the fused depthwise backward run in WORKSPACE mode: every CTA stores its split partial
+    # sum in a fixed slot of one workspace (plain stores, no atomics) and `dfd_ordered_reduce` - one table-driven launch per
+    # block of the network, right behind that block's backward ops - adds the partials into the gradient arena in slot
+    # order. Gradients (and with them every later step) therefore do not depend on the arrival order of CTAs; the reduce
+    # launches are also the points at which a block's gradients become final for the DDP bucketing.
+    # DFD_NONDET=1 switches back to the atomic flushes (diagnostics / timing comparison).
     def _wgrad(self, G, X, dW, M, Nw, Kw):
         if self._wgrad_name != "dfd_gemm_wgrad":
             return (self._wgrad_name, (G, X, dW, M, Nw, Kw, self.dt))
-        self._ws_kib = max(getattr(self, "_ws_kib", 0), self.L.cdll.dfd_gemm_wgrad_workspace_kib(M, Nw, Kw))
-        return ("dfd_gemm_wgrad", [G, X, dW, M, Nw, Kw, self.dt, "WS", "WSB"])
+        if os.environ.get("DFD_NONDET"):
+            return ("dfd_gemm_wgrad", (G, X, dW, M, Nw, Kw, self.dt, None, 0))
+        splits = self.L.cdll.dfd_gemm_wgrad_splits(M, Nw, Kw)
+        off, nbytes = self._ws_take(splits * Nw * Kw * 4)
+        self._red_pending.append((off, dW, Nw * Kw, Nw * Kw, splits))
+        return ("dfd_gemm_wgrad", [G, X, dW, M, Nw, Kw, self.dt, ("WS", off), nbytes])
 
     def _dw_bwd(self, args, N, H, W, C, k, stride):
-        self._ws_kib = max(getattr(self, "_ws_kib", 0), self.L.cdll.dfd_dwconv_bwd_workspace_kib(N, H, W, C, k, stride))
-        return ("dfd_dwconv_bwd", list(args) + ["WS", "WSB"])
+        if os.environ.get("DFD_NONDET"):
+            return ("dfd_dwconv_bwd", list(args) + [None, 0])
+        parts = self.L.cdll.dfd_dwconv_bwd_parts(N, H, W, C, k, stride)
+        cbs = (C + 63) // 64
+        off, nbytes = self._ws_take(cbs * parts * 64 * k * k * 4)
+        dW = args[13]
+        for cb in range(cbs):
+            n = min(64, C - 64 * cb) * k * k
+            self._red_pending.append((off + cb * parts * 64 * k * k * 4, dW + cb * 64 * k * k * 4, n, 64 * k * k, parts))
+        return ("dfd_dwconv_bwd", list(args) + [("WS", off), nbytes])
+
+    def _ws_take(self, nbytes):
+        off = getattr(self, "_ws_bytes", 0)
+        self._ws_bytes = off + (nbytes + 255) // 256 * 256
+        return off, nbytes
+
+    def _flush_reduce(self, ops):
+        """emit the ordered-reduce launch for the partial sums produced since the last flush (call at block boundaries)"""
+        pend = self.__dict__.setdefault("_red_pending", [])
+        if pend:
+            ops.append(("dfd_ordered_reduce", ["REDUCE", list(pend)]))
+            del pend[:]
 
     def _patch_workspace(self, ops):
-        det = not os.environ.get("DFD_NONDET")
-        kib = getattr(self, "_ws_kib", 0)
-        if det and kib:
-            self.det_ws = torch.zeros(kib * 256, dtype=torch.int32, device=self.device)      # tickets must start at zero
-        out = []
+        import struct
+        self._flush_reduce(ops)
+        total = getattr(self, "_ws_bytes", 0)
+        if not total:
+            return ops
+        self.det_ws = torch.empty(total // 4, dtype=torch.float32, device=self.device)
+        base = _ptr(self.det_ws)
+        entries = [e for n, a in ops if n == "dfd_ordered_reduce" for e in a[1]]
+        raw = b"".join(struct.pack("<QQqqii", base + off, dst, n, stride, parts, 0) for off, dst, n, stride, parts in entries)
+        self._red_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+        out, pos = [], 0
         for n, a in ops:
-            if isinstance(a, list) and "WS" in a:
-                a = [(_ptr(self.det_ws) if det else None) if v == "WS" else ((kib * 1024 if det else 0) if v == "WSB" else v) for v in a]
+            if n == "dfd_ordered_reduce":
+                ents = a[1]
+                a = (_ptr(self._red_table, pos * 40), len(ents), min(e[1] for e in ents), max(e[2] for e in ents))
+                pos += len(ents)
+            elif isinstance(a, list):
+                a = [base + v[1] if isinstance(v, tuple) and v[0] == "WS" else v for v in a]
             out.append((n, a))
         return out
 
@@ -532,6 +574,7 @@ class Engine:
         cur = 0
         bwd.append(gemm(mid_b, T16("conv_head.weight"), sm[cur], Mf, spec.head_in, F))
         bwd.append(self._wgrad(mid_b, _ptr(self._head_in), G32("conv_head.weight"), Mf, F, spec.head_in))
+        self._flush_reduce(bwd)
         for rec in reversed(recs):
             b, h, w, ho, wo, xin = rec["b"], rec["h"], rec["w"], rec["ho"], rec["wo"], rec["x"]
             p = b.name
@@ -599,6 +642,7 @@ class Engine:
                                          _ptr(xin), None, None, None, None, dout if b.has_residual else None, t2,
                                          G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt, None, None),
                                         N, h, w, b.cmid, b.k, b.stride))
+            self._flush_reduce(bwd)
             cur = (cur + 2) % 3
         # stem
         bn = self.bns["bn1"]
@@ -609,6 +653,7 @@ class Engine:
             bwd.append(("dfd_bn_bwd_apply", (mid_a, _ptr(y0), None, bn.cA, bn.cB, bn.cC, mid_b, N, Hs * Ws, spec.stem, dt)))
             bwd.append(("dfd_memset_async", (_ptr(self.stem_gpad), 0, spec.stem * Kp * 4)))
             bwd.append(self._wgrad(mid_b, _ptr(self.stem_cols), _ptr(self.stem_gpad), N * Hs * Ws, spec.stem, Kp))
+            self._flush_reduce(bwd)          # the padded gradient must be complete before it is un-padded into the arena
             bwd.append(("dfd_unpad_grad", (_ptr(self.stem_gpad), G32("conv_stem.weight"), spec.stem, taps, Kp)))
         else:
             bwd.append(("dfd_stem_wgrad", (_ptr(self.x_in), mid_a, _ptr(y0), bn.cA, bn.cB, bn.cC, G32("conv_stem.weight"), N,
@@ -635,11 +680,13 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # execution
     # ------------------------------------------------------------------------------------------
-    def _run(self, ops, stream, training=None):
+    def _run(self, ops, stream, training=None, skip_finalize=False):
         if self._plan_only:
             raise _lib.NativeError("plan-only engine cannot execute (no CUDA device)")
         L = self.L
         for fn, name, args in ops:
+            if skip_finalize and name == "dfd_bn_finalize":
+                continue
             if name.endswith("_train"):
                 if not training:
                     continue
@@ -653,6 +700,7 @@ class Engine:
                                            "dfd_stem_fwd"):
                 args = tuple(args[:-2]) + (None, None)      # eval: no batch statistics
             rc = fn(*args, stream)
+            _lib.N_CALLS[0] += 1
             if rc != 0:
                 raise _lib.NativeError("%s failed (%d): %s" % (name, rc, L.last_error()))
 
@@ -679,7 +727,17 @@ class Engine:
     def forward(self, training=True, stream=None):
         """Runs the network on self.x_in; logits land in self.logits ([N, num_classes] fp32)."""
         st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-        self._run(self.fwd_ops, st, training)
+        ar = self.arena
+        if training:
+            ar.state_version += 1            # running statistics move
+            self._run(self.fwd_ops, st, True)
+        else:
+            # inference: BN is an affine map with constants (running statistics). Its per-channel scale / shift - the
+            # "folded" form every consumer kernel applies on load - is computed ONCE per weight state and kept, so a
+            # steady-state eval forward launches no BN kernel at all (test_img, validate; dfd/runners/test.py:29-60)
+            frozen = self._eval_version == ar.state_version
+            self._run(self.fwd_ops, st, False, skip_finalize=frozen)
+            self._eval_version = ar.state_version
         return self.logits
 
     def head(self, with_loss, smoothing=0.0, loss_scale=1.0, soft=False, stream=None, loss_scale_dev=None):

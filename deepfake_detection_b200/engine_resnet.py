@@ -199,8 +199,9 @@ def build_resnet(e):
                ("dfd_col2im", (COLS, dx_add, dx_out, N, n_h, n_w, Cin, 3, stride, 1, dt)),
                ("dfd_im2col", (_ptr(xin_t), COLS, N, n_h, n_w, Cin, 3, stride, 1, dt)),
                zero_gperm(Cout * 9 * Cin),
-               e._wgrad(dy, COLS, _ptr(e.gperm), M_out, Cout, 9 * Cin),
-               ("dfd_unpack_grad", (_ptr(e.gperm), G32(name), Cout, Cin, 3))]
+               e._wgrad(dy, COLS, _ptr(e.gperm), M_out, Cout, 9 * Cin)]
+        e._flush_reduce(ops)             # the permuted gradient must be complete before it is unpacked into the arena
+        ops.append(("dfd_unpack_grad", (_ptr(e.gperm), G32(name), Cout, Cin, 3)))
         return ops
 
     bwd.append(("dfd_head_bwd", (_ptr(e.dlogits), _ptr(e.pooled), P32("fc.weight"), G32("fc.weight"), G32("fc.bias"),
@@ -264,6 +265,7 @@ def build_resnet(e):
         else:
             bwd.append(("dfd_add_inplace", (t3, gm, M1 * b.cin, dt)))
             new_dout = t3
+        e._flush_reduce(bwd)
         allb = [dout] + free
         free = [g for g in allb if g != new_dout]
         dout = new_dout
@@ -277,6 +279,7 @@ def build_resnet(e):
         bwd.append(("dfd_bn_bwd_apply", (t2, _ptr(y0), None, bn0.cA, bn0.cB, bn0.cC, t1, N, H1 * W1, 64, dt)))
         bwd.append(("dfd_memset_async", (_ptr(e.stem_gpad), 0, 64 * Kp * 4)))
         bwd.append(e._wgrad(t1, _ptr(e.stem_cols), _ptr(e.stem_gpad), N * H1 * W1, 64, Kp))
+        e._flush_reduce(bwd)
         bwd.append(("dfd_unpad_grad", (_ptr(e.stem_gpad), G32("conv1.weight"), 64, taps, Kp)))
     else:
         bwd.append(("dfd_stem_wgrad", (_ptr(e.x_in), t2, _ptr(y0), bn0.cA, bn0.cB, bn0.cC, G32("conv1.weight"), N, spec.in_chans,

@@ -21,11 +21,12 @@ class Trainer:
     def __init__(self, arch, batch, height=None, width=None, dtype="bf16", opt="sgd", lr=0.01, momentum=0.9,
                  weight_decay=1e-4, opt_eps=1e-8, smoothing=0.0, num_classes=2, in_chans=3, bn_momentum=0.1,
                  bn_eps=1e-5, use_graph=True, gemm_impl="tc", process_group=None, bucket_mb=8.0, loss_scale=None,
-                 scale_window=2000):
+                 scale_window=2000, drop_rate=0.0, drop_path_rate=0.0, opt_alpha=0.9):
         self.engine = Engine(arch, batch, height, width, num_classes=num_classes, in_chans=in_chans, dtype=dtype,
-                             bn_momentum=bn_momentum, bn_eps=bn_eps, gemm_impl=gemm_impl)
+                             bn_momentum=bn_momentum, bn_eps=bn_eps, gemm_impl=gemm_impl, drop_rate=drop_rate,
+                             drop_path_rate=drop_path_rate)
         self.optimizer = ArenaOptimizer(self.engine, opt=opt, lr=lr, momentum=momentum, weight_decay=weight_decay,
-                                        eps=opt_eps)
+                                        eps=opt_eps, alpha=opt_alpha)
         self.smoothing = float(smoothing)
         # fp16: dynamic loss scaling with skip-on-overflow (apex AMP O1 semantics, train.py:353,632-634), entirely on the
         # device: scale / 1/scale / overflow flag / clean-step counter live in engine.loss_scale_state and engine.flags
@@ -84,6 +85,7 @@ class Trainer:
 
     def step_resident(self, soft=False):
         """One full train step on the batch already resident in engine.x_in / target_i|target_f."""
+        self.engine.arena.state_version += 1     # weights and running statistics move (a graph replay does not run Python)
         self.optimizer.push_hyper()          # param_groups[i]['lr'] of THIS step -> device (outside the captured graph)
         if not self.use_graph:
             self._launch_step(soft)

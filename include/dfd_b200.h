@@ -65,10 +65,14 @@ int dfd_gemm_wgrad_mma(const void* G, const void* X, float* dW, long long M, int
  * accumulator in TMEM over a contiguous range of rows per CTA, one red.global.add flush */
 int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* ws, long long ws_bytes,
                    void* stream);
-/* ws (optional, zero-initialised once by the caller, >= dfd_gemm_wgrad_workspace_kib KiB): makes the flush ORDER-DETERMINISTIC -
- * every split stores its fp32 partial tile and the last split of a tile to arrive adds them in split order (per-tile ticket
- * counters, self-resetting), instead of red.global.add from every split in arrival order. NULL: the atomic flush. */
-int dfd_gemm_wgrad_workspace_kib(long long M, int Nw, int Kw);
+/* ws (optional): ORDER-DETERMINISTIC mode - split z stores its fp32 partial matrix at ws[z][Nw][Kw] with plain stores, dW is
+ * not touched, and dfd_ordered_reduce adds the dfd_gemm_wgrad_splits(M, Nw, Kw) partials into dW in split order afterwards
+ * (ws_bytes >= splits * Nw * Kw * 4). NULL: red.global.add from every split straight into dW, in arrival order. */
+int dfd_gemm_wgrad_splits(long long M, int Nw, int Kw);
+/* dst[i] += sum_{p < parts} src[p * stride + i], i < n, partials added in index order. table: device array of
+ * { const float* src; float* dst; long long n; long long stride; int parts; int _pad; } (n % 4 == 0, 16-byte aligned);
+ * max_n sizes the grid; first_dst (the lowest gradient address written) is informational for host-side planners. */
+int dfd_ordered_reduce(const void* table, int count, const float* first_dst, long long max_n, void* stream);
 
 /* ---- depthwise k x k convolution: nn.Conv2d(groups=C), efficientnet_blocks.py:152-153,283-285 -------- */
 int dfd_dwconv_fwd(const void* x, const float* scale, const float* shift, const float* w, void* out, int N, int H,
@@ -90,10 +94,11 @@ int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const floa
                    const float* w, const void* xin, const float* scale, const float* shift, const float* mean,
                    const float* rstd, const void* add, void* gx, float* dW, int N, int H, int W, int C, int k,
                    int stride, int dt, double* s1, double* s2, void* ws, long long ws_bytes, void* stream);
-/* ws (optional, zero-initialised once by the caller, >= dfd_dwconv_bwd_workspace_kib KiB): order-deterministic dW - every CTA
- * stores its k*k x 64 partial in a fixed slot; the last CTA of a tile's image groups adds them in group order, the last tile
- * of a channel block adds the tile sums in tile order into dW (ticket counters, self-resetting). NULL: fp32 atomics. */
-int dfd_dwconv_bwd_workspace_kib(int N, int H, int W, int C, int k, int stride);
+/* ws (optional): ORDER-DETERMINISTIC dW - CTA (tile x, 64-channel block y, image group z) stores its partial at
+ * ws[y][x * groups + z][64 * k*k] laid out like dW[64y .. 64y+64)[k*k] and dfd_ordered_reduce adds the
+ * dfd_dwconv_bwd_parts(...) = tiles * groups partials of every channel block into dW in slot order afterwards
+ * (ws_bytes >= ceil(C/64) * parts * 64*k*k * 4). NULL: fp32 atomics into dW. */
+int dfd_dwconv_bwd_parts(int N, int H, int W, int C, int k, int stride);
 
 /* ---- stem convolution: conv_stem 3x3 s2 (efficientnet.py:275,321) / conv1 7x7 s2 (resnet.py:379,451) ---- */
 int dfd_stem_fwd(const void* x_nchw, const float* w, void* out_nhwc, int N, int Cin, int H, int W, int Cout, int k,

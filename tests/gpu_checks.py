@@ -95,21 +95,24 @@ def check_wgrad(M, Nw, Kw, dtype=torch.bfloat16, seed=0, impl="dfd_gemm_wgrad_mm
     dW = torch.zeros(Nw, Kw, device="cuda")
     out = {}
     if impl == "dfd_gemm_wgrad":
-        ws, wsb = None, 0
-        if det:
-            kib = _lib.lib().cdll.dfd_gemm_wgrad_workspace_kib(M, Nw, Kw)
-            ws = torch.zeros(kib * 256, dtype=torch.int32, device="cuda")
-            wsb = kib * 1024
-        _lib.call(impl, P(G), P(X), P(dW), M, Nw, Kw, DT[dtype], P(ws), wsb, st())
-        if det:
+        if not det:
+            _lib.call(impl, P(G), P(X), P(dW), M, Nw, Kw, DT[dtype], None, 0, st())
+        else:
+            import struct
+            splits = _lib.lib().cdll.dfd_gemm_wgrad_splits(M, Nw, Kw)
+            ws = torch.full((splits, Nw, Kw), float("nan"), device="cuda")
             again = torch.zeros(Nw, Kw, device="cuda")
-            _lib.call(impl, P(G), P(X), P(again), M, Nw, Kw, DT[dtype], P(ws), wsb, st())
+            for dst in (dW, again):
+                _lib.call(impl, P(G), P(X), P(dst), M, Nw, Kw, DT[dtype], P(ws), ws.numel() * 4, st())
+                table = torch.frombuffer(bytearray(struct.pack("<QQqqii", P(ws), P(dst), Nw * Kw, Nw * Kw, splits, 0)), dtype=torch.uint8).cuda()
+                _lib.call("dfd_ordered_reduce", P(table), 1, P(dst), Nw * Kw, st())
+                torch.cuda.synchronize()
             atomic = torch.zeros(Nw, Kw, device="cuda")
             _lib.call(impl, P(G), P(X), P(atomic), M, Nw, Kw, DT[dtype], None, 0, st())
             torch.cuda.synchronize()
             out["bitwise"] = bool(torch.equal(dW, again))
             out["vs_atomic"] = relerr(dW, atomic)
-            out["tickets_at_rest"] = int(ws[:1024].abs().sum()) == 0
+            out["splits"] = splits
     else:
         _lib.call(impl, P(G), P(X), P(dW), M, Nw, Kw, DT[dtype], st())
     torch.cuda.synchronize()
@@ -187,15 +190,22 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0, fw
         c1, c2 = stat_buf(C), stat_buf(C)
         _lib.call("dfd_dwconv_bwd", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), P(scale), P(shift), P(mean), P(rstd), None,
                   P(gx2), P(dW2), N, H, W, C, k, s, DT[dtype], P(c1), P(c2), None, 0, st())
-        # the order-deterministic flush: two launches agree bit for bit, and with the atomic flush to fp32 round-off
-        kib = _lib.lib().cdll.dfd_dwconv_bwd_workspace_kib(N, H, W, C, k, s)
-        ws = torch.zeros(kib * 256, dtype=torch.int32, device="cuda")
+        # order-deterministic mode: partials in fixed slots + ordered reduce; two runs agree bit for bit, and with the atomic
+        # flush to fp32 round-off
+        import struct
+        parts = _lib.lib().cdll.dfd_dwconv_bwd_parts(N, H, W, C, k, s)
+        cbs = (C + 63) // 64
+        ws = torch.full((cbs, parts, 64 * k * k), float("nan"), device="cuda")
         dW3 = [torch.zeros_like(w), torch.zeros_like(w)]
         for t in dW3:
             c3, c4 = stat_buf(C), stat_buf(C)
             _lib.call("dfd_dwconv_bwd", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), P(scale), P(shift), P(mean), P(rstd), None,
-                      P(gx2), P(t), N, H, W, C, k, s, DT[dtype], P(c3), P(c4), P(ws), kib * 1024, st())
-        torch.cuda.synchronize()
+                      P(gx2), P(t), N, H, W, C, k, s, DT[dtype], P(c3), P(c4), P(ws), ws.numel() * 4, st())
+            raw = b"".join(struct.pack("<QQqqii", P(ws) + cb * parts * 64 * k * k * 4, P(t) + cb * 64 * k * k * 4,
+                                       min(64, C - 64 * cb) * k * k, 64 * k * k, parts, 0) for cb in range(cbs))
+            table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
+            _lib.call("dfd_ordered_reduce", P(table), cbs, P(t), 64 * k * k, st())
+            torch.cuda.synchronize()
         res["det_bitwise"] = bool(torch.equal(dW3[0], dW3[1]))
         res["det_vs_atomic"] = relerr(dW3[0], dW2)
         res["fused_gx_diff"] = float((gx2.float() - gx.float()).abs().max())
@@ -414,12 +424,12 @@ def check_optimizer(kind, n=10007, steps=3, dtype=torch.bfloat16, seed=0):
         gr = torch.randn(n, device="cuda", generator=g)
         OT.optimizer_step(opt, p_ref, {"w": gr.cpu().view(n, 1)})
         if kind == "sgd":
-            _lib.call("dfd_sgd_step", P(p), P(gr), P(a), n, lr, mom, wd, 1, 1.0, None, None, P(p16), DT[dtype], st())
+            _lib.call("dfd_sgd_step", P(p), P(gr), P(a), n, lr, mom, wd, 1, 1.0, None, None, P(p16), DT[dtype], None, st())
         elif kind in ("adam", "adamw"):
             _lib.call("dfd_adam_step", P(p), P(gr), P(a), P(b), n, lr, 0.9, 0.999, eps, wd, 1 if kind == "adamw" else 0, s + 1, 1.0,
-                      None, None, P(p16), DT[dtype], st())
+                      None, None, P(p16), DT[dtype], None, None, st())
         else:
-            _lib.call("dfd_rmsprop_tf_step", P(p), P(gr), P(a), P(b), n, lr, 0.9, eps, wd, mom, 1.0, None, None, P(p16), DT[dtype], st())
+            _lib.call("dfd_rmsprop_tf_step", P(p), P(gr), P(a), P(b), n, lr, 0.9, eps, wd, mom, 1.0, None, None, P(p16), DT[dtype], None, st())
         torch.cuda.synchronize()
         worst = max(worst, relerr(p.cpu(), p_ref["w"].view(-1)))
     return dict(rel=worst, p16_rel=relerr(p16.float(), p.to(dtype).float()))

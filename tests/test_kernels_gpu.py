@@ -59,10 +59,10 @@ def test_wgrad_tcgen05(M, Nw, Kw):
 @pytest.mark.parametrize("M,Nw,Kw", [(50176, 672, 112), (12544, 1280, 320), (3211264 // 8, 96, 16), (130, 40, 240), (70, 8, 8),
                                      (12544, 512, 4608)])
 def test_wgrad_tcgen05_deterministic(M, Nw, Kw):
-    """order-deterministic flush (split partials in fixed slots, last split of a tile adds them in split order): two launches
-    agree bit for bit, the result matches fp64 and the atomic flush, the ticket counters return to zero"""
+    """order-deterministic mode (split partials in fixed workspace slots + dfd_ordered_reduce in split order): two runs agree
+    bit for bit, the result matches fp64 and the atomic flush"""
     r = _gc().check_wgrad(M, Nw, Kw, impl="dfd_gemm_wgrad", det=True)
-    assert r["bitwise"] and r["tickets_at_rest"] and r["rel"] < 1e-4 and r["vs_atomic"] < 1e-5, r
+    assert r["bitwise"] and r["rel"] < 1e-4 and r["vs_atomic"] < 1e-5, r
 
 
 def test_wgrad_tcgen05_fp16():

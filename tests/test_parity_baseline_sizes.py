@@ -54,20 +54,30 @@ def _oracle(arch, batch, res, init="synthetic", act_dtype=None):
 
 def _native(arch, batch, res, dtype, init="synthetic", per_tensor=False):
     import engine_checks as EC
-    from deepfake_detection_b200.engine import Engine
-    from deepfake_detection_b200.optim import ArenaOptimizer
+    from deepfake_detection_b200.trainer import Trainer
     o = _oracle(arch, batch, res, init)
-    eng = Engine(arch, batch, res, res, dtype=dtype)
-    eng.load_state_dict(_weights(o["spec"], init))
-    opt = ArenaOptimizer(eng, opt="sgd", lr=0.01, momentum=0.9, weight_decay=1e-4)
-    EC.engine_step(eng, opt, o["x"].cuda(), o["y"].cuda())
+    # the public one-call step; fp16 runs with dynamic loss scaling on the device, as the reference does under apex AMP O1
+    # (train.py:353,632-634) - without it fp16 gradients of this size underflow and parity is meaningless
+    tr = Trainer(arch, batch, res, res, dtype=dtype, opt="sgd", lr=0.01, momentum=0.9, weight_decay=1e-4, use_graph=False)
+    eng, opt = tr.engine, tr.optimizer
+    for attempt in range(8):
+        # apex semantics: an overflowing step is skipped and the scale halves; parity is stated on the first APPLIED step,
+        # from the same starting state (the scale found so far is kept)
+        tr.load_state_dict(_weights(o["spec"], init))
+        tr.train_step(o["x"].cuda(), o["y"].cuda())
+        torch.cuda.synchronize()
+        if not tr.dynamic_scale or int(eng.flags[1]) == 1:
+            break
+    else:
+        raise AssertionError("no fp16 step was applied in 8 attempts (loss scale %g)" % float(eng.loss_scale_state[0]))
+    worst = max((EC.relerr(eng.param_view(n), o["sd"][n]), n) for n in o["pnames"])
     r = dict(loss_rel=abs(float(eng.loss) - o["loss"]) / abs(o["loss"]), logits_rel=EC.relerr(eng.logits, o["logits"]),
-             weights_rel_worst=max(EC.relerr(eng.param_view(n), o["sd"][n]) for n in o["pnames"]),
+             weights_rel_worst=worst[0], weights_worst_name=worst[1],
              buffers_rel_worst=max(EC.relerr(eng.buffer_view(n).float(), o["sd"][n].float()) for n in o["sd"]
                                    if n not in o["pnames"] and not n.endswith("num_batches_tracked")))
     if per_tensor:
         r["weights_rel"] = {n: EC.relerr(eng.param_view(n), o["sd"][n]) for n in o["pnames"]}
-    del eng, opt
+    del eng, opt, tr
     torch.cuda.empty_cache()
     return r
 

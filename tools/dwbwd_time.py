@@ -12,11 +12,21 @@ def t(N, H, W, C, k, s, reps=10, det=True):
     v = [torch.rand(C, device="cuda") + 0.5 for _ in range(7)]
     s1 = torch.zeros(8, C, dtype=torch.float64, device="cuda"); s2 = torch.zeros_like(s1)
     st = torch.cuda.current_stream().cuda_stream
-    kib = _lib.lib().cdll.dfd_dwconv_bwd_workspace_kib(N, H, W, C, k, s)
-    ws = torch.zeros(kib * 256, dtype=torch.int32, device="cuda") if det else None
-    f = lambda: _lib.call("dfd_dwconv_bwd", gy.data_ptr(), y.data_ptr(), v[0].data_ptr(), v[1].data_ptr(), v[2].data_ptr(), w.data_ptr(),
+    import struct
+    parts = _lib.lib().cdll.dfd_dwconv_bwd_parts(N, H, W, C, k, s)
+    cbs = (C + 63) // 64
+    ws = torch.empty(cbs * parts * 64 * k * k, device="cuda") if det else None
+    if det:
+        raw = b"".join(struct.pack("<QQqqii", ws.data_ptr() + cb * parts * 64 * k * k * 4, dW.data_ptr() + cb * 64 * k * k * 4,
+                                   min(64, C - 64 * cb) * k * k, 64 * k * k, parts, 0) for cb in range(cbs))
+        table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
+    f0 = lambda: _lib.call("dfd_dwconv_bwd", gy.data_ptr(), y.data_ptr(), v[0].data_ptr(), v[1].data_ptr(), v[2].data_ptr(), w.data_ptr(),
                           x.data_ptr(), v[3].data_ptr(), v[4].data_ptr(), v[5].data_ptr(), v[6].data_ptr(), None, gx.data_ptr(), dW.data_ptr(),
-                          N, H, W, C, k, s, 0, s1.data_ptr(), s2.data_ptr(), ws.data_ptr() if det else None, kib * 1024 if det else 0, st)
+                          N, H, W, C, k, s, 0, s1.data_ptr(), s2.data_ptr(), ws.data_ptr() if det else None, ws.numel() * 4 if det else 0, st)
+    def f():
+        f0()
+        if det:
+            _lib.call("dfd_ordered_reduce", table.data_ptr(), cbs, dW.data_ptr(), 64 * k * k, st)
     for _ in range(3): f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

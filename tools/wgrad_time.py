@@ -8,11 +8,17 @@ def t(impl, M, Nw, Kw, reps=10):
     st = torch.cuda.current_stream().cuda_stream
     name = impl.replace("+det", "")
     extra = ()
+    det = impl.endswith("+det")
     if name == "dfd_gemm_wgrad":
-        kib = _lib.lib().cdll.dfd_gemm_wgrad_workspace_kib(M, Nw, Kw)
-        ws = torch.zeros(kib * 256, dtype=torch.int32, device="cuda")
-        extra = (ws.data_ptr(), kib * 1024) if impl.endswith("+det") else (None, 0)
-    f = lambda: _lib.call(name, G.data_ptr(), X.data_ptr(), dW.data_ptr(), M, Nw, Kw, 0, *extra, st)
+        import struct
+        splits = _lib.lib().cdll.dfd_gemm_wgrad_splits(M, Nw, Kw)
+        ws = torch.empty(splits * Nw * Kw, device="cuda")
+        extra = (ws.data_ptr(), ws.numel() * 4) if det else (None, 0)
+        table = torch.frombuffer(bytearray(struct.pack("<QQqqii", ws.data_ptr(), dW.data_ptr(), Nw * Kw, Nw * Kw, splits, 0)), dtype=torch.uint8).cuda()
+    def f():
+        _lib.call(name, G.data_ptr(), X.data_ptr(), dW.data_ptr(), M, Nw, Kw, 0, *extra, st)
+        if det:
+            _lib.call("dfd_ordered_reduce", table.data_ptr(), 1, dW.data_ptr(), Nw * Kw, st)
     for _ in range(3): f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
