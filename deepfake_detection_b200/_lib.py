@@ -23,7 +23,7 @@ SIGNATURES = {
     "dfd_gemm_wgrad_mma": "ppp" "lii" "i" "p",
     "dfd_gemm_wgrad": "ppp" "lii" "i" "pl" "p",
     "dfd_gemm_wgrad_splits": "lii",
-    "dfd_ordered_reduce": "pi" "pl" "p",
+    "dfd_ordered_reduce": "pi" "pi" "p",
     "dfd_dwconv_fwd": "ppppp" "iiiiii" "ii" "ppp",
     "dfd_dwconv_fwd_tc": "ppppp" "iiiiii" "ii" "ppp",
     "dfd_dwconv_dgrad": "ppppp" "pppppp" "pp" "iiiiii" "ii" "ppp",
@@ -44,6 +44,9 @@ SIGNATURES = {
     "dfd_add_inplace": "pp" "li" "p",
     "dfd_se_fc_fwd": "pppppp" "iii" "p",
     "dfd_se_fc_bwd": "pppppp" "pppppppp" "iii" "p",
+    "dfd_se_fc_wgrad": "pppp" "pppp" "iii" "p",
+    "dfd_pool_se": "pppp" "ppppp" "ili" "iii" "i" "p",
+    "dfd_se_bwd_chain": "ppppp" "ppppp" "pppp" "ili" "ii" "p",
     "dfd_head_fwd": "pppp" "iii" "pp" "ff" "pppp" "p",
     "dfd_head_bwd": "pppppp" "iii" "p",
     "dfd_sgd_step": "ppp" "l" "fffi" "f" "ppp" "i" "p" "p",

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) ordered_reduce_kernel(const RedDesc* __re
     if (d.parts <= 64) {
         for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
             float4 acc = dst[i];
-#pragma unroll 4
+#pragma unroll 8
             for (int p = 0; p < d.parts; p++) {
                 const float4 a = __ldcg(src + p * s4 + i);
                 acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
@@ -94,14 +94,14 @@ __global__ void __launch_bounds__(256) ordered_reduce_kernel(const RedDesc* __re
 }
 }  // namespace
 
-extern "C" int dfd_ordered_reduce(const void* table, int count, const float* first_dst, long long max_n, void* stream) {
+extern "C" int dfd_ordered_reduce(const void* table, int count, const float* first_dst, int blocks_x, void* stream) {
     (void)first_dst;       // lowest gradient address this launch writes: lets a host-side planner place it (no device use)
     if (count <= 0) return DFD_OK;
-    if (!table || max_n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_ordered_reduce: operands");
-    long long bx = (max_n / 4 + 255) / 256;
-    if (bx < 1) bx = 1;
-    if (bx > 64) bx = 64;
-    ordered_reduce_kernel<<<dim3((unsigned)bx, (unsigned)count), 256, 0, (cudaStream_t)stream>>>((const RedDesc*)table);
+    if (!table || blocks_x <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_ordered_reduce: operands");
+    // blocks_x: CTAs per entry. A CTA covers 256 float4 per trip of an entry with <= 64 parts and 8 float4 per trip of an
+    // entry with more (32 part-lanes each); the caller sizes it for its largest entry (any value is correct)
+    if (blocks_x > 2048) blocks_x = 2048;
+    ordered_reduce_kernel<<<dim3((unsigned)blocks_x, (unsigned)count), 256, 0, (cudaStream_t)stream>>>((const RedDesc*)table);
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

@@ -13,8 +13,28 @@
 //   SE gate, residual    dfd/timm/models/efficientnet_blocks.py:104-110, 343-346
 //   global average pool  dfd/timm/models/efficientnet.py:340-343
 #include "common.cuh"
+#include "se_chain.cuh"
 
 namespace {
+
+// scratch of the chunked per-image reductions (library-owned, zero at load; tickets self-reset): when an image is reduced
+// by several CTAs their partial sums go to fixed slots [chunk][image][C] and the last CTA of the image to arrive (ticket)
+// adds them in chunk order - and then carries on with whatever depends on the completed per-image vector (the SE FCs)
+constexpr long long ROWRED_WS_FLOATS = 4LL << 20;
+constexpr int ROWRED_TICKETS = 65536;
+__device__ float g_rowred_ws[ROWRED_WS_FLOATS];
+__device__ int g_rowred_tk[ROWRED_TICKETS];
+
+struct SeFwdArgs {          // squeeze-excite forward chain behind a pooling (Wr == NULL: plain pooling)
+    const float *Wr, *br, *We, *be;
+    float* gate;            // [n, C]
+    int Cse;
+};
+struct SeBwdArgs {          // squeeze-excite backward chain behind the gate-gradient reduction (Wr == NULL: reduce only)
+    const float *pooled, *Wr, *br, *We, *be;
+    float *d_e, *r, *d_rpre, *dpool;
+    int Cse;
+};
 
 struct RowGeom {
     dim3 block;
@@ -193,8 +213,8 @@ __global__ void bn_act_kernel(const T* __restrict__ y, const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 template <typename T, int ACT>
 __global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ scale,
-                            const float* __restrict__ shift, float* __restrict__ pooled, float* __restrict__ partial,
-                            long long hw, long long rows_per_block) {
+                            const float* __restrict__ shift, float* __restrict__ pooled,
+                            long long hw, long long rows_per_block, const SeFwdArgs se) {
     extern __shared__ float sm[];
     const int V = blockDim.x, C = V * 8;
     const int c0 = threadIdx.x * 8;
@@ -207,7 +227,7 @@ __global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ s
     }
     const T* base = y + (size_t)blockIdx.y * hw * C + c0;
     // gridDim.x row chunks per image: one (the usual case: the batch alone fills the GPU) stores the mean directly; several
-    // write their partial sums to `partial` [chunk][image][C] for pool_finish_kernel, which adds them in chunk order -
+    // write their partial sums to fixed slots of the library scratch and the last of them adds these in chunk order -
     // the forward stays bit-reproducible (no float atomics). 4 independent loads per thread keep HBM busy.
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     long long r1 = r0 + rows_per_block;
@@ -232,23 +252,39 @@ __global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ s
 #pragma unroll
         for (int i = 0; i < 8; i++) acc[i] += act_fwd<ACT>(fmaf(f[i], sc[i], sh[i]));
     }
+    const float inv = 1.f / (float)hw;
+    float* dst = pooled + (size_t)blockIdx.y * C;
+    float* pv = sm + (size_t)blockDim.y * C;         // [C] the image's pooled vector, [Cse] FC scratch behind it
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
     if (gridDim.x == 1) {
-        const float inv = 1.f / (float)hw;
-        float* dst = pooled + (size_t)blockIdx.y * C;
-        reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v * inv; });
+        reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v * inv; pv[c] = v * inv; });
     } else {
-        float* dst = partial + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * C;
-        reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v; });
+        // several row chunks per image (the batch alone cannot fill the SMs): fixed-slot partials, added in chunk order by
+        // the last chunk to arrive - the forward stays bit-reproducible (no float atomics)
+        float* part = g_rowred_ws + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * C;
+        reduce_rows_and_emit(sm, acc, [&](int c, float v) { part[c] = v; });
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int t = atomicAdd(g_rowred_tk + blockIdx.y, 1);
+            s_last = (t == (int)gridDim.x - 1);
+            if (s_last) g_rowred_tk[blockIdx.y] = 0;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        for (int c = tid; c < C; c += nt) {
+            float v = 0.f;
+            for (int k = 0; k < (int)gridDim.x; k++) v += __ldcg(g_rowred_ws + ((size_t)k * gridDim.y + blockIdx.y) * C + c);
+            dst[c] = v * inv;
+            pv[c] = v * inv;
+        }
     }
-}
-
-__global__ void pool_finish_kernel(const float* __restrict__ partial, float* __restrict__ pooled, int chunks, long long nc,
-                                   float inv) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nc) return;
-    float s = 0.f;
-    for (int k = 0; k < chunks; k++) s += partial[(size_t)k * nc + i];      // fixed order: deterministic
-    pooled[i] = s * inv;
+    if (!se.Wr) return;
+    __syncthreads();
+    // the CTA that completed this image's squeeze carries on with its excite FCs (efficientnet_blocks.py:104-110)
+    se_fwd_chain(pv, pv + C, se.Wr, se.br, se.We, se.be, se.gate + (size_t)blockIdx.y * C, C, se.Cse, tid, nt);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -380,16 +416,10 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict
 // ---------------------------------------------------------------------------------------------
 // SE backward reduce: draw[n,c] = sum_hw da[n,hw,c] * act(scale*y + shift)
 // ---------------------------------------------------------------------------------------------
-// scratch of the chunked per-image reductions (library-owned, zero at load; tickets self-reset)
-constexpr long long ROWRED_WS_FLOATS = 4LL << 20;
-constexpr int ROWRED_TICKETS = 65536;
-__device__ float g_rowred_ws[ROWRED_WS_FLOATS];
-__device__ int g_rowred_tk[ROWRED_TICKETS];
-
 template <typename T, int ACT>
 __global__ void se_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
-                                     float* __restrict__ draw, long long hw, long long rows_per_block) {
+                                     float* __restrict__ draw, long long hw, long long rows_per_block, const SeBwdArgs se) {
     extern __shared__ float sm[];
     const int V = blockDim.x, C = V * 8;
     const int c0 = threadIdx.x * 8;
@@ -411,28 +441,41 @@ __global__ void se_bwd_reduce_kernel(const T* __restrict__ da, const T* __restri
         for (int i = 0; i < 8; i++) acc[i] = fmaf(d[i], act_fwd<ACT>(fmaf(f[i], sc[i], sh[i])), acc[i]);
     }
     float* dst = draw + (size_t)blockIdx.y * C;
-    if (gridDim.x == 1) { reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v; }); return; }
-    // several chunks per image: fixed-slot partials [chunk][image][C] in the library scratch; the last chunk of an image to
-    // arrive (ticket) adds them in chunk order - no fp32 atomics, the result does not depend on CTA arrival order
-    float* part = g_rowred_ws + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * C;
-    reduce_rows_and_emit(sm, acc, [&](int c, float v) { part[c] = v; });
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        const int t = atomicAdd(g_rowred_tk + blockIdx.y, 1);
-        s_last = (t == (int)gridDim.x - 1);
-        if (s_last) g_rowred_tk[blockIdx.y] = 0;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    // chain scratch (after the row-reduction area): p [C] | de / draw [C] | rpre, r, drp [Cse] | r_part [nw][Cse]
+    float* cs = sm + (size_t)blockDim.y * C;
+    if (gridDim.x == 1) {
+        reduce_rows_and_emit(sm, acc, [&](int c, float v) { dst[c] = v; cs[C + c] = v; });
+    } else {
+        // several chunks per image: fixed-slot partials [chunk][image][C] in the library scratch; the last chunk of an image
+        // to arrive (ticket) adds them in chunk order - no fp32 atomics, the result does not depend on CTA arrival order
+        float* part = g_rowred_ws + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * C;
+        reduce_rows_and_emit(sm, acc, [&](int c, float v) { part[c] = v; });
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int t = atomicAdd(g_rowred_tk + blockIdx.y, 1);
+            s_last = (t == (int)gridDim.x - 1);
+            if (s_last) g_rowred_tk[blockIdx.y] = 0;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        for (int c = tid; c < C; c += nt) {
+            float v = 0.f;
+            for (int k = 0; k < (int)gridDim.x; k++) v += __ldcg(g_rowred_ws + ((size_t)k * gridDim.y + blockIdx.y) * C + c);
+            dst[c] = v;
+            cs[C + c] = v;
+        }
     }
+    if (!se.Wr) return;
+    // the CTA that completed dL/dgate of this image carries on with the backward FC chain of its squeeze-excite
+    const size_t n = blockIdx.y;
+    for (int c = tid; c < C; c += nt) cs[c] = se.pooled[n * C + c];
     __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    for (int c = tid; c < C; c += blockDim.x * blockDim.y) {
-        float v = 0.f;
-        for (int k = 0; k < (int)gridDim.x; k++) v += __ldcg(g_rowred_ws + ((size_t)k * gridDim.y + blockIdx.y) * C + c);
-        dst[c] = v;
-    }
+    se_bwd_chain(cs, cs + C, se.Wr, se.br, se.We, se.be, se.d_e + n * C, se.r + n * se.Cse, se.d_rpre + n * se.Cse,
+                 se.dpool + n * C, C, se.Cse, tid, nt);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -577,32 +620,49 @@ int dfd_bn_act(const void* y, const float* scale, const float* shift, const floa
     return DFD_OK;
 }
 
-int dfd_pool(const void* y, const float* scale, const float* shift, float* pooled, int n, long long hw, int C,
-             int act, int dt, float* partial, int max_chunks, void* stream) {
+static int launch_pool(const void* y, const float* scale, const float* shift, float* pooled, int n, long long hw, int C,
+                       int act, int dt, int max_chunks, const SeFwdArgs& se, void* stream) {
     if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_pool: C%8, sizes");
-    // one CTA per image while the batch fills the GPU; otherwise up to max_chunks row chunks per image through `partial`
-    RowGeom g = make_geom(C, hw, n, (partial && max_chunks > 1 && n < 296) ? 592 : 1);
-    if (!(partial && max_chunks > 1 && n < 296)) { g.grid = dim3(1, n, 1); g.rows_per_block = (int)hw; }
+    // one CTA per image while the batch fills the GPU; otherwise up to max_chunks row chunks per image (fixed-slot partials
+    // in the library scratch, summed in chunk order by the last chunk of the image to arrive)
+    const bool chunked = max_chunks > 1 && n < 296 && n <= ROWRED_TICKETS;
+    RowGeom g = make_geom(C, hw, n, chunked ? 592 : 1);
+    if (!chunked) { g.grid = dim3(1, n, 1); g.rows_per_block = (int)hw; }
     if ((int)g.grid.x > max_chunks && g.grid.x > 1) {
         long long rpb = (hw + max_chunks - 1) / max_chunks;
         rpb = ((rpb + g.block.y - 1) / g.block.y) * g.block.y;
         g.rows_per_block = (int)rpb;
         g.grid.x = (unsigned)((hw + rpb - 1) / rpb);
     }
+    if ((long long)g.grid.x * n * C > ROWRED_WS_FLOATS) { g.grid = dim3(1, n, 1); g.rows_per_block = (int)hw; }
     cudaStream_t st = (cudaStream_t)stream;
     const long long rpb = g.rows_per_block;
+    const size_t smem = reduce_smem(g) + (size_t)(C + se.Cse) * sizeof(float);
+    if (smem > 48 * 1024) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_pool: channel count exceeds shared memory");
     DISPATCH_T(dt, {
-        if (act == DFD_ACT_SWISH) pool_kernel<T, 1><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)y, scale, shift, pooled, partial, hw, rpb);
-        else if (act == DFD_ACT_RELU) pool_kernel<T, 2><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)y, scale, shift, pooled, partial, hw, rpb);
-        else pool_kernel<T, 0><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)y, scale, shift, pooled, partial, hw, rpb);
+        if (act == DFD_ACT_SWISH) pool_kernel<T, 1><<<g.grid, g.block, smem, st>>>((const T*)y, scale, shift, pooled, hw, rpb, se);
+        else if (act == DFD_ACT_RELU) pool_kernel<T, 2><<<g.grid, g.block, smem, st>>>((const T*)y, scale, shift, pooled, hw, rpb, se);
+        else pool_kernel<T, 0><<<g.grid, g.block, smem, st>>>((const T*)y, scale, shift, pooled, hw, rpb, se);
     });
     DFD_LAUNCH_CHECK();
-    if (g.grid.x > 1) {
-        const long long nc = (long long)n * C;
-        pool_finish_kernel<<<cdiv(nc, 256), 256, 0, st>>>(partial, pooled, (int)g.grid.x, nc, 1.f / (float)hw);
-        DFD_LAUNCH_CHECK();
-    }
     return DFD_OK;
+}
+
+int dfd_pool(const void* y, const float* scale, const float* shift, float* pooled, int n, long long hw, int C,
+             int act, int dt, float* partial, int max_chunks, void* stream) {
+    (void)partial;       // kept in the signature: the chunk partials now live in the library's own scratch
+    SeFwdArgs se = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    return launch_pool(y, scale, shift, pooled, n, hw, C, act, dt, max_chunks, se, stream);
+}
+
+// global pooling + the whole squeeze-excite gate in ONE launch: pooled[n,c] = mean_hw act(scale*y + shift), then
+// gate[n,:] = sigmoid(We * swish(Wr * pooled[n,:] + br) + be) computed by the CTA that completed image n
+int dfd_pool_se(const void* y, const float* scale, const float* shift, float* pooled, const float* Wr, const float* br,
+                const float* We, const float* be, float* gate, int n, long long hw, int C, int Cse, int act, int dt,
+                int max_chunks, void* stream) {
+    if (!Wr || !br || !We || !be || !gate || Cse <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_pool_se: operands");
+    SeFwdArgs se = {Wr, br, We, be, gate, Cse};
+    return launch_pool(y, scale, shift, pooled, n, hw, C, act, dt, max_chunks, se, stream);
 }
 
 int dfd_bn_bwd_reduce(const void* g_, const void* y, const void* out, const float* mean, const float* rstd, int n,
@@ -641,17 +701,48 @@ int dfd_bn_bwd_apply(const void* g_, const void* y, const void* out, const float
     return DFD_OK;
 }
 
-int dfd_se_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift, float* draw, int n,
-                      long long hw, int C, int dt, void* stream) {
+static int launch_se_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift, float* draw, int n,
+                                long long hw, int C, int dt, const SeBwdArgs& se, void* stream) {
     if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_bwd_reduce: C%8, sizes");
     // one CTA per image while the batch fills the GPU (>= 2 CTAs per SM); otherwise several row chunks per image
     RowGeom g = make_geom(C, hw, n, n >= 296 ? 1 : 592);
     if ((long long)g.grid.x * n * C > ROWRED_WS_FLOATS || n > ROWRED_TICKETS) g = make_geom(C, hw, n, 1);   // one chunk per image
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH_T(dt, (se_bwd_reduce_kernel<T, 1><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)da, (const T*)y, scale, shift, draw, hw,
-                                                                                         (long long)g.rows_per_block)));
+    const int nw = (int)(g.block.x * g.block.y) / 32;
+    const size_t smem = reduce_smem(g) + (size_t)(2 * C + (3 + nw) * se.Cse) * sizeof(float);
+    if (smem > 48 * 1024) {
+        static bool attr[2] = {false, false};
+        const int ti = dt == DFD_DT_FP16 ? 1 : 0;
+        if (!attr[ti]) {
+            cudaError_t e = dt == DFD_DT_FP16
+                ? cudaFuncSetAttribute(se_bwd_reduce_kernel<__half, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)
+                : cudaFuncSetAttribute(se_bwd_reduce_kernel<bf16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            if (e != cudaSuccess) return dfd_set_cuda_error(e, __FILE__, __LINE__);
+            attr[ti] = true;
+        }
+        if (smem > 160 * 1024) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_se_bwd: channel count exceeds shared memory");
+    }
+    DISPATCH_T(dt, (se_bwd_reduce_kernel<T, 1><<<g.grid, g.block, smem, st>>>((const T*)da, (const T*)y, scale, shift, draw, hw,
+                                                                               (long long)g.rows_per_block, se)));
     DFD_LAUNCH_CHECK();
     return DFD_OK;
+}
+
+int dfd_se_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift, float* draw, int n,
+                      long long hw, int C, int dt, void* stream) {
+    SeBwdArgs se = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    return launch_se_bwd_reduce(da, y, scale, shift, draw, n, hw, C, dt, se, stream);
+}
+
+// dfd_se_bwd_reduce + the per-image backward FC chain of dfd_se_fc_bwd in ONE launch (the CTA that completes dL/dgate of
+// image n runs the chain); the SE parameter gradients still take dfd_se_fc_wgrad afterwards
+int dfd_se_bwd_chain(const void* da, const void* y, const float* scale, const float* shift, float* draw, const float* pooled,
+                     const float* Wr, const float* br, const float* We, const float* be, float* d_e, float* r, float* d_rpre,
+                     float* dpool, int n, long long hw, int C, int Cse, int dt, void* stream) {
+    if (!pooled || !Wr || !br || !We || !be || !d_e || !r || !d_rpre || !dpool || Cse <= 0)
+        return dfd_set_error(DFD_ERR_ARG, "dfd_se_bwd_chain: operands");
+    SeBwdArgs se = {pooled, Wr, br, We, be, d_e, r, d_rpre, dpool, Cse};
+    return launch_se_bwd_reduce(da, y, scale, shift, draw, n, hw, C, dt, se, stream);
 }
 
 int dfd_act_bwd(const void* da, const void* y, const float* scale, const float* shift, const float* mean,

@@ -493,6 +493,15 @@ int dfd_se_fc_bwd(const float* draw, const float* pooled, const float* Wr, const
     }
     se_fc_bwd_kernel<<<N, nthr, smem, st>>>(draw, pooled, Wr, br, We, be, d_e, r, d_rpre, dpool, C, Cse);
     DFD_LAUNCH_CHECK();
+    return dfd_se_fc_wgrad(d_e, r, d_rpre, pooled, dWr, dbr, dWe, dbe, N, C, Cse, stream);
+}
+
+// SE parameter gradients from the per-image vectors of the backward chain (dfd_se_fc_bwd / dfd_se_bwd_chain):
+// dWe += d_e^T r, dbe += sum d_e, dWr += d_rpre^T pooled, dbr += sum d_rpre   (order-deterministic)
+int dfd_se_fc_wgrad(const float* d_e, const float* r, const float* d_rpre, const float* pooled, float* dWr, float* dbr,
+                    float* dWe, float* dbe, int N, int C, int Cse, void* stream) {
+    if (N <= 0 || C <= 0 || Cse <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_fc_wgrad: sizes");
+    cudaStream_t st = (cudaStream_t)stream;
     // image splits: only as many as it takes to fill the GPU (the split partials are summed in order by the last block of
     // every column group: fixed slots in the library scratch, no atomics)
     const int bx = cdiv((long long)C * Cse, 128);

@@ -269,7 +269,8 @@ class Engine:
         for n, a in ops:
             if n == "dfd_ordered_reduce":
                 ents = a[1]
-                a = (_ptr(self._red_table, pos * 40), len(ents), min(e[1] for e in ents), max(e[2] for e in ents))
+                bx = max((e[2] // 4 + 7) // 8 if e[4] > 64 else (e[2] // 4 + 255) // 256 for e in ents)
+                a = (_ptr(self._red_table, pos * 40), len(ents), min(e[1] for e in ents), max(1, min(bx, 1024)))
                 pos += len(ents)
             elif isinstance(a, list):
                 a = [base + v[1] if isinstance(v, tuple) and v[0] == "WS" else v for v in a]
@@ -499,11 +500,12 @@ class Engine:
                 gate = torch.zeros(N, b.cmid, dtype=torch.float32, device=dev)
                 self._keep += [pooled, gate]
                 rec.update(pooled=pooled, gate=gate)
-                fwd.append(("dfd_pool", (_ptr(y2), bn_mid.scale, bn_mid.shift, _ptr(pooled), N, ho * wo, b.cmid, ACT_SWISH, dt,
-                                         _ptr(self.pool_partial), POOL_CHUNKS)))
-                fwd.append(("dfd_se_fc_fwd", (_ptr(pooled), P32(p + ".se.conv_reduce.weight"), P32(p + ".se.conv_reduce.bias"),
-                                              P32(p + ".se.conv_expand.weight"), P32(p + ".se.conv_expand.bias"),
-                                              _ptr(gate), N, b.cmid, b.cse)))
+                # squeeze (global pool of swish(bn(y2))) + excite (both FCs, sigmoid gate) in ONE launch: the CTA that completes
+                # an image's pooled vector carries on with that image's FC chain
+                fwd.append(("dfd_pool_se", (_ptr(y2), bn_mid.scale, bn_mid.shift, _ptr(pooled), P32(p + ".se.conv_reduce.weight"),
+                                            P32(p + ".se.conv_reduce.bias"), P32(p + ".se.conv_expand.weight"),
+                                            P32(p + ".se.conv_expand.bias"), _ptr(gate), N, ho * wo, b.cmid, b.cse, ACT_SWISH, dt,
+                                            POOL_CHUNKS)))
                 gate_ptr = _ptr(gate)
             a2 = self._alloc16(N, ho, wo, b.cmid)
             fwd.append(("dfd_bn_act", (_ptr(y2), bn_mid.scale, bn_mid.shift, gate_ptr, None, _ptr(a2), N, ho * wo, b.cmid,
@@ -600,13 +602,15 @@ class Engine:
             gate_ptr = dpool_ptr = None
             if b.cse:
                 gate_ptr, dpool_ptr = _ptr(rec["gate"]), se_dpool
-                bwd.append(("dfd_se_bwd_reduce", (mid_a, _ptr(y2), bn_mid.scale, bn_mid.shift, se_draw, N, ho * wo, b.cmid, dt)))
-                bwd.append(("dfd_se_fc_bwd", (se_draw, _ptr(rec["pooled"]), P32(p + ".se.conv_reduce.weight"),
-                                              P32(p + ".se.conv_reduce.bias"), P32(p + ".se.conv_expand.weight"),
-                                              P32(p + ".se.conv_expand.bias"), se_de, se_r, se_drp, se_dpool,
-                                              G32(p + ".se.conv_reduce.weight"), G32(p + ".se.conv_reduce.bias"),
-                                              G32(p + ".se.conv_expand.weight"), G32(p + ".se.conv_expand.bias"),
-                                              N, b.cmid, b.cse)))
+                # dL/dgate reduction + the per-image backward FC chain in one launch, then the SE parameter gradients
+                bwd.append(("dfd_se_bwd_chain", (mid_a, _ptr(y2), bn_mid.scale, bn_mid.shift, se_draw, _ptr(rec["pooled"]),
+                                                 P32(p + ".se.conv_reduce.weight"), P32(p + ".se.conv_reduce.bias"),
+                                                 P32(p + ".se.conv_expand.weight"), P32(p + ".se.conv_expand.bias"),
+                                                 se_de, se_r, se_drp, se_dpool, N, ho * wo, b.cmid, b.cse, dt)))
+                bwd.append(("dfd_se_fc_wgrad", (se_de, se_r, se_drp, _ptr(rec["pooled"]),
+                                                G32(p + ".se.conv_reduce.weight"), G32(p + ".se.conv_reduce.bias"),
+                                                G32(p + ".se.conv_expand.weight"), G32(p + ".se.conv_expand.bias"),
+                                                N, b.cmid, b.cse)))
             bwd.append(("dfd_act_bwd", (mid_a, _ptr(y2), bn_mid.scale, bn_mid.shift, bn_mid.mean, bn_mid.rstd, gate_ptr,
                                         dpool_ptr, mid_b, N, ho * wo, b.cmid, ACT_SWISH, dt, bn_mid.bs1, bn_mid.bs2)))
             bwd.append(bwd_finalize(bn_mid, M2))

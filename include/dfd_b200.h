@@ -71,8 +71,9 @@ int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw,
 int dfd_gemm_wgrad_splits(long long M, int Nw, int Kw);
 /* dst[i] += sum_{p < parts} src[p * stride + i], i < n, partials added in index order. table: device array of
  * { const float* src; float* dst; long long n; long long stride; int parts; int _pad; } (n % 4 == 0, 16-byte aligned);
- * max_n sizes the grid; first_dst (the lowest gradient address written) is informational for host-side planners. */
-int dfd_ordered_reduce(const void* table, int count, const float* first_dst, long long max_n, void* stream);
+ * blocks_x = CTAs per entry (a CTA covers 256 float4 per trip of an entry with <= 64 parts, 8 float4 per trip otherwise);
+ * first_dst (the lowest gradient address written) is informational for host-side planners. */
+int dfd_ordered_reduce(const void* table, int count, const float* first_dst, int blocks_x, void* stream);
 
 /* ---- depthwise k x k convolution: nn.Conv2d(groups=C), efficientnet_blocks.py:152-153,283-285 -------- */
 int dfd_dwconv_fwd(const void* x, const float* scale, const float* shift, const float* w, void* out, int N, int H,
@@ -163,6 +164,21 @@ int dfd_se_fc_fwd(const float* pooled, const float* Wr, const float* br, const f
 int dfd_se_fc_bwd(const float* draw, const float* pooled, const float* Wr, const float* br, const float* We,
                   const float* be, float* d_e, float* r, float* d_rpre, float* dpool, float* dWr, float* dbr,
                   float* dWe, float* dbe, int N, int C, int Cse, void* stream);
+
+/* SE parameter gradients from the per-image vectors of the backward chain: dWe += d_e^T r, dbe += sum d_e,
+ * dWr += d_rpre^T pooled, dbr += sum d_rpre (split partials in fixed slots, added in order) */
+int dfd_se_fc_wgrad(const float* d_e, const float* r, const float* d_rpre, const float* pooled, float* dWr, float* dbr,
+                    float* dWe, float* dbe, int N, int C, int Cse, void* stream);
+/* Fused forms (one launch each; the CTA that completes an image's reduction carries on with that image's FC chain, which is
+ * latency-bound and hides in the tail of the streaming kernel):
+ *   dfd_pool_se      = dfd_pool + dfd_se_fc_fwd            (squeeze + excite gate)
+ *   dfd_se_bwd_chain = dfd_se_bwd_reduce + the per-image part of dfd_se_fc_bwd   (dfd_se_fc_wgrad follows) */
+int dfd_pool_se(const void* y, const float* scale, const float* shift, float* pooled, const float* Wr, const float* br,
+                const float* We, const float* be, float* gate, int n, long long hw, int C, int Cse, int act, int dt,
+                int max_chunks, void* stream);
+int dfd_se_bwd_chain(const void* da, const void* y, const float* scale, const float* shift, float* draw, const float* pooled,
+                     const float* Wr, const float* br, const float* We, const float* be, float* d_e, float* r, float* d_rpre,
+                     float* dpool, int n, long long hw, int C, int Cse, int dt, void* stream);
 
 /* ---- classifier + loss + accuracy: nn.Linear (efficientnet.py:348, resnet.py:467), LabelSmoothing /
  *      SoftTarget / nn.CrossEntropyLoss (loss/cross_entropy.py:20-36, train.py:509-520), accuracy

@@ -105,7 +105,7 @@ def check_wgrad(M, Nw, Kw, dtype=torch.bfloat16, seed=0, impl="dfd_gemm_wgrad_mm
             for dst in (dW, again):
                 _lib.call(impl, P(G), P(X), P(dst), M, Nw, Kw, DT[dtype], P(ws), ws.numel() * 4, st())
                 table = torch.frombuffer(bytearray(struct.pack("<QQqqii", P(ws), P(dst), Nw * Kw, Nw * Kw, splits, 0)), dtype=torch.uint8).cuda()
-                _lib.call("dfd_ordered_reduce", P(table), 1, P(dst), Nw * Kw, st())
+                _lib.call("dfd_ordered_reduce", P(table), 1, P(dst), min(1024, (Nw * Kw // 4 + 255) // 256), st())
                 torch.cuda.synchronize()
             atomic = torch.zeros(Nw, Kw, device="cuda")
             _lib.call(impl, P(G), P(X), P(atomic), M, Nw, Kw, DT[dtype], None, 0, st())
@@ -204,7 +204,7 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0, fw
             raw = b"".join(struct.pack("<QQqqii", P(ws) + cb * parts * 64 * k * k * 4, P(t) + cb * 64 * k * k * 4,
                                        min(64, C - 64 * cb) * k * k, 64 * k * k, parts, 0) for cb in range(cbs))
             table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
-            _lib.call("dfd_ordered_reduce", P(table), cbs, P(t), 64 * k * k, st())
+            _lib.call("dfd_ordered_reduce", P(table), cbs, P(t), (64 * k * k // 4 + 7) // 8 if parts > 64 else 1, st())
             torch.cuda.synchronize()
         res["det_bitwise"] = bool(torch.equal(dW3[0], dW3[1]))
         res["det_vs_atomic"] = relerr(dW3[0], dW2)
@@ -374,6 +374,48 @@ def check_se_fc(N, C, Cse, seed=0):
     torch.cuda.synchronize()
     return dict(gate_rel=relerr(gate, ref.detach()), dpool_rel=relerr(dpool, pr.grad), dWr_rel=relerr(dWr, Wr.grad),
                 dbr_rel=relerr(dbr, br.grad), dWe_rel=relerr(dWe, We.grad), dbe_rel=relerr(dbe, be.grad))
+
+
+def check_se_fused(N, HW, C, Cse, dtype=torch.bfloat16, seed=0):
+    """the one-launch forms (pool + excite gate; dL/dgate reduction + backward FC chain) against the separate kernels they
+    replace, on an activation tensor: same pooled vector and gate bit for bit (identical arithmetic order), backward vectors to
+    fp32 round-off (the cross-warp sum of d_r is partitioned by the CTA's warp count)"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    y = torch.randn(N, HW, C, device="cuda", generator=g).to(dtype)
+    da = (0.1 * torch.randn(N, HW, C, device="cuda", generator=g)).to(dtype)
+    scale, shift = _bn_params(C, g)
+    Wr = torch.randn(Cse, C, device="cuda", generator=g) / math.sqrt(C)
+    br = 0.1 * torch.randn(Cse, device="cuda", generator=g)
+    We = torch.randn(C, Cse, device="cuda", generator=g) / math.sqrt(Cse)
+    be = 0.1 * torch.randn(C, device="cuda", generator=g)
+    d = DT[dtype]
+    pooled_a, gate_a = torch.zeros(N, C, device="cuda"), torch.zeros(N, C, device="cuda")
+    pooled_b, gate_b = torch.zeros(N, C, device="cuda"), torch.zeros(N, C, device="cuda")
+    _lib.call("dfd_pool", P(y), P(scale), P(shift), P(pooled_a), N, HW, C, 1, d, None, 8, st())
+    _lib.call("dfd_se_fc_fwd", P(pooled_a), P(Wr), P(br), P(We), P(be), P(gate_a), N, C, Cse, st())
+    _lib.call("dfd_pool_se", P(y), P(scale), P(shift), P(pooled_b), P(Wr), P(br), P(We), P(be), P(gate_b), N, HW, C, Cse, 1, d, 8, st())
+    torch.cuda.synchronize()
+    ref_pool = (lambda u: u * torch.sigmoid(u))(y.float() * scale + shift).mean(1)
+    out = dict(pool_equal=bool(torch.equal(pooled_a, pooled_b)), gate_equal=bool(torch.equal(gate_a, gate_b)),
+               pool_rel=relerr(pooled_b, ref_pool))
+
+    def zeros(*shape):
+        return torch.zeros(*shape, device="cuda")
+
+    va = dict(draw=zeros(N, C), d_e=zeros(N, C), r=zeros(N, Cse), drp=zeros(N, Cse), dpool=zeros(N, C),
+              dWr=zeros(Cse, C), dbr=zeros(Cse), dWe=zeros(C, Cse), dbe=zeros(C))
+    vb = {k: torch.zeros_like(v) for k, v in va.items()}
+    _lib.call("dfd_se_bwd_reduce", P(da), P(y), P(scale), P(shift), P(va["draw"]), N, HW, C, d, st())
+    _lib.call("dfd_se_fc_bwd", P(va["draw"]), P(pooled_a), P(Wr), P(br), P(We), P(be), P(va["d_e"]), P(va["r"]), P(va["drp"]),
+              P(va["dpool"]), P(va["dWr"]), P(va["dbr"]), P(va["dWe"]), P(va["dbe"]), N, C, Cse, st())
+    _lib.call("dfd_se_bwd_chain", P(da), P(y), P(scale), P(shift), P(vb["draw"]), P(pooled_a), P(Wr), P(br), P(We), P(be),
+              P(vb["d_e"]), P(vb["r"]), P(vb["drp"]), P(vb["dpool"]), N, HW, C, Cse, d, st())
+    _lib.call("dfd_se_fc_wgrad", P(vb["d_e"]), P(vb["r"]), P(vb["drp"]), P(pooled_a), P(vb["dWr"]), P(vb["dbr"]), P(vb["dWe"]),
+              P(vb["dbe"]), N, C, Cse, st())
+    torch.cuda.synchronize()
+    out["draw_equal"] = bool(torch.equal(va["draw"], vb["draw"]))
+    out["bwd_rel"] = max(relerr(vb[k], va[k]) for k in va)
+    return out
 
 
 def check_head(N, Fdim, smoothing=0.0, soft=False, seed=0):

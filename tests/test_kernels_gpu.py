@@ -118,6 +118,15 @@ def test_se_fc(N, C, Cse):
     assert max(r.values()) < F32 * 5, r
 
 
+@pytest.mark.parametrize("N,HW,C,Cse,dtype", [(5, 196, 144, 6, torch.bfloat16), (3, 49, 1152, 48, torch.bfloat16),
+                                               (300, 64, 32, 8, torch.float16), (2, 3136, 96, 4, torch.bfloat16),
+                                               (3, 361, 3840, 160, torch.float16)])
+def test_se_fused_launches(N, HW, C, Cse, dtype):
+    """dfd_pool_se / dfd_se_bwd_chain (the CTA that completes an image's reduction runs its FC chain) == the separate kernels"""
+    r = _gc().check_se_fused(N, HW, C, Cse, dtype)
+    assert r["pool_equal"] and r["gate_equal"] and r["draw_equal"] and r["pool_rel"] < RED and r["bwd_rel"] < 1e-5, r
+
+
 @pytest.mark.parametrize("kw", [dict(), dict(smoothing=0.1), dict(soft=True)])
 def test_head_loss(kw):
     r = _gc().check_head(16, 1280, **kw)

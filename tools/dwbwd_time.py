@@ -26,7 +26,7 @@ def t(N, H, W, C, k, s, reps=10, det=True):
     def f():
         f0()
         if det:
-            _lib.call("dfd_ordered_reduce", table.data_ptr(), cbs, dW.data_ptr(), 64 * k * k, st)
+            _lib.call("dfd_ordered_reduce", table.data_ptr(), cbs, dW.data_ptr(), (64 * k * k // 4 + 7) // 8 if parts > 64 else 1, st)
     for _ in range(3): f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
