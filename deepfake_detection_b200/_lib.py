@@ -16,19 +16,18 @@ SIGNATURES = {
     "dfd_abi_version": "",
     "dfd_stat_slots": "",
     "dfd_memset_async": "pilp",
-    "dfd_gemm_tn": "ppplii" "i" "ppp",
-    "dfd_gemm_tn_rowpack": "ppplii" "ii" "ppp",
+    "dfd_gemm_tn": "ppplii" "i" "ppp" "p",
+    "dfd_gemm_tn_rowpack": "ppplii" "ii" "ppp" "p",
     "dfd_blockdiag_weights": "piip",
     "dfd_gemm_tn_mma": "pppp" "lii" "i" "ppp",
     "dfd_gemm_wgrad_mma": "ppp" "lii" "i" "p",
     "dfd_gemm_wgrad": "ppp" "lii" "i" "pl" "p",
     "dfd_gemm_wgrad_splits": "lii",
     "dfd_ordered_reduce": "pi" "pi" "p",
-    "dfd_dwconv_fwd": "ppppp" "iiiiii" "ii" "ppp",
-    "dfd_dwconv_fwd_tc": "ppppp" "iiiiii" "ii" "ppp",
+    "dfd_dwconv_fwd": "ppppp" "iiiiii" "ii" "ppp" "p",
     "dfd_dwconv_dgrad": "ppppp" "pppppp" "pp" "iiiiii" "ii" "ppp",
     "dfd_dwconv_wgrad": "ppppp" "pppp" "iiiiii" "i" "p",
-    "dfd_dwconv_bwd": "ppppp" "pppppp" "ppp" "iiiiii" "i" "pp" "pl" "p",
+    "dfd_dwconv_bwd": "ppppp" "pppppp" "ppp" "iiiiii" "i" "pp" "pl" "p" "p",
     "dfd_dwconv_bwd_parts": "iiiiii",
     "dfd_stem_fwd": "ppp" "iiiiiiii" "i" "ppp",
     "dfd_stem_wgrad": "ppppppp" "iiiiiiii" "i" "p",
@@ -36,11 +35,11 @@ SIGNATURES = {
     "dfd_bn_finalize": "ppd" "ppppp" "ffii" "ppppp",
     "dfd_bn_act": "pppppp" "ili" "iii" "p",
     "dfd_pool": "pppp" "ili" "ii" "pi" "p",
-    "dfd_bn_bwd_reduce": "ppppp" "ili" "i" "ppp",
+    "dfd_bn_bwd_reduce": "ppppp" "ili" "i" "ppp" "p",
     "dfd_bn_bwd_finalize": "ppd" "pppppppp" "i" "p",
     "dfd_bn_bwd_apply": "ppppppp" "ili" "i" "p",
     "dfd_se_bwd_reduce": "ppppp" "ili" "i" "p",
-    "dfd_act_bwd": "ppppppppp" "ili" "ii" "ppp",
+    "dfd_act_bwd": "ppppppppp" "ili" "ii" "ppp" "p",
     "dfd_add_inplace": "pp" "li" "p",
     "dfd_se_fc_fwd": "pppppp" "iii" "p",
     "dfd_se_fc_bwd": "pppppp" "pppppppp" "iii" "p",

@@ -14,6 +14,7 @@
 //   global average pool  dfd/timm/models/efficientnet.py:340-343
 #include "common.cuh"
 #include "se_chain.cuh"
+#include "bn_finalize.cuh"
 
 namespace {
 
@@ -295,7 +296,7 @@ template <typename T, bool RELU_MASK>
 __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ y, const T* __restrict__ out,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      long long hw, int rows_per_block, double* __restrict__ s1,
-                                     double* __restrict__ s2) {
+                                     double* __restrict__ s2, const BnBwdFinDesc* __restrict__ fin) {
     extern __shared__ float sm[];
     const int V = blockDim.x, C = V * 8;
     const int c0 = threadIdx.x * 8;
@@ -342,6 +343,7 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restric
     double* p2 = stat_slot(s2, C);
     reduce_rows_and_emit(sm, a1, [&](int c, float v) { atomicAdd(p1 + c, (double)v); });
     reduce_rows_and_emit(sm, a2, [&](int c, float v) { atomicAdd(p2 + c, (double)v); });
+    bn_bwd_finalize_tail(fin, threadIdx.y * blockDim.x + threadIdx.x, blockDim.x * blockDim.y);
 }
 
 // BN backward, phase 2 (per channel): parameter gradients and the affine coefficients of
@@ -488,7 +490,8 @@ __global__ void act_bwd_kernel(const T* __restrict__ da, const T* __restrict__ y
                                const float* __restrict__ shift, const float* __restrict__ mean,
                                const float* __restrict__ rstd, const float* __restrict__ gate,
                                const float* __restrict__ dpool, float inv_hw, T* __restrict__ gu, long long hw,
-                               int rows_per_block, double* __restrict__ s1, double* __restrict__ s2) {
+                               int rows_per_block, double* __restrict__ s1, double* __restrict__ s2,
+                               const BnBwdFinDesc* __restrict__ fin) {
     extern __shared__ float sm[];
     const int V = blockDim.x, C = V * 8;
     const int c0 = threadIdx.x * 8;
@@ -541,6 +544,7 @@ __global__ void act_bwd_kernel(const T* __restrict__ da, const T* __restrict__ y
     double* p2 = stat_slot(s2, C);
     reduce_rows_and_emit(sm, a1, [&](int c, float v) { atomicAdd(p1 + c, (double)v); });
     reduce_rows_and_emit(sm, a2, [&](int c, float v) { atomicAdd(p2 + c, (double)v); });
+    bn_bwd_finalize_tail(fin, threadIdx.y * blockDim.x + threadIdx.x, blockDim.x * blockDim.y);
 }
 
 // elementwise a += b (residual gradient accumulation) over a flat 16-bit tensor
@@ -666,13 +670,13 @@ int dfd_pool_se(const void* y, const float* scale, const float* shift, float* po
 }
 
 int dfd_bn_bwd_reduce(const void* g_, const void* y, const void* out, const float* mean, const float* rstd, int n,
-                      long long hw, int C, int dt, double* s1, double* s2, void* stream) {
+                      long long hw, int C, int dt, double* s1, double* s2, const void* fin, void* stream) {
     if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_bn_bwd_reduce: C%8, sizes");
     RowGeom g = make_geom(C, hw, n);
     cudaStream_t st = (cudaStream_t)stream;
     DISPATCH_T(dt, {
-        if (out) bn_bwd_reduce_kernel<T, true><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)g_, (const T*)y, (const T*)out, mean, rstd, hw, g.rows_per_block, s1, s2);
-        else bn_bwd_reduce_kernel<T, false><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)g_, (const T*)y, nullptr, mean, rstd, hw, g.rows_per_block, s1, s2);
+        if (out) bn_bwd_reduce_kernel<T, true><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)g_, (const T*)y, (const T*)out, mean, rstd, hw, g.rows_per_block, s1, s2, (const BnBwdFinDesc*)fin);
+        else bn_bwd_reduce_kernel<T, false><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)g_, (const T*)y, nullptr, mean, rstd, hw, g.rows_per_block, s1, s2, (const BnBwdFinDesc*)fin);
     });
     DFD_LAUNCH_CHECK();
     return DFD_OK;
@@ -747,7 +751,7 @@ int dfd_se_bwd_chain(const void* da, const void* y, const float* scale, const fl
 
 int dfd_act_bwd(const void* da, const void* y, const float* scale, const float* shift, const float* mean,
                 const float* rstd, const float* gate, const float* dpool, void* gu, int n, long long hw, int C,
-                int act, int dt, double* s1, double* s2, void* stream) {
+                int act, int dt, double* s1, double* s2, const void* fin, void* stream) {
     if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_act_bwd: C%8, sizes");
     if (!da && !dpool) return dfd_set_error(DFD_ERR_ARG, "dfd_act_bwd: need da or dpool");
     RowGeom g = make_geom(C, hw, n);
@@ -756,7 +760,7 @@ int dfd_act_bwd(const void* da, const void* y, const float* scale, const float* 
 #define LAUNCH(ACT, HAS)                                                                                            \
     act_bwd_kernel<T, ACT, HAS><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)da, (const T*)y, scale, shift, mean, \
                                                                             rstd, gate, dpool, inv_hw, (T*)gu, hw,     \
-                                                                            g.rows_per_block, s1, s2)
+                                                                            g.rows_per_block, s1, s2, (const BnBwdFinDesc*)fin)
     DISPATCH_T(dt, {
         if (act == DFD_ACT_SWISH) { if (da) LAUNCH(1, true); else LAUNCH(1, false); }
         else if (act == DFD_ACT_RELU) { if (da) LAUNCH(2, true); else LAUNCH(2, false); }

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "bn_finalize.cuh"
 
 namespace {
 
@@ -230,7 +231,7 @@ template <typename T, int K, int S, int ACT, bool AFFINE, int NT>
 __global__ void __launch_bounds__(NT)
 dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                   const float* __restrict__ wgt, T* __restrict__ out, double* __restrict__ dsum,
-                  double* __restrict__ dsq, DwGeom g) {
+                  double* __restrict__ dsq, const BnFinDesc* __restrict__ fin, DwGeom g) {
     extern __shared__ __align__(16) uint32_t tile[];
     __shared__ float red[NTHREADS / 32 * 64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -282,6 +283,7 @@ dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, cons
         reduce_warps_emit(red, s0, s1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(ps + c0 + c, (double)v); });
         reduce_warps_emit(red, q0, q1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(pq + c0 + c, (double)v); });
     }
+    bn_finalize_tail(fin, threadIdx.x, NT);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -551,7 +553,8 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
                   const T* __restrict__ xin, const float* __restrict__ scale, const float* __restrict__ shift,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const T* __restrict__ add,
                   T* __restrict__ gx,
-                  float* __restrict__ dW, double* __restrict__ ds1, double* __restrict__ ds2, DwGeom g) {
+                  float* __restrict__ dW, double* __restrict__ ds1, double* __restrict__ ds2,
+                  const BnBwdFinDesc* __restrict__ fin, DwGeom g) {
     extern __shared__ __align__(16) uint32_t tile[];
     __shared__ float red[NTHREADS / 32 * 64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -681,6 +684,7 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
         reduce_warps_emit(red, a0, a1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p1 + c0 + c, (double)v); });
         reduce_warps_emit(red, b0, b1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p2 + c0 + c, (double)v); });
     }
+    bn_bwd_finalize_tail(fin, threadIdx.x, NT);      // the last CTA turns the BN-backward sums into dgamma / dbeta / cA,cB,cC
     __syncthreads();      // every warp is done with the dy tile before it is reused
     // weight-gradient partials: all taps through the (now free) tile memory in one go, [warp][tap][64 channels]
     float* wr = reinterpret_cast<float*>(tile);
@@ -795,7 +799,8 @@ extern "C" {
 // out[N,Ho,Wo,C] = dwconv(act_in(scale*x + shift)); scale == NULL: x is consumed as is (act_in must be 0).
 // dsum/dsq (optional): per-channel sum / sum of squares of the rounded outputs (fp64, accumulated).
 int dfd_dwconv_fwd(const void* x, const float* scale, const float* shift, const float* w, void* out, int N, int H,
-                   int W, int C, int k, int stride, int act_in, int dt, double* dsum, double* dsq, void* stream) {
+                   int W, int C, int k, int stride, int act_in, int dt, double* dsum, double* dsq, const void* fin,
+                   void* stream) {
     if (C % 8 || N <= 0 || H <= 0 || W <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_fwd: sizes");
     if (!scale && act_in != DFD_ACT_NONE) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_fwd: act without BN");
     if (scale && act_in != DFD_ACT_SWISH) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_dwconv_fwd: BN input implies Swish");
@@ -806,8 +811,8 @@ int dfd_dwconv_fwd(const void* x, const float* scale, const float* shift, const 
     dim3 grid(g.tiles_x * g.tiles_y, (C + CB - 1) / CB, N);
     cudaStream_t st = (cudaStream_t)stream;
     DW_DISPATCH_T(dt, DW_DISPATCH_KS(k, stride, {
-        if (scale) DW_LAUNCH((dwconv_fwd_kernel<T, K, S, DFD_ACT_SWISH, true, NT>), grid, smem, st, (const T*)x, scale, shift, w, (T*)out, dsum, dsq, g);
-        else DW_LAUNCH((dwconv_fwd_kernel<T, K, S, DFD_ACT_NONE, false, NT>), grid, smem, st, (const T*)x, scale, shift, w, (T*)out, dsum, dsq, g);
+        if (scale) DW_LAUNCH((dwconv_fwd_kernel<T, K, S, DFD_ACT_SWISH, true, NT>), grid, smem, st, (const T*)x, scale, shift, w, (T*)out, dsum, dsq, (const BnFinDesc*)fin, g);
+        else DW_LAUNCH((dwconv_fwd_kernel<T, K, S, DFD_ACT_NONE, false, NT>), grid, smem, st, (const T*)x, scale, shift, w, (T*)out, dsum, dsq, (const BnFinDesc*)fin, g);
     }));
     DFD_LAUNCH_CHECK();
     return DFD_OK;
@@ -886,7 +891,7 @@ int dfd_dwconv_bwd_parts(int N, int H, int W, int C, int k, int stride) {
 int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const float* cB, const float* cC,
                    const float* w, const void* xin, const float* scale, const float* shift, const float* mean,
                    const float* rstd, const void* add, void* gx, float* dW, int N, int H, int W, int C, int k,
-                   int stride, int dt, double* s1, double* s2, void* ws, long long ws_bytes, void* stream) {
+                   int stride, int dt, double* s1, double* s2, void* ws, long long ws_bytes, const void* fin, void* stream) {
     if (C % 8 || N <= 0 || H <= 0 || W <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: sizes");
     if (!xin || !dW) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: operands");
     if (scale && (!shift || !mean || !rstd || !s1 || !s2)) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: mode 1 operands");
@@ -907,7 +912,7 @@ int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const floa
     static int pb3 = 0, pb5 = 0;       // strip width per kernel size: 4 for k = 3 (four CTAs per SM, measured -1..-14 %), 8 for k = 5 (4 measured slower); DFD_DW_PB3 / DFD_DW_PB5 override
     if (!pb3) { const char* e3 = getenv("DFD_DW_PB3"); const char* e5 = getenv("DFD_DW_PB5"); pb3 = (e3 && atoi(e3) == 8) ? 8 : 4; pb5 = (e5 && atoi(e5) == 4) ? 4 : 8; }
     const int pb = k == 3 ? pb3 : pb5;
-#define BW1(K_, S_, AFF, MODE_) if (pb == 4) DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT, 4>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, dW, s1, s2, g); else DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT, 8>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, dW, s1, s2, g)
+#define BW1(K_, S_, AFF, MODE_) if (pb == 4) DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT, 4>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, dW, s1, s2, (const BnBwdFinDesc*)fin, g); else DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT, 8>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, dW, s1, s2, (const BnBwdFinDesc*)fin, g)
 #define BW(K_, S_) do { if (scale) { if (cA) BW1(K_, S_, true, 1); else BW1(K_, S_, false, 1); } else { if (cA) BW1(K_, S_, true, 0); else BW1(K_, S_, false, 0); } } while (0)
     DW_DISPATCH_T(dt, {
         if (k == 3 && stride == 1) BW(3, 1);

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "bn_finalize.cuh"
 
 namespace {
 
@@ -148,6 +149,7 @@ struct TcParams {
     double* dsum;         // optional [DFD_STAT_SLOTS][N]
     double* dsq;
     int stat_n;           // statistics channel of output column c is c % stat_n (== N unless rows are packed)
+    const BnFinDesc* fin; // optional: the last CTA finalises the BatchNorm behind this convolution (bn_finalize.cuh)
     int dbg;              // debug switches (DFD_DBG env): 1 = skip TMA store, 2 = skip stats pass, 4 = skip slabs, 8 = A from L2
     long long* ts;        // optional trace (DFD_TS env): CTA 0 records clock64 at 8 pipeline points for its first 32 tiles
 };
@@ -374,6 +376,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+    bn_finalize_tail(p.fin, threadIdx.x, NUM_THREADS);
 }
 
 // =============================================================================================
@@ -573,8 +576,9 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, int cols, 
 
 // C[M,N] = A[M,K] * B[N,K]^T; statistics of output column c go to channel c % stat_n
 static int launch_gemm_tc(const void* A, const void* B, void* C, long long M, int N, int K, int dt, double* dsum,
-                          double* dsq, int stat_n, void* stream) {
+                          double* dsq, int stat_n, const void* fin, void* stream) {
     TcParams p;
+    p.fin = (const BnFinDesc*)fin;
     p.M = (int)M; p.N = N; p.K = K;
     p.stat_n = stat_n;
     p.is_bf16 = dt == DFD_DT_BF16;
@@ -663,10 +667,10 @@ extern "C" {
 // C[M,N] = A[M,K] * B[N,K]^T on tcgen05; optional fp64 column statistics of the stored C ([8][N] slots).
 // All pointers must be 16-byte aligned, K % 8 == 0 and N % 8 == 0 (TMA global strides are multiples of 16 B).
 int dfd_gemm_tn(const void* A, const void* B, void* C, long long M, int N, int K, int dt, double* dsum, double* dsq,
-                void* stream) {
+                const void* fin, void* stream) {
     if (M <= 0 || N <= 0 || K <= 0 || (N % 8) || (K % 8)) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn: N%8, K%8");
     if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn: dtype");
-    return launch_gemm_tc(A, B, C, M, N, K, dt, dsum, dsq, N, stream);
+    return launch_gemm_tc(A, B, C, M, N, K, dt, dsum, dsq, N, fin, stream);
 }
 
 // The same product for SMALL K (a pointwise conv with 16 / 24 / 32 input channels): `pack` consecutive rows of A are
@@ -675,11 +679,11 @@ int dfd_gemm_tn(const void* A, const void* B, void* C, long long M, int N, int K
 // per request, so 32-byte rows (K = 16) leave the load path request-bound at a quarter of the HBM rate; the packed view
 // issues 128-byte rows. The extra MMA work multiplies zeros and is free at these K.
 int dfd_gemm_tn_rowpack(const void* A, const void* Bd, void* C, long long M, int N, int K, int pack, int dt,
-                        double* dsum, double* dsq, void* stream) {
+                        double* dsum, double* dsq, const void* fin, void* stream) {
     if (M <= 0 || N <= 0 || K <= 0 || (N % 8) || (K % 8)) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn_rowpack: N%8, K%8");
     if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn_rowpack: dtype");
     if (pack < 1 || pack > 8 || (M % pack)) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_tn_rowpack: M % pack");
-    return launch_gemm_tc(A, Bd, C, M / pack, N * pack, K * pack, dt, dsum, dsq, N, stream);
+    return launch_gemm_tc(A, Bd, C, M / pack, N * pack, K * pack, dt, dsum, dsq, N, fin, stream);
 }
 
 // table: device array of {src [N,K], dst [pack*N, pack*K], N, K, pack}; dst(j*N+n, j'*K+k) = (j == j') ? src(n,k) : 0

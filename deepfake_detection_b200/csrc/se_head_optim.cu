@@ -43,98 +43,169 @@ __device__ __forceinline__ float softplus_precise(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// SE excite, one CTA per image: gate[n,:] = sigmoid(We * swish(Wr * pooled[n,:] + br) + be)
+// SE excite: gate[n,:] = sigmoid(We * swish(Wr * pooled[n,:] + br) + be).  A CTA handles IMG images: every weight element
+// is fetched once per CTA and used for IMG images (with one image per CTA the 256 CTAs of a batch re-read both weight
+// matrices - 113 MB of L2 traffic for the 1152-channel layers, which is what bounded this kernel at ~20 us).  The arithmetic
+// order per image does not depend on IMG.
 // ---------------------------------------------------------------------------------------------
+template <int IMG>
 __global__ void se_fc_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ Wr,
                                  const float* __restrict__ br, const float* __restrict__ We,
-                                 const float* __restrict__ be, float* __restrict__ gate, int C, int Cse) {
+                                 const float* __restrict__ be, float* __restrict__ gate, int N, int C, int Cse) {
     extern __shared__ float sm[];
-    float* p = sm;           // [C]
-    float* r = sm + C;       // [Cse]
-    const int n = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    for (int c = tid; c < C; c += nt) p[c] = pooled[(size_t)n * C + c];
+    float* p = sm;                 // [IMG][C]
+    float* r = sm + IMG * C;       // [IMG][Cse]
+    const int n0 = blockIdx.x * IMG, tid = threadIdx.x, nt = blockDim.x;
+    const int ni = min(IMG, N - n0);
+    for (int e = tid; e < IMG * C; e += nt) {
+        const int i = e / C;
+        p[e] = i < ni ? pooled[(size_t)n0 * C + e] : 0.f;
+    }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     for (int j = warp; j < Cse; j += nw) {
         const float* w = Wr + (size_t)j * C;
-        float s = 0.f;
-        for (int c = lane; c < C; c += 32) s = fmaf(w[c], p[c], s);
-        s = warp_sum(s);
-        if (lane == 0) r[j] = swish_precise(s + br[j]);
+        float s[IMG];
+#pragma unroll
+        for (int i = 0; i < IMG; i++) s[i] = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float wv = w[c];
+#pragma unroll
+            for (int i = 0; i < IMG; i++) s[i] = fmaf(wv, p[i * C + c], s[i]);
+        }
+        const float bj = br[j];
+#pragma unroll
+        for (int i = 0; i < IMG; i++) {
+            const float t = warp_sum(s[i]);
+            if (lane == 0) r[i * Cse + j] = swish_precise(t + bj);
+        }
     }
     __syncthreads();
     // one thread per output row: a row is Cse consecutive floats, so the warp's 32 rows stay L1-resident across the j loop
-    // (a lanes-walk-j variant with a shuffle reduction exposed one L2 round trip per row and measured 2.6x slower)
     for (int c = tid; c < C; c += nt) {
         const float* w = We + (size_t)c * Cse;
-        float s = be[c];
-        for (int j = 0; j < Cse; j++) s = fmaf(w[j], r[j], s);
-        gate[(size_t)n * C + c] = sigmoid_precise(s);
+        float s[IMG];
+        const float bc = be[c];
+#pragma unroll
+        for (int i = 0; i < IMG; i++) s[i] = bc;
+        for (int j = 0; j < Cse; j++) {
+            const float wv = w[j];
+#pragma unroll
+            for (int i = 0; i < IMG; i++) s[i] = fmaf(wv, r[i * Cse + j], s[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < IMG; i++)
+            if (i < ni) gate[(size_t)(n0 + i) * C + c] = sigmoid_precise(s[i]);
     }
 }
 
-// SE backward, per image: from draw = dL/dgate recompute the FC chain and emit
+// SE backward, IMG images per CTA: from draw = dL/dgate recompute the FC chain and emit
 //   d_e [N,C], r [N,Cse], d_rpre [N,Cse] (for the parameter-gradient kernel) and dpool [N,C].
+template <int IMG>
 __global__ void se_fc_bwd_kernel(const float* __restrict__ draw, const float* __restrict__ pooled,
                                  const float* __restrict__ Wr, const float* __restrict__ br,
                                  const float* __restrict__ We, const float* __restrict__ be,
                                  float* __restrict__ d_e, float* __restrict__ r_out, float* __restrict__ d_rpre,
-                                 float* __restrict__ dpool, int C, int Cse) {
+                                 float* __restrict__ dpool, int N, int C, int Cse) {
     extern __shared__ float sm[];
-    float* p = sm;                 // [C]
-    float* de = sm + C;            // [C]
-    float* rpre = sm + 2 * C;      // [Cse]
-    float* r = rpre + Cse;         // [Cse]
-    float* drp = r + Cse;          // [Cse]
-    float* r_part = drp + Cse;     // [warps][Cse] per-warp partials of d_r, summed in warp order
-    const int n = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    for (int c = tid; c < C; c += nt) p[c] = pooled[(size_t)n * C + c];
+    float* p = sm;                         // [IMG][C]
+    float* de = p + IMG * C;               // [IMG][C]
+    float* rpre = de + IMG * C;            // [IMG][Cse]
+    float* r = rpre + IMG * Cse;           // [IMG][Cse]
+    float* drp = r + IMG * Cse;            // [IMG][Cse]
+    float* r_part = drp + IMG * Cse;       // [warps][IMG][Cse] per-warp partials of d_r, summed in warp order
+    const int n0 = blockIdx.x * IMG, tid = threadIdx.x, nt = blockDim.x;
+    const int ni = min(IMG, N - n0);
+    for (int e = tid; e < IMG * C; e += nt) {
+        const int i = e / C;
+        p[e] = i < ni ? pooled[(size_t)n0 * C + e] : 0.f;
+    }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     for (int j = warp; j < Cse; j += nw) {
         const float* w = Wr + (size_t)j * C;
-        float s = 0.f;
-        for (int c = lane; c < C; c += 32) s = fmaf(w[c], p[c], s);
-        s = warp_sum(s);
-        if (lane == 0) { rpre[j] = s + br[j]; r[j] = swish_precise(s + br[j]); }
-    }
-    __syncthreads();
-    for (int c = tid; c < C; c += nt) {
-        const float* w = We + (size_t)c * Cse;
-        float s = be[c];
-        for (int j = 0; j < Cse; j++) s = fmaf(w[j], r[j], s);
-        float g = sigmoid_precise(s);
-        float v = draw[(size_t)n * C + c] * g * (1.f - g);
-        de[c] = v;
-        d_e[(size_t)n * C + c] = v;
-    }
-    __syncthreads();
-    // d_r[j] = sum_c We[c,j] * de[c]: lanes walk j (contiguous in We's rows), warps split c; partials meet in smem
-    for (int j0 = 0; j0 < Cse; j0 += 32) {
-        const int j = j0 + lane;
-        float s = 0.f;
-        if (j < Cse)
-            for (int c = warp; c < C; c += nw) s = fmaf(We[(size_t)c * Cse + j], de[c], s);
-        if (j < Cse) r_part[warp * Cse + j] = s;
-    }
-    __syncthreads();
-    for (int j = tid; j < Cse; j += nt) {
-        float s = 0.f;
-        for (int w = 0; w < nw; w++) s += r_part[w * Cse + j];
-        {
-            float x = rpre[j];
-            float sg = sigmoid_precise(x);
-            float v = s * (sg * (1.f + x * (1.f - sg)));
-            drp[j] = v;
-            d_rpre[(size_t)n * Cse + j] = v;
-            r_out[(size_t)n * Cse + j] = r[j];
+        float s[IMG];
+#pragma unroll
+        for (int i = 0; i < IMG; i++) s[i] = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float wv = w[c];
+#pragma unroll
+            for (int i = 0; i < IMG; i++) s[i] = fmaf(wv, p[i * C + c], s[i]);
+        }
+        const float bj = br[j];
+#pragma unroll
+        for (int i = 0; i < IMG; i++) {
+            const float t = warp_sum(s[i]);
+            if (lane == 0) { rpre[i * Cse + j] = t + bj; r[i * Cse + j] = swish_precise(t + bj); }
         }
     }
     __syncthreads();
     for (int c = tid; c < C; c += nt) {
+        const float* w = We + (size_t)c * Cse;
+        float s[IMG];
+        const float bc = be[c];
+#pragma unroll
+        for (int i = 0; i < IMG; i++) s[i] = bc;
+        for (int j = 0; j < Cse; j++) {
+            const float wv = w[j];
+#pragma unroll
+            for (int i = 0; i < IMG; i++) s[i] = fmaf(wv, r[i * Cse + j], s[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < IMG; i++) {
+            float v = 0.f;
+            if (i < ni) {
+                const float g = sigmoid_precise(s[i]);
+                v = draw[(size_t)(n0 + i) * C + c] * g * (1.f - g);
+                d_e[(size_t)(n0 + i) * C + c] = v;
+            }
+            de[i * C + c] = v;
+        }
+    }
+    __syncthreads();
+    // d_r[i][j] = sum_c We[c,j] * de[i][c]: lanes walk j (contiguous in We's rows), warps split c; partials meet in smem
+    for (int j0 = 0; j0 < Cse; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < Cse) {
+            float s[IMG];
+#pragma unroll
+            for (int i = 0; i < IMG; i++) s[i] = 0.f;
+            for (int c = warp; c < C; c += nw) {
+                const float wv = We[(size_t)c * Cse + j];
+#pragma unroll
+                for (int i = 0; i < IMG; i++) s[i] = fmaf(wv, de[i * C + c], s[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < IMG; i++) r_part[(warp * IMG + i) * Cse + j] = s[i];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < IMG * Cse; e += nt) {
+        const int i = e / Cse, j = e - i * Cse;
         float s = 0.f;
-        for (int j = 0; j < Cse; j++) s = fmaf(Wr[(size_t)j * C + c], drp[j], s);
-        dpool[(size_t)n * C + c] = s;
+        for (int w = 0; w < nw; w++) s += r_part[(w * IMG + i) * Cse + j];
+        const float x = rpre[e];
+        const float sg = sigmoid_precise(x);
+        const float v = s * (sg * (1.f + x * (1.f - sg)));
+        drp[e] = v;
+        if (i < ni) {
+            d_rpre[(size_t)(n0 + i) * Cse + j] = v;
+            r_out[(size_t)(n0 + i) * Cse + j] = r[e];
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += nt) {
+        float s[IMG];
+#pragma unroll
+        for (int i = 0; i < IMG; i++) s[i] = 0.f;
+        for (int j = 0; j < Cse; j++) {
+            const float wv = Wr[(size_t)j * C + c];
+#pragma unroll
+            for (int i = 0; i < IMG; i++) s[i] = fmaf(wv, drp[i * Cse + j], s[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < IMG; i++)
+            if (i < ni) dpool[(size_t)(n0 + i) * C + c] = s[i];
     }
 }
 
@@ -466,6 +537,23 @@ static int flat_blocks(size_t n) {
     return (int)b;
 }
 
+// images per CTA of the SE FC kernels: as many (1, 2, 4) as keep >= ~64 CTAs and fit shared memory
+static int se_img(int N, size_t floats_per_image, size_t fixed_floats) {
+    int img = 4;
+    while (img > 1 && (N / img < 64 || (img * floats_per_image + fixed_floats) * sizeof(float) > 200 * 1024)) img >>= 1;
+    return img;
+}
+
+template <typename K>
+static int se_smem_attr(K kern, size_t smem, bool* done) {
+    if (smem > 48 * 1024 && !*done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return dfd_set_cuda_error(e, __FILE__, __LINE__);
+        *done = true;
+    }
+    return smem > 200 * 1024 ? dfd_set_error(DFD_ERR_UNSUPPORTED, "squeeze-excite: channel count exceeds shared memory") : DFD_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -473,8 +561,15 @@ extern "C" {
 int dfd_se_fc_fwd(const float* pooled, const float* Wr, const float* br, const float* We, const float* be,
                   float* gate, int N, int C, int Cse, void* stream) {
     if (N <= 0 || C <= 0 || Cse <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_fc_fwd: sizes");
-    size_t smem = (size_t)(C + Cse) * sizeof(float);
-    se_fc_fwd_kernel<<<N, se_threads(C), smem, (cudaStream_t)stream>>>(pooled, Wr, br, We, be, gate, C, Cse);
+    const int img = se_img(N, (size_t)C + Cse, 0);
+    const size_t smem = (size_t)img * (C + Cse) * sizeof(float);
+    const int blocks = (N + img - 1) / img, nthr = se_threads(C);
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool a4 = false, a2 = false, a1 = false;
+    int rc;
+    if (img == 4) { if ((rc = se_smem_attr(se_fc_fwd_kernel<4>, smem, &a4))) return rc; se_fc_fwd_kernel<4><<<blocks, nthr, smem, st>>>(pooled, Wr, br, We, be, gate, N, C, Cse); }
+    else if (img == 2) { if ((rc = se_smem_attr(se_fc_fwd_kernel<2>, smem, &a2))) return rc; se_fc_fwd_kernel<2><<<blocks, nthr, smem, st>>>(pooled, Wr, br, We, be, gate, N, C, Cse); }
+    else { if ((rc = se_smem_attr(se_fc_fwd_kernel<1>, smem, &a1))) return rc; se_fc_fwd_kernel<1><<<blocks, nthr, smem, st>>>(pooled, Wr, br, We, be, gate, N, C, Cse); }
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }
@@ -483,15 +578,16 @@ int dfd_se_fc_bwd(const float* draw, const float* pooled, const float* Wr, const
                   const float* be, float* d_e, float* r, float* d_rpre, float* dpool, float* dWr, float* dbr,
                   float* dWe, float* dbe, int N, int C, int Cse, void* stream) {
     if (N <= 0 || C <= 0 || Cse <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_fc_bwd: sizes");
-    const int nthr = se_threads(C);
-    size_t smem = (size_t)(2 * C + 3 * Cse + (nthr / 32) * Cse) * sizeof(float);
+    const int nthr = se_threads(C), nw = nthr / 32;
+    const int img = se_img(N, (size_t)2 * C + (size_t)(3 + nw) * Cse, 0);
+    const size_t smem = (size_t)img * (2 * C + (3 + nw) * Cse) * sizeof(float);
+    const int blocks = (N + img - 1) / img;
     cudaStream_t st = (cudaStream_t)stream;
-    if (smem > 48 * 1024) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(se_fc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
-        if (smem > 160 * 1024) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_se_fc_bwd: channel count exceeds shared memory");
-    }
-    se_fc_bwd_kernel<<<N, nthr, smem, st>>>(draw, pooled, Wr, br, We, be, d_e, r, d_rpre, dpool, C, Cse);
+    static bool a4 = false, a2 = false, a1 = false;
+    int rc;
+    if (img == 4) { if ((rc = se_smem_attr(se_fc_bwd_kernel<4>, smem, &a4))) return rc; se_fc_bwd_kernel<4><<<blocks, nthr, smem, st>>>(draw, pooled, Wr, br, We, be, d_e, r, d_rpre, dpool, N, C, Cse); }
+    else if (img == 2) { if ((rc = se_smem_attr(se_fc_bwd_kernel<2>, smem, &a2))) return rc; se_fc_bwd_kernel<2><<<blocks, nthr, smem, st>>>(draw, pooled, Wr, br, We, be, d_e, r, d_rpre, dpool, N, C, Cse); }
+    else { if ((rc = se_smem_attr(se_fc_bwd_kernel<1>, smem, &a1))) return rc; se_fc_bwd_kernel<1><<<blocks, nthr, smem, st>>>(draw, pooled, Wr, br, We, be, d_e, r, d_rpre, dpool, N, C, Cse); }
     DFD_LAUNCH_CHECK();
     return dfd_se_fc_wgrad(d_e, r, d_rpre, pooled, dWr, dbr, dWe, dbe, N, C, Cse, stream);
 }

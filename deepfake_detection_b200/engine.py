@@ -30,7 +30,7 @@ def _ptr(t, off_elems=0):
 class _BN:
     """Pointers of one BatchNorm layer (parameters, running stats, per-step statistics, bwd coefficients)."""
     __slots__ = ("name", "C", "gamma", "beta", "dgamma", "dbeta", "rm", "rv", "nbt", "scale", "shift", "mean",
-                 "rstd", "cA", "cB", "cC", "fsum", "fsq", "bs1", "bs2")
+                 "rstd", "cA", "cB", "cC", "fsum", "fsq", "bs1", "bs2", "fin", "bfin", "count", "idx", "fused")
 
 
 class Engine:
@@ -230,9 +230,9 @@ class Engine:
         self._red_pending.append((off, dW, Nw * Kw, Nw * Kw, splits))
         return ("dfd_gemm_wgrad", [G, X, dW, M, Nw, Kw, self.dt, ("WS", off), nbytes])
 
-    def _dw_bwd(self, args, N, H, W, C, k, stride):
+    def _dw_bwd(self, args, N, H, W, C, k, stride, fin=None):
         if os.environ.get("DFD_NONDET"):
-            return ("dfd_dwconv_bwd", list(args) + [None, 0])
+            return ("dfd_dwconv_bwd", list(args) + [None, 0, fin])
         parts = self.L.cdll.dfd_dwconv_bwd_parts(N, H, W, C, k, stride)
         cbs = (C + 63) // 64
         off, nbytes = self._ws_take(cbs * parts * 64 * k * k * 4)
@@ -240,7 +240,7 @@ class Engine:
         for cb in range(cbs):
             n = min(64, C - 64 * cb) * k * k
             self._red_pending.append((off + cb * parts * 64 * k * k * 4, dW + cb * 64 * k * k * 4, n, 64 * k * k, parts))
-        return ("dfd_dwconv_bwd", list(args) + [("WS", off), nbytes])
+        return ("dfd_dwconv_bwd", list(args) + [("WS", off), nbytes, fin])
 
     def _ws_take(self, nbytes):
         off = getattr(self, "_ws_bytes", 0)
@@ -300,6 +300,23 @@ class Engine:
     # Derived 16-bit weight layouts (block-diagonal small-K copies, the padded stem weight, the packed k x k weights of
     # the ResNet path) are registered with, owned by and refreshed through the ARENA engine, whichever plan asked for them:
     # the optimizer refreshes them once per step for every plan that shares the weights.
+    def _upload_fin_descs(self):
+        """fill the BatchNorm finalisation descriptors once the plan knows every layer's element count"""
+        import struct
+        n = len(self.bns)
+        raw = bytearray(2 * n * 128)
+        for bn in self.bns.values():
+            if bn.count is None:
+                continue
+            cnt = float(bn.count)
+            unb = cnt / (cnt - 1.0) if cnt > 1 else 1.0
+            struct.pack_into("<12Qddffii", raw, bn.idx * 128, bn.fsum, bn.fsq, bn.gamma, bn.beta, bn.rm, bn.rv, bn.nbt, bn.scale,
+                             bn.shift, bn.mean, bn.rstd, _ptr(self._fin_tickets, bn.idx), 1.0 / cnt, unb, self.bn_momentum,
+                             self.bn_eps, bn.C, 0)
+            struct.pack_into("<11Qdii", raw, (n + bn.idx) * 128, bn.bs1, bn.bs2, bn.gamma, bn.mean, bn.rstd, bn.dgamma, bn.dbeta,
+                             bn.cA, bn.cB, bn.cC, _ptr(self._fin_tickets, n + bn.idx), 1.0 / cnt, bn.C, 0)
+        self._fin_buf.copy_(torch.frombuffer(raw, dtype=torch.int32).to(self._fin_buf.device))
+
     def _blockdiag(self, B, Nn, K, pack):
         """block-diagonal [pack*Nn, pack*K] copy of the weight at B"""
         o = self.arena
@@ -351,9 +368,16 @@ class Engine:
         self.stats = torch.zeros(4 * S * tot_c + 8, dtype=torch.float64, device=dev)  # fsum fsq bs1 bs2 (+ loss/correct)
         self.bns = {}
         co = 0
-        for name, c in bn_specs:
+        # finalisation descriptors (csrc/bn_finalize.cuh: BnFinDesc / BnBwdFinDesc, 128-byte stride) + one ticket each: the
+        # last CTA of the kernel that produced a layer's statistics finalises that BatchNorm (no one-block launches)
+        self._fin_buf = torch.zeros(2 * len(bn_specs) * 32, dtype=torch.int32, device=dev)
+        self._fin_tickets = torch.zeros(2 * len(bn_specs), dtype=torch.int32, device=dev)
+        for bi, (name, c) in enumerate(bn_specs):
             bn = _BN()
             bn.name, bn.C = name, c
+            bn.idx, bn.count, bn.fused = bi, None, False
+            bn.fin = _ptr(self._fin_buf, bi * 32)
+            bn.bfin = _ptr(self._fin_buf, (len(bn_specs) + bi) * 32)
             bn.gamma = _ptr(self.params32, self.p_off[name + ".weight"][0])
             bn.beta = _ptr(self.params32, self.p_off[name + ".bias"][0])
             bn.dgamma = _ptr(self.grads32, self.p_off[name + ".weight"][0])
@@ -410,23 +434,39 @@ class Engine:
         dt = self.dt
         mom, eps = self.bn_momentum, self.bn_eps
 
+        fused_fin = not os.environ.get("DFD_NO_FUSED_FINALIZE")
+
         def gemm(A, B, C, M, Nn, K, bn=None):
             fs, fq = (bn.fsum, bn.fsq) if bn is not None else (None, None)
             if self.gemm_impl == "tc":
+                fin = bn.fin if (bn is not None and fused_fin) else None
+                if bn is not None:
+                    bn.fused = fin is not None
                 pack = self._row_pack(M, K)
                 if pack > 1:
-                    return ("dfd_gemm_tn_rowpack", (A, self._blockdiag(B, Nn, K, pack), C, M, Nn, K, pack, dt, fs, fq))
-                return ("dfd_gemm_tn", (A, B, C, M, Nn, K, dt, fs, fq))
+                    return ("dfd_gemm_tn_rowpack", (A, self._blockdiag(B, Nn, K, pack), C, M, Nn, K, pack, dt, fs, fq, fin))
+                return ("dfd_gemm_tn", (A, B, C, M, Nn, K, dt, fs, fq, fin))
             return ("dfd_gemm_tn_mma", (A, B, C, None, M, Nn, K, dt, fs, fq))
 
         def finalize(bn, count):
-            # training flag is patched at run time (see _run)
-            return ("dfd_bn_finalize", [bn.fsum, bn.fsq, float(count), bn.gamma, bn.beta, bn.rm, bn.rv, bn.nbt, mom, eps,
-                                        "TRAINING", bn.C, bn.scale, bn.shift, bn.mean, bn.rstd])
+            # Training: the producing kernel's last CTA finalises (descriptor bn.fin), this op is skipped (see _run); it runs
+            # in eval mode (running statistics -> scale / shift, once per weight state) and when the producer cannot finalise.
+            bn.count = count
+            return ("dfd_bn_finalize" + ("_evalonly" if bn.fused else ""),
+                    [bn.fsum, bn.fsq, float(count), bn.gamma, bn.beta, bn.rm, bn.rv, bn.nbt, mom, eps,
+                     "TRAINING", bn.C, bn.scale, bn.shift, bn.mean, bn.rstd])
 
         def bwd_finalize(bn, count):
+            bn.count = count
+            if fused_fin:
+                return None         # done by the last CTA of the kernel that produced bs1 / bs2 (descriptor bn.bfin)
             return ("dfd_bn_bwd_finalize", (bn.bs1, bn.bs2, float(count), bn.gamma, bn.mean, bn.rstd, bn.dgamma, bn.dbeta,
                                             bn.cA, bn.cB, bn.cC, bn.C))
+
+        BF = (lambda bn: bn.bfin) if fused_fin else (lambda bn: None)
+        def FF(bn):         # forward producer other than the GEMM (depthwise conv): fused finalisation of its BatchNorm
+            bn.fused = fused_fin
+            return bn.fin if fused_fin else None
 
         # ---- scratch for backward ----------------------------------------------------------------
         mid_max = max([N * h * w * b.cmid for b, h, w, ho, wo in blocks if b.kind == "ir"] +
@@ -492,7 +532,7 @@ class Engine:
             self.acts[p + ".conv_dw"] = y2
             fwd.append(("dfd_dwconv_fwd", (_ptr(dw_in), dw_bn.scale if dw_bn else None, dw_bn.shift if dw_bn else None,
                                            P32(p + ".conv_dw.weight"), _ptr(y2), N, h, w, b.cmid, b.k, b.stride,
-                                           ACT_SWISH if dw_bn else ACT_NONE, dt, bn_mid.fsum, bn_mid.fsq)))
+                                           ACT_SWISH if dw_bn else ACT_NONE, dt, bn_mid.fsum, bn_mid.fsq, FF(bn_mid))))
             fwd.append(finalize(bn_mid, M2))
             gate_ptr = None
             if b.cse:
@@ -500,12 +540,20 @@ class Engine:
                 gate = torch.zeros(N, b.cmid, dtype=torch.float32, device=dev)
                 self._keep += [pooled, gate]
                 rec.update(pooled=pooled, gate=gate)
-                # squeeze (global pool of swish(bn(y2))) + excite (both FCs, sigmoid gate) in ONE launch: the CTA that completes
-                # an image's pooled vector carries on with that image's FC chain
-                fwd.append(("dfd_pool_se", (_ptr(y2), bn_mid.scale, bn_mid.shift, _ptr(pooled), P32(p + ".se.conv_reduce.weight"),
-                                            P32(p + ".se.conv_reduce.bias"), P32(p + ".se.conv_expand.weight"),
-                                            P32(p + ".se.conv_expand.bias"), _ptr(gate), N, ho * wo, b.cmid, b.cse, ACT_SWISH, dt,
-                                            POOL_CHUNKS)))
+                if os.environ.get("DFD_SE_FUSED"):
+                    # squeeze + excite in ONE launch (the CTA that completes an image's pooled vector runs its FC chain):
+                    # measured SLOWER than the two launches (+0.2 ms per step: a 256-thread CTA walks the latency-bound chain
+                    # four times longer than the 1024-thread FC kernel and the tail is not hidden); kept selectable
+                    fwd.append(("dfd_pool_se", (_ptr(y2), bn_mid.scale, bn_mid.shift, _ptr(pooled), P32(p + ".se.conv_reduce.weight"),
+                                                P32(p + ".se.conv_reduce.bias"), P32(p + ".se.conv_expand.weight"),
+                                                P32(p + ".se.conv_expand.bias"), _ptr(gate), N, ho * wo, b.cmid, b.cse, ACT_SWISH, dt,
+                                                POOL_CHUNKS)))
+                else:
+                    fwd.append(("dfd_pool", (_ptr(y2), bn_mid.scale, bn_mid.shift, _ptr(pooled), N, ho * wo, b.cmid, ACT_SWISH, dt,
+                                             None, POOL_CHUNKS)))
+                    fwd.append(("dfd_se_fc_fwd", (_ptr(pooled), P32(p + ".se.conv_reduce.weight"), P32(p + ".se.conv_reduce.bias"),
+                                                  P32(p + ".se.conv_expand.weight"), P32(p + ".se.conv_expand.bias"),
+                                                  _ptr(gate), N, b.cmid, b.cse)))
                 gate_ptr = _ptr(gate)
             a2 = self._alloc16(N, ho, wo, b.cmid)
             fwd.append(("dfd_bn_act", (_ptr(y2), bn_mid.scale, bn_mid.shift, gate_ptr, None, _ptr(a2), N, ho * wo, b.cmid,
@@ -538,7 +586,7 @@ class Engine:
         fwd.append(finalize(bnh, Mf))
         self.pooled = torch.zeros(N, F, dtype=torch.float32, device=dev)
         fwd.append(("dfd_pool", (_ptr(yh), bnh.scale, bnh.shift, _ptr(self.pooled), N, Hf * Wf, F, ACT_SWISH, dt,
-                             _ptr(self.pool_partial), POOL_CHUNKS)))
+                             None, POOL_CHUNKS)))
         self.drop_masks = OrderedDict()
         if self.drop_rate > 0.0:
             self.dropout_mask = torch.ones(N, F, dtype=torch.float32, device=dev)
@@ -570,7 +618,7 @@ class Engine:
         if self.drop_rate > 0.0:
             bwd.append(("dfd_mul_f32", (_ptr(self.dpooled), _ptr(self.dropout_mask), N * F)))
         bwd.append(("dfd_act_bwd", (None, _ptr(yh), bnh.scale, bnh.shift, bnh.mean, bnh.rstd, None, _ptr(self.dpooled),
-                                    mid_a, N, Hf * Wf, F, ACT_SWISH, dt, bnh.bs1, bnh.bs2)))
+                                    mid_a, N, Hf * Wf, F, ACT_SWISH, dt, bnh.bs1, bnh.bs2, BF(bnh))))
         bwd.append(bwd_finalize(bnh, Mf))
         bwd.append(("dfd_bn_bwd_apply", (mid_a, _ptr(yh), None, bnh.cA, bnh.cB, bnh.cC, mid_b, N, Hf * Wf, F, dt)))
         cur = 0
@@ -594,7 +642,7 @@ class Engine:
                                            N, ho * wo, b.cout, ACT_NONE, 0, dt)))
                 gbn = t2
             bwd.append(("dfd_bn_bwd_reduce", (gbn, _ptr(y3), None, bn_out.mean, bn_out.rstd, N, ho * wo, b.cout, dt,
-                                              bn_out.bs1, bn_out.bs2)))
+                                              bn_out.bs1, bn_out.bs2, BF(bn_out))))
             bwd.append(bwd_finalize(bn_out, M2))
             bwd.append(("dfd_bn_bwd_apply", (gbn, _ptr(y3), None, bn_out.cA, bn_out.cB, bn_out.cC, t1, N, ho * wo, b.cout, dt)))
             bwd.append(gemm(t1, T16(p + pw_name + ".weight"), mid_a, M2, b.cmid, b.cout))
@@ -602,17 +650,25 @@ class Engine:
             gate_ptr = dpool_ptr = None
             if b.cse:
                 gate_ptr, dpool_ptr = _ptr(rec["gate"]), se_dpool
-                # dL/dgate reduction + the per-image backward FC chain in one launch, then the SE parameter gradients
-                bwd.append(("dfd_se_bwd_chain", (mid_a, _ptr(y2), bn_mid.scale, bn_mid.shift, se_draw, _ptr(rec["pooled"]),
-                                                 P32(p + ".se.conv_reduce.weight"), P32(p + ".se.conv_reduce.bias"),
-                                                 P32(p + ".se.conv_expand.weight"), P32(p + ".se.conv_expand.bias"),
-                                                 se_de, se_r, se_drp, se_dpool, N, ho * wo, b.cmid, b.cse, dt)))
-                bwd.append(("dfd_se_fc_wgrad", (se_de, se_r, se_drp, _ptr(rec["pooled"]),
-                                                G32(p + ".se.conv_reduce.weight"), G32(p + ".se.conv_reduce.bias"),
-                                                G32(p + ".se.conv_expand.weight"), G32(p + ".se.conv_expand.bias"),
-                                                N, b.cmid, b.cse)))
+                if os.environ.get("DFD_SE_FUSED"):
+                    bwd.append(("dfd_se_bwd_chain", (mid_a, _ptr(y2), bn_mid.scale, bn_mid.shift, se_draw, _ptr(rec["pooled"]),
+                                                     P32(p + ".se.conv_reduce.weight"), P32(p + ".se.conv_reduce.bias"),
+                                                     P32(p + ".se.conv_expand.weight"), P32(p + ".se.conv_expand.bias"),
+                                                     se_de, se_r, se_drp, se_dpool, N, ho * wo, b.cmid, b.cse, dt)))
+                    bwd.append(("dfd_se_fc_wgrad", (se_de, se_r, se_drp, _ptr(rec["pooled"]),
+                                                    G32(p + ".se.conv_reduce.weight"), G32(p + ".se.conv_reduce.bias"),
+                                                    G32(p + ".se.conv_expand.weight"), G32(p + ".se.conv_expand.bias"),
+                                                    N, b.cmid, b.cse)))
+                else:
+                    bwd.append(("dfd_se_bwd_reduce", (mid_a, _ptr(y2), bn_mid.scale, bn_mid.shift, se_draw, N, ho * wo, b.cmid, dt)))
+                    bwd.append(("dfd_se_fc_bwd", (se_draw, _ptr(rec["pooled"]), P32(p + ".se.conv_reduce.weight"),
+                                                  P32(p + ".se.conv_reduce.bias"), P32(p + ".se.conv_expand.weight"),
+                                                  P32(p + ".se.conv_expand.bias"), se_de, se_r, se_drp, se_dpool,
+                                                  G32(p + ".se.conv_reduce.weight"), G32(p + ".se.conv_reduce.bias"),
+                                                  G32(p + ".se.conv_expand.weight"), G32(p + ".se.conv_expand.bias"),
+                                                  N, b.cmid, b.cse)))
             bwd.append(("dfd_act_bwd", (mid_a, _ptr(y2), bn_mid.scale, bn_mid.shift, bn_mid.mean, bn_mid.rstd, gate_ptr,
-                                        dpool_ptr, mid_b, N, ho * wo, b.cmid, ACT_SWISH, dt, bn_mid.bs1, bn_mid.bs2)))
+                                        dpool_ptr, mid_b, N, ho * wo, b.cmid, ACT_SWISH, dt, bn_mid.bs1, bn_mid.bs2, BF(bn_mid))))
             bwd.append(bwd_finalize(bn_mid, M2))
             if b.kind == "ir":
                 y1 = rec["y1"]
@@ -627,7 +683,7 @@ class Engine:
                     bwd.append(self._dw_bwd((mid_b, _ptr(y2), bn_mid.cA, bn_mid.cB, bn_mid.cC, P32(p + ".conv_dw.weight"),
                                              _ptr(y1), dw_bn.scale, dw_bn.shift, dw_bn.mean, dw_bn.rstd, None, mid_a,
                                              G32(p + ".conv_dw.weight"), N, h, w, b.cmid, b.k, b.stride, dt,
-                                             dw_bn.bs1, dw_bn.bs2), N, h, w, b.cmid, b.k, b.stride))
+                                             dw_bn.bs1, dw_bn.bs2), N, h, w, b.cmid, b.k, b.stride, BF(dw_bn)))
                 bwd.append(bwd_finalize(dw_bn, M1))
                 bwd.append(("dfd_bn_bwd_apply", (mid_a, _ptr(y1), None, dw_bn.cA, dw_bn.cB, dw_bn.cC, mid_b, N, h * w, b.cmid, dt)))
                 bwd.append(gemm(mid_b, T16(p + ".conv_pw.weight"), t2, M1, b.cin, b.cmid))
@@ -651,7 +707,7 @@ class Engine:
         # stem
         bn = self.bns["bn1"]
         bwd.append(("dfd_act_bwd", (sm[cur], _ptr(y0), bn.scale, bn.shift, bn.mean, bn.rstd, None, None, mid_a, N, Hs * Ws,
-                                    spec.stem, ACT_SWISH, dt, bn.bs1, bn.bs2)))
+                                    spec.stem, ACT_SWISH, dt, bn.bs1, bn.bs2, BF(bn))))
         bwd.append(bwd_finalize(bn, N * Hs * Ws))
         if self.stem_impl == "gemm":
             bwd.append(("dfd_bn_bwd_apply", (mid_a, _ptr(y0), None, bn.cA, bn.cB, bn.cC, mid_b, N, Hs * Ws, spec.stem, dt)))
@@ -662,9 +718,17 @@ class Engine:
         else:
             bwd.append(("dfd_stem_wgrad", (_ptr(self.x_in), mid_a, _ptr(y0), bn.cA, bn.cB, bn.cC, G32("conv_stem.weight"), N,
                                            spec.in_chans, self.H, self.W, spec.stem, 3, 2, 1, dt)))
-        bwd = self._patch_workspace(bwd)
+        bwd = self._patch_workspace([op for op in bwd if op is not None])
+        self._upload_fin_descs()
+
+        def base_name(n):
+            for suf in ("_train", "_evalonly"):
+                if n.endswith(suf):
+                    return n[:-len(suf)]
+            return n
+
         for n, a in fwd + bwd:      # arity / type check of the plan against the ABI table
-            codes = _lib.SIGNATURES[n[:-6] if n.endswith("_train") else n]
+            codes = _lib.SIGNATURES[base_name(n)]
             if len(a) != len(codes) - 1:
                 raise AssertionError("%s: %d args for signature %r" % (n, len(a), codes))
             for v, c in zip(a, codes):
@@ -676,7 +740,7 @@ class Engine:
                     raise AssertionError("%s: argument %r does not fit code %r" % (n, v, c))
         # `<name>_train` ops run in training mode only (mask generation, dropout); ("TRAIN_ONLY", ptr) operands are NULL in eval
         fwd = [(n, a) for n, a in fwd]
-        self.fwd_ops = [(getattr(L, n[:-6] if n.endswith("_train") else n), n, a) for n, a in fwd]
+        self.fwd_ops = [(getattr(L, base_name(n)), n, a) for n, a in fwd]
         self.bwd_ops = [(getattr(L, n), n, tuple(a)) for n, a in bwd]
         self.n_launch["fwd"] = len(fwd)
         self.n_launch["bwd"] = len(bwd)
@@ -689,20 +753,22 @@ class Engine:
             raise _lib.NativeError("plan-only engine cannot execute (no CUDA device)")
         L = self.L
         for fn, name, args in ops:
-            if skip_finalize and name == "dfd_bn_finalize":
-                continue
-            if name.endswith("_train"):
+            if name.startswith("dfd_bn_finalize"):
+                # `_evalonly`: in training the producing kernel's last CTA finalised this BatchNorm already
+                if skip_finalize or (training and name.endswith("_evalonly")):
+                    continue
+                args = tuple((1 if training else 0) if a == "TRAINING" else a for a in args)
+                if not training:
+                    args = (None, None) + args[2:]
+            elif name.endswith("_train"):
                 if not training:
                     continue
             elif name == "dfd_bn_act" and any(isinstance(a, tuple) for a in args):
                 args = tuple((a[1] if training else None) if isinstance(a, tuple) else a for a in args)
-            if name == "dfd_bn_finalize":
-                args = tuple((1 if training else 0) if a == "TRAINING" else a for a in args)
-                if not training:
-                    args = (None, None) + args[2:]
-            elif not training and name in ("dfd_gemm_tn", "dfd_gemm_tn_rowpack", "dfd_gemm_tn_mma", "dfd_dwconv_fwd",
-                                           "dfd_stem_fwd"):
-                args = tuple(args[:-2]) + (None, None)      # eval: no batch statistics
+            elif not training and name in ("dfd_gemm_tn", "dfd_gemm_tn_rowpack", "dfd_dwconv_fwd"):
+                args = tuple(args[:-3]) + (None, None, None)      # eval: no batch statistics, no finalisation
+            elif not training and name in ("dfd_gemm_tn_mma", "dfd_stem_fwd"):
+                args = tuple(args[:-2]) + (None, None)
             rc = fn(*args, stream)
             _lib.N_CALLS[0] += 1
             if rc != 0:

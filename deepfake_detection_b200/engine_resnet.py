@@ -75,19 +75,32 @@ def build_resnet(e):
     e._alloc_bn(bn_specs)
     bns = e.bns
 
+    import os
+    fused_fin = not os.environ.get("DFD_NO_FUSED_FINALIZE")
+
     def gemm(A, B, C, M, Nn, K, bn=None):
         fs, fq = (bn.fsum, bn.fsq) if bn is not None else (None, None)
         if e.gemm_impl == "tc":
-            return ("dfd_gemm_tn", (A, B, C, M, Nn, K, dt, fs, fq))
+            if bn is not None:
+                bn.fused = fused_fin
+            return ("dfd_gemm_tn", (A, B, C, M, Nn, K, dt, fs, fq, bn.fin if (bn is not None and fused_fin) else None))
         return ("dfd_gemm_tn_mma", (A, B, C, None, M, Nn, K, dt, fs, fq))
 
     def finalize(bn, count):
-        return ("dfd_bn_finalize", [bn.fsum, bn.fsq, float(count), bn.gamma, bn.beta, bn.rm, bn.rv, bn.nbt, mom, eps,
-                                    "TRAINING", bn.C, bn.scale, bn.shift, bn.mean, bn.rstd])
+        # training: finalised by the last CTA of the producing GEMM (bn.fin); this op runs in eval mode only (see Engine._run)
+        bn.count = count
+        return ("dfd_bn_finalize" + ("_evalonly" if bn.fused else ""),
+                [bn.fsum, bn.fsq, float(count), bn.gamma, bn.beta, bn.rm, bn.rv, bn.nbt, mom, eps,
+                 "TRAINING", bn.C, bn.scale, bn.shift, bn.mean, bn.rstd])
 
     def bwd_finalize(bn, count):
+        bn.count = count
+        if fused_fin:
+            return None             # the last CTA of dfd_act_bwd / dfd_bn_bwd_reduce does it (bn.bfin)
         return ("dfd_bn_bwd_finalize", (bn.bs1, bn.bs2, float(count), bn.gamma, bn.mean, bn.rstd, bn.dgamma, bn.dbeta,
                                         bn.cA, bn.cB, bn.cC, bn.C))
+
+    BF = (lambda bn: bn.bfin) if fused_fin else (lambda bn: None)
 
     def bn_relu(y, bn, out, hw, C):
         return ("dfd_bn_act", (_ptr(y), bn.scale, bn.shift, None, None, _ptr(out), N, hw, C, ACT_RELU, 0, dt))
@@ -216,7 +229,7 @@ def build_resnet(e):
         gm, t1, t2, t3 = free
         bl = rec["bnlast"]
         bwd.append(("dfd_relu_bwd", (dout, _ptr(rec["out"]), gm, M2 * b.cout, dt)))
-        bwd.append(("dfd_bn_bwd_reduce", (gm, _ptr(rec["ylast"]), None, bl.mean, bl.rstd, N, ho * wo, b.cout, dt, bl.bs1, bl.bs2)))
+        bwd.append(("dfd_bn_bwd_reduce", (gm, _ptr(rec["ylast"]), None, bl.mean, bl.rstd, N, ho * wo, b.cout, dt, bl.bs1, bl.bs2, BF(bl))))
         bwd.append(bwd_finalize(bl, M2))
         bwd.append(("dfd_bn_bwd_apply", (gm, _ptr(rec["ylast"]), None, bl.cA, bl.cB, bl.cC, t1, N, ho * wo, b.cout, dt)))
         if b.kind == "basic":
@@ -224,7 +237,7 @@ def build_resnet(e):
             # conv2 (3x3 s1): dy2 = t1 -> da1 = t2
             bwd += conv3x3_bwd(p + ".conv2.weight", t1, M2, b.planes, b.cout, rec["a1"], ho, wo, 1, t2)
             bwd.append(("dfd_act_bwd", (t2, _ptr(rec["y1"]), bn1.scale, bn1.shift, bn1.mean, bn1.rstd, None, None, t1, N,
-                                        ho * wo, b.planes, ACT_RELU, dt, bn1.bs1, bn1.bs2)))
+                                        ho * wo, b.planes, ACT_RELU, dt, bn1.bs1, bn1.bs2, BF(bn1))))
             bwd.append(bwd_finalize(bn1, M2))
             bwd.append(("dfd_bn_bwd_apply", (t1, _ptr(rec["y1"]), None, bn1.cA, bn1.cB, bn1.cC, t2, N, ho * wo, b.planes, dt)))
             # conv1 (3x3 stride s): dy1 = t2 -> dx = t3 [M1, cin]
@@ -235,13 +248,13 @@ def build_resnet(e):
             bwd.append(gemm(t1, T16(p + ".conv3.weight"), t2, M2, b.planes, b.cout))
             bwd.append(e._wgrad(t1, _ptr(rec["a2"]), G32(p + ".conv3.weight"), M2, b.cout, b.planes))
             bwd.append(("dfd_act_bwd", (t2, _ptr(rec["y2"]), bn2.scale, bn2.shift, bn2.mean, bn2.rstd, None, None, t1, N,
-                                        ho * wo, b.planes, ACT_RELU, dt, bn2.bs1, bn2.bs2)))
+                                        ho * wo, b.planes, ACT_RELU, dt, bn2.bs1, bn2.bs2, BF(bn2))))
             bwd.append(bwd_finalize(bn2, M2))
             bwd.append(("dfd_bn_bwd_apply", (t1, _ptr(rec["y2"]), None, bn2.cA, bn2.cB, bn2.cC, t2, N, ho * wo, b.planes, dt)))
             # conv2 (3x3 stride s): dy2 = t2 -> da1 = t1 [M1, planes]
             bwd += conv3x3_bwd(p + ".conv2.weight", t2, M2, b.planes, b.planes, rec["a1"], h, w, b.stride, t1)
             bwd.append(("dfd_act_bwd", (t1, _ptr(rec["y1"]), bn1.scale, bn1.shift, bn1.mean, bn1.rstd, None, None, t2, N,
-                                        h * w, b.planes, ACT_RELU, dt, bn1.bs1, bn1.bs2)))
+                                        h * w, b.planes, ACT_RELU, dt, bn1.bs1, bn1.bs2, BF(bn1))))
             bwd.append(bwd_finalize(bn1, M1))
             bwd.append(("dfd_bn_bwd_apply", (t2, _ptr(rec["y1"]), None, bn1.cA, bn1.cB, bn1.cC, t1, N, h * w, b.planes, dt)))
             # conv1 (1x1): dy1 = t1 -> dx = t3 [M1, cin]
@@ -250,7 +263,7 @@ def build_resnet(e):
         # identity / downsample path: gradient gm flows to the block input too
         if b.downsample:
             bnd = rec["bnd"]
-            bwd.append(("dfd_bn_bwd_reduce", (gm, _ptr(rec["yd"]), None, bnd.mean, bnd.rstd, N, ho * wo, b.cout, dt, bnd.bs1, bnd.bs2)))
+            bwd.append(("dfd_bn_bwd_reduce", (gm, _ptr(rec["yd"]), None, bnd.mean, bnd.rstd, N, ho * wo, b.cout, dt, bnd.bs1, bnd.bs2, BF(bnd))))
             bwd.append(bwd_finalize(bnd, M2))
             bwd.append(("dfd_bn_bwd_apply", (gm, _ptr(rec["yd"]), None, bnd.cA, bnd.cB, bnd.cC, t1, N, ho * wo, b.cout, dt)))
             bwd.append(gemm(t1, T16(p + ".downsample.0.weight"), t2, M2, b.cin, b.cout))
@@ -273,7 +286,7 @@ def build_resnet(e):
     t1, t2 = free[0], free[1]
     bwd.append(("dfd_maxpool_bwd", (dout, _ptr(e.pool_idx), t1, N, H1, W1, 64, dt)))
     bwd.append(("dfd_act_bwd", (t1, _ptr(y0), bn0.scale, bn0.shift, bn0.mean, bn0.rstd, None, None, t2, N, H1 * W1, 64,
-                                ACT_RELU, dt, bn0.bs1, bn0.bs2)))
+                                ACT_RELU, dt, bn0.bs1, bn0.bs2, BF(bn0))))
     bwd.append(bwd_finalize(bn0, N * H1 * W1))
     if e.stem_impl == "gemm":
         bwd.append(("dfd_bn_bwd_apply", (t2, _ptr(y0), None, bn0.cA, bn0.cB, bn0.cC, t1, N, H1 * W1, 64, dt)))
@@ -285,12 +298,17 @@ def build_resnet(e):
         bwd.append(("dfd_stem_wgrad", (_ptr(e.x_in), t2, _ptr(y0), bn0.cA, bn0.cB, bn0.cC, G32("conv1.weight"), N, spec.in_chans,
                                        e.H, e.W, 64, 7, 2, 3, dt)))
 
-    bwd = e._patch_workspace(bwd)
+    bwd = e._patch_workspace([op for op in bwd if op is not None])
+    e._upload_fin_descs()
+
+    def base_name(n):
+        return n[:-9] if n.endswith("_evalonly") else n
+
     for n, a in fwd + bwd:
-        codes = _lib.SIGNATURES[n]
+        codes = _lib.SIGNATURES[base_name(n)]
         if len(a) != len(codes) - 1:
             raise AssertionError("%s: %d args for signature %r" % (n, len(a), codes))
     L = e.L
-    e.fwd_ops = [(getattr(L, n), n, a) for n, a in fwd]
+    e.fwd_ops = [(getattr(L, base_name(n)), n, a) for n, a in fwd]
     e.bwd_ops = [(getattr(L, n), n, tuple(a)) for n, a in bwd]
     e.n_launch["fwd"], e.n_launch["bwd"] = len(fwd), len(bwd)

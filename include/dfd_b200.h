@@ -48,12 +48,16 @@ int dfd_memset_async(void* p, int value, long long bytes, void* stream);
  * B = weight [Cout, Cin]. Input gradient: A = dY [N*H*W, Cout], B = weight^T [Cin, Cout].
  * dsum/dsq (optional): per-column sum / sum of squares of the stored C for the following BatchNorm. */
 int dfd_gemm_tn(const void* A, const void* B, void* C, long long M, int N, int K, int dt, double* dsum, double* dsq,
-                void* stream);
+                const void* fin, void* stream);
+/* `fin` (optional; here and on dfd_gemm_tn_rowpack / dfd_dwconv_fwd): device pointer to a BnFinDesc (csrc/bn_finalize.cuh) -
+ * the LAST CTA of the launch then finalises the BatchNorm behind the convolution (what dfd_bn_finalize does in its own
+ * one-block launch): scale / shift / mean / rstd and the running statistics. The backward producers (dfd_act_bwd,
+ * dfd_bn_bwd_reduce, dfd_dwconv_bwd) take a BnBwdFinDesc the same way (what dfd_bn_bwd_finalize does). NULL: no finalisation. */
 /* Small-K variant (Cin = 16 / 24 / 32 pointwise convs and their input gradients): `pack` consecutive rows of A are read
  * as one row of pack*K values against the block-diagonal weight Bd[pack*N, pack*K] built by dfd_blockdiag_weights; the
  * result is byte-identical row-major C[M,N], statistics are folded back onto the N channels. Requires M % pack == 0. */
 int dfd_gemm_tn_rowpack(const void* A, const void* Bd, void* C, long long M, int N, int K, int pack, int dt,
-                        double* dsum, double* dsq, void* stream);
+                        double* dsum, double* dsq, const void* fin, void* stream);
 /* table: device array of { const void* src; void* dst; int N; int K; int pack; int _pad; } */
 int dfd_blockdiag_weights(const void* table, int count, int dt, void* stream);
 /* same contract on the warp-level mma.sync path (+ optional residual `add` [M,N]); cross-check / fallback */
@@ -77,10 +81,8 @@ int dfd_ordered_reduce(const void* table, int count, const float* first_dst, int
 
 /* ---- depthwise k x k convolution: nn.Conv2d(groups=C), efficientnet_blocks.py:152-153,283-285 -------- */
 int dfd_dwconv_fwd(const void* x, const float* scale, const float* shift, const float* w, void* out, int N, int H,
-                   int W, int C, int k, int stride, int act_in, int dt, double* dsum, double* dsq, void* stream);
-/* stride-1 forward on tcgen05: per-tap diagonal weight tiles x shifted shared-memory descriptors (csrc/dwconv_tc.cu) */
-int dfd_dwconv_fwd_tc(const void* x, const float* scale, const float* shift, const float* w, void* out, int N, int H,
-                      int W, int C, int k, int stride, int act_in, int dt, double* dsum, double* dsq, void* stream);
+                   int W, int C, int k, int stride, int act_in, int dt, double* dsum, double* dsq, const void* fin,
+                   void* stream);
 int dfd_dwconv_dgrad(const void* gy, const void* yout, const float* cA, const float* cB, const float* cC,
                      const float* w, const void* xin, const float* scale, const float* shift, const float* mean,
                      const float* rstd, const void* add, void* gx, int N, int H, int W, int C, int k, int stride,
@@ -94,7 +96,7 @@ int dfd_dwconv_wgrad(const void* x, const float* scale, const float* shift, cons
 int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const float* cB, const float* cC,
                    const float* w, const void* xin, const float* scale, const float* shift, const float* mean,
                    const float* rstd, const void* add, void* gx, float* dW, int N, int H, int W, int C, int k,
-                   int stride, int dt, double* s1, double* s2, void* ws, long long ws_bytes, void* stream);
+                   int stride, int dt, double* s1, double* s2, void* ws, long long ws_bytes, const void* fin, void* stream);
 /* ws (optional): ORDER-DETERMINISTIC dW - CTA (tile x, 64-channel block y, image group z) stores its partial at
  * ws[y][x * groups + z][64 * k*k] laid out like dW[64y .. 64y+64)[k*k] and dfd_ordered_reduce adds the
  * dfd_dwconv_bwd_parts(...) = tiles * groups partials of every channel block into dW in slot order afterwards
@@ -145,7 +147,7 @@ int dfd_bn_act(const void* y, const float* scale, const float* shift, const floa
 int dfd_pool(const void* y, const float* scale, const float* shift, float* pooled, int n, long long hw, int C,
              int act, int dt, float* partial, int max_chunks, void* stream);
 int dfd_bn_bwd_reduce(const void* g, const void* y, const void* out, const float* mean, const float* rstd, int n,
-                      long long hw, int C, int dt, double* s1, double* s2, void* stream);
+                      long long hw, int C, int dt, double* s1, double* s2, const void* fin, void* stream);
 int dfd_bn_bwd_finalize(const double* s1, const double* s2, double count, const float* gamma, const float* mean,
                         const float* rstd, float* dgamma, float* dbeta, float* cA, float* cB, float* cC, int C,
                         void* stream);
@@ -155,7 +157,7 @@ int dfd_se_bwd_reduce(const void* da, const void* y, const float* scale, const f
                       long long hw, int C, int dt, void* stream);
 int dfd_act_bwd(const void* da, const void* y, const float* scale, const float* shift, const float* mean,
                 const float* rstd, const float* gate, const float* dpool, void* gu, int n, long long hw, int C,
-                int act, int dt, double* s1, double* s2, void* stream);
+                int act, int dt, double* s1, double* s2, const void* fin, void* stream);
 int dfd_add_inplace(void* a, const void* b, long long numel, int dt, void* stream);
 
 /* ---- squeeze-excite FCs: SqueezeExcite.forward, efficientnet_blocks.py:104-110 ------------------------ */

@@ -63,7 +63,7 @@ def check_gemm(impl, M, K, N, dtype=torch.bfloat16, with_stats=True, with_add=Fa
     s1, s2 = (stat_buf(N), stat_buf(N)) if with_stats else (None, None)
     if impl == "tc":
         assert not with_add
-        _lib.call("dfd_gemm_tn", P(A), P(B), P(C), M, N, K, DT[dtype], P(s1), P(s2), st())
+        _lib.call("dfd_gemm_tn", P(A), P(B), P(C), M, N, K, DT[dtype], P(s1), P(s2), None, st())
     elif impl.startswith("rowpack"):
         # small-K path: block-diagonal weight built on the device, `pack` rows of A per TMA row
         import struct
@@ -71,7 +71,7 @@ def check_gemm(impl, M, K, N, dtype=torch.bfloat16, with_stats=True, with_add=Fa
         Bd = torch.full((pack * N, pack * K), float("nan"), device="cuda", dtype=dtype)
         table = torch.frombuffer(bytearray(struct.pack("<QQiiii", P(B), P(Bd), N, K, pack, 0)), dtype=torch.uint8).cuda()
         _lib.call("dfd_blockdiag_weights", P(table), 1, DT[dtype], st())
-        _lib.call("dfd_gemm_tn_rowpack", P(A), P(Bd), P(C), M, N, K, pack, DT[dtype], P(s1), P(s2), st())
+        _lib.call("dfd_gemm_tn_rowpack", P(A), P(Bd), P(C), M, N, K, pack, DT[dtype], P(s1), P(s2), None, st())
     else:
         _lib.call("dfd_gemm_tn_mma", P(A), P(B), P(C), P(add), M, N, K, DT[dtype], P(s1), P(s2), st())
     torch.cuda.synchronize()
@@ -139,7 +139,7 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0, fw
     s1, s2 = stat_buf(C), stat_buf(C)
     act = 1 if affine else 0
     _lib.call(fwd_impl, P(x), P(scale) if affine else None, P(shift) if affine else None, P(w), P(out), N, H, W, C,
-              k, s, act, DT[dtype], P(s1), P(s2), st())
+              k, s, act, DT[dtype], P(s1), P(s2), None, st())
     torch.cuda.synchronize()
     # reference (fp32, same rounding points: activated input rounded to `dtype`)
     xr = nchw(x.float()).requires_grad_(True)
@@ -189,7 +189,7 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0, fw
         dW2 = torch.zeros_like(w)
         c1, c2 = stat_buf(C), stat_buf(C)
         _lib.call("dfd_dwconv_bwd", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), P(scale), P(shift), P(mean), P(rstd), None,
-                  P(gx2), P(dW2), N, H, W, C, k, s, DT[dtype], P(c1), P(c2), None, 0, st())
+                  P(gx2), P(dW2), N, H, W, C, k, s, DT[dtype], P(c1), P(c2), None, 0, None, st())
         # order-deterministic mode: partials in fixed slots + ordered reduce; two runs agree bit for bit, and with the atomic
         # flush to fp32 round-off
         import struct
@@ -200,7 +200,7 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0, fw
         for t in dW3:
             c3, c4 = stat_buf(C), stat_buf(C)
             _lib.call("dfd_dwconv_bwd", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), P(scale), P(shift), P(mean), P(rstd), None,
-                      P(gx2), P(t), N, H, W, C, k, s, DT[dtype], P(c3), P(c4), P(ws), ws.numel() * 4, st())
+                      P(gx2), P(t), N, H, W, C, k, s, DT[dtype], P(c3), P(c4), P(ws), ws.numel() * 4, None, st())
             raw = b"".join(struct.pack("<QQqqii", P(ws) + cb * parts * 64 * k * k * 4, P(t) + cb * 64 * k * k * 4,
                                        min(64, C - 64 * cb) * k * k, 64 * k * k, parts, 0) for cb in range(cbs))
             table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
@@ -225,7 +225,7 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0, fw
         gx2 = torch.full((N, H, W, C), float("nan"), device="cuda", dtype=dtype)
         dW2 = torch.zeros_like(w)
         _lib.call("dfd_dwconv_bwd", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), None, None, None, None, P(add), P(gx2), P(dW2),
-                  N, H, W, C, k, s, DT[dtype], None, None, None, 0, st())
+                  N, H, W, C, k, s, DT[dtype], None, None, None, 0, None, st())
         torch.cuda.synchronize()
         res["fused_gx_diff"] = float((gx2.float() - gx.float()).abs().max())
         res["fused_nan"] = int(torch.isnan(gx2.float()).sum())
@@ -326,14 +326,14 @@ def check_bn_chain(N, HW, C, dtype=torch.bfloat16, seed=0):
     dpool = torch.randn(N, C, device="cuda", generator=g) * 0.1
     gu = torch.full((N, HW, C), float("nan"), device="cuda", dtype=dtype)
     b1, b2 = stat_buf(C), stat_buf(C)
-    _lib.call("dfd_act_bwd", P(da), P(y), P(scale), P(shift), P(mean), P(rstd), P(gate), P(dpool), P(gu), N, HW, C, 1, d, P(b1), P(b2), st())
+    _lib.call("dfd_act_bwd", P(da), P(y), P(scale), P(shift), P(mean), P(rstd), P(gate), P(dpool), P(gu), N, HW, C, 1, d, P(b1), P(b2), None, st())
     dgamma, dbeta, cA, cB, cC = (torch.zeros(C, device="cuda") for _ in range(5))
     _lib.call("dfd_bn_bwd_finalize", P(b1), P(b2), float(N * HW), P(gamma), P(mean), P(rstd), P(dgamma), P(dbeta), P(cA), P(cB), P(cC), C, st())
     dy = torch.full((N, HW, C), float("nan"), device="cuda", dtype=dtype)
     _lib.call("dfd_bn_bwd_apply", P(gu), P(y), None, P(cA), P(cB), P(cC), P(dy), N, HW, C, d, st())
     # also the two-pass reduce variant used for un-activated BN outputs
     c1, c2 = stat_buf(C), stat_buf(C)
-    _lib.call("dfd_bn_bwd_reduce", P(da), P(y), None, P(mean), P(rstd), N, HW, C, d, P(c1), P(c2), st())
+    _lib.call("dfd_bn_bwd_reduce", P(da), P(y), None, P(mean), P(rstd), N, HW, C, d, P(c1), P(c2), None, st())
     draw = torch.zeros(N, C, device="cuda")
     _lib.call("dfd_se_bwd_reduce", P(da), P(y), P(scale), P(shift), P(draw), N, HW, C, d, st())
     torch.cuda.synchronize()
@@ -374,6 +374,123 @@ def check_se_fc(N, C, Cse, seed=0):
     torch.cuda.synchronize()
     return dict(gate_rel=relerr(gate, ref.detach()), dpool_rel=relerr(dpool, pr.grad), dWr_rel=relerr(dWr, Wr.grad),
                 dbr_rel=relerr(dbr, br.grad), dWe_rel=relerr(dWe, We.grad), dbe_rel=relerr(dbe, be.grad))
+
+
+def _fin_desc(s1, s2, gamma, beta, rm, rv, nbt, scale, shift, mean, rstd, ticket, count, C, momentum=0.1, eps=1e-5):
+    """BnFinDesc (csrc/bn_finalize.cuh) on the device"""
+    import struct
+    raw = struct.pack("<12Qddffii", P(s1), P(s2), P(gamma), P(beta), P(rm), P(rv), P(nbt), P(scale), P(shift), P(mean), P(rstd),
+                      P(ticket), 1.0 / count, count / (count - 1.0), momentum, eps, C, 0)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
+
+
+def _bfin_desc(s1, s2, gamma, mean, rstd, dgamma, dbeta, cA, cB, cC, ticket, count, C):
+    import struct
+    raw = struct.pack("<11Qdii", P(s1), P(s2), P(gamma), P(mean), P(rstd), P(dgamma), P(dbeta), P(cA), P(cB), P(cC), P(ticket),
+                      1.0 / count, C, 0)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
+
+
+def check_fused_finalize(kind, dtype=torch.bfloat16, seed=0):
+    """The BatchNorm finalisation done by the LAST CTA of the kernel that produced the statistics == the standalone
+    dfd_bn_finalize / dfd_bn_bwd_finalize launch on the same statistics (bit for bit: same device function, same fp64 sums up to
+    the order of the slot atomics), twice in a row (the ticket returns to zero), running statistics included."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    d = DT[dtype]
+    out = {}
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def vecs(C, n):
+        return [torch.zeros(C, device="cuda") for _ in range(n)]
+
+    if kind in ("gemm", "gemm_rowpack", "dwconv_fwd"):
+        if kind == "dwconv_fwd":
+            N, H, W, C, k, s_ = 3, 19, 17, 96, 3, 1
+            x = torch.randn(N, H, W, C, device="cuda", generator=g).to(dtype)
+            w = (torch.randn(C, 1, k, k, device="cuda", generator=g) / k).contiguous()
+            sc, sh = _bn_params(C, g)
+            y = torch.empty(N, H, W, C, device="cuda", dtype=dtype)
+            count = N * H * W
+            launch = lambda a, b, fin: _lib.call("dfd_dwconv_fwd", P(x), P(sc), P(sh), P(w), P(y), N, H, W, C, k, s_, 1, d, P(a), P(b), fin, st())
+        else:
+            M, K, C = 5000, 32 if kind == "gemm_rowpack" else 144, 96
+            A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(dtype)
+            B = (torch.randn(C, K, device="cuda", generator=g) / math.sqrt(K)).to(dtype)
+            y = torch.empty(M, C, device="cuda", dtype=dtype)
+            count = M
+            if kind == "gemm":
+                launch = lambda a, b, fin: _lib.call("dfd_gemm_tn", P(A), P(B), P(y), M, C, K, d, P(a), P(b), fin, st())
+            else:
+                import struct
+                pack = 4
+                Bd = torch.zeros(pack * C, pack * K, device="cuda", dtype=dtype)
+                table = torch.frombuffer(bytearray(struct.pack("<QQiiii", P(B), P(Bd), C, K, pack, 0)), dtype=torch.uint8).cuda()
+                _lib.call("dfd_blockdiag_weights", P(table), 1, d, st())
+                launch = lambda a, b, fin: _lib.call("dfd_gemm_tn_rowpack", P(A), P(Bd), P(y), M, C, K, pack, d, P(a), P(b), fin, st())
+        gamma = 1.0 + 0.1 * torch.randn(C, device="cuda", generator=g)
+        beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+        res = []
+        for fused in (True, False):
+            rm, rv = torch.full((C,), 0.05, device="cuda"), torch.full((C,), 1.1, device="cuda")
+            nbt = torch.zeros(1, dtype=torch.int64, device="cuda")
+            o = vecs(C, 4)
+            for rep in range(2):
+                s1, s2 = stat_buf(C), stat_buf(C)
+                if fused:
+                    desc = _fin_desc(s1, s2, gamma, beta, rm, rv, nbt, *o, ticket, float(count), C)
+                    launch(s1, s2, P(desc))
+                else:
+                    launch(s1, s2, None)
+                    _lib.call("dfd_bn_finalize", P(s1), P(s2), float(count), P(gamma), P(beta), P(rm), P(rv), P(nbt), 0.1, 1e-5, 1, C,
+                              P(o[0]), P(o[1]), P(o[2]), P(o[3]), st())
+                torch.cuda.synchronize()
+            res.append([t.clone() for t in o] + [rm, rv, nbt.float()])
+        out["max_diff"] = max(float((a - b).abs().max() / (b.abs().max() + 1e-30)) for a, b in zip(res[0], res[1]))
+        out["nbt"] = int(res[0][6])
+    else:
+        N, HW, C = 3, 77, 144
+        y = (torch.randn(N, HW, C, device="cuda", generator=g) * 1.5).to(dtype)
+        da = (0.1 * torch.randn(N, HW, C, device="cuda", generator=g)).to(dtype)
+        sc, sh = _bn_params(C, g)
+        mean = 0.1 * torch.randn(C, device="cuda", generator=g)
+        rstd = 1.0 + 0.1 * torch.rand(C, device="cuda", generator=g)
+        gamma = 1.0 + 0.1 * torch.randn(C, device="cuda", generator=g)
+        gu = torch.empty(N, HW, C, device="cuda", dtype=dtype)
+        count = N * HW
+        if kind == "act_bwd":
+            launch = lambda a, b, fin: _lib.call("dfd_act_bwd", P(da), P(y), P(sc), P(sh), P(mean), P(rstd), None, None, P(gu), N, HW, C, 1, d,
+                                                 P(a), P(b), fin, st())
+        elif kind == "bn_bwd_reduce":
+            launch = lambda a, b, fin: _lib.call("dfd_bn_bwd_reduce", P(da), P(y), None, P(mean), P(rstd), N, HW, C, d, P(a), P(b), fin, st())
+        else:       # dwconv_bwd (mode 1)
+            Nn, H, W, k, s_ = 3, 14, 14, 5, 1
+            C = 144
+            x = torch.randn(Nn, H, W, C, device="cuda", generator=g).to(dtype)
+            w = (torch.randn(C, 1, k, k, device="cuda", generator=g) / k).contiguous()
+            gy = (0.1 * torch.randn(Nn, H, W, C, device="cuda", generator=g)).to(dtype)
+            yo = torch.randn(Nn, H, W, C, device="cuda", generator=g).to(dtype)
+            cv = [torch.rand(C, device="cuda", generator=g) + 0.5 for _ in range(3)]
+            gx, dW = torch.empty_like(x), torch.zeros_like(w)
+            count = Nn * H * W
+            launch = lambda a, b, fin: _lib.call("dfd_dwconv_bwd", P(gy), P(yo), P(cv[0]), P(cv[1]), P(cv[2]), P(w), P(x), P(sc), P(sh),
+                                                 P(mean), P(rstd), None, P(gx), P(dW), Nn, H, W, C, k, s_, d, P(a), P(b), None, 0, fin, st())
+        res = []
+        for fused in (True, False):
+            o = vecs(C, 5)
+            for rep in range(2):
+                s1, s2 = stat_buf(C), stat_buf(C)
+                if fused:
+                    desc = _bfin_desc(s1, s2, gamma, mean, rstd, *o, ticket, float(count), C)
+                    launch(s1, s2, P(desc))
+                else:
+                    launch(s1, s2, None)
+                    _lib.call("dfd_bn_bwd_finalize", P(s1), P(s2), float(count), P(gamma), P(mean), P(rstd), P(o[0]), P(o[1]), P(o[2]),
+                              P(o[3]), P(o[4]), C, st())
+                torch.cuda.synchronize()
+            res.append([t.clone() for t in o])
+        out["max_diff"] = max(float((a - b).abs().max() / (b.abs().max() + 1e-30)) for a, b in zip(res[0], res[1]))
+    out["ticket_at_rest"] = int(ticket) == 0
+    return out
 
 
 def check_se_fused(N, HW, C, Cse, dtype=torch.bfloat16, seed=0):
@@ -507,7 +624,7 @@ def check_conv_dense(N, H, W, Cin, Cout, k, s, dtype=torch.bfloat16, seed=0):
     cols = torch.full((M, k * k * Cin), float("nan"), device="cuda", dtype=dtype)
     y = torch.full((M, Cout), float("nan"), device="cuda", dtype=dtype)
     _lib.call("dfd_im2col", P(x), P(cols), N, H, W, Cin, k, s, pad, d, st())
-    _lib.call("dfd_gemm_tn", P(cols), P(wp), P(y), M, Cout, k * k * Cin, d, None, None, st())
+    _lib.call("dfd_gemm_tn", P(cols), P(wp), P(y), M, Cout, k * k * Cin, d, None, None, None, st())
     torch.cuda.synchronize()
     xr = nchw(x.float()).requires_grad_(True)
     wr = w.float().clone().requires_grad_(True)
@@ -518,7 +635,7 @@ def check_conv_dense(N, H, W, Cin, Cout, k, s, dtype=torch.bfloat16, seed=0):
     dcols = torch.full((M, k * k * Cin), float("nan"), device="cuda", dtype=dtype)
     add = torch.randn(N, H, W, Cin, device="cuda", generator=g).to(dtype)
     dx = torch.full((N, H, W, Cin), float("nan"), device="cuda", dtype=dtype)
-    _lib.call("dfd_gemm_tn", P(dy), P(wpT), P(dcols), M, k * k * Cin, Cout, d, None, None, st())
+    _lib.call("dfd_gemm_tn", P(dy), P(wpT), P(dcols), M, k * k * Cin, Cout, d, None, None, None, st())
     _lib.call("dfd_col2im", P(dcols), P(add), P(dx), N, H, W, Cin, k, s, pad, d, st())
     gperm = torch.zeros(Cout, k * k * Cin, device="cuda")
     gw = torch.zeros(Cout, Cin, k, k, device="cuda")

@@ -112,6 +112,14 @@ def test_bn_chain(N, HW, C):
     assert r["reduce1_rel"] < 1e-5 and r["reduce2_rel"] < 1e-5 and r["draw_rel"] < RED, r
 
 
+@pytest.mark.parametrize("kind", ["gemm", "gemm_rowpack", "dwconv_fwd", "act_bwd", "bn_bwd_reduce", "dwconv_bwd"])
+def test_fused_bn_finalize(kind):
+    """the last CTA of the statistics-producing kernel finalises the BatchNorm: same vectors as the standalone finalise launch
+    (the fp64 slot sums may differ in their last bit with the order of the atomics: 1e-6 relative covers it)"""
+    r = _gc().check_fused_finalize(kind)
+    assert r["max_diff"] < 1e-6 and r["ticket_at_rest"] and r.get("nbt", 2) == 2, r
+
+
 @pytest.mark.parametrize("N,C,Cse", [(5, 144, 6), (3, 1152, 48)])
 def test_se_fc(N, C, Cse):
     r = _gc().check_se_fc(N, C, Cse)

@@ -22,7 +22,7 @@ def t(N, H, W, C, k, s, reps=10, det=True):
         table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
     f0 = lambda: _lib.call("dfd_dwconv_bwd", gy.data_ptr(), y.data_ptr(), v[0].data_ptr(), v[1].data_ptr(), v[2].data_ptr(), w.data_ptr(),
                           x.data_ptr(), v[3].data_ptr(), v[4].data_ptr(), v[5].data_ptr(), v[6].data_ptr(), None, gx.data_ptr(), dW.data_ptr(),
-                          N, H, W, C, k, s, 0, s1.data_ptr(), s2.data_ptr(), ws.data_ptr() if det else None, ws.numel() * 4 if det else 0, st)
+                          N, H, W, C, k, s, 0, s1.data_ptr(), s2.data_ptr(), ws.data_ptr() if det else None, ws.numel() * 4 if det else 0, None, st)
     def f():
         f0()
         if det:

@@ -12,7 +12,7 @@ def t(N, H, W, C, k, s, reps=10):
     s1 = torch.zeros(8, C, dtype=torch.float64, device="cuda"); s2 = torch.zeros_like(s1)
     st = torch.cuda.current_stream().cuda_stream
     f = lambda: _lib.call("dfd_dwconv_fwd", x.data_ptr(), sc.data_ptr(), sh.data_ptr(), w.data_ptr(), out.data_ptr(), N, H, W, C, k, s, 1, 0,
-                          s1.data_ptr(), s2.data_ptr(), st)
+                          s1.data_ptr(), s2.data_ptr(), None, st)
     for _ in range(3): f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

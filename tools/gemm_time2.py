@@ -12,9 +12,9 @@ def t(M, N, K, pack, stats=True, reps=20):
         Bd = torch.empty(pack * N, pack * K, device='cuda', dtype=torch.bfloat16)
         tb = torch.frombuffer(bytearray(struct.pack("<QQiiii", B.data_ptr(), Bd.data_ptr(), N, K, pack, 0)), dtype=torch.uint8).cuda()
         _lib.call("dfd_blockdiag_weights", tb.data_ptr(), 1, 0, st)
-        f = lambda: _lib.call("dfd_gemm_tn_rowpack", A.data_ptr(), Bd.data_ptr(), C.data_ptr(), M, N, K, pack, 0, *sp, st)
+        f = lambda: _lib.call("dfd_gemm_tn_rowpack", A.data_ptr(), Bd.data_ptr(), C.data_ptr(), M, N, K, pack, 0, *sp, None, st)
     else:
-        f = lambda: _lib.call("dfd_gemm_tn", A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, 0, *sp, st)
+        f = lambda: _lib.call("dfd_gemm_tn", A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, 0, *sp, None, st)
     for _ in range(3): f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -8,4 +8,4 @@ A = torch.randn(M, K, device='cuda').bfloat16(); B = torch.randn(N, K, device='c
 C = torch.empty(M, N, device='cuda', dtype=torch.bfloat16)
 st = torch.cuda.current_stream().cuda_stream
 for _ in range(2):
-    _lib.call("dfd_gemm_tn", A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, 0, None, None, st)
+    _lib.call("dfd_gemm_tn", A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, 0, None, None, None, st)
