@@ -537,10 +537,13 @@ static int flat_blocks(size_t n) {
     return (int)b;
 }
 
-// images per CTA of the SE FC kernels: as many (1, 2, 4) as keep >= ~64 CTAs and fit shared memory
+// images per CTA of the SE FC kernels. Several images per CTA fetch every weight element once for all of them, but
+// MEASURED (B0, batch 256): 4 images per CTA are 12 % slower than 1 (0.80 vs 0.69 ms over the 16 backward launches) - the
+// kernels are bound by the dependent FC chain of a CTA, which gets longer, not by the L2 traffic of the weights. So: one
+// image per CTA until the batch is so large that the grid exceeds a few waves.
 static int se_img(int N, size_t floats_per_image, size_t fixed_floats) {
-    int img = 4;
-    while (img > 1 && (N / img < 64 || (img * floats_per_image + fixed_floats) * sizeof(float) > 200 * 1024)) img >>= 1;
+    int img = N >= 2048 ? 4 : (N >= 1024 ? 2 : 1);
+    while (img > 1 && (img * floats_per_image + fixed_floats) * sizeof(float) > 200 * 1024) img >>= 1;
     return img;
 }
 

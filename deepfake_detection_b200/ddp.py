@@ -42,6 +42,19 @@ def distribute_bn(model, world_size, reduce=False, group=None):
     engine.arena.state_version += 1          # eval plans re-derive their BN scale / shift from the new running statistics
 
 
+def convert_syncbn_model(model):
+    """apex.parallel.convert_syncbn_model / nn.SyncBatchNorm.convert_sync_batchnorm for a NativeModel (train.py:388-394):
+    every BatchNorm of the plans built from now on all-reduces its batch statistics (forward) and its BN-backward sums over
+    the default process group. Call it before DDP wrapping, as the reference does."""
+    m = getattr(model, "module", model)
+    if m.spec.family != "efficientnet":
+        raise _lib.NativeError("synchronised BatchNorm is implemented for the EfficientNet family")
+    m.sync_bn = True
+    m._engines.clear()                      # plans built without the collectives are dropped
+    m.__dict__.get("_trainers", {}).clear()
+    return model
+
+
 def plan_buckets(spans, bucket_elems):
     """spans: list of (lo, hi) arena ranges in the order backward completes them. Greedily merges consecutive spans
     into buckets of at least `bucket_elems` elements. Returns list of lists of (lo, hi)."""
@@ -64,7 +77,10 @@ class GradReducer:
     execution plan of a model, but the cut points are positions in ONE plan's backward op list, so the bucket plan is
     computed (and cached) per engine: `backward_and_reduce(engine)` always replays the plan that ran the forward."""
 
-    def __init__(self, engine, group=None, bucket_mb=8.0):
+    def __init__(self, engine, group=None, bucket_mb=1.0):
+        # bucket_mb: the arena is cut greedily in backward order. Parameters concentrate in the LAST layers (EfficientNet-B0:
+        # 11.6 of 16 MB sit in the head and stages 5-6), so small buckets start reducing early and leave only a few hundred KB
+        # (the first stages and the stem) for the one collective that cannot overlap with anything - the final one
         self.engine = engine                      # default plan (Trainer) or the arena (NativeDDP)
         self.arena = engine.arena
         self.group = group
@@ -224,7 +240,7 @@ class NativeDDP(nn.Module):
     gradients across the group before `optimizer.step()` (train.py:402-406: `DDP(model, delay_allreduce=True)` /
     `DDP(model, device_ids=[local_rank])`).  Extra keyword arguments of either constructor are accepted and ignored."""
 
-    def __init__(self, module, process_group=None, bucket_mb=8.0, delay_allreduce=None, device_ids=None, **unused):
+    def __init__(self, module, process_group=None, bucket_mb=1.0, delay_allreduce=None, device_ids=None, **unused):
         super().__init__()
         if not (dist.is_available() and dist.is_initialized()):
             raise _lib.NativeError("NativeDDP needs an initialised torch.distributed process group")

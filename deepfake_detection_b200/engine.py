@@ -30,13 +30,13 @@ def _ptr(t, off_elems=0):
 class _BN:
     """Pointers of one BatchNorm layer (parameters, running stats, per-step statistics, bwd coefficients)."""
     __slots__ = ("name", "C", "gamma", "beta", "dgamma", "dbeta", "rm", "rv", "nbt", "scale", "shift", "mean",
-                 "rstd", "cA", "cB", "cC", "fsum", "fsq", "bs1", "bs2", "fin", "bfin", "count", "idx", "fused")
+                 "rstd", "cA", "cB", "cC", "fsum", "fsq", "bs1", "bs2", "fin", "bfin", "count", "idx", "fused", "stat_off")
 
 
 class Engine:
     def __init__(self, arch, batch, height=None, width=None, num_classes=2, in_chans=3, dtype="bf16",
                  bn_momentum=0.1, bn_eps=1e-5, device=None, gemm_impl="tc", share_from=None, stem_impl="gemm",
-                 params_only=False, drop_rate=0.0, drop_path_rate=0.0):
+                 params_only=False, drop_rate=0.0, drop_path_rate=0.0, sync_bn=False):
         # _plan_only: build the arenas and the call plan on the CPU for host-logic tests; nothing can be executed
         self._plan_only = device == "plan-only"
         if self._plan_only:
@@ -59,6 +59,15 @@ class Engine:
             raise ValueError("dtype %r: the native path computes in 'bf16' or 'fp16' (fp32 master weights)" % (dtype,))
         self.drop_rate = float(drop_rate)
         self.drop_path_rate = float(drop_path_rate)
+        # synchronised BatchNorm (train.py:388-400 `convert_syncbn_model`): batch statistics and the BN-backward sums are
+        # all-reduced over the process group between the kernel that produces them and the finalisation
+        self.sync_bn = bool(sync_bn)
+        self.sync_world = 1
+        if self.sync_bn:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.sync_world = dist.get_world_size()
+            self.sync_bn = self.sync_world > 1
         self.bn_momentum = float(bn_momentum)
         self.bn_eps = float(bn_eps)
         self.gemm_impl = gemm_impl
@@ -387,8 +396,11 @@ class Engine:
             bn.nbt = _ptr(self.nbt, self.bn_names.index(name))
             for i, f in enumerate(("scale", "shift", "mean", "rstd", "cA", "cB", "cC")):
                 setattr(bn, f, _ptr(self.bnstate, i * tot_c + co))
+            # per layer [fsum | fsq | bs1 | bs2], S slots x C doubles each: the forward pair and the backward pair are contiguous
+            # (one collective each under synchronised BatchNorm)
             for i, f in enumerate(("fsum", "fsq", "bs1", "bs2")):
-                setattr(bn, f, _ptr(self.stats, (i * tot_c + co) * S))
+                setattr(bn, f, _ptr(self.stats, (4 * co + i * c) * S))
+            bn.stat_off = 4 * co * S
             co += (c + 3) // 4 * 4
             self.bns[name] = bn
         self.scalars = torch.zeros(4, dtype=torch.float32, device=dev)     # loss_acc, correct_acc, (spare)
@@ -434,7 +446,12 @@ class Engine:
         dt = self.dt
         mom, eps = self.bn_momentum, self.bn_eps
 
-        fused_fin = not os.environ.get("DFD_NO_FUSED_FINALIZE")
+        # BatchNorm finalisation by the last CTA of the statistics-producing kernel (descriptors, csrc/bn_finalize.cuh) instead of
+        # 98 one-block launches: implemented and tested, but MEASURED SLOWER inside the captured graph (17.29 vs 16.69 ms per
+        # B0 step): every CTA pays a __threadfence + a same-address ticket atomic before it may retire (the depthwise kernels
+        # run ~14k short CTAs), and the one finalising CTA walks C channels with a fraction of the threads of the standalone
+        # launch. Off unless DFD_FUSED_FINALIZE=1.
+        fused_fin = bool(os.environ.get("DFD_FUSED_FINALIZE")) and not self.sync_bn
 
         def gemm(A, B, C, M, Nn, K, bn=None):
             fs, fq = (bn.fsum, bn.fsq) if bn is not None else (None, None)
@@ -452,12 +469,23 @@ class Engine:
             # Training: the producing kernel's last CTA finalises (descriptor bn.fin), this op is skipped (see _run); it runs
             # in eval mode (running statistics -> scale / shift, once per weight state) and when the producer cannot finalise.
             bn.count = count
+            if self.sync_bn:
+                # SUM of every rank's statistics, finalised against the GLOBAL element count (torch SyncBatchNorm semantics)
+                fwd.append(("ALLREDUCE_train", (self.stats[bn.stat_off:bn.stat_off + 2 * S * bn.C], "sum")))
+                return ("dfd_bn_finalize_sync", [bn.fsum, bn.fsq, float(count), bn.gamma, bn.beta, bn.rm, bn.rv, bn.nbt, mom, eps,
+                                                 "TRAINING", bn.C, bn.scale, bn.shift, bn.mean, bn.rstd])
             return ("dfd_bn_finalize" + ("_evalonly" if bn.fused else ""),
                     [bn.fsum, bn.fsq, float(count), bn.gamma, bn.beta, bn.rm, bn.rv, bn.nbt, mom, eps,
                      "TRAINING", bn.C, bn.scale, bn.shift, bn.mean, bn.rstd])
 
         def bwd_finalize(bn, count):
             bn.count = count
+            if self.sync_bn:
+                # MEAN over the ranks of (sum g, sum g*xhat) with the LOCAL count: the coefficients of dy then use the global
+                # means, and dgamma / dbeta receive global_sum / world - what the DDP gradient mean of the per-rank sums gives
+                bwd.append(("ALLREDUCE", (self.stats[bn.stat_off + 2 * S * bn.C:bn.stat_off + 4 * S * bn.C], "avg")))
+                return ("dfd_bn_bwd_finalize", (bn.bs1, bn.bs2, float(count), bn.gamma, bn.mean, bn.rstd, bn.dgamma, bn.dbeta,
+                                                bn.cA, bn.cB, bn.cC, bn.C))
             if fused_fin:
                 return None         # done by the last CTA of the kernel that produced bs1 / bs2 (descriptor bn.bfin)
             return ("dfd_bn_bwd_finalize", (bn.bs1, bn.bs2, float(count), bn.gamma, bn.mean, bn.rstd, bn.dgamma, bn.dbeta,
@@ -722,12 +750,14 @@ class Engine:
         self._upload_fin_descs()
 
         def base_name(n):
-            for suf in ("_train", "_evalonly"):
+            for suf in ("_train", "_evalonly", "_sync"):
                 if n.endswith(suf):
                     return n[:-len(suf)]
             return n
 
         for n, a in fwd + bwd:      # arity / type check of the plan against the ABI table
+            if n.startswith("ALLREDUCE"):
+                continue
             codes = _lib.SIGNATURES[base_name(n)]
             if len(a) != len(codes) - 1:
                 raise AssertionError("%s: %d args for signature %r" % (n, len(a), codes))
@@ -740,8 +770,8 @@ class Engine:
                     raise AssertionError("%s: argument %r does not fit code %r" % (n, v, c))
         # `<name>_train` ops run in training mode only (mask generation, dropout); ("TRAIN_ONLY", ptr) operands are NULL in eval
         fwd = [(n, a) for n, a in fwd]
-        self.fwd_ops = [(getattr(L, base_name(n)), n, a) for n, a in fwd]
-        self.bwd_ops = [(getattr(L, n), n, tuple(a)) for n, a in bwd]
+        self.fwd_ops = [(None if n.startswith("ALLREDUCE") else getattr(L, base_name(n)), n, a) for n, a in fwd]
+        self.bwd_ops = [(None if n.startswith("ALLREDUCE") else getattr(L, n), n, tuple(a)) for n, a in bwd]
         self.n_launch["fwd"] = len(fwd)
         self.n_launch["bwd"] = len(bwd)
 
@@ -753,6 +783,16 @@ class Engine:
             raise _lib.NativeError("plan-only engine cannot execute (no CUDA device)")
         L = self.L
         for fn, name, args in ops:
+            if name.startswith("ALLREDUCE"):
+                if training:
+                    import torch.distributed as dist
+                    dist.all_reduce(args[0], op=dist.ReduceOp.SUM if args[1] == "sum" else dist.ReduceOp.AVG)
+                continue
+            if name == "dfd_bn_finalize_sync":
+                args = list(args)
+                if training:
+                    args[2] = args[2] * self.sync_world          # global element count behind the summed statistics
+                name = "dfd_bn_finalize"
             if name.startswith("dfd_bn_finalize"):
                 # `_evalonly`: in training the producing kernel's last CTA finalised this BatchNorm already
                 if skip_finalize or (training and name.endswith("_evalonly")):

@@ -117,6 +117,7 @@ class NativeModel(nn.Module):
         self.drop_path_rate = float(drop_path_rate)    # efficientnet_builder.py:322-323 (linear ramp over the blocks)
         self.max_plans = 4                             # execution plans kept alive (LRU); each owns an activation arena
         self.allow_local_grads = False
+        self.sync_bn = False                           # set by ddp.convert_syncbn_model (train.py:388-394)
         self._reducer = None
         self.spec = get_spec(arch, num_classes=num_classes, in_chans=in_chans)
         if self.spec.family != "efficientnet" and (self.drop_rate or self.drop_path_rate):
@@ -133,7 +134,8 @@ class NativeModel(nn.Module):
     # ---- engines ------------------------------------------------------------------------------------
     def _engine_kwargs(self):
         return dict(num_classes=self.num_classes, in_chans=self.in_chans, dtype=self.dtype_name, bn_momentum=self.bn_momentum,
-                    bn_eps=self.bn_eps, gemm_impl=self.gemm_impl, drop_rate=self.drop_rate, drop_path_rate=self.drop_path_rate)
+                    bn_eps=self.bn_eps, gemm_impl=self.gemm_impl, drop_rate=self.drop_rate, drop_path_rate=self.drop_path_rate,
+                    sync_bn=self.sync_bn)
 
     @property
     def engine(self):

@@ -10,6 +10,8 @@ What it checks (boundary rows H6 / 8b, dfd/runners/train.py:402-406,621-637):
     execution plan in mid-epoch (the configuration in which a reducer bound to the wrong plan all-reduced garbage);
   * both against the CPU oracle: per-rank gradients on each rank's batch (rank-local BN statistics, apex semantics),
     `grad_hook` = mean over ranks, one optimizer step per batch; replicas must hold bit-identical weights afterwards;
+  * synchronised BatchNorm (`convert_syncbn_model`, train.py:388-394): the same protocol loop equals ONE oracle process
+    training on the concatenation of both ranks' batches (global batch statistics, global-mean loss);
   * an unwrapped NativeModel refuses to run backward in a multi-rank job.
 """
 import json
@@ -84,11 +86,24 @@ def main():
     del m0
 
     sd_o, losses_o = oracle_epoch(spec, sd0, rank_batches, world) if rank == 0 else (None, None)
+    sd_sync, losses_sync = None, None
+    if rank == 0:
+        from oracle import train as OT
+        sd_sync = {k: v.clone() for k, v in sd0.items()}
+        ost = OT.OptState(kind="sgd", lr=0.01, momentum=0.9, weight_decay=1e-4)
+        losses_sync = []
+        for i in range(len(sizes)):
+            gx = torch.cat([rank_batches[r][i][0] for r in range(world)])
+            gy = torch.cat([rank_batches[r][i][1] for r in range(world)])
+            losses_sync.append(float(OT.train_step(spec, sd_sync, gx, gy, ost, act_dtype=torch.float16)["loss"]))
 
-    for flavour in ("protocol", "fused"):
+    for flavour in ("protocol", "fused", "syncbn"):
         model = create_model("efficientnet_b0", num_classes=2, dtype="fp16")
         sd_r = {k: (v + 0.01 * rank if v.dtype.is_floating_point and rank else v) for k, v in sd0.items()}   # ranks start apart ...
         model.load_state_dict(sd_r)
+        if flavour == "syncbn":
+            from deepfake_detection_b200.ddp import convert_syncbn_model
+            model = convert_syncbn_model(model)
         model = NativeDDP(model, delay_allreduce=True)                                                   # ... DDP broadcasts rank 0
         optimizer = create_optimizer(args, model)
 
@@ -96,7 +111,7 @@ def main():
             mixup_enabled = False
 
         loader = Loader((x.cuda(), y.cuda()) for x, y in mine)
-        if flavour == "protocol":
+        if flavour in ("protocol", "syncbn"):
             # the reference loop body verbatim (train.py:621-637), apex loss scaling left out (use_amp=False)
             model.train()
             loss_fn = torch.nn.CrossEntropyLoss()
@@ -121,9 +136,12 @@ def main():
         gathered = [torch.zeros_like(flat) for _ in range(world)]
         dist.all_gather(gathered, flat)
         if rank == 0:
-            worst = max(rel(sd[k], sd_o[k]) for k in sd_o if sd_o[k].dtype.is_floating_point and sd_o[k].dim() > 1)
-            lo = sum(losses_o) / len(losses_o) if flavour == "protocol" else \
-                sum(l * n for l, n in zip(losses_o, sizes)) / sum(sizes)
+            ref_sd, ref_losses = (sd_sync, losses_sync) if flavour == "syncbn" else (sd_o, losses_o)
+            worst = max(rel(sd[k], ref_sd[k]) for k in ref_sd if ref_sd[k].dtype.is_floating_point and ref_sd[k].dim() > 1)
+            if flavour == "syncbn":     # running statistics are global too: identical on every rank and equal to the oracle's
+                worst = max(worst, max(rel(sd[k], ref_sd[k]) for k in ref_sd if "running" in k))
+            lo = sum(ref_losses) / len(ref_losses) if flavour != "fused" else \
+                sum(l * n for l, n in zip(ref_losses, sizes)) / sum(sizes)
             report[flavour] = dict(weights_rel_worst=worst, ranks_identical=all(torch.equal(g, gathered[0]) for g in gathered),
                                    loss=loss_mean, loss_oracle=lo, plans=len(model.module._engines),
                                    reduce_calls=model.reducer.n_reduce_calls)

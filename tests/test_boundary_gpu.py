@@ -326,7 +326,7 @@ def test_native_ddp_two_ranks_match_oracle(tmp_path):
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     rep = json.load(open(out))
-    for flavour in ("protocol", "fused"):
+    for flavour in ("protocol", "fused", "syncbn"):
         f = rep[flavour]
         assert f["weights_rel_worst"] < 2e-3, (flavour, f)          # post-step weights vs oracle with grad_hook mean
         assert f["ranks_identical"], flavour                        # replicas hold bit-identical weights after the epoch
