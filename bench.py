@@ -229,6 +229,14 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # C-ABI calls of ONE step, counted (not derived): an eager step with the call counter of the binding read before / after
+    # (on every rank, before the timed region: the step contains the gradient collectives)
+    from deepfake_detection_b200 import _lib as _L
+    c0 = _L.N_CALLS[0]
+    tr.optimizer.push_hyper()
+    tr._launch_step(False)
+    torch.cuda.synchronize()
+    n_launch = _L.N_CALLS[0] - c0
     for _ in range(max(args.warmup, 3)):
         tr.step_resident()
     barrier()
@@ -327,13 +335,6 @@ def run_native(args):
                     families={k: dict(ms=round(v["ms"], 3), gbs=round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1), n=v["launches"])
                               for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:8]})
     cpu = cpu_baseline(arch, sample_steps=args.cpu_steps) if world == 1 and not args.no_cpu else None
-    # C-ABI calls of ONE step, counted (not derived): an eager step with the call counter of the binding read before / after
-    from deepfake_detection_b200 import _lib as _L
-    c0 = _L.N_CALLS[0]
-    tr.optimizer.push_hyper()
-    tr._launch_step(False)
-    torch.cuda.synchronize()
-    n_launch = _L.N_CALLS[0] - c0
     line = dict(metric="images/sec (device-timed, max over ranks) %s 3x%dx%d train step" % (arch, res, res),
                 value=round(img_s, 1), unit="images/sec", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=round(ms / args.steps, 4), higher_is_better=True, scaling="weak", vs_baseline=None,

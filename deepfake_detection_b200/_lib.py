@@ -29,6 +29,7 @@ SIGNATURES = {
     "dfd_dwconv_wgrad": "ppppp" "pppp" "iiiiii" "i" "p",
     "dfd_dwconv_bwd": "ppppp" "pppppp" "ppp" "iiiiii" "i" "pp" "pl" "p" "p",
     "dfd_dwconv_bwd_parts": "iiiiii",
+    "dfd_dwconv_block_channels": "i",
     "dfd_stem_fwd": "ppp" "iiiiiiii" "i" "ppp",
     "dfd_stem_wgrad": "ppppppp" "iiiiiiii" "i" "p",
     "dfd_colstats": "p" "ili" "i" "ppp",

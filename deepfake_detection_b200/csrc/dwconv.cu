@@ -20,7 +20,13 @@
 
 namespace {
 
-constexpr int CB = 64;       // channels per CTA
+constexpr int CB = 64;       // channels per CTA of the split (diagnostic) kernels and the default of the hot ones
+// Lane mapping of the hot kernels (forward, fused backward): CPW channel PAIRS per sub-strip, 32 / CPW sub-strips per warp.
+// CPW = 32: a lane is a channel pair, a warp works on one strip of 64 channels (every layer whose channel count fills
+// 64-channel blocks). CPW = 16 / 8: a CTA covers 32 / 16 channels and the lanes of a warp split into 2 / 4 sub-strips on
+// consecutive tile rows - so that C = 32, 96 or 144 (the three LARGEST layers of EfficientNet-B0, which left half or a
+// quarter of every warp idle in the last 64-channel block) keep all 32 lanes busy. The staged tile is [pixel][CPW words];
+// an odd tile width puts the sub-strips of a warp on disjoint shared-memory banks.
 constexpr int P = 8;         // output columns per strip
 constexpr int NTHREADS = 256;            // largest CTA (sizes the static reduction buffer); see dw_nt() for the per-k choice
 constexpr int DW_MAX_SMEM = 200 * 1024;
@@ -48,22 +54,23 @@ __device__ __forceinline__ void load_chan_params(const float* p, int cbase, int 
 // UNR independent 16-byte loads are issued per thread before any is consumed (memory-level parallelism: with one
 // load in flight per thread the kernel is latency-bound at ~1/3 of HBM speed).
 constexpr int UNR = 4;
-template <typename T, int ACT, bool AFFINE>
+template <typename T, int ACT, bool AFFINE, int CPW = 32>
 __device__ __forceinline__ void stage_input_tile(uint32_t* tile, const T* __restrict__ img, int H, int W, int C,
                                                  int c0, int iy0, int ix0, int IH, int IW,
                                                  const float* __restrict__ scale, const float* __restrict__ shift) {
-    const int v = threadIdx.x & 7;
+    constexpr int VPP = CPW / 4;                 // 16-byte vectors (8 channels) per pixel
+    const int v = threadIdx.x % VPP;
     const int cbase = c0 + v * 8;
     const bool cvalid = cbase < C;
     float sc[8], sh[8];
     if (AFFINE) { load_chan_params(scale, cbase, C, sc, 1.f); load_chan_params(shift, cbase, C, sh, 0.f); }
     const int npix = IH * IW;
-    const int PSTEP = blockDim.x / 8;
+    const int PSTEP = blockDim.x / VPP;
     // (row, col) of the visited pixels advance by PSTEP each: kept incrementally (an integer division per pixel cost
     // more issue slots than the activation it feeds)
     const int dq = PSTEP / IW, dr = PSTEP - dq * IW;
-    int r = (threadIdx.x >> 3) / IW, c = (threadIdx.x >> 3) - r * IW;
-    for (int base = threadIdx.x >> 3; base < npix; base += PSTEP * UNR) {
+    int r = (threadIdx.x / VPP) / IW, c = (threadIdx.x / VPP) - r * IW;
+    for (int base = threadIdx.x / VPP; base < npix; base += PSTEP * UNR) {
         uint4 raw[UNR];
         bool ok[UNR];
 #pragma unroll
@@ -94,7 +101,7 @@ __device__ __forceinline__ void stage_input_tile(uint32_t* tile, const T* __rest
                     o = raw[u];
                 }
             }
-            *reinterpret_cast<uint4*>(tile + pix * 32 + v * 4) = o;
+            *reinterpret_cast<uint4*>(tile + pix * CPW + v * 4) = o;
         }
     }
 }
@@ -102,22 +109,23 @@ __device__ __forceinline__ void stage_input_tile(uint32_t* tile, const T* __rest
 // Stage the output gradient dy = A*g + B*y + C (BN backward folded into the load): tile pixel (r, c) <-> dy[oy0 + r,
 // ox0 + c], zero outside [0,Ho) x [0,Wo).  (Compact: the stride-2 input-gradient kernel indexes it by parity, nothing is
 // zero-upsampled.)
-template <typename T, bool AFFINE, int UG_ = 0>
+template <typename T, bool AFFINE, int UG_ = 0, int CPW = 32>
 __device__ __forceinline__ void stage_grad_tile(uint32_t* tile, const T* __restrict__ g, const T* __restrict__ y,
                                                 int Ho, int Wo, int C, int c0, int oy0, int ox0, int IH, int IW,
                                                 const float* __restrict__ cA, const float* __restrict__ cB,
                                                 const float* __restrict__ cC) {
-    const int v = threadIdx.x & 7;
+    constexpr int VPP = CPW / 4;
+    const int v = threadIdx.x % VPP;
     const int cbase = c0 + v * 8;
     const bool cvalid = cbase < C;
     float A[8], B[8], Cc[8];
     if (AFFINE) { load_chan_params(cA, cbase, C, A, 1.f); load_chan_params(cB, cbase, C, B, 0.f); load_chan_params(cC, cbase, C, Cc, 0.f); }
     const int npix = IH * IW;
-    const int PSTEP = blockDim.x / 8;
+    const int PSTEP = blockDim.x / VPP;
     constexpr int UG = UG_ ? UG_ : (AFFINE ? 2 : 4);     // two tensors are read when the BN backward is folded in
     const int dq = PSTEP / IW, dr = PSTEP - dq * IW;          // incremental (row, col), see stage_input_tile
-    int r = (threadIdx.x >> 3) / IW, c = (threadIdx.x >> 3) - r * IW;
-    for (int base = threadIdx.x >> 3; base < npix; base += PSTEP * UG) {
+    int r = (threadIdx.x / VPP) / IW, c = (threadIdx.x / VPP) - r * IW;
+    for (int base = threadIdx.x / VPP; base < npix; base += PSTEP * UG) {
         uint4 graw[UG], yraw[UG];
         bool ok[UG];
 #pragma unroll
@@ -150,7 +158,7 @@ __device__ __forceinline__ void stage_grad_tile(uint32_t* tile, const T* __restr
                     o = graw[u];
                 }
             }
-            *reinterpret_cast<uint4*>(tile + pix * 32 + v * 4) = o;
+            *reinterpret_cast<uint4*>(tile + pix * CPW + v * 4) = o;
         }
     }
 }
@@ -187,15 +195,15 @@ __device__ __forceinline__ void strip_dgrad_s2(const uint32_t* __restrict__ tile
 }
 
 // acc[p][:] += sum_{kh,kw} tile[r0+kh][c0 + p*S + kw] * w[kh*K+kw]
-template <typename T, int K, int S>
+template <typename T, int K, int S, int CPW = 32>
 __device__ __forceinline__ void strip_conv(const uint32_t* __restrict__ tile, int IW, int r0, int c0, int lane,
                                            const float (&w)[K * K][2], float (&acc)[P][2]) {
 #pragma unroll
     for (int kh = 0; kh < K; kh++) {
-        const uint32_t* row = tile + ((r0 + kh) * IW + c0) * 32 + lane;
+        const uint32_t* row = tile + ((r0 + kh) * IW + c0) * CPW + lane;      // `lane`: the channel-pair index in [0, CPW)
 #pragma unroll
         for (int j = 0; j < (P - 1) * S + K; j++) {
-            float2 x = unpack2<T>(row[j * 32]);
+            float2 x = unpack2<T>(row[j * CPW]);
 #pragma unroll
             for (int kw = 0; kw < K; kw++) {
                 int pj = j - kw;
@@ -209,13 +217,21 @@ __device__ __forceinline__ void strip_conv(const uint32_t* __restrict__ tile, in
 }
 
 // block reduction of per-thread channel-pair values across the 8 warps, then fn(channel_in_block, value)
-template <typename F>
+// (CPW < 32: the lanes cp, cp + CPW, ... of a warp hold the same channel pair on different sub-strips and are added first)
+template <int CPW = 32, typename F>
 __device__ __forceinline__ void reduce_warps_emit(float* sm, float a, float b, F fn) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    sm[warp * 64 + lane * 2] = a;
-    sm[warp * 64 + lane * 2 + 1] = b;
+#pragma unroll
+    for (int o = CPW; o < 32; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane < CPW) {
+        sm[warp * 64 + lane * 2] = a;
+        sm[warp * 64 + lane * 2 + 1] = b;
+    }
     __syncthreads();
-    if (threadIdx.x < 64) {
+    if (threadIdx.x < 2 * CPW) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sm[w * 64 + threadIdx.x];
@@ -227,21 +243,23 @@ __device__ __forceinline__ void reduce_warps_emit(float* sm, float a, float b, F
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <typename T, int K, int S, int ACT, bool AFFINE, int NT>
+template <typename T, int K, int S, int ACT, bool AFFINE, int NT, int CPW = 32>
 __global__ void __launch_bounds__(NT)
 dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                   const float* __restrict__ wgt, T* __restrict__ out, double* __restrict__ dsum,
                   double* __restrict__ dsq, const BnFinDesc* __restrict__ fin, DwGeom g) {
     extern __shared__ __align__(16) uint32_t tile[];
     __shared__ float red[NTHREADS / 32 * 64];
+    constexpr int SUB = 32 / CPW;               // sub-strips (consecutive tile rows) per warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cp = lane % CPW, sub = lane / CPW;
     const int tx = blockIdx.x % g.tiles_x, ty = blockIdx.x / g.tiles_x;
-    const int c0 = blockIdx.y * CB, n = blockIdx.z;
+    const int c0 = blockIdx.y * (2 * CPW), n = blockIdx.z;
     const int oy0 = ty * g.TH, ox0 = tx * g.TW;
     const T* img = x + (size_t)n * g.H * g.W * g.C;
-    stage_input_tile<T, ACT, AFFINE>(tile, img, g.H, g.W, g.C, c0, oy0 * S - g.pad, ox0 * S - g.pad, g.IH, g.IW, scale, shift);
+    stage_input_tile<T, ACT, AFFINE, CPW>(tile, img, g.H, g.W, g.C, c0, oy0 * S - g.pad, ox0 * S - g.pad, g.IH, g.IW, scale, shift);
 
-    const int ch = c0 + lane * 2;
+    const int ch = c0 + cp * 2;
     const bool chv = ch < g.C;
     float w[K * K][2];
 #pragma unroll
@@ -254,16 +272,16 @@ dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, cons
     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
     const int strips_x = g.TW / P;              // TW in {8,16,32}, P in {4,8}: a power of two
     const int xsh = 31 - __clz(strips_x);
-    const int nstrips = g.TH * strips_x;
+    const int nstrips = ((g.TH + SUB - 1) / SUB) * strips_x;
     T* oimg = out + (size_t)n * g.Ho * g.Wo * g.C;
     for (int s = warp; s < nstrips; s += (int)(blockDim.x >> 5)) {
-        const int sy = s >> xsh, sx = (s & (strips_x - 1)) * P;
+        const int sy = (s >> xsh) * SUB + sub, sx = (s & (strips_x - 1)) * P;
         int oy = oy0 + sy, ox = ox0 + sx;
-        if (oy >= g.Ho || ox >= g.Wo) continue;
+        if (sy >= g.TH || oy >= g.Ho || ox >= g.Wo) continue;
         float acc[P][2];
 #pragma unroll
         for (int p = 0; p < P; p++) { acc[p][0] = 0.f; acc[p][1] = 0.f; }
-        strip_conv<T, K, S>(tile, g.IW, sy * S, sx * S, lane, w, acc);
+        strip_conv<T, K, S, CPW>(tile, g.IW, sy * S, sx * S, cp, w, acc);
         if (chv) {
 #pragma unroll
             for (int p = 0; p < P; p++) {
@@ -280,8 +298,8 @@ dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, cons
     if (dsum) {
         double* ps = stat_slot(dsum, g.C);
         double* pq = stat_slot(dsq, g.C);
-        reduce_warps_emit(red, s0, s1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(ps + c0 + c, (double)v); });
-        reduce_warps_emit(red, q0, q1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(pq + c0 + c, (double)v); });
+        reduce_warps_emit<CPW>(red, s0, s1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(ps + c0 + c, (double)v); });
+        reduce_warps_emit<CPW>(red, q0, q1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(pq + c0 + c, (double)v); });
     }
     bn_finalize_tail(fin, threadIdx.x, NT);
 }
@@ -487,7 +505,7 @@ dwconv_wgrad_kernel(const T* __restrict__ x, const float* __restrict__ scale, co
 // sigmoid of the input pixel serves both a and swish'.  A CTA walks images blockIdx.z, +gridDim.z, ... so that its
 // k*k weight-gradient partials (registers) are reduced and flushed once, not once per image.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int K, bool WG, int P>
+template <typename T, int K, bool WG, int P, int CPW = 32>
 __device__ __forceinline__ void strip_bwd_s2(const uint32_t* __restrict__ tile, int IW, int sy, int sx, int lane,
                                              const float (&w)[K * K][2], float (&acc)[P][2],
                                              const float (&av)[P][2], float (&wacc)[K * K][2]) {
@@ -495,12 +513,12 @@ __device__ __forceinline__ void strip_bwd_s2(const uint32_t* __restrict__ tile, 
 #pragma unroll
     for (int kh = 0; kh < K; kh++) {
         const int q = sy + PAD - kh;
-        if (q & 1) continue;                          // warp-uniform
+        if (q & 1) continue;                          // warp-uniform: the sub-strips of a warp sit on rows of one parity
         const int row = (q >> 1) + 1;
-        const uint32_t* rp = tile + (row * IW + (sx >> 1)) * 32 + lane;
+        const uint32_t* rp = tile + (row * IW + (sx >> 1)) * CPW + lane;
         float2 vv[P / 2 + 2];
 #pragma unroll
-        for (int j = 0; j < P / 2 + 2; j++) vv[j] = unpack2<T>(rp[j * 32]);
+        for (int j = 0; j < P / 2 + 2; j++) vv[j] = unpack2<T>(rp[j * CPW]);
 #pragma unroll
         for (int p = 0; p < P; p++) {
 #pragma unroll
@@ -520,16 +538,16 @@ __device__ __forceinline__ void strip_bwd_s2(const uint32_t* __restrict__ tile, 
     }
 }
 
-template <typename T, int K, int P>
+template <typename T, int K, int P, int CPW = 32>
 __device__ __forceinline__ void strip_bwd_s1(const uint32_t* __restrict__ tile, int IW, int r0, int c0, int lane,
                                              const float (&w)[K * K][2], float (&acc)[P][2],
                                              const float (&av)[P][2], float (&wacc)[K * K][2]) {
 #pragma unroll
     for (int kh = 0; kh < K; kh++) {
-        const uint32_t* row = tile + ((r0 + kh) * IW + c0) * 32 + lane;
+        const uint32_t* row = tile + ((r0 + kh) * IW + c0) * CPW + lane;
 #pragma unroll
         for (int j = 0; j < P - 1 + K; j++) {
-            float2 x = unpack2<T>(row[j * 32]);
+            float2 x = unpack2<T>(row[j * CPW]);
 #pragma unroll
             for (int kw = 0; kw < K; kw++) {
                 const int pj = j - kw;
@@ -546,7 +564,7 @@ __device__ __forceinline__ void strip_bwd_s1(const uint32_t* __restrict__ tile, 
 
 // MODE 1: xin is the pre-BN expand output (a = swish(scale*xin + shift), gx = ga * swish', BN-backward sums);
 // MODE 0: xin is the block input itself (DS block): a = xin, gx = ga (+ add).
-template <typename T, int K, int S, bool AFFINE, int MODE, int NT, int P>
+template <typename T, int K, int S, bool AFFINE, int MODE, int NT, int P, int CPW = 32>
 __global__ void __launch_bounds__(NT, K == 3 ? (P == 4 ? 4 : 3) : 2)
 dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const float* __restrict__ cA,
                   const float* __restrict__ cB, const float* __restrict__ cC, const float* __restrict__ wgt,
@@ -559,11 +577,14 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
     __shared__ float red[NTHREADS / 32 * 64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NW = NT / 32;
+    constexpr int SUB = 32 / CPW;           // sub-strips per warp (see the lane mapping note at the top)
+    constexpr int CW = 2 * CPW;             // channels per CTA
+    const int cp = lane % CPW, sub = lane / CPW;
     const int tx = blockIdx.x % g.tiles_x, ty = blockIdx.x / g.tiles_x;
-    const int c0 = blockIdx.y * CB;
+    const int c0 = blockIdx.y * CW;
     const int y0 = ty * g.TH, x0 = tx * g.TW;           // input-space tile origin
     const int pp = K - 1 - g.pad;
-    const int ch = c0 + lane * 2;
+    const int ch = c0 + cp * 2;
     const bool chv = ch < g.C;
     float w[K * K][2], wacc[K * K][2];
 #pragma unroll
@@ -582,7 +603,16 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
     float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
     const int strips_x = g.TW / P;              // TW in {8,16,32}, P in {4,8}: a power of two
     const int xsh = 31 - __clz(strips_x);
-    const int nstrips = g.TH * strips_x;
+    // A warp visits SUB tile rows at once. Stride 1: rows g*SUB + sub. Stride 2: the taps of an input row depend on its
+    // parity, so a warp's rows share one parity - rows 2*(g*SUB + sub) + par, all even groups first, then the odd ones.
+    const int row_groups = S == 1 ? (g.TH + SUB - 1) / SUB : ((g.TH + 1) / 2 + SUB - 1) / SUB;
+    const int nstrips = (S == 1 ? row_groups : 2 * row_groups) * strips_x;
+    auto strip_row = [&](int s) {
+        const int r = s >> xsh;
+        if (S == 1) return r * SUB + sub;
+        const int par = r >= row_groups ? 1 : 0;
+        return 2 * ((r - par * row_groups) * SUB + sub) + par;
+    };
 
     for (int n = blockIdx.z; n < g.N; n += gridDim.z) {
         const size_t ooff = (size_t)n * g.Ho * g.Wo * g.C;
@@ -593,9 +623,9 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
         // first one before the tile is staged, so their latency hides behind staging / the previous strip's FMAs
         uint32_t pre[P];
         auto prefetch = [&](int s) {
-            const int sy = s >> xsh, sx = (s & (strips_x - 1)) * P;
+            const int sy = strip_row(s), sx = (s & (strips_x - 1)) * P;
             const int iy = y0 + sy, ix = x0 + sx;
-            const bool rowok = chv && iy < g.H;
+            const bool rowok = chv && sy < g.TH && iy < g.H;
             const uint32_t off0 = (uint32_t)((iy * g.W + ix) * g.C + ch);
 #pragma unroll
             for (int p = 0; p < P; p++)
@@ -606,17 +636,17 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
         // staging batch (16-byte loads in flight per thread and tensor): 4 for k = 5 (two CTAs per SM either way, measured
         // -8 %), 2 for k = 3 where the deeper batch costs the third resident CTA (measured +3..16 %)
         if (!(g.dbg & 2))
-            stage_grad_tile<T, AFFINE, (K == 5 ? 4 : 2)>(tile, gy + ooff, AFFINE ? yout + ooff : nullptr, g.Ho, g.Wo, g.C, c0,
+            stage_grad_tile<T, AFFINE, (K == 5 ? 4 : 2), CPW>(tile, gy + ooff, AFFINE ? yout + ooff : nullptr, g.Ho, g.Wo, g.C, c0,
                                    S == 1 ? y0 - pp : (y0 >> 1) - 1, S == 1 ? x0 - pp : (x0 >> 1) - 1, g.IH, g.IW, cA, cB, cC);
         __syncthreads();
         if (!(g.dbg & 1))
         for (int s = warp; s < nstrips; s += NW) {
-            const int sy = s >> xsh, sx = (s & (strips_x - 1)) * P;
+            const int sy = strip_row(s), sx = (s & (strips_x - 1)) * P;
             const int iy = y0 + sy, ix = x0 + sx;
             float av[P][2], da[P][2], xh[P][2];
-            // interior strips (warp-uniform) need no per-pixel masking: lanes beyond C compute garbage that is never
-            // stored, reduced or flushed
-            const bool interior = iy < g.H && ix + P <= g.W;
+            // interior strips need no per-pixel masking: lanes beyond C compute garbage that is never stored, reduced or
+            // flushed (pre[] is zero for rows outside the tile / image)
+            const bool interior = sy < g.TH && iy < g.H && ix + P <= g.W;
 #pragma unroll
             for (int p = 0; p < P; p++) {
                 const float2 xi = unpack2<T>(pre[p]);
@@ -641,18 +671,18 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
             if (MODE == 1 && !interior) {
 #pragma unroll
                 for (int p = 0; p < P; p++) {
-                    const bool ok = iy < g.H && ix + p < g.W;
+                    const bool ok = sy < g.TH && iy < g.H && ix + p < g.W;
                     av[p][0] = ok ? av[p][0] : 0.f;
                     av[p][1] = ok ? av[p][1] : 0.f;
                 }
             }
             if (s + NW < nstrips) prefetch(s + NW);
-            if (iy >= g.H || ix >= g.W) continue;
+            if (sy >= g.TH || iy >= g.H || ix >= g.W) continue;
             float acc[P][2];
 #pragma unroll
             for (int p = 0; p < P; p++) { acc[p][0] = 0.f; acc[p][1] = 0.f; }
-            if (S == 1) strip_bwd_s1<T, K, P>(tile, g.IW, sy, sx, lane, w, acc, av, wacc);
-            else strip_bwd_s2<T, K, true, P>(tile, g.IW, sy, sx, lane, w, acc, av, wacc);
+            if (S == 1) strip_bwd_s1<T, K, P, CPW>(tile, g.IW, sy, sx, cp, w, acc, av, wacc);
+            else strip_bwd_s2<T, K, true, P, CPW>(tile, g.IW, sy, sx, cp, w, acc, av, wacc);
             if (chv) {
                 const uint32_t off0 = (uint32_t)((iy * g.W + ix) * g.C + ch);
 #pragma unroll
@@ -681,46 +711,68 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
     if (MODE == 1) {
         double* p1 = stat_slot(ds1, g.C);
         double* p2 = stat_slot(ds2, g.C);
-        reduce_warps_emit(red, a0, a1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p1 + c0 + c, (double)v); });
-        reduce_warps_emit(red, b0, b1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p2 + c0 + c, (double)v); });
+        reduce_warps_emit<CPW>(red, a0, a1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p1 + c0 + c, (double)v); });
+        reduce_warps_emit<CPW>(red, b0, b1, [&](int c, float v) { if (c0 + c < g.C) atomicAdd(p2 + c0 + c, (double)v); });
     }
     bn_bwd_finalize_tail(fin, threadIdx.x, NT);      // the last CTA turns the BN-backward sums into dgamma / dbeta / cA,cB,cC
     __syncthreads();      // every warp is done with the dy tile before it is reused
-    // weight-gradient partials: all taps through the (now free) tile memory in one go, [warp][tap][64 channels]
+    // weight-gradient partials: the sub-strips of a warp are added first (lanes cp, cp + CPW, ... hold the same channel
+    // pair), then all taps go through the (now free) tile memory in one go, [warp][tap][CW channels]
     float* wr = reinterpret_cast<float*>(tile);
 #pragma unroll
     for (int i = 0; i < K * K; i++) {
-        wr[(warp * K * K + i) * 64 + lane * 2] = wacc[i][0];
-        wr[(warp * K * K + i) * 64 + lane * 2 + 1] = wacc[i][1];
+        float v0 = wacc[i][0], v1 = wacc[i][1];
+#pragma unroll
+        for (int o = CPW; o < 32; o <<= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        }
+        if (lane < CPW) {
+            wr[(warp * K * K + i) * CW + cp * 2] = v0;
+            wr[(warp * K * K + i) * CW + cp * 2 + 1] = v1;
+        }
     }
     __syncthreads();
+    constexpr int KKCW = K * K * CW;
     if (!g.part) {
-        for (int e = threadIdx.x; e < K * K * 64; e += NT) {
-            const int i = e >> 6, c = e & 63;
+        for (int e = threadIdx.x; e < KKCW; e += NT) {
+            const int i = e / CW, c = e % CW;
             if (c0 + c < g.C) {
                 float v = 0.f;
 #pragma unroll
-                for (int q = 0; q < NW; q++) v += wr[(q * K * K + i) * 64 + c];
+                for (int q = 0; q < NW; q++) v += wr[(q * K * K + i) * CW + c];
                 const int tap = S == 1 ? (K * K - 1 - i) : i;
                 atomicAdd(dW + (size_t)(c0 + c) * K * K + tap, v);
             }
         }
         return;
     }
-    // ---- order-deterministic mode: this CTA's partial goes to its fixed slot, laid out like dW[c0 .. c0+64) x taps ----
-    constexpr int KK64 = K * K * 64;
-    float* slot = g.part + ((size_t)blockIdx.y * gridDim.x * gridDim.z + (size_t)blockIdx.x * gridDim.z + blockIdx.z) * KK64;
-    for (int e = threadIdx.x; e < KK64; e += NT) {
+    // ---- order-deterministic mode: this CTA's partial goes to its fixed slot, laid out like dW[c0 .. c0+CW) x taps ----
+    float* slot = g.part + ((size_t)blockIdx.y * gridDim.x * gridDim.z + (size_t)blockIdx.x * gridDim.z + blockIdx.z) * KKCW;
+    for (int e = threadIdx.x; e < KKCW; e += NT) {
         const int c = e / (K * K), tap = e - c * (K * K);            // consecutive threads -> consecutive slot words
         const int i = S == 1 ? (K * K - 1 - tap) : tap;
         float v = 0.f;
 #pragma unroll
-        for (int q = 0; q < NW; q++) v += wr[(q * K * K + i) * 64 + c];
+        for (int q = 0; q < NW; q++) v += wr[(q * K * K + i) * CW + c];
         slot[e] = v;
     }
 }
 
-static int fill_geom(DwGeom& g, int N, int H, int W, int C, int K, int S, bool input_space) {
+// channel pairs per sub-strip of the hot kernels for a layer of C channels (see the lane mapping note at the top): 32 unless
+// the last 64-channel block would idle a fifth or more of the lanes; then the narrowest waste among 16 / 8 (C = 32, 96 ->
+// 16; C = 144 -> 8). DFD_DW_CPW forces a value (diagnostics).
+static int dw_cpw(int C) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("DFD_DW_CPW"); forced = e ? atoi(e) : 0; }
+    if (forced == 32 || forced == 16 || forced == 8) return forced;
+    const int w32 = (C + 63) / 64 * 64 - C;
+    if (w32 * 5 < C) return 32;
+    const int w16 = (C + 31) / 32 * 32 - C, w8 = (C + 15) / 16 * 16 - C;
+    return w8 < w16 ? 8 : 16;
+}
+
+static int fill_geom(DwGeom& g, int N, int H, int W, int C, int K, int S, bool input_space, int cpw = 32) {
     // input_space: tiles partition the INPUT pixels (dgrad); the staged tile is then dy: shifted (S=1) or compact (S=2)
     g.N = N; g.H = H; g.W = W; g.C = C; g.pad = (K - 1) / 2;
     g.Ho = (H + 2 * g.pad - K) / S + 1;
@@ -738,11 +790,12 @@ static int fill_geom(DwGeom& g, int N, int H, int W, int C, int K, int S, bool i
         g.IW = (g.TW - 1) * eff_s + K;
         g.IH = (g.TH - 1) * eff_s + K;
     }
+    if (cpw < 32 && !(g.IW & 1)) g.IW++;      // odd tile width: the sub-strips of a warp (consecutive rows) use disjoint banks
     g.tiles_x = (tw_dim + g.TW - 1) / g.TW;
     g.tiles_y = (th_dim + g.TH - 1) / g.TH;
     { const char* e = getenv("DFD_DW_DBG"); g.dbg = e ? atoi(e) : 0; }
     g.part = nullptr;
-    return g.IH * g.IW * 32 * (int)sizeof(uint32_t);
+    return g.IH * g.IW * cpw * (int)sizeof(uint32_t);
 }
 
 template <typename KernelT>
@@ -805,15 +858,20 @@ int dfd_dwconv_fwd(const void* x, const float* scale, const float* shift, const 
     if (!scale && act_in != DFD_ACT_NONE) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_fwd: act without BN");
     if (scale && act_in != DFD_ACT_SWISH) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_dwconv_fwd: BN input implies Swish");
     DwGeom g;
-    int smem = fill_geom(g, N, H, W, C, k, stride, false);
-    // one CTA per (tile, 64 channels, image): walking several images per CTA (as the fused backward does) measured 25 % slower
+    const int cpw = dw_cpw(C);
+    int smem = fill_geom(g, N, H, W, C, k, stride, false, cpw);
+    // one CTA per (tile, 2*cpw channels, image): walking several images per CTA (as the fused backward does) measured 25 % slower
     // here - the forward has no per-CTA state worth amortising and loses the overlap between resident CTAs
-    dim3 grid(g.tiles_x * g.tiles_y, (C + CB - 1) / CB, N);
+    dim3 grid(g.tiles_x * g.tiles_y, (C + 2 * cpw - 1) / (2 * cpw), N);
     cudaStream_t st = (cudaStream_t)stream;
+#define FW(ACT_, AFF_, CPW_) DW_LAUNCH((dwconv_fwd_kernel<T, K, S, ACT_, AFF_, NT, CPW_>), grid, smem, st, (const T*)x, scale, shift, w, (T*)out, dsum, dsq, (const BnFinDesc*)fin, g)
+#define FWC(ACT_, AFF_) do { if (cpw == 32) FW(ACT_, AFF_, 32); else if (cpw == 16) FW(ACT_, AFF_, 16); else FW(ACT_, AFF_, 8); } while (0)
     DW_DISPATCH_T(dt, DW_DISPATCH_KS(k, stride, {
-        if (scale) DW_LAUNCH((dwconv_fwd_kernel<T, K, S, DFD_ACT_SWISH, true, NT>), grid, smem, st, (const T*)x, scale, shift, w, (T*)out, dsum, dsq, (const BnFinDesc*)fin, g);
-        else DW_LAUNCH((dwconv_fwd_kernel<T, K, S, DFD_ACT_NONE, false, NT>), grid, smem, st, (const T*)x, scale, shift, w, (T*)out, dsum, dsq, (const BnFinDesc*)fin, g);
+        if (scale) FWC(DFD_ACT_SWISH, true);
+        else FWC(DFD_ACT_NONE, false);
     }));
+#undef FWC
+#undef FW
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }
@@ -870,21 +928,25 @@ int dfd_dwconv_wgrad(const void* x, const float* scale, const float* shift, cons
 // expansion, `add` unused); scale == NULL: `xin` is consumed as is (mode 0: DS block), gx = dgrad (+ add).
 // grid of the fused backward: (tiles, 64-channel blocks, image groups); enough CTAs for ~6 per SM, each walking N / gz images
 // (gz a divisor of N keeps them balanced)
-static void dw_bwd_grid(const DwGeom& g, int N, int C, int& tiles, int& cbs, int& gz) {
+static void dw_bwd_grid(const DwGeom& g, int N, int C, int cpw, int& tiles, int& cbs, int& gz) {
     tiles = g.tiles_x * g.tiles_y;
-    cbs = (C + CB - 1) / CB;
+    cbs = (C + 2 * cpw - 1) / (2 * cpw);
     gz = (148 * 6 + tiles * cbs - 1) / (tiles * cbs);
     if (gz > N) gz = N;
     while (gz < N && N % gz) gz++;
 }
-// partial slots per 64-channel block that the order-deterministic mode of dfd_dwconv_bwd writes (tiles x image groups); the
-// workspace holds ceil(C/64) x that x 64*k*k floats
+// channels per CTA (= per partial slot / per reduce entry) of the depthwise kernels for a layer of C channels: 64, 32 or 16
+int dfd_dwconv_block_channels(int C) { return C > 0 ? 2 * dw_cpw(C) : 0; }
+
+// partial slots per channel block that the order-deterministic mode of dfd_dwconv_bwd writes (tiles x image groups); the
+// workspace holds ceil(C / B) x that x B*k*k floats, B = dfd_dwconv_block_channels(C)
 int dfd_dwconv_bwd_parts(int N, int H, int W, int C, int k, int stride) {
     if (C % 8 || N <= 0 || H <= 0 || W <= 0 || (k != 3 && k != 5) || (stride != 1 && stride != 2)) return 0;
     DwGeom g;
-    fill_geom(g, N, H, W, C, k, stride, true);
+    const int cpw = dw_cpw(C);
+    fill_geom(g, N, H, W, C, k, stride, true, cpw);
     int tiles, cbs, gz;
-    dw_bwd_grid(g, N, C, tiles, cbs, gz);
+    dw_bwd_grid(g, N, C, cpw, tiles, cbs, gz);
     return tiles * gz;
 }
 
@@ -896,15 +958,16 @@ int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const floa
     if (!xin || !dW) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: operands");
     if (scale && (!shift || !mean || !rstd || !s1 || !s2)) return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: mode 1 operands");
     DwGeom g;
-    int smem = fill_geom(g, N, H, W, C, k, stride, true);
+    const int cpw = dw_cpw(C);
+    int smem = fill_geom(g, N, H, W, C, k, stride, true, cpw);
     constexpr int NT = 128;
-    const int red_bytes = (NT / 32) * k * k * 64 * (int)sizeof(float);
+    const int red_bytes = (NT / 32) * k * k * 2 * cpw * (int)sizeof(float);
     if (smem < red_bytes) smem = red_bytes;
     int tiles, cbs, gz;
-    dw_bwd_grid(g, N, C, tiles, cbs, gz);
+    dw_bwd_grid(g, N, C, cpw, tiles, cbs, gz);
     if (ws) {
-        if ((long long)cbs * tiles * gz * k * k * 64 * 4 > ws_bytes)
-            return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: workspace too small (ceil(C/64) x dfd_dwconv_bwd_parts x 64*k*k floats)");
+        if ((long long)cbs * tiles * gz * k * k * 2 * cpw * 4 > ws_bytes)
+            return dfd_set_error(DFD_ERR_ARG, "dfd_dwconv_bwd: workspace too small (blocks x dfd_dwconv_bwd_parts x block_channels*k*k floats)");
         g.part = (float*)ws;
     }
     dim3 grid(tiles, cbs, gz);
@@ -912,7 +975,15 @@ int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const floa
     static int pb3 = 0, pb5 = 0;       // strip width per kernel size: 4 for k = 3 (four CTAs per SM, measured -1..-14 %), 8 for k = 5 (4 measured slower); DFD_DW_PB3 / DFD_DW_PB5 override
     if (!pb3) { const char* e3 = getenv("DFD_DW_PB3"); const char* e5 = getenv("DFD_DW_PB5"); pb3 = (e3 && atoi(e3) == 8) ? 8 : 4; pb5 = (e5 && atoi(e5) == 4) ? 4 : 8; }
     const int pb = k == 3 ? pb3 : pb5;
-#define BW1(K_, S_, AFF, MODE_) if (pb == 4) DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT, 4>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, dW, s1, s2, (const BnBwdFinDesc*)fin, g); else DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT, 8>), grid, smem, st, (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, dW, s1, s2, (const BnBwdFinDesc*)fin, g)
+#define BWARGS (const T*)gy, (const T*)yout, cA, cB, cC, w, (const T*)xin, scale, shift, mean, rstd, (const T*)add, (T*)gx, dW, s1, s2, (const BnBwdFinDesc*)fin, g
+    // narrow lane groups (cpw 16 / 8) are instantiated for the default strip width of each kernel size only
+#define BW1(K_, S_, AFF, MODE_) do {                                                                                          \
+        constexpr int PD = K_ == 3 ? 4 : 8;                                                                                   \
+        if (cpw == 16) DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT, PD, 16>), grid, smem, st, BWARGS);             \
+        else if (cpw == 8) DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT, PD, 8>), grid, smem, st, BWARGS);          \
+        else if (pb == 4) DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT, 4>), grid, smem, st, BWARGS);               \
+        else DW_LAUNCH((dwconv_bwd_kernel<T, K_, S_, AFF, MODE_, NT, 8>), grid, smem, st, BWARGS);                            \
+    } while (0)
 #define BW(K_, S_) do { if (scale) { if (cA) BW1(K_, S_, true, 1); else BW1(K_, S_, false, 1); } else { if (cA) BW1(K_, S_, true, 0); else BW1(K_, S_, false, 0); } } while (0)
     DW_DISPATCH_T(dt, {
         if (k == 3 && stride == 1) BW(3, 1);
@@ -923,6 +994,7 @@ int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const floa
     });
 #undef BW
 #undef BW1
+#undef BWARGS
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

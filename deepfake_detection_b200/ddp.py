@@ -77,10 +77,11 @@ class GradReducer:
     execution plan of a model, but the cut points are positions in ONE plan's backward op list, so the bucket plan is
     computed (and cached) per engine: `backward_and_reduce(engine)` always replays the plan that ran the forward."""
 
-    def __init__(self, engine, group=None, bucket_mb=1.0):
+    def __init__(self, engine, group=None, bucket_mb=4.0):
         # bucket_mb: the arena is cut greedily in backward order. Parameters concentrate in the LAST layers (EfficientNet-B0:
-        # 11.6 of 16 MB sit in the head and stages 5-6), so small buckets start reducing early and leave only a few hundred KB
-        # (the first stages and the stem) for the one collective that cannot overlap with anything - the final one
+        # 11.6 of 16 MB sit in the head and stages 5-6), so 4 MB buckets start reducing early and leave ~2.6 MB (stages 1-4
+        # and the stem) for the one collective that cannot overlap with anything - the final one. 1 MB buckets (12
+        # collectives) measured WORSE at 2 GPUs (17.03 vs 16.64 ms: NCCL CTAs compete with the memory-bound kernels)
         self.engine = engine                      # default plan (Trainer) or the arena (NativeDDP)
         self.arena = engine.arena
         self.group = group
@@ -240,7 +241,7 @@ class NativeDDP(nn.Module):
     gradients across the group before `optimizer.step()` (train.py:402-406: `DDP(model, delay_allreduce=True)` /
     `DDP(model, device_ids=[local_rank])`).  Extra keyword arguments of either constructor are accepted and ignored."""
 
-    def __init__(self, module, process_group=None, bucket_mb=1.0, delay_allreduce=None, device_ids=None, **unused):
+    def __init__(self, module, process_group=None, bucket_mb=4.0, delay_allreduce=None, device_ids=None, **unused):
         super().__init__()
         if not (dist.is_available() and dist.is_initialized()):
             raise _lib.NativeError("NativeDDP needs an initialised torch.distributed process group")

@@ -243,12 +243,13 @@ class Engine:
         if os.environ.get("DFD_NONDET"):
             return ("dfd_dwconv_bwd", list(args) + [None, 0, fin])
         parts = self.L.cdll.dfd_dwconv_bwd_parts(N, H, W, C, k, stride)
-        cbs = (C + 63) // 64
-        off, nbytes = self._ws_take(cbs * parts * 64 * k * k * 4)
+        cw = self.L.cdll.dfd_dwconv_block_channels(C)          # channels per CTA: 64, or 32 / 16 for C = 32, 96 / 144
+        cbs = (C + cw - 1) // cw
+        off, nbytes = self._ws_take(cbs * parts * cw * k * k * 4)
         dW = args[13]
         for cb in range(cbs):
-            n = min(64, C - 64 * cb) * k * k
-            self._red_pending.append((off + cb * parts * 64 * k * k * 4, dW + cb * 64 * k * k * 4, n, 64 * k * k, parts))
+            n = min(cw, C - cw * cb) * k * k
+            self._red_pending.append((off + cb * parts * cw * k * k * 4, dW + cb * cw * k * k * 4, n, cw * k * k, parts))
         return ("dfd_dwconv_bwd", list(args) + [("WS", off), nbytes, fin])
 
     def _ws_take(self, nbytes):

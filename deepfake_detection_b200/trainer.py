@@ -20,7 +20,7 @@ from .optim import ArenaOptimizer
 class Trainer:
     def __init__(self, arch, batch, height=None, width=None, dtype="bf16", opt="sgd", lr=0.01, momentum=0.9,
                  weight_decay=1e-4, opt_eps=1e-8, smoothing=0.0, num_classes=2, in_chans=3, bn_momentum=0.1,
-                 bn_eps=1e-5, use_graph=True, gemm_impl="tc", process_group=None, bucket_mb=1.0, loss_scale=None,
+                 bn_eps=1e-5, use_graph=True, gemm_impl="tc", process_group=None, bucket_mb=4.0, loss_scale=None,
                  scale_window=2000, drop_rate=0.0, drop_path_rate=0.0, opt_alpha=0.9):
         self.engine = Engine(arch, batch, height, width, num_classes=num_classes, in_chans=in_chans, dtype=dtype,
                              bn_momentum=bn_momentum, bn_eps=bn_eps, gemm_impl=gemm_impl, drop_rate=drop_rate,

@@ -97,11 +97,14 @@ int dfd_dwconv_bwd(const void* gy, const void* yout, const float* cA, const floa
                    const float* w, const void* xin, const float* scale, const float* shift, const float* mean,
                    const float* rstd, const void* add, void* gx, float* dW, int N, int H, int W, int C, int k,
                    int stride, int dt, double* s1, double* s2, void* ws, long long ws_bytes, const void* fin, void* stream);
-/* ws (optional): ORDER-DETERMINISTIC dW - CTA (tile x, 64-channel block y, image group z) stores its partial at
- * ws[y][x * groups + z][64 * k*k] laid out like dW[64y .. 64y+64)[k*k] and dfd_ordered_reduce adds the
- * dfd_dwconv_bwd_parts(...) = tiles * groups partials of every channel block into dW in slot order afterwards
- * (ws_bytes >= ceil(C/64) * parts * 64*k*k * 4). NULL: fp32 atomics into dW. */
+/* ws (optional): ORDER-DETERMINISTIC dW - CTA (tile x, channel block y, image group z) stores its partial at
+ * ws[y][x * groups + z][B * k*k] laid out like dW[By .. By+B)[k*k], B = dfd_dwconv_block_channels(C), and
+ * dfd_ordered_reduce adds the dfd_dwconv_bwd_parts(...) = tiles * groups partials of every channel block into dW in slot order
+ * afterwards (ws_bytes >= ceil(C/B) * parts * B*k*k * 4). NULL: fp32 atomics into dW. */
 int dfd_dwconv_bwd_parts(int N, int H, int W, int C, int k, int stride);
+/* channels per CTA of the depthwise kernels for a layer of C channels (64, or 32 / 16 where 64-channel blocks would leave a
+ * fifth or more of the lanes idle): the slot width and the channel-block size of the ws layout above */
+int dfd_dwconv_block_channels(int C);
 
 /* ---- stem convolution: conv_stem 3x3 s2 (efficientnet.py:275,321) / conv1 7x7 s2 (resnet.py:379,451) ---- */
 int dfd_stem_fwd(const void* x_nchw, const float* w, void* out_nhwc, int N, int Cin, int H, int W, int Cout, int k,

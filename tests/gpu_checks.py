@@ -194,17 +194,18 @@ def check_dwconv(N, H, W, C, k, s, dtype=torch.bfloat16, affine=True, seed=0, fw
         # flush to fp32 round-off
         import struct
         parts = _lib.lib().cdll.dfd_dwconv_bwd_parts(N, H, W, C, k, s)
-        cbs = (C + 63) // 64
-        ws = torch.full((cbs, parts, 64 * k * k), float("nan"), device="cuda")
+        cw = _lib.lib().cdll.dfd_dwconv_block_channels(C)
+        cbs = (C + cw - 1) // cw
+        ws = torch.full((cbs, parts, cw * k * k), float("nan"), device="cuda")
         dW3 = [torch.zeros_like(w), torch.zeros_like(w)]
         for t in dW3:
             c3, c4 = stat_buf(C), stat_buf(C)
             _lib.call("dfd_dwconv_bwd", P(gy), P(out), P(cA), P(cB), P(cC), P(w), P(x), P(scale), P(shift), P(mean), P(rstd), None,
                       P(gx2), P(t), N, H, W, C, k, s, DT[dtype], P(c3), P(c4), P(ws), ws.numel() * 4, None, st())
-            raw = b"".join(struct.pack("<QQqqii", P(ws) + cb * parts * 64 * k * k * 4, P(t) + cb * 64 * k * k * 4,
-                                       min(64, C - 64 * cb) * k * k, 64 * k * k, parts, 0) for cb in range(cbs))
+            raw = b"".join(struct.pack("<QQqqii", P(ws) + cb * parts * cw * k * k * 4, P(t) + cb * cw * k * k * 4,
+                                       min(cw, C - cw * cb) * k * k, cw * k * k, parts, 0) for cb in range(cbs))
             table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
-            _lib.call("dfd_ordered_reduce", P(table), cbs, P(t), (64 * k * k // 4 + 7) // 8 if parts > 64 else 1, st())
+            _lib.call("dfd_ordered_reduce", P(table), cbs, P(t), (cw * k * k // 4 + 7) // 8 if parts > 64 else 1, st())
             torch.cuda.synchronize()
         res["det_bitwise"] = bool(torch.equal(dW3[0], dW3[1]))
         res["det_vs_atomic"] = relerr(dW3[0], dW2)

@@ -14,11 +14,12 @@ def t(N, H, W, C, k, s, reps=10, det=True):
     st = torch.cuda.current_stream().cuda_stream
     import struct
     parts = _lib.lib().cdll.dfd_dwconv_bwd_parts(N, H, W, C, k, s)
-    cbs = (C + 63) // 64
-    ws = torch.empty(cbs * parts * 64 * k * k, device="cuda") if det else None
+    cw = _lib.lib().cdll.dfd_dwconv_block_channels(C)
+    cbs = (C + cw - 1) // cw
+    ws = torch.empty(cbs * parts * cw * k * k, device="cuda") if det else None
     if det:
-        raw = b"".join(struct.pack("<QQqqii", ws.data_ptr() + cb * parts * 64 * k * k * 4, dW.data_ptr() + cb * 64 * k * k * 4,
-                                   min(64, C - 64 * cb) * k * k, 64 * k * k, parts, 0) for cb in range(cbs))
+        raw = b"".join(struct.pack("<QQqqii", ws.data_ptr() + cb * parts * cw * k * k * 4, dW.data_ptr() + cb * cw * k * k * 4,
+                                   min(cw, C - cw * cb) * k * k, cw * k * k, parts, 0) for cb in range(cbs))
         table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
     f0 = lambda: _lib.call("dfd_dwconv_bwd", gy.data_ptr(), y.data_ptr(), v[0].data_ptr(), v[1].data_ptr(), v[2].data_ptr(), w.data_ptr(),
                           x.data_ptr(), v[3].data_ptr(), v[4].data_ptr(), v[5].data_ptr(), v[6].data_ptr(), None, gx.data_ptr(), dW.data_ptr(),
@@ -26,7 +27,7 @@ def t(N, H, W, C, k, s, reps=10, det=True):
     def f():
         f0()
         if det:
-            _lib.call("dfd_ordered_reduce", table.data_ptr(), cbs, dW.data_ptr(), (64 * k * k // 4 + 7) // 8 if parts > 64 else 1, st)
+            _lib.call("dfd_ordered_reduce", table.data_ptr(), cbs, dW.data_ptr(), (cw * k * k // 4 + 7) // 8 if parts > 64 else 1, st)
     for _ in range(3): f()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
