@@ -760,16 +760,17 @@ dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const fl
 }
 
 // channel pairs per sub-strip of the hot kernels for a layer of C channels (see the lane mapping note at the top): 32 unless
-// the last 64-channel block would idle a fifth or more of the lanes; then the narrowest waste among 16 / 8 (C = 32, 96 ->
-// 16; C = 144 -> 8). DFD_DW_CPW forces a value (diagnostics).
+// the last 64-channel block would idle a fifth or more of the lanes; then 16 (C = 32, 96, 144: measured best, also where 8
+// would waste nothing - 56x56x144: backward 0.618 / 0.479 / 0.511 ms, forward 0.254 / 0.254 / 0.281 ms for 32 / 16 / 8), and
+// 8 only where 16 would still idle a fifth (C = 16, 48). DFD_DW_CPW forces a value (diagnostics).
 static int dw_cpw(int C) {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("DFD_DW_CPW"); forced = e ? atoi(e) : 0; }
     if (forced == 32 || forced == 16 || forced == 8) return forced;
     const int w32 = (C + 63) / 64 * 64 - C;
     if (w32 * 5 < C) return 32;
-    const int w16 = (C + 31) / 32 * 32 - C, w8 = (C + 15) / 16 * 16 - C;
-    return w8 < w16 ? 8 : 16;
+    const int w16 = (C + 31) / 32 * 32 - C;
+    return w16 * 5 < C ? 16 : 8;
 }
 
 static int fill_geom(DwGeom& g, int N, int H, int W, int C, int K, int S, bool input_space, int cpw = 32) {
