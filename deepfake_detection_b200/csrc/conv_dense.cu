@@ -76,7 +76,8 @@ struct RepackDesc {
     const void* src;   // 16-bit [O][I][k][k]  (or fp32 permuted gradient for the inverse)
     void* dst;         // 16-bit [O][k][k][I]
     void* dstT;        // 16-bit [k][k][I][O] = transpose of dst as a [O, k*k*I] matrix (dgrad B operand), may be null
-    int O, I, k;
+    void* dstD;        // 16-bit [I][k'][k'][O] with flipped taps (kh' = k-1-kh): B operand of the implicit-GEMM dgrad, may be null
+    int O, I, k, pad_;
 };
 // weights: OIHW 16-bit -> [O][kh][kw][I] (GEMM B operand) and its transpose [(kh,kw,I)][O]
 template <typename T>
@@ -85,6 +86,7 @@ __global__ void repack_weights_kernel(const RepackDesc* __restrict__ table) {
     const T* src = (const T*)d.src;
     T* dst = (T*)d.dst;
     T* dstT = (T*)d.dstT;
+    T* dstD = (T*)d.dstD;
     const int kk = d.k * d.k;
     const long long total = (long long)d.O * d.I * kk;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -96,6 +98,7 @@ __global__ void repack_weights_kernel(const RepackDesc* __restrict__ table) {
         T v = src[((size_t)o * d.I + ci) * kk + tap];
         dst[i] = v;
         if (dstT) dstT[((size_t)tap * d.I + ci) * d.O + o] = v;
+        if (dstD) dstD[((size_t)ci * kk + (kk - 1 - tap)) * d.O + o] = v;      // (k-1-kh)*k + (k-1-kw) = kk-1-tap
     }
 }
 // gradients: fp32 [O][kh][kw][I] (wgrad GEMM output) accumulated into the OIHW fp32 arena
@@ -312,7 +315,7 @@ int dfd_col2im(const void* dcols, const void* add, void* dx, int N, int H, int W
     return DFD_OK;
 }
 
-// table: device array of { const void* src; void* dst; void* dstT; int O, I, k; int pad_; }
+// table: device array of { const void* src; void* dst; void* dstT; void* dstD; int O, I, k; int pad_; }
 int dfd_repack_weights(const void* table, int count, int dt, void* stream) {
     if (count <= 0) return DFD_OK;
     dim3 grid(64, count);

@@ -70,6 +70,16 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_addr(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -150,6 +160,17 @@ struct TcParams {
     double* dsq;
     int stat_n;           // statistics channel of output column c is c % stat_n (== N unless rows are packed)
     const BnFinDesc* fin; // optional: the last CTA finalises the BatchNorm behind this convolution (bn_finalize.cuh)
+    // ---- implicit-GEMM convolution mode (conv != 0): k x k, stride 1, "same" padding, NHWC ------------------------------
+    // The A operand is never materialised: an M tile is a (TW x TH x TN) patch of output pixels, and for every tap (kh, kw) and
+    // 64-channel block the producer issues ONE 4-D TMA load of the input box shifted by the tap - rows outside the image
+    // arrive as zeros (TMA out-of-bounds fill), which IS the padding. K runs over (tap, channel block); B is the packed weight
+    // [Cout][kh][kw][Cin]. The C tile goes back through a 4-D map over the output tensor (the store clips at the borders).
+    int conv;
+    int cv_TW, cv_TH, cv_TN;          // output patch of one M tile (cv_rows = TW * TH * TN <= 128 rows are real)
+    int cv_rows;
+    int cv_tiles_x, cv_tiles_y;       // patches per image row / column; M tile index = (n_tile * tiles_y + ty) * tiles_x + tx
+    int cv_W, cv_H, cv_N;             // output (= input) extent
+    int cv_k, cv_pad, cv_cpb;         // kernel size, padding, 64-channel blocks per tap
     int dbg;              // debug switches (DFD_DBG env): 1 = skip TMA store, 2 = skip stats pass, 4 = skip slabs, 8 = A from L2
     long long* ts;        // optional trace (DFD_TS env): CTA 0 records clock64 at 8 pipeline points for its first 32 tiles
 };
@@ -203,11 +224,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             int lt = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, lt++) {
                 const int m_idx = tile / p.num_n_tiles, n_idx = tile - m_idx * p.num_n_tiles;
+                int cx0 = 0, cy0 = 0, cn0 = 0;
+                if (p.conv) {
+                    const int txi = m_idx % p.cv_tiles_x, r = m_idx / p.cv_tiles_x;
+                    cx0 = txi * p.cv_TW; cy0 = (r % p.cv_tiles_y) * p.cv_TH; cn0 = (r / p.cv_tiles_y) * p.cv_TN;
+                }
                 for (int kb = 0; kb < p.num_k_blocks; kb++) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
                     if (p.ts && kb == 0 && blockIdx.x == 0 && lt < 32) p.ts[lt * 8 + 0] = clock64();
-                    mbar_arrive_expect_tx(full_bar + stage, a_bytes + b_bytes);
-                    tma_load_2d(smem_a + (size_t)stage * a_bytes, &tmap_a, full_bar + stage, kb * BLOCK_K, (p.dbg & 8) ? 0 : m_idx * BLOCK_M);
+                    if (p.conv) {
+                        const int tap = kb / p.cv_cpb, cb = kb - tap * p.cv_cpb;
+                        const int kh = tap / p.cv_k, kw = tap - kh * p.cv_k;
+                        mbar_arrive_expect_tx(full_bar + stage, (uint32_t)p.cv_rows * 128u + b_bytes);
+                        tma_load_4d(smem_a + (size_t)stage * a_bytes, &tmap_a, full_bar + stage, cb * BLOCK_K, cx0 + kw - p.cv_pad,
+                                    cy0 + kh - p.cv_pad, cn0);
+                    } else {
+                        mbar_arrive_expect_tx(full_bar + stage, a_bytes + b_bytes);
+                        tma_load_2d(smem_a + (size_t)stage * a_bytes, &tmap_a, full_bar + stage, kb * BLOCK_K, (p.dbg & 8) ? 0 : m_idx * BLOCK_M);
+                    }
                     tma_load_2d(smem_b + (size_t)stage * b_stride, &tmap_b, full_bar + stage, kb * BLOCK_K, n_idx * p.block_n);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -270,6 +304,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int tile = blockIdx.x + wg * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, lt += 2) {
             const int m_idx = tile / p.num_n_tiles, n_idx = tile - m_idx * p.num_n_tiles;
             const bool rec = p.ts && leader && blockIdx.x == 0 && lt < 32;
+            // convolution mode: this thread's row is output pixel (n0 + tn, y0 + ty, x0 + tx) of the patch; rows beyond the patch
+            // or the image hold garbage accumulators and are zeroed (they would otherwise enter the BatchNorm statistics)
+            int cx0 = 0, cy0 = 0, cn0 = 0;
+            bool row_ok = true;
+            if (p.conv) {
+                const int txi = m_idx % p.cv_tiles_x, r = m_idx / p.cv_tiles_x;
+                cx0 = txi * p.cv_TW; cy0 = (r % p.cv_tiles_y) * p.cv_TH; cn0 = (r / p.cv_tiles_y) * p.cv_TN;
+                const int px = et % p.cv_TW, q2 = et / p.cv_TW;
+                const int py = q2 % p.cv_TH, pn = q2 / p.cv_TH;
+                row_ok = et < p.cv_rows && cx0 + px < p.cv_W && cy0 + py < p.cv_H && cn0 + pn < p.cv_N;
+            }
             if (rec) p.ts[lt * 8 + 4] = clock64();
             mbar_wait(tmem_full + wg, acc_phase);
             tc_fence_after();
@@ -289,7 +334,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                 for (int q4 = 0; q4 < SLAB / 16; q4++) {
                     if (q4 * 16 < ncols) {
-                        const uint32_t (&w)[16] = v[q4];
+                        uint32_t (&w)[16] = v[q4];
+                        if (!row_ok) {
+#pragma unroll
+                            for (int z = 0; z < 16; z++) w[z] = 0u;
+                        }
                         uint4 lo, hi;
                         lo.x = pack2<T>(__uint_as_float(w[0]), __uint_as_float(w[1]));
                         lo.y = pack2<T>(__uint_as_float(w[2]), __uint_as_float(w[3]));
@@ -319,7 +368,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 epi_barrier(wg);
                 if (leader && !(p.dbg & 1)) {
-                    tma_store_2d(&tmap_c, cbuf, n_idx * p.block_n + s * SLAB, m_idx * BLOCK_M);
+                    if (p.conv) tma_store_4d(&tmap_c, cbuf, n_idx * p.block_n + s * SLAB, cx0, cy0, cn0);
+                    else tma_store_2d(&tmap_c, cbuf, n_idx * p.block_n + s * SLAB, m_idx * BLOCK_M);
                     tma_store_commit();
                 }
                 if (p.dsum && !(p.dbg & 2)) {
@@ -413,6 +463,14 @@ struct WgParams {
     // split straight into dW (the order of the fp32 additions then varies run to run).
     float* part;
     int splits;
+    // ---- implicit-GEMM convolution mode (conv != 0): G = dY [N,H,W,Cout] and X = the layer input [N,H,W,Cin] through 4-D
+    // tensor maps; one pipeline stage = one patch of cv_rows <= 64 output pixels (TW x TH x TN); column block j of dW
+    // (64 wide) = (tap = j / cpb, channel block = j % cpb): its X box is the patch shifted by the tap, padding and rows past
+    // the image arrive as zeros. Rows cv_rows..63 of every box are never written by TMA and are zeroed once at kernel start.
+    int conv;
+    int cv_TW, cv_TH, cv_TN, cv_rows;
+    int cv_tiles_x, cv_tiles_y;
+    int cv_k, cv_pad, cv_cpb;
 };
 
 template <typename T>
@@ -441,6 +499,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constan
     const bool b_box1 = nbox_b == 2 && n0 + 64 < p.Kw;
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_g); prefetch_tmap(&tmap_x); }
+    if (p.conv && p.cv_rows < WG_KP) {
+        uint4* z = reinterpret_cast<uint4*>(smem_a);
+        const int n16 = (int)((size_t)p.stages * (a_bytes + b_bytes) / 16);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.stages; i++) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
         mbar_init(tmem_full, 1);
@@ -456,12 +520,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constan
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx = (a_box1 ? 2u : 1u) * WG_BOX_BYTES + (b_box1 ? 2u : 1u) * WG_BOX_BYTES;
+            const uint32_t box_bytes = p.conv ? (uint32_t)p.cv_rows * 128u : (uint32_t)WG_BOX_BYTES;
+            const uint32_t tx = ((a_box1 ? 2u : 1u) + (b_box1 ? 2u : 1u)) * box_bytes;
+            // convolution mode: (tap, channel block) of this tile's one or two 64-column blocks
+            int bt_c[2] = {0, 0}, bt_dx[2] = {0, 0}, bt_dy[2] = {0, 0};
+            if (p.conv) {
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const int jb = n0 / 64 + i, tap = jb / p.cv_cpb;
+                    bt_c[i] = (jb - tap * p.cv_cpb) * 64;
+                    bt_dy[i] = tap / p.cv_k - p.cv_pad;
+                    bt_dx[i] = tap % p.cv_k - p.cv_pad;
+                }
+            }
             for (long long kb = kb0; kb < kb1; kb++) {
                 mbar_wait(empty_bar + stage, phase ^ 1);
                 mbar_arrive_expect_tx(full_bar + stage, tx);
                 uint8_t* a = smem_a + (size_t)stage * a_bytes;
                 uint8_t* b = smem_b + (size_t)stage * b_bytes;
+                if (p.conv) {
+                    const int pt = (int)kb, txi = pt % p.cv_tiles_x, r = pt / p.cv_tiles_x;
+                    const int cx0 = txi * p.cv_TW, cy0 = (r % p.cv_tiles_y) * p.cv_TH, cn0 = (r / p.cv_tiles_y) * p.cv_TN;
+                    tma_load_4d(a, &tmap_g, full_bar + stage, m0, cx0, cy0, cn0);
+                    if (a_box1) tma_load_4d(a + WG_BOX_BYTES, &tmap_g, full_bar + stage, m0 + 64, cx0, cy0, cn0);
+                    tma_load_4d(b, &tmap_x, full_bar + stage, bt_c[0], cx0 + bt_dx[0], cy0 + bt_dy[0], cn0);
+                    if (b_box1) tma_load_4d(b + WG_BOX_BYTES, &tmap_x, full_bar + stage, bt_c[1], cx0 + bt_dx[1], cy0 + bt_dy[1], cn0);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 const int row = (int)(kb * WG_KP);
                 tma_load_2d(a, &tmap_g, full_bar + stage, m0, row);
                 if (a_box1) tma_load_2d(a + WG_BOX_BYTES, &tmap_g, full_bar + stage, m0 + 64, row);
@@ -574,11 +660,96 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, int cols, 
 }
 
 
+// 4-D NHWC tensor [N, H, W, C] (16-bit) seen as dims {C, W, H, N}; box = {64 channels, bw, bh, bn}, 128-byte swizzle, OOB -> zeros
+static int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn, int is_bf16) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return dfd_set_error(DFD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[200];
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled (4-D) failed (%d) N=%d H=%d W=%d C=%d box=%dx%dx%d", (int)r, N, H, W, C, bw, bh, bn);
+        return dfd_set_error(DFD_ERR_CUDA, buf);
+    }
+    return DFD_OK;
+}
+
+// Implicit-GEMM convolution on the kernel above (conv mode): y[N,H,W,Cout] = conv_{k x k, stride 1, pad (k-1)/2}(x[N,H,W,Cin]),
+// wpk = packed weight [Cout][kh][kw][Cin] (K-major rows of k*k*Cin). Cin % 64 == 0 keeps every 64-channel K block inside one tap.
+static int launch_conv_tc(const void* x, const void* wpk, void* y, int N, int H, int W, int Cin, int Cout, int k, int dt,
+                          double* dsum, double* dsq, const void* fin, void* stream) {
+    TcParams p;
+    p.fin = (const BnFinDesc*)fin;
+    p.conv = 1;
+    // output patch of an M tile: whole rows when they fit (W <= 128), as many rows as 128 / W allows, split evenly over the
+    // image height; images stacked when a whole image is smaller than half a tile (7 x 7 -> two images per tile)
+    int TW = W <= 128 ? W : 128;
+    int maxTH = 128 / TW; if (maxTH < 1) maxTH = 1;
+    int ty = (H + maxTH - 1) / maxTH;
+    int TH = (H + ty - 1) / ty;
+    int TN = TH == H && TW == W ? 128 / (TW * TH) : 1;
+    if (TN < 1) TN = 1;
+    if (TN > N) TN = N;
+    p.cv_TW = TW; p.cv_TH = TH; p.cv_TN = TN; p.cv_rows = TW * TH * TN;
+    p.cv_tiles_x = (W + TW - 1) / TW; p.cv_tiles_y = (H + TH - 1) / TH;
+    p.cv_W = W; p.cv_H = H; p.cv_N = N;
+    p.cv_k = k; p.cv_pad = (k - 1) / 2; p.cv_cpb = Cin / BLOCK_K;
+    const int K = k * k * Cin;
+    p.M = N * H * W; p.N = Cout; p.K = K;
+    p.stat_n = Cout;
+    p.is_bf16 = dt == DFD_DT_BF16;
+    p.block_n = Cout <= MAX_BLOCK_N ? ((Cout + 15) / 16) * 16 : MAX_BLOCK_N;
+    p.num_m_tiles = p.cv_tiles_x * p.cv_tiles_y * ((N + TN - 1) / TN);
+    p.num_n_tiles = cdiv(Cout, p.block_n);
+    p.num_k_blocks = k * k * p.cv_cpb;
+    p.dsum = dsum; p.dsq = dsq;
+    { const char* e = getenv("DFD_DBG"); p.dbg = e ? atoi(e) : 0; }
+    p.ts = nullptr;
+    const int a_bytes = BLOCK_M * BLOCK_K * 2;
+    const int b_stride = ((p.block_n * BLOCK_K * 2) + 1023) & ~1023;
+    const int fixed = 4 * BLOCK_M * SLAB * 2 + 22 * 8 + 2 * 4 * 64 * 4 + 1024;
+    int stages = (SMEM_BUDGET - fixed) / (a_bytes + b_stride);
+    if (stages > 6) stages = 6;
+    if (stages < 2) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_conv_tc: smem");
+    p.stages = stages;
+    size_t smem = (size_t)stages * (a_bytes + b_stride) + fixed;
+    CUtensorMap ma, mb, mc;
+    int rc;
+    if ((rc = make_map_nhwc(&ma, x, N, H, W, Cin, TW, TH, TN, p.is_bf16))) return rc;
+    if ((rc = make_map(&mb, wpk, Cout, K, p.block_n, p.is_bf16))) return rc;
+    if ((rc = make_map_nhwc(&mc, y, N, H, W, Cout, TW, TH, TN, p.is_bf16))) return rc;
+    int device = 0, sms = 148;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int grid = p.num_m_tiles * p.num_n_tiles;
+    if (grid > sms) grid = sms;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.is_bf16) {
+        auto kf = gemm_tc_kernel<bf16>;
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET); attr = true; }
+        kf<<<grid, NUM_THREADS, smem, st>>>(ma, mb, mc, p);
+    } else {
+        auto kf = gemm_tc_kernel<__half>;
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET); attr = true; }
+        kf<<<grid, NUM_THREADS, smem, st>>>(ma, mb, mc, p);
+    }
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
 // C[M,N] = A[M,K] * B[N,K]^T; statistics of output column c go to channel c % stat_n
 static int launch_gemm_tc(const void* A, const void* B, void* C, long long M, int N, int K, int dt, double* dsum,
                           double* dsq, int stat_n, const void* fin, void* stream) {
     TcParams p;
     p.fin = (const BnFinDesc*)fin;
+    p.conv = 0;
     p.M = (int)M; p.N = N; p.K = K;
     p.stat_n = stat_n;
     p.is_bf16 = dt == DFD_DT_BF16;
@@ -686,6 +857,19 @@ int dfd_gemm_tn_rowpack(const void* A, const void* Bd, void* C, long long M, int
     return launch_gemm_tc(A, Bd, C, M / pack, N * pack, K * pack, dt, dsum, dsq, N, fin, stream);
 }
 
+// Dense k x k convolution (stride 1, padding (k-1)/2) as an IMPLICIT GEMM on tcgen05: no im2col matrix exists in memory - the
+// TMA producer fetches, per tap and 64-channel block, the input box shifted by the tap through a 4-D tensor map over the NHWC
+// tensor (out-of-bounds rows arrive as zeros = the padding) straight into the swizzled MMA operand buffer.
+//   forward : x = input,  wpk = [Cout][kh][kw][Cin]                      (resnet.py:129-136,195-197: nn.Conv2d 3x3)
+//   dgrad   : x = dY,     wpk = [Cin][kh'][kw'][Cout] with flipped taps   (autograd input gradient of the same conv)
+int dfd_conv_tc(const void* x, const void* wpk, void* y, int N, int H, int W, int Cin, int Cout, int k, int dt, double* dsum,
+                double* dsq, const void* fin, void* stream) {
+    if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (Cin % 64) || (Cout % 64) || (k != 1 && k != 3 && k != 5 && k != 7))
+        return dfd_set_error(DFD_ERR_ARG, "dfd_conv_tc: Cin % 64, Cout % 64, k in {1,3,5,7}");
+    if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_conv_tc: dtype");
+    return launch_conv_tc(x, wpk, y, N, H, W, Cin, Cout, k, dt, dsum, dsq, fin, stream);
+}
+
 // table: device array of {src [N,K], dst [pack*N, pack*K], N, K, pack}; dst(j*N+n, j'*K+k) = (j == j') ? src(n,k) : 0
 int dfd_blockdiag_weights(const void* table, int count, int dt, void* stream) {
     if (count <= 0) return DFD_OK;
@@ -698,9 +882,9 @@ int dfd_blockdiag_weights(const void* table, int count, int dt, void* stream) {
 // dW[Nw,Kw] (fp32, accumulated) += G[M,Nw]^T * X[M,Kw] on tcgen05 (MN-major operands straight from NHWC, split over M)
 // split count of the workspace (order-deterministic) mode: as many row ranges as fill the GPU once, but no more than keep
 // the partial-sum traffic (one write + one read of splits x Nw x Kw floats) under half of the operand traffic
-static long long wgrad_ws_splits(long long M, int Nw, int Kw, int sms) {
+static long long wgrad_ws_splits(long long M, int Nw, int Kw, int sms, long long kblocks = 0) {
     const int block_n = Kw >= 128 ? 128 : ((Kw + 15) / 16) * 16;
-    const long long kblocks = (M + WG_KP - 1) / WG_KP;
+    if (!kblocks) kblocks = (M + WG_KP - 1) / WG_KP;
     const int tm = cdiv(Nw, 128), tn = cdiv(Kw, block_n);
     long long splits = (2LL * sms + tm * tn - 1) / (tm * tn);
     const long long max_splits = (kblocks + 3) / 4;
@@ -718,15 +902,64 @@ int dfd_gemm_wgrad_splits(long long M, int Nw, int Kw) {
     return (int)wgrad_ws_splits(M, Nw, Kw, 148);
 }
 
+// patch (TW x TH x TN <= 64 output pixels) of one pipeline stage of the implicit-GEMM weight gradient: the shape that covers
+// the N x H x W pixels with the fewest patches (ties: the widest, longest contiguous runs for TMA)
+struct WgPatch { int TW, TH, TN; long long patches; };
+static WgPatch wg_patch(int N, int H, int W) {
+    WgPatch best = {1, 1, 1, -1};
+    for (int tw = 1; tw <= W && tw <= WG_KP; tw++) {
+        for (int th = 1; th <= H && tw * th <= WG_KP; th++) {
+            int tn = (tw == W && th == H) ? WG_KP / (tw * th) : 1;
+            if (tn > N) tn = N;
+            long long n = (long long)cdiv(W, tw) * cdiv(H, th) * cdiv(N, tn);
+            if (best.patches < 0 || n < best.patches || (n == best.patches && tw > best.TW)) best = {tw, th, tn, n};
+        }
+    }
+    return best;
+}
+
+static int launch_wgrad_tc(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* ws,
+                           long long ws_bytes, void* stream, int cvN, int cvH, int cvW, int cvCin, int cvk);
+
 int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* ws, long long ws_bytes,
                    void* stream) {
     if (M <= 0 || Nw <= 0 || Kw <= 0 || (Nw % 8) || (Kw % 8)) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_wgrad: Nw%8, Kw%8");
     if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_wgrad: dtype");
+    return launch_wgrad_tc(G, X, dW, M, Nw, Kw, dt, ws, ws_bytes, stream, 0, 0, 0, 0, 0);
+}
+
+// Weight gradient of a dense k x k convolution (stride 1, padding (k-1)/2) as an IMPLICIT GEMM: dW[Cout][kh][kw][Cin] (fp32,
+// the packed order of dfd_repack_weights; accumulated, or written as split partials into `ws` like dfd_gemm_wgrad) =
+// sum over output pixels of dY[pixel, co] * x[pixel shifted by the tap, ci]; no im2col matrix in memory.
+int dfd_conv_wgrad_splits(int N, int H, int W, int Cin, int Cout, int k) {
+    if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return 0;
+    WgPatch pt = wg_patch(N, H, W);
+    return (int)wgrad_ws_splits((long long)N * H * W, Cout, k * k * Cin, 148, pt.patches);
+}
+
+int dfd_conv_wgrad_tc(const void* dy, const void* x, float* dW, int N, int H, int W, int Cin, int Cout, int k, int dt, void* ws,
+                      long long ws_bytes, void* stream) {
+    if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (Cin % 64) || (Cout % 8) || (k != 1 && k != 3 && k != 5 && k != 7))
+        return dfd_set_error(DFD_ERR_ARG, "dfd_conv_wgrad_tc: Cin % 64, Cout % 8, k in {1,3,5,7}");
+    if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_conv_wgrad_tc: dtype");
+    return launch_wgrad_tc(dy, x, dW, (long long)N * H * W, Cout, k * k * Cin, dt, ws, ws_bytes, stream, N, H, W, Cin, k);
+}
+
+static int launch_wgrad_tc(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* ws,
+                           long long ws_bytes, void* stream, int cvN, int cvH, int cvW, int cvCin, int cvk) {
     WgParams p;
     p.M = M; p.Nw = Nw; p.Kw = Kw;
     p.is_bf16 = dt == DFD_DT_BF16;
     p.block_n = Kw >= 128 ? 128 : ((Kw + 15) / 16) * 16;
     p.kblocks = (M + WG_KP - 1) / WG_KP;
+    p.conv = cvN > 0;
+    if (p.conv) {
+        WgPatch pt = wg_patch(cvN, cvH, cvW);
+        p.cv_TW = pt.TW; p.cv_TH = pt.TH; p.cv_TN = pt.TN; p.cv_rows = pt.TW * pt.TH * pt.TN;
+        p.cv_tiles_x = cdiv(cvW, pt.TW); p.cv_tiles_y = cdiv(cvH, pt.TH);
+        p.cv_k = cvk; p.cv_pad = (cvk - 1) / 2; p.cv_cpb = cvCin / 64;
+        p.kblocks = pt.patches;
+    }
     const int tm = cdiv(Nw, 128), tn = cdiv(Kw, p.block_n);
     int device = 0, sms = 148;
     cudaGetDevice(&device);
@@ -738,7 +971,7 @@ int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw,
     if (splits > 65535) splits = 65535;
     p.part = nullptr;
     if (ws) {
-        splits = wgrad_ws_splits(M, Nw, Kw, 148);
+        splits = wgrad_ws_splits(M, Nw, Kw, 148, p.conv ? p.kblocks : 0);
         if (splits * (long long)Nw * Kw * 4 > ws_bytes)
             return dfd_set_error(DFD_ERR_ARG, "dfd_gemm_wgrad: workspace too small (dfd_gemm_wgrad_splits x Nw x Kw floats)");
         p.part = (float*)ws;
@@ -756,8 +989,13 @@ int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw,
     size_t smem = (size_t)stages * stage_bytes + fixed;
     CUtensorMap mg, mx;
     int rc;
-    if ((rc = make_map(&mg, G, M, Nw, WG_KP, p.is_bf16))) return rc;
-    if ((rc = make_map(&mx, X, M, Kw, WG_KP, p.is_bf16))) return rc;
+    if (p.conv) {
+        if ((rc = make_map_nhwc(&mg, G, cvN, cvH, cvW, Nw, p.cv_TW, p.cv_TH, p.cv_TN, p.is_bf16))) return rc;
+        if ((rc = make_map_nhwc(&mx, X, cvN, cvH, cvW, cvCin, p.cv_TW, p.cv_TH, p.cv_TN, p.is_bf16))) return rc;
+    } else {
+        if ((rc = make_map(&mg, G, M, Nw, WG_KP, p.is_bf16))) return rc;
+        if ((rc = make_map(&mx, X, M, Kw, WG_KP, p.is_bf16))) return rc;
+    }
     dim3 grid(tm, tn, (unsigned)splits);
     cudaStream_t st = (cudaStream_t)stream;
     if (p.is_bf16) {

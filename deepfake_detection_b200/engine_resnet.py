@@ -3,10 +3,15 @@
 Reference graph: dfd/timm/models/resnet.py:450-468 (stem 7x7 s2 -> BN -> ReLU -> maxpool 3x3 s2 -> 4 stages -> GAP
 -> fc), BasicBlock :150-175, Bottleneck :215-246 (stride on the 3x3, :195-197), downsample 1x1 conv + BN :249-260.
 
-Round-1 formulation of the dense k x k convolutions (see csrc/conv_dense.cu): materialised im2col -> tcgen05 GEMM
-(forward), GEMM -> col2im (input gradient), mma.sync wgrad GEMM on the re-computed im2col matrix. 1x1 convolutions are
-plain GEMMs on the NHWC tensors. BN + ReLU outputs are materialised (`dfd_bn_act`) because three consumers read them.
+Dense 3x3 convolutions with stride 1 (13 of the 16 in resnet50, all but 3 in resnet18) run as IMPLICIT GEMMs on tcgen05
+(`dfd_conv_tc`, csrc/gemm_tc.cu conv mode: the TMA producer fetches the input box shifted by the tap through a 4-D tensor
+map, no im2col matrix in memory) in the forward pass and for the input gradient (same kernel on dY with the tap-flipped
+[Cin][kh'][kw'][Cout] weights). The strided 3x3 convolutions keep the round-1 formulation (csrc/conv_dense.cu):
+materialised im2col -> tcgen05 GEMM (forward), GEMM -> col2im (input gradient). The weight gradient of every 3x3 is the
+MN-major tcgen05 wgrad GEMM: implicit too for the stride-1 layers (`dfd_conv_wgrad_tc`: one pipeline stage = one patch of
+<= 64 output pixels of dY and the input box shifted by the tap), on the re-computed im2col matrix for the strided ones. 1x1 convolutions are plain GEMMs on the NHWC tensors. BN + ReLU outputs are materialised (`dfd_bn_act`) because three consumers read them.
 """
+import os
 import struct
 
 import torch
@@ -37,12 +42,14 @@ def build_resnet(e):
     if getattr(ar, "wpack16", None) is None:
         ar.wpack16 = torch.zeros(max(off, 8), dtype=e.tdtype, device=dev)
         ar.wpackT16 = torch.zeros(max(off, 8), dtype=e.tdtype, device=dev)
-        raw = b"".join(struct.pack("<QQQiiii", _ptr(e.params16, e.p_off[n][0]), _ptr(ar.wpack16, o), _ptr(ar.wpackT16, o), O, I, k, 0)
+        ar.wpackD16 = torch.zeros(max(off, 8), dtype=e.tdtype, device=dev)
+        raw = b"".join(struct.pack("<QQQQiiii", _ptr(e.params16, e.p_off[n][0]), _ptr(ar.wpack16, o), _ptr(ar.wpackT16, o),
+                                   _ptr(ar.wpackD16, o), O, I, k, 0)
                        for n, (o, O, I, k) in pk_off.items())
         ar._rtable = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         ar._rtable_count = len(pk_off)
         ar._derived_dirty = True
-    e.wpack16, e.wpackT16 = ar.wpack16, ar.wpackT16
+    e.wpack16, e.wpackT16, e.wpackD16 = ar.wpack16, ar.wpackT16, ar.wpackD16
     e.gperm = torch.zeros(max([O * I * k * k for (_, O, I, k) in pk_off.values()] + [8]), dtype=torch.float32, device=dev)
 
     P32 = lambda n: _ptr(e.params32, e.p_off[n][0])
@@ -51,6 +58,7 @@ def build_resnet(e):
     T16 = lambda n: _ptr(e.paramsT16, e.t_off[n][0])
     PK = lambda n: _ptr(e.wpack16, pk_off[n][0])
     PKT = lambda n: _ptr(e.wpackT16, pk_off[n][0])
+    PKD = lambda n: _ptr(e.wpackD16, pk_off[n][0])
 
     # ---- shapes ------------------------------------------------------------------------------------------
     H1, W1 = conv_out(e.H, 7, 2, 3), conv_out(e.W, 7, 2, 3)
@@ -75,7 +83,6 @@ def build_resnet(e):
     e._alloc_bn(bn_specs)
     bns = e.bns
 
-    import os
     fused_fin = bool(os.environ.get("DFD_FUSED_FINALIZE"))       # measured slower than the standalone launches, see engine.py
 
     def gemm(A, B, C, M, Nn, K, bn=None):
@@ -85,6 +92,20 @@ def build_resnet(e):
                 bn.fused = fused_fin
             return ("dfd_gemm_tn", (A, B, C, M, Nn, K, dt, fs, fq, bn.fin if (bn is not None and fused_fin) else None))
         return ("dfd_gemm_tn_mma", (A, B, C, None, M, Nn, K, dt, fs, fq))
+
+    implicit = e.gemm_impl == "tc" and not os.environ.get("DFD_NO_IMPLICIT_CONV")
+    implicit_wgrad = not os.environ.get("DFD_NO_IMPLICIT_WGRAD")
+    e.n_implicit = 0
+
+    def conv3x3(xin, name, y, h, w, cin, cout, stride, bn):
+        """3x3 / padding 1 forward into y (+ BatchNorm statistics of y)"""
+        if implicit and stride == 1 and cin % 64 == 0 and cout % 64 == 0:
+            bn.fused = fused_fin
+            e.n_implicit += 1
+            return [("dfd_conv_tc", (xin, PK(name), y, N, h, w, cin, cout, 3, dt, bn.fsum, bn.fsq, bn.fin if fused_fin else None))]
+        ho, wo = conv_out(h, 3, stride, 1), conv_out(w, 3, stride, 1)
+        return [("dfd_im2col", (xin, COLS, N, h, w, cin, 3, stride, 1, dt)),
+                gemm(COLS, PK(name), y, N * ho * wo, cout, 9 * cin, bn)]
 
     def finalize(bn, count):
         # training: finalised by the last CTA of the producing GEMM (bn.fin); this op runs in eval mode only (see Engine._run)
@@ -144,12 +165,10 @@ def build_resnet(e):
             y1 = e._alloc16(N, ho, wo, b.planes)
             a1 = e._alloc16(N, ho, wo, b.planes)
             y2 = e._alloc16(N, ho, wo, b.cout)
-            fwd.append(("dfd_im2col", (_ptr(x), COLS, N, h, w, b.cin, 3, b.stride, 1, dt)))
-            fwd.append(gemm(COLS, PK(p + ".conv1.weight"), _ptr(y1), M2, b.planes, 9 * b.cin, bn1))
+            fwd += conv3x3(_ptr(x), p + ".conv1.weight", _ptr(y1), h, w, b.cin, b.planes, b.stride, bn1)
             fwd.append(finalize(bn1, M2))
             fwd.append(bn_relu(y1, bn1, a1, ho * wo, b.planes))
-            fwd.append(("dfd_im2col", (_ptr(a1), COLS, N, ho, wo, b.planes, 3, 1, 1, dt)))
-            fwd.append(gemm(COLS, PK(p + ".conv2.weight"), _ptr(y2), M2, b.cout, 9 * b.planes, bn2))
+            fwd += conv3x3(_ptr(a1), p + ".conv2.weight", _ptr(y2), ho, wo, b.planes, b.cout, 1, bn2)
             fwd.append(finalize(bn2, M2))
             rec.update(y1=y1, a1=a1, ylast=y2, bnlast=bn2)
         else:
@@ -162,8 +181,7 @@ def build_resnet(e):
             fwd.append(gemm(_ptr(x), P16(p + ".conv1.weight"), _ptr(y1), M1, b.planes, b.cin, bn1))
             fwd.append(finalize(bn1, M1))
             fwd.append(bn_relu(y1, bn1, a1, h * w, b.planes))
-            fwd.append(("dfd_im2col", (_ptr(a1), COLS, N, h, w, b.planes, 3, b.stride, 1, dt)))
-            fwd.append(gemm(COLS, PK(p + ".conv2.weight"), _ptr(y2), M2, b.planes, 9 * b.planes, bn2))
+            fwd += conv3x3(_ptr(a1), p + ".conv2.weight", _ptr(y2), h, w, b.planes, b.planes, b.stride, bn2)
             fwd.append(finalize(bn2, M2))
             fwd.append(bn_relu(y2, bn2, a2, ho * wo, b.planes))
             fwd.append(gemm(_ptr(a2), P16(p + ".conv3.weight"), _ptr(y3), M2, b.cout, b.planes, bn3))
@@ -208,11 +226,19 @@ def build_resnet(e):
 
     def conv3x3_bwd(name, dy, M_out, Cin, Cout, xin_t, n_h, n_w, stride, dx_out, dx_add=None):
         """dy [M_out, Cout] -> dx_out [N, n_h, n_w, Cin] (+dx_add) and the weight gradient of `name`"""
-        ops = [gemm(dy, PKT(name), COLS, M_out, 9 * Cin, Cout),
-               ("dfd_col2im", (COLS, dx_add, dx_out, N, n_h, n_w, Cin, 3, stride, 1, dt)),
-               ("dfd_im2col", (_ptr(xin_t), COLS, N, n_h, n_w, Cin, 3, stride, 1, dt)),
-               zero_gperm(Cout * 9 * Cin),
-               e._wgrad(dy, COLS, _ptr(e.gperm), M_out, Cout, 9 * Cin)]
+        if implicit and stride == 1 and dx_add is None and Cin % 64 == 0 and Cout % 64 == 0:
+            # input gradient = the same implicit GEMM on dY with the tap-flipped [Cin][kh'][kw'][Cout] weights
+            ops = [("dfd_conv_tc", (dy, PKD(name), dx_out, N, n_h, n_w, Cout, Cin, 3, dt, None, None, None))]
+        else:
+            ops = [gemm(dy, PKT(name), COLS, M_out, 9 * Cin, Cout),
+                   ("dfd_col2im", (COLS, dx_add, dx_out, N, n_h, n_w, Cin, 3, stride, 1, dt))]
+        if implicit and implicit_wgrad and stride == 1 and Cin % 64 == 0 and e._wgrad_name == "dfd_gemm_wgrad":
+            ops += [zero_gperm(Cout * 9 * Cin),
+                    e._wgrad_conv(dy, _ptr(xin_t), _ptr(e.gperm), N, n_h, n_w, Cin, Cout, 3)]
+        else:
+            ops += [("dfd_im2col", (_ptr(xin_t), COLS, N, n_h, n_w, Cin, 3, stride, 1, dt)),
+                    zero_gperm(Cout * 9 * Cin),
+                    e._wgrad(dy, COLS, _ptr(e.gperm), M_out, Cout, 9 * Cin)]
         e._flush_reduce(ops)             # the permuted gradient must be complete before it is unpacked into the arena
         ops.append(("dfd_unpack_grad", (_ptr(e.gperm), G32(name), Cout, Cin, 3)))
         return ops

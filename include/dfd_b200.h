@@ -126,8 +126,24 @@ int dfd_unpad_grad(const float* g_padded, float* g_accum, int O, int taps, int K
 int dfd_im2col(const void* x, void* cols, int N, int H, int W, int C, int k, int stride, int pad, int dt, void* stream);
 int dfd_col2im(const void* dcols, const void* add, void* dx, int N, int H, int W, int C, int k, int stride, int pad, int dt,
                void* stream);
-/* table: device array of { const void* src_OIHW16; void* dst_OHWI16; void* dstT_HWI_O16; int O; int I; int k; int pad; } */
+/* table: device array of { const void* src_OIHW16; void* dst_OHWI16; void* dstT_HWI_O16; void* dstD_IH'W'O16 (flipped taps);
+ *                          int O; int I; int k; int pad; }  - dstT / dstD may be null */
 int dfd_repack_weights(const void* table, int count, int dt, void* stream);
+/* Dense k x k convolution, stride 1, padding (k-1)/2, as an IMPLICIT GEMM on tcgen05 (no im2col matrix in memory): the TMA
+ * producer loads, per tap and 64-channel block, the NHWC input box shifted by the tap through a 4-D tensor map; out-of-image
+ * rows arrive as zeros (= the padding). Replaces nn.Conv2d 3x3 stride 1 of BasicBlock / Bottleneck (resnet.py:129-136,195-197):
+ *   forward: x = input [N,H,W,Cin],  wpk = dst_OHWI16,             y [N,H,W,Cout]; dsum/dsq = BatchNorm statistics of y
+ *   dgrad  : x = dY    [N,H,W,Cout], wpk = dstD (flipped, [Cin]..), y = dX [N,H,W,Cin]  (call with Cin/Cout exchanged)
+ * Cin % 64 == 0, Cout % 64 == 0. */
+int dfd_conv_tc(const void* x, const void* wpk, void* y, int N, int H, int W, int Cin, int Cout, int k, int dt, double* dsum,
+                double* dsq, const void* fin, void* stream);
+/* Weight gradient of the same convolution, also an implicit GEMM (MN-major tcgen05 operands straight from the NHWC tensors,
+ * one pipeline stage = one patch of <= 64 output pixels, its input box shifted by the tap): dW_OHWI fp32 [Cout][kh][kw][Cin]
+ * += sum_pixels dY[pixel, co] * x[pixel + tap, ci]. `ws` / `ws_bytes` as for dfd_gemm_wgrad: when given, the split partials
+ * (dfd_conv_wgrad_splits x Cout x k*k*Cin floats) are written there for dfd_ordered_reduce and dW is left alone. */
+int dfd_conv_wgrad_tc(const void* dy, const void* x, float* dW_ohwi, int N, int H, int W, int Cin, int Cout, int k, int dt,
+                      void* ws, long long ws_bytes, void* stream);
+int dfd_conv_wgrad_splits(int N, int H, int W, int Cin, int Cout, int k);
 int dfd_unpack_grad(const float* g_ohwi, float* g_oihw_accum, int O, int I, int k, void* stream);
 int dfd_maxpool_fwd(const void* x, void* out, void* argmax_u8, int N, int H, int W, int C, int dt, void* stream);
 int dfd_maxpool_bwd(const void* gy, const void* argmax_u8, void* gx, int N, int H, int W, int C, int dt, void* stream);

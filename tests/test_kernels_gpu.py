@@ -158,6 +158,24 @@ def test_conv_dense(N, H, W, Cin, Cout, k, s):
     assert r["nan"] == 0 and r["nan_b"] == 0 and r["fwd_max"] < OUT16 and r["dgrad_rel"] < 6e-3 and r["wgrad_rel"] < 1e-4, r
 
 
+# the resnet50 / resnet18 stride-1 3x3 shapes (56 / 28 / 14 / 7: patch = 2 / 4 / 7 rows of an image, two stacked 7x7 images with
+# an odd batch), ragged extents that do not divide into patches, a second N tile (Cout 512 > 256), 5x5
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k", [(2, 56, 56, 64, 64, 3), (3, 28, 28, 128, 128, 3), (3, 14, 14, 256, 256, 3),
+                                                 (5, 7, 7, 512, 512, 3), (2, 13, 20, 64, 128, 3), (1, 9, 130, 64, 64, 3),
+                                                 (2, 11, 11, 128, 64, 5)])
+def test_conv_implicit(N, H, W, Cin, Cout, k):
+    r = _gc().check_conv_implicit(N, H, W, Cin, Cout, k)
+    assert r["nan"] == 0 and r["nan_b"] == 0 and r["fwd_max"] < OUT16 and r["dgrad_rel"] < 6e-3, r
+    assert r["sum_rel"] < 1e-6 and r["sq_rel"] < 1e-6 and r["vs_im2col_mismatch"] == 0, r
+    assert r["wgrad_rel"] < 1e-4 and r["wgrad_det_bitwise"] and r["wgrad_det_vs_atomic"] < 1e-5, r
+
+
+def test_conv_implicit_fp16():
+    r = _gc().check_conv_implicit(2, 14, 14, 64, 128, 3, dtype=torch.float16)
+    assert r["nan"] == 0 and r["fwd_max"] < OUT16 and r["dgrad_rel"] < 6e-3 and r["vs_im2col_mismatch"] == 0, r
+    assert r["wgrad_rel"] < 1e-4 and r["wgrad_det_bitwise"], r
+
+
 @pytest.mark.parametrize("N,H,W,C", [(2, 16, 16, 64), (3, 15, 13, 64)])
 def test_maxpool_relu_pool(N, H, W, C):
     r = _gc().check_maxpool_relu_pool(N, H, W, C)
