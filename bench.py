@@ -106,6 +106,12 @@ def op_bytes(name, a):
     if name in ("dfd_gemm_wgrad_mma", "dfd_gemm_wgrad"):
         M, Nw, Kw = a[3], a[4], a[5]
         return 2 * M * (Nw + Kw) + 4 * Nw * Kw
+    if name == "dfd_conv_tc":                              # input once, output once, weights once (no im2col matrix)
+        N, H, W, Cin, Cout, k = a[3:9]
+        return 2 * (N * H * W * (Cin + Cout) + k * k * Cin * Cout)
+    if name == "dfd_conv_wgrad_tc":
+        N, H, W, Cin, Cout, k = a[3:9]
+        return 2 * N * H * W * (Cin + Cout) + 4 * k * k * Cin * Cout
     if name == "dfd_dwconv_fwd":
         N, H, W, C, k, s = a[5:11]
         return 2 * N * C * (H * W + ((H + s - 1) // s) * ((W + s - 1) // s))
@@ -157,6 +163,9 @@ def op_flops(name, a):
         return 2 * a[4] * a[5] * a[6]
     if name in ("dfd_gemm_wgrad_mma", "dfd_gemm_wgrad"):
         return 2 * a[3] * a[4] * a[5]
+    if name in ("dfd_conv_tc", "dfd_conv_wgrad_tc"):       # implicit GEMM: M = N*H*W pixels, K = k*k*Cin, N = Cout
+        N, H, W, Cin, Cout, k = a[3:9]
+        return 2 * N * H * W * Cout * k * k * Cin
     return 0
 
 
