@@ -37,6 +37,25 @@ struct SeBwdArgs {          // squeeze-excite backward chain behind the gate-gra
     int Cse;
 };
 
+// 16-byte load of 4 consecutive floats when the address allows it (every arena array does; plain loads otherwise)
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) return __ldg(reinterpret_cast<const float4*>(p));
+    return make_float4(p[0], p[1], p[2], p[3]);
+}
+
+// the 8 per-channel operands of a thread (two 16-byte loads instead of eight 4-byte ones: on the small late layers the
+// operand prologue was more load instructions than the data itself); p == NULL -> dflt
+__device__ __forceinline__ void ldg_f8(const float* p, float* out, float dflt = 0.f) {
+    if (!p) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) out[i] = dflt;
+        return;
+    }
+    const float4 a = ldg_f4(p), b = ldg_f4(p + 4);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+    out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+}
+
 struct RowGeom {
     dim3 block;
     dim3 grid;
@@ -44,10 +63,22 @@ struct RowGeom {
 };
 
 // hw rows per image, n images; target enough CTAs to fill 148 SMs a few times over
-static RowGeom make_geom(int C, long long hw, int n, int target_blocks = 148 * 6) {
+// max_threads: CTA size (256 by default) - target_blocks is scaled so that the resident thread count stays the same.
+// MEASURED (B0 shapes, batch 256, L2 flushed): 512-thread CTAs help the two per-image reductions on the large layers
+// (dfd_se_bwd_reduce 110 -> 93 us at 112x112x32, 124 -> 107 us at 56x56x144; dfd_pool 69 -> 59, 77 -> 68 us: half as many
+// cross-row reductions and tickets per image), change nothing below 28x28 and HURT dfd_bn_act (85 -> 99 us: no reduction
+// to amortise, coarser tail). DFD_ROW_MAXT forces a value for every user (diagnostic).
+static int row_maxt(long long hw, bool reduces_per_image) {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DFD_ROW_MAXT"); v = e ? atoi(e) : 0; if (v != 256 && v != 512 && v != 1024) v = 0; }
+    if (v) return v;
+    return reduces_per_image && hw >= 784 ? 512 : 256;
+}
+static RowGeom make_geom(int C, long long hw, int n, int target_blocks = 148 * 6, int max_threads = 256) {
     RowGeom g;
     int V = C / 8;
-    int RY = V >= 256 ? 1 : (256 / V);
+    int RY = V >= max_threads ? 1 : (max_threads / V);
+    if (max_threads > 256 && target_blocks > 1) target_blocks = target_blocks * 256 / max_threads;
     if (RY > 64) RY = 64;
     if ((long long)RY > hw) RY = (int)hw;
     if (RY < 1) RY = 1;
@@ -160,12 +191,9 @@ __global__ void bn_act_kernel(const T* __restrict__ y, const float* __restrict__
     const int V = blockDim.x, C = V * 8;
     const int c0 = threadIdx.x * 8;
     float sc[8], sh[8], gt[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        sc[i] = scale ? scale[c0 + i] : 1.f;
-        sh[i] = shift ? shift[c0 + i] : 0.f;
-        gt[i] = GATE ? gate[(size_t)blockIdx.y * C + c0 + i] : 1.f;
-    }
+    ldg_f8(scale ? scale + c0 : nullptr, sc, 1.f);
+    ldg_f8(shift ? shift + c0 : nullptr, sh, 0.f);
+    ldg_f8(GATE ? gate + (size_t)blockIdx.y * C + c0 : nullptr, gt, 1.f);
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     long long r1 = r0 + rows_per_block;
     if (r1 > hw) r1 = hw;
@@ -220,12 +248,10 @@ __global__ void pool_kernel(const T* __restrict__ y, const float* __restrict__ s
     const int V = blockDim.x, C = V * 8;
     const int c0 = threadIdx.x * 8;
     float sc[8], sh[8], acc[8];
+    ldg_f8(scale ? scale + c0 : nullptr, sc, 1.f);
+    ldg_f8(shift ? shift + c0 : nullptr, sh, 0.f);
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        sc[i] = scale ? scale[c0 + i] : 1.f;
-        sh[i] = shift ? shift[c0 + i] : 0.f;
-        acc[i] = 0.f;
-    }
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
     const T* base = y + (size_t)blockIdx.y * hw * C + c0;
     // gridDim.x row chunks per image: one (the usual case: the batch alone fills the GPU) stores the mean directly; several
     // write their partial sums to fixed slots of the library scratch and the last of them adds these in chunk order -
@@ -302,7 +328,9 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restric
     const int c0 = threadIdx.x * 8;
     float mu[8], rs[8], a1[8], a2[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { mu[i] = mean[c0 + i]; rs[i] = rstd[c0 + i]; a1[i] = 0.f; a2[i] = 0.f; }
+    for (int i = 0; i < 8; i++) { a1[i] = 0.f; a2[i] = 0.f; }
+    ldg_f8(mean + c0, mu);
+    ldg_f8(rstd + c0, rs);
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     long long r1 = r0 + rows_per_block;
     if (r1 > hw) r1 = hw;
@@ -377,7 +405,10 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict
     const int c0 = threadIdx.x * 8;
     float A[8], B[8], Cc[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { A[i] = cA[c0 + i]; B[i] = cB[c0 + i]; Cc[i] = cC[c0 + i]; }
+    for (int i = 0; i < 8; i++) { A[i] = 0.f; }
+    ldg_f8(cA + c0, A);
+    ldg_f8(cB + c0, B);
+    ldg_f8(cC + c0, Cc);
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     long long r1 = r0 + rows_per_block;
     if (r1 > hw) r1 = hw;
@@ -427,7 +458,9 @@ __global__ void se_bwd_reduce_kernel(const T* __restrict__ da, const T* __restri
     const int c0 = threadIdx.x * 8;
     float sc[8], sh[8], acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { sc[i] = scale[c0 + i]; sh[i] = shift[c0 + i]; acc[i] = 0.f; }
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    ldg_f8(scale + c0, sc);
+    ldg_f8(shift + c0, sh);
     const size_t img = (size_t)blockIdx.y * hw * C + c0;
     // gridDim.x chunks per image (several when the batch alone cannot fill the SMs): partial sums meet in fp32 atomics on
     // the pre-zeroed output; a single chunk stores directly
@@ -485,29 +518,52 @@ __global__ void se_bwd_reduce_kernel(const T* __restrict__ da, const T* __restri
 //   gu = (da * gate[n,c] + dpool[n,c] * inv_hw) * act'(u)        (HAS_DA: da present; dpool may be null)
 // plus the BN backward reductions of gu: s1 += sum gu, s2 += sum gu * xhat.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int ACT, bool HAS_DA>
-__global__ void act_bwd_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
+// The six per-channel operands (BN scale / shift, -mean*rstd, rstd, SE gate, pooled gradient) live in SHARED memory, not in
+// registers: with them in registers (48 of 122) only 2 CTAs x 256 threads fit an SM and 4 x 16 bytes in flight per thread
+// (32 KB per SM) cannot cover the HBM latency (Little: ~44 KB). Layout [operand][half][V] float4, so that a warp's 16-byte
+// reads are consecutive (conflict-free); 12 LDS.128 per row of 8 channels next to ~100 ALU instructions.
+template <typename T, int ACT, bool HAS_DA, int MAXT, int OCC>
+__global__ void __launch_bounds__(MAXT, OCC) act_bwd_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
                                const float* __restrict__ shift, const float* __restrict__ mean,
                                const float* __restrict__ rstd, const float* __restrict__ gate,
                                const float* __restrict__ dpool, float inv_hw, T* __restrict__ gu, long long hw,
                                int rows_per_block, double* __restrict__ s1, double* __restrict__ s2,
                                const BnBwdFinDesc* __restrict__ fin) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     const int V = blockDim.x, C = V * 8;
     const int c0 = threadIdx.x * 8;
-    float sc[8], sh[8], mu[8], rs[8], gt[8], dp[8], a1[8], a2[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        sc[i] = scale[c0 + i]; sh[i] = shift[c0 + i]; mu[i] = mean[c0 + i]; rs[i] = rstd[c0 + i];
-        gt[i] = gate ? gate[(size_t)blockIdx.y * C + c0 + i] : 1.f;
-        dp[i] = dpool ? dpool[(size_t)blockIdx.y * C + c0 + i] * inv_hw : 0.f;
-        a1[i] = 0.f; a2[i] = 0.f;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    float4* ps = reinterpret_cast<float4*>(sm + (size_t)blockDim.y * C);      // behind the [RY][C] reduction scratch
+    for (int e = tid; e < 12 * V; e += nt) {
+        const int k = e / (2 * V), rem = e - k * 2 * V, h = rem / V, v = rem - h * V;
+        const int c = v * 8 + h * 4;
+        float4 val;
+        if (k == 0) val = ldg_f4(scale + c);
+        else if (k == 1) val = ldg_f4(shift + c);
+        else if (k == 2) {
+            const float4 m = ldg_f4(mean + c), r = ldg_f4(rstd + c);
+            val = make_float4(-m.x * r.x, -m.y * r.y, -m.z * r.z, -m.w * r.w);
+        } else if (k == 3) val = ldg_f4(rstd + c);
+        else if (k == 4) val = gate ? ldg_f4(gate + (size_t)blockIdx.y * C + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+        else {
+            val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dpool) {
+                const float4 d = ldg_f4(dpool + (size_t)blockIdx.y * C + c);
+                val = make_float4(d.x * inv_hw, d.y * inv_hw, d.z * inv_hw, d.w * inv_hw);
+            }
+        }
+        ps[e] = val;
     }
+    __syncthreads();
+    float a1[8], a2[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a1[i] = 0.f; a2[i] = 0.f; }
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     long long r1 = r0 + rows_per_block;
     if (r1 > hw) r1 = hw;
     const size_t img = (size_t)blockIdx.y * hw * C + c0;
-    constexpr int U = 2;                   // 4 independent 16-byte loads in flight per thread (see bn_act_kernel)
+    // independent 16-byte loads in flight per thread: OCC 2 (128 registers, 512 threads per SM) 6; OCC 3 (80 registers) 4
+    constexpr int U = OCC == 3 ? 2 : (HAS_DA ? 3 : 4);
     for (long long r = r0 + threadIdx.y; r < r1; r += (long long)U * blockDim.y) {
         uint4 draw_[U], yraw[U];
 #pragma unroll
@@ -527,15 +583,26 @@ __global__ void act_bwd_kernel(const T* __restrict__ da, const T* __restrict__ y
             if (HAS_DA) unpack8<T>(draw_[u], d);
             unpack8<T>(yraw[u], f);
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                float uu = fmaf(f[i], sc[i], sh[i]);
-                float gin = HAS_DA ? fmaf(d[i], gt[i], dp[i]) : dp[i];
-                float o = gin * act_bwd<ACT>(uu);
-                // the stored (rounded) value is what the consumers see: reduce the rounded value
-                o = round_t<T>(o);
-                d[i] = o;
-                a1[i] += o;
-                a2[i] = fmaf(o, (f[i] - mu[i]) * rs[i], a2[i]);
+            for (int h = 0; h < 2; h++) {
+                if (OCC == 3) asm volatile("" ::: "memory");     // keep one half's operands live at a time
+                const float4 sc4 = ps[(0 * 2 + h) * V + threadIdx.x], sh4 = ps[(1 * 2 + h) * V + threadIdx.x];
+                const float4 nm4 = ps[(2 * 2 + h) * V + threadIdx.x], rs4 = ps[(3 * 2 + h) * V + threadIdx.x];
+                const float4 gt4 = ps[(4 * 2 + h) * V + threadIdx.x], dp4 = ps[(5 * 2 + h) * V + threadIdx.x];
+                const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+                const float nm[4] = {nm4.x, nm4.y, nm4.z, nm4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+                const float gt[4] = {gt4.x, gt4.y, gt4.z, gt4.w}, dp[4] = {dp4.x, dp4.y, dp4.z, dp4.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int i = h * 4 + j;
+                    float uu = fmaf(f[i], sc[j], sh[j]);
+                    float gin = HAS_DA ? fmaf(d[i], gt[j], dp[j]) : dp[j];
+                    float o = gin * act_bwd<ACT>(uu);
+                    // the stored (rounded) value is what the consumers see: reduce the rounded value
+                    o = round_t<T>(o);
+                    d[i] = o;
+                    a1[i] += o;
+                    a2[i] = fmaf(o, fmaf(f[i], rs[j], nm[j]), a2[i]);      // xhat = (y - mean) * rstd
+                }
             }
             stg16(gu + img + (size_t)rr * C, pack8<T>(d));
         }
@@ -544,7 +611,7 @@ __global__ void act_bwd_kernel(const T* __restrict__ da, const T* __restrict__ y
     double* p2 = stat_slot(s2, C);
     reduce_rows_and_emit(sm, a1, [&](int c, float v) { atomicAdd(p1 + c, (double)v); });
     reduce_rows_and_emit(sm, a2, [&](int c, float v) { atomicAdd(p2 + c, (double)v); });
-    bn_bwd_finalize_tail(fin, threadIdx.y * blockDim.x + threadIdx.x, blockDim.x * blockDim.y);
+    bn_bwd_finalize_tail(fin, tid, nt);
 }
 
 // elementwise a += b (residual gradient accumulation) over a flat 16-bit tensor
@@ -600,7 +667,7 @@ int dfd_bn_act(const void* y, const float* scale, const float* shift, const floa
                int n, long long hw, int C, int act, int res_mode, int dt, void* stream) {
     if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_bn_act: C%8, sizes");
     if ((res_mode != 0) != (res != nullptr)) return dfd_set_error(DFD_ERR_ARG, "dfd_bn_act: res/res_mode");
-    RowGeom g = make_geom(C, hw, n);
+    RowGeom g = make_geom(C, hw, n, 148 * 6, row_maxt(hw, false));
     cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(ACT, GATE, RES)                                                                                    \
     bn_act_kernel<T, ACT, GATE, RES><<<g.grid, g.block, 0, st>>>((const T*)y, scale, shift, gate, (const T*)res, \
@@ -630,7 +697,7 @@ static int launch_pool(const void* y, const float* scale, const float* shift, fl
     // one CTA per image while the batch fills the GPU; otherwise up to max_chunks row chunks per image (fixed-slot partials
     // in the library scratch, summed in chunk order by the last chunk of the image to arrive)
     const bool chunked = max_chunks > 1 && n < 296 && n <= ROWRED_TICKETS;
-    RowGeom g = make_geom(C, hw, n, chunked ? 592 : 1);
+    RowGeom g = make_geom(C, hw, n, chunked ? 592 : 1, row_maxt(hw, true));
     if (!chunked) { g.grid = dim3(1, n, 1); g.rows_per_block = (int)hw; }
     if ((int)g.grid.x > max_chunks && g.grid.x > 1) {
         long long rpb = (hw + max_chunks - 1) / max_chunks;
@@ -672,7 +739,7 @@ int dfd_pool_se(const void* y, const float* scale, const float* shift, float* po
 int dfd_bn_bwd_reduce(const void* g_, const void* y, const void* out, const float* mean, const float* rstd, int n,
                       long long hw, int C, int dt, double* s1, double* s2, const void* fin, void* stream) {
     if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_bn_bwd_reduce: C%8, sizes");
-    RowGeom g = make_geom(C, hw, n);
+    RowGeom g = make_geom(C, hw, n, 148 * 6, row_maxt(hw, false));
     cudaStream_t st = (cudaStream_t)stream;
     DISPATCH_T(dt, {
         if (out) bn_bwd_reduce_kernel<T, true><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)g_, (const T*)y, (const T*)out, mean, rstd, hw, g.rows_per_block, s1, s2, (const BnBwdFinDesc*)fin);
@@ -709,8 +776,8 @@ static int launch_se_bwd_reduce(const void* da, const void* y, const float* scal
                                 long long hw, int C, int dt, const SeBwdArgs& se, void* stream) {
     if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_bwd_reduce: C%8, sizes");
     // one CTA per image while the batch fills the GPU (>= 2 CTAs per SM); otherwise several row chunks per image
-    RowGeom g = make_geom(C, hw, n, n >= 296 ? 1 : 592);
-    if ((long long)g.grid.x * n * C > ROWRED_WS_FLOATS || n > ROWRED_TICKETS) g = make_geom(C, hw, n, 1);   // one chunk per image
+    RowGeom g = make_geom(C, hw, n, n >= 296 ? 1 : 592, row_maxt(hw, true));
+    if ((long long)g.grid.x * n * C > ROWRED_WS_FLOATS || n > ROWRED_TICKETS) g = make_geom(C, hw, n, 1, row_maxt(hw, true));   // one chunk per image
     cudaStream_t st = (cudaStream_t)stream;
     const int nw = (int)(g.block.x * g.block.y) / 32;
     const size_t smem = reduce_smem(g) + (size_t)(2 * C + (3 + nw) * se.Cse) * sizeof(float);
@@ -757,10 +824,28 @@ int dfd_act_bwd(const void* da, const void* y, const float* scale, const float* 
     RowGeom g = make_geom(C, hw, n);
     cudaStream_t st = (cudaStream_t)stream;
     float inv_hw = 1.f / (float)hw;
-#define LAUNCH(ACT, HAS)                                                                                            \
-    act_bwd_kernel<T, ACT, HAS><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)da, (const T*)y, scale, shift, mean, \
-                                                                            rstd, gate, dpool, inv_hw, (T*)gu, hw,     \
-                                                                            g.rows_per_block, s1, s2, (const BnBwdFinDesc*)fin)
+    const size_t smem_ab = reduce_smem(g) + (size_t)12 * g.block.x * sizeof(float4);     // + the per-channel operands
+    if (smem_ab > 200 * 1024) return dfd_set_error(DFD_ERR_UNSUPPORTED, "dfd_act_bwd: channel count exceeds shared memory");
+    static bool smem_attr[2][3][2][3] = {};
+    static int occ3 = -1;
+    if (occ3 < 0) { const char* e = getenv("DFD_ACTBWD_OCC3"); occ3 = e ? atoi(e) : 0; }
+    // variant: 0 = 256 threads x 2 CTAs per SM with 6 loads in flight per thread (default), 1 = 256 x 3 with 4 loads in flight
+    // (DFD_ACTBWD_OCC3, diagnostic: MEASURED slower on the large layers, 142 -> 148 us at 112x112x32, 114 -> 131 us at 56x56x96,
+    // and only 10 % faster at 7x7), 2 = more than 2048 channels (one row of C / 8 threads)
+    const int var = g.block.x * g.block.y > 256 ? 2 : (occ3 ? 1 : 0);
+#define ABARGS (const T*)da, (const T*)y, scale, shift, mean, rstd, gate, dpool, inv_hw, (T*)gu, hw, g.rows_per_block, s1, s2, (const BnBwdFinDesc*)fin
+#define LAUNCH(ACT, HAS) do {                                                                                       \
+    if (smem_ab > 48 * 1024 && !smem_attr[(dt) == DFD_DT_FP16][ACT][HAS][var]) {                                     \
+        cudaError_t e_ = var == 2 ? cudaFuncSetAttribute(act_bwd_kernel<T, ACT, HAS, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) \
+                       : var == 1 ? cudaFuncSetAttribute(act_bwd_kernel<T, ACT, HAS, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) \
+                                  : cudaFuncSetAttribute(act_bwd_kernel<T, ACT, HAS, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+        if (e_ != cudaSuccess) return dfd_set_cuda_error(e_, __FILE__, __LINE__);                                    \
+        smem_attr[(dt) == DFD_DT_FP16][ACT][HAS][var] = true;                                                        \
+    }                                                                                                                \
+    if (var == 2) act_bwd_kernel<T, ACT, HAS, 512, 1><<<g.grid, g.block, smem_ab, st>>>(ABARGS);                     \
+    else if (var == 1) act_bwd_kernel<T, ACT, HAS, 256, 3><<<g.grid, g.block, smem_ab, st>>>(ABARGS);                \
+    else act_bwd_kernel<T, ACT, HAS, 256, 2><<<g.grid, g.block, smem_ab, st>>>(ABARGS);                              \
+    } while (0)
     DISPATCH_T(dt, {
         if (act == DFD_ACT_SWISH) { if (da) LAUNCH(1, true); else LAUNCH(1, false); }
         else if (act == DFD_ACT_RELU) { if (da) LAUNCH(2, true); else LAUNCH(2, false); }
