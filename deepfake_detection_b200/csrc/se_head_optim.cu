@@ -540,9 +540,13 @@ static int flat_blocks(size_t n) {
 // images per CTA of the SE FC kernels. Several images per CTA fetch every weight element once for all of them, but
 // MEASURED (B0, batch 256): 4 images per CTA are 12 % slower than 1 (0.80 vs 0.69 ms over the 16 backward launches) - the
 // kernels are bound by the dependent FC chain of a CTA, which gets longer, not by the L2 traffic of the weights. So: one
-// image per CTA until the batch is so large that the grid exceeds a few waves.
-static int se_img(int N, size_t floats_per_image, size_t fixed_floats) {
+// image per CTA until the batch is so large that the grid exceeds a few waves - EXCEPT for the widest layers, where the
+// weight traffic does bound the kernel (1152 x 48: 2 x 221 KB per CTA; per layer, weights L2-resident: forward 43 / 31 / 37 us
+// and backward + wgrad 98 / 77 / 82 us for 1 / 2 / 4 images per CTA; 672 x 28 and below: 1 is best).
+static int se_img(int N, int C, int Cse, size_t floats_per_image, size_t fixed_floats) {
     int img = N >= 2048 ? 4 : (N >= 1024 ? 2 : 1);
+    if (img < 2 && N >= 128 && (long long)C * Cse >= 32768) img = 2;
+    { static int f = -1; if (f < 0) { const char* e = getenv("DFD_SE_IMG"); f = e ? atoi(e) : 0; } if (f == 1 || f == 2 || f == 4) img = f; }
     while (img > 1 && (img * floats_per_image + fixed_floats) * sizeof(float) > 200 * 1024) img >>= 1;
     return img;
 }
@@ -564,7 +568,7 @@ extern "C" {
 int dfd_se_fc_fwd(const float* pooled, const float* Wr, const float* br, const float* We, const float* be,
                   float* gate, int N, int C, int Cse, void* stream) {
     if (N <= 0 || C <= 0 || Cse <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_fc_fwd: sizes");
-    const int img = se_img(N, (size_t)C + Cse, 0);
+    const int img = se_img(N, C, Cse, (size_t)C + Cse, 0);
     const size_t smem = (size_t)img * (C + Cse) * sizeof(float);
     const int blocks = (N + img - 1) / img, nthr = se_threads(C);
     cudaStream_t st = (cudaStream_t)stream;
@@ -582,7 +586,7 @@ int dfd_se_fc_bwd(const float* draw, const float* pooled, const float* Wr, const
                   float* dWe, float* dbe, int N, int C, int Cse, void* stream) {
     if (N <= 0 || C <= 0 || Cse <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_se_fc_bwd: sizes");
     const int nthr = se_threads(C), nw = nthr / 32;
-    const int img = se_img(N, (size_t)2 * C + (size_t)(3 + nw) * Cse, 0);
+    const int img = se_img(N, C, Cse, (size_t)2 * C + (size_t)(3 + nw) * Cse, 0);
     const size_t smem = (size_t)img * (2 * C + (3 + nw) * Cse) * sizeof(float);
     const int blocks = (N + img - 1) / img;
     cudaStream_t st = (cudaStream_t)stream;
