@@ -14,6 +14,8 @@ gradients live in ONE flat fp32 arena laid out in forward execution order, so:
 `NativeDDP` is the object the runner sees: `.module` unwraps, calling it runs the model, and the wrapped model's
 backward (autograd bridge and fused step alike) goes through `GradReducer.backward_and_reduce`.
 """
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -86,7 +88,7 @@ class GradReducer:
         self.arena = engine.arena
         self.group = group
         self.world = dist.get_world_size(group)
-        self.bucket_mb = float(bucket_mb)
+        self.bucket_mb = float(os.environ.get("DFD_DDP_BUCKET_MB", bucket_mb))      # env: diagnostic override
         self.side = None if self.arena._plan_only else torch.cuda.Stream(device=self.arena.device)
         backend = dist.get_backend(group)
         self._avg = backend == "nccl"              # gloo has no AVG: SUM, then scale

@@ -462,12 +462,17 @@ class Engine:
         # B0 step): every CTA pays a __threadfence + a same-address ticket atomic before it may retire (the depthwise kernels
         # run ~14k short CTAs), and the one finalising CTA walks C channels with a fraction of the threads of the standalone
         # launch. Off unless DFD_FUSED_FINALIZE=1.
-        fused_fin = bool(os.environ.get("DFD_FUSED_FINALIZE")) and not self.sync_bn
+        # DFD_FUSED_FINALIZE=gemm: only the BatchNorms whose statistics come from the persistent tcgen05 GEMM (148 CTAs: the
+        # ticket is free there) are finalised by their producer - MEASURED slower too (15.38 vs 15.30 ms: one CTA finalising C
+        # channels is a longer dependent chain than the standalone launch); =1: every producer, forward and backward.
+        ff_mode = os.environ.get("DFD_FUSED_FINALIZE", "")
+        fused_fin = ff_mode not in ("", "0", "gemm") and not self.sync_bn
+        fused_gemm = (fused_fin or ff_mode == "gemm") and not self.sync_bn
 
         def gemm(A, B, C, M, Nn, K, bn=None):
             fs, fq = (bn.fsum, bn.fsq) if bn is not None else (None, None)
             if self.gemm_impl == "tc":
-                fin = bn.fin if (bn is not None and fused_fin) else None
+                fin = bn.fin if (bn is not None and fused_gemm) else None
                 if bn is not None:
                     bn.fused = fin is not None
                 pack = self._row_pack(M, K)

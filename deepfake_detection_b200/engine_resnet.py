@@ -83,7 +83,7 @@ def build_resnet(e):
     e._alloc_bn(bn_specs)
     bns = e.bns
 
-    fused_fin = bool(os.environ.get("DFD_FUSED_FINALIZE"))       # measured slower than the standalone launches, see engine.py
+    fused_fin = os.environ.get("DFD_FUSED_FINALIZE", "") not in ("", "0", "gemm")   # measured slower than the standalone launches, see engine.py
 
     def gemm(A, B, C, M, Nn, K, bn=None):
         fs, fq = (bn.fsum, bn.fsq) if bn is not None else (None, None)
