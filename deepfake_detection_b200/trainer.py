@@ -30,7 +30,8 @@ class Trainer:
         self.smoothing = float(smoothing)
         # fp16: dynamic loss scaling with skip-on-overflow (apex AMP O1 semantics, train.py:353,632-634), entirely on the
         # device: scale / 1/scale / overflow flag / clean-step counter live in engine.loss_scale_state and engine.flags
-        self.dynamic_scale = dtype in ("fp16", torch.float16) if loss_scale is None else loss_scale == "dynamic"
+        # (the engine resolved the dtype string: "float16" / "half" are fp16 too and get the same scaling)
+        self.dynamic_scale = (self.engine.tdtype == torch.float16) if loss_scale is None else loss_scale == "dynamic"
         self.scale_window = int(scale_window)
         if self.dynamic_scale:
             e0 = self.engine
