@@ -407,6 +407,62 @@ def cpu_baseline(arch, sample_steps=4, batch=None, world=1):
                 ms_per_step=round(dt / done * 1e3, 1))
 
 
+def _cpu_ddp_worker(rank, world, arch, b, threads, steps, port, out):
+    """one rank of the CPU data-parallel leg: the oracle step with a gloo mean-all-reduce of the gradients (the reference's
+    torch DDP on gloo, train.py:402-406), `threads` intra-op threads per rank"""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from deepfake_detection_b200.arch import get_spec
+    from oracle import train as OT
+    from oracle.weights import synth_batch, synth_state
+    torch.set_num_threads(threads)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    spec = get_spec(arch)
+    res = WORK[arch]["res"]
+    sd = synth_state(spec, seed=42)
+    opt = OT.OptState(kind="sgd", lr=0.01, momentum=0.9, weight_decay=1e-4)
+    x, y = synth_batch(b, 3, res, res, seed=1234 + rank)
+
+    def mean_hook(grads):
+        flat = torch.cat([g.reshape(-1) for g in grads.values()])
+        dist.all_reduce(flat)
+        flat /= world
+        o = 0
+        for g in grads.values():
+            g.copy_(flat[o:o + g.numel()].view_as(g))
+            o += g.numel()
+
+    OT.train_step(spec, sd, x, y, opt, grad_hook=mean_hook)          # warm-up
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        OT.train_step(spec, sd, x, y, opt, grad_hook=mean_hook)
+    dist.barrier()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        out.put(dt)
+    dist.destroy_process_group()
+
+
+def cpu_ddp_baseline(arch, world, threads_total, steps=3):
+    """the reference's CPU DDP path - `world` gloo ranks on the host cores, the threads split evenly"""
+    import torch.multiprocessing as mp
+    b = {"efficientnet_b0": 16, "efficientnet_b4": 4, "resnet50": 8, "resnet18": 8}[arch]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    threads = max(1, threads_total // world)
+    procs = [ctx.Process(target=_cpu_ddp_worker, args=(r, world, arch, b, threads, steps, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    dt = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=60)
+    return dict(value=round(world * b * steps / dt, 2), unit="images/sec", world_size=world, threads_per_rank=threads, backend="gloo",
+                per_rank_batch=b, steps=steps, ms_per_step=round(dt / steps * 1e3, 1))
+
+
 def run_library(args):
     """Stock PyTorch eager on the same B200: the reference's module graph as torch.nn modules (baseline/library_model.py),
     autocast to the benchmark dtype, channels_last, SGD-nesterov, torch DDP over NCCL when launched under torchrun.
@@ -522,6 +578,9 @@ def run_reference(args):
     res = WORK[arch]["res"]
     steps = min(args.steps, 6)
     cb = cpu_baseline(arch, sample_steps=steps)
+    if args.cpu_world > 1:
+        # optional: the same arithmetic as `cpu_world` gloo ranks with the thread pool split (the reference's CPU DDP scaling)
+        cb["ddp"] = cpu_ddp_baseline(arch, args.cpu_world, cb["cores"], steps=min(steps, 3))
     line = dict(impl="reference", metric="images/sec (device-timed, max over ranks) %s 3x%dx%d train step" % (arch, res, res),
                 value=cb["value"], unit="images/sec", n_gpus=int(os.environ.get("WORLD_SIZE", "1")), steps=steps,
                 warmup=1, ms_per_step=cb["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
@@ -545,6 +604,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--cpu-world", type=int, default=1, help="--impl reference: also time N gloo ranks on the host cores")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
