@@ -565,7 +565,10 @@ __device__ __forceinline__ void strip_bwd_s1(const uint32_t* __restrict__ tile, 
 // MODE 1: xin is the pre-BN expand output (a = swish(scale*xin + shift), gx = ga * swish', BN-backward sums);
 // MODE 0: xin is the block input itself (DS block): a = xin, gx = ga (+ add).
 template <typename T, int K, int S, bool AFFINE, int MODE, int NT, int P, int CPW = 32>
-__global__ void __launch_bounds__(NT, K == 3 ? (P == 4 ? 4 : 3) : 2)
+#ifndef DW_BWD_OCC3
+#define DW_BWD_OCC3 4
+#endif
+__global__ void __launch_bounds__(NT, K == 3 ? (P == 4 ? DW_BWD_OCC3 : 3) : 2)
 dwconv_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ yout, const float* __restrict__ cA,
                   const float* __restrict__ cB, const float* __restrict__ cC, const float* __restrict__ wgt,
                   const T* __restrict__ xin, const float* __restrict__ scale, const float* __restrict__ shift,
