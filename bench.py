@@ -135,6 +135,9 @@ def op_bytes(name, a):
         idx = 4 if name == "dfd_pool" else 1
         n, hw, C = a[idx], a[idx + 1], a[idx + 2]
         return 2 * n * hw * C
+    if name == "dfd_relu_bn_bwd_reduce":                  # g (+ g2), y, out read; masked gradient written
+        n, hw, C = a[7], a[8], a[9]
+        return 2 * n * hw * C * (5 if a[1] else 4)
     if name in ("dfd_bn_bwd_reduce", "dfd_se_bwd_reduce"):
         n, hw, C = a[5], a[6], a[7]
         return 2 * n * hw * C * 2

@@ -40,6 +40,7 @@ SIGNATURES = {
     "dfd_bn_act": "pppppp" "ili" "iii" "p",
     "dfd_pool": "pppp" "ili" "ii" "pi" "p",
     "dfd_bn_bwd_reduce": "ppppp" "ili" "i" "ppp" "p",
+    "dfd_relu_bn_bwd_reduce": "ppppppp" "ili" "i" "pp" "p",
     "dfd_bn_bwd_finalize": "ppd" "pppppppp" "i" "p",
     "dfd_bn_bwd_apply": "ppppppp" "ili" "i" "p",
     "dfd_se_bwd_reduce": "ppppp" "ili" "i" "p",

@@ -322,7 +322,8 @@ template <typename T, bool RELU_MASK>
 __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ y, const T* __restrict__ out,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      long long hw, int rows_per_block, double* __restrict__ s1,
-                                     double* __restrict__ s2, const BnBwdFinDesc* __restrict__ fin) {
+                                     double* __restrict__ s2, const BnBwdFinDesc* __restrict__ fin,
+                                     T* __restrict__ gm_out = nullptr, const T* __restrict__ g2 = nullptr) {
     extern __shared__ float sm[];
     const int V = blockDim.x, C = V * 8;
     const int c0 = threadIdx.x * 8;
@@ -337,7 +338,7 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restric
     const size_t img = (size_t)blockIdx.y * hw * C + c0;
     constexpr int U = 2;
     for (long long r = r0 + threadIdx.y; r < r1; r += (long long)U * blockDim.y) {
-        uint4 graw[U], yraw[U], oraw[U];
+        uint4 graw[U], yraw[U], oraw[U], g2raw[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const long long rr = r + (long long)u * blockDim.y;
@@ -346,6 +347,7 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restric
                 graw[u] = ldg16(g + off);
                 yraw[u] = ldg16(y + off);
                 if (RELU_MASK) oraw[u] = ldg16(out + off);
+                if (RELU_MASK && g2) g2raw[u] = ldg16(g2 + off);
             }
         }
 #pragma unroll
@@ -354,11 +356,21 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restric
             float gg[8], yy[8];
             unpack8<T>(graw[u], gg);
             unpack8<T>(yraw[u], yy);
+            if (RELU_MASK && g2) {
+                // two-source gradient (main path + identity path of the block above): what dfd_add_inplace would have stored
+                float hh[8];
+                unpack8<T>(g2raw[u], hh);
+#pragma unroll
+                for (int i = 0; i < 8; i++) gg[i] = round_t<T>(gg[i] + hh[i]);
+            }
             if (RELU_MASK) {
                 float oo[8];
                 unpack8<T>(oraw[u], oo);
 #pragma unroll
                 for (int i = 0; i < 8; i++) gg[i] = oo[i] > 0.f ? gg[i] : 0.f;
+                // the masked gradient is also the gradient of the block's identity path: stored here, it saves the separate
+                // ReLU-backward pass (one read of g and out, one write) over the same tensor
+                if (gm_out) stg16(gm_out + img + (size_t)(r + (long long)u * blockDim.y) * C, pack8<T>(gg));
             }
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -755,6 +767,22 @@ int dfd_bn_bwd_finalize(const double* s1, const double* s2, double count, const 
     if (C <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_bn_bwd_finalize: C");
     bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(s1, s2, 1.0 / count, gamma, mean, rstd, dgamma,
                                                                              dbeta, cA, cB, cC, C);
+    DFD_LAUNCH_CHECK();
+    return DFD_OK;
+}
+
+// ReLU backward + BN backward reduction in one pass (ResNet block tail, resnet.py:172-173,243-244): gm = (g + g2) * (out > 0)
+// is stored AND reduced (s1 += sum gm, s2 += sum gm * xhat); replaces [dfd_add_inplace,] dfd_relu_bwd, dfd_bn_bwd_reduce.
+// g2 (optional): second gradient source - the residual add of the block above (main path + identity path), rounded to the
+// 16-bit type before the mask exactly as the materialised sum was
+int dfd_relu_bn_bwd_reduce(const void* g_, const void* g2, const void* y, const void* out, void* gm, const float* mean,
+                           const float* rstd, int n, long long hw, int C, int dt, double* s1, double* s2, void* stream) {
+    if (C % 8 || C <= 0 || hw <= 0 || n <= 0) return dfd_set_error(DFD_ERR_ARG, "dfd_relu_bn_bwd_reduce: C%8, sizes");
+    if (!out || !gm) return dfd_set_error(DFD_ERR_ARG, "dfd_relu_bn_bwd_reduce: operands");
+    RowGeom g = make_geom(C, hw, n, 148 * 6, row_maxt(hw, false));
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_T(dt, (bn_bwd_reduce_kernel<T, true><<<g.grid, g.block, reduce_smem(g), st>>>((const T*)g_, (const T*)y, (const T*)out, mean, rstd,
+                                                                                           hw, g.rows_per_block, s1, s2, nullptr, (T*)gm, (const T*)g2)));
     DFD_LAUNCH_CHECK();
     return DFD_OK;
 }

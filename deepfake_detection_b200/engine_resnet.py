@@ -131,10 +131,10 @@ def build_resnet(e):
                   [N * ho * wo * b.cout for b, hh, ww, ho, wo in shapes])
     max_cols = max([N * ho * wo * 9 * (b.cin if b.kind == "basic" else b.planes) for b, hh, ww, ho, wo in shapes] +
                    [N * ho * wo * 9 * b.planes for b, hh, ww, ho, wo in shapes])
-    e.gbuf = [e._alloc16(max_act) for _ in range(5)]
+    e.gbuf = [e._alloc16(max_act) for _ in range(6)]
     e.cols = e._alloc16(max_cols)
     COLS = _ptr(e.cols)
-    gA, gB, gC, gD, gE = [_ptr(t) for t in e.gbuf]
+    gA, gB, gC, gD, gE, gF = [_ptr(t) for t in e.gbuf]
 
     # ---- forward -----------------------------------------------------------------------------------------
     e.x_in = torch.zeros(N, spec.in_chans, e.H, e.W, dtype=e.tdtype, device=dev)
@@ -246,16 +246,26 @@ def build_resnet(e):
     bwd.append(("dfd_head_bwd", (_ptr(e.dlogits), _ptr(e.pooled), P32("fc.weight"), G32("fc.weight"), G32("fc.bias"),
                                  _ptr(e.dpooled), N, F, K)))
     bwd.append(("dfd_pool_bwd", (_ptr(e.dpooled), gA, N, Hf * Wf, F, dt)))
-    dout = gA
-    free = [gB, gC, gD, gE]
+    # The gradient entering a block is kept as up to TWO tensors (main-path dx + identity-path gm of the block above): the
+    # fused ReLU / BN-backward reduction adds them on the fly (dfd_relu_bn_bwd_reduce), which removes the materialised
+    # residual add of every block without a downsample branch. DFD_NO_RELU_FUSE=1 restores the three separate passes.
+    relu_fuse = not (fused_fin or os.environ.get("DFD_NO_RELU_FUSE"))
+    bufs = [gA, gB, gC, gD, gE, gF]
+    dout, dout2 = gA, None
     for rec in reversed(recs):
         b, h, w, ho, wo, xin = rec["b"], rec["h"], rec["w"], rec["ho"], rec["wo"], rec["x"]
         p = b.name
         M1, M2 = N * h * w, N * ho * wo
-        gm, t1, t2, t3 = free
+        gm, t1, t2, t3 = [g for g in bufs if g not in (dout, dout2)][:4]
         bl = rec["bnlast"]
-        bwd.append(("dfd_relu_bwd", (dout, _ptr(rec["out"]), gm, M2 * b.cout, dt)))
-        bwd.append(("dfd_bn_bwd_reduce", (gm, _ptr(rec["ylast"]), None, bl.mean, bl.rstd, N, ho * wo, b.cout, dt, bl.bs1, bl.bs2, BF(bl))))
+        if not relu_fuse:
+            bwd.append(("dfd_relu_bwd", (dout, _ptr(rec["out"]), gm, M2 * b.cout, dt)))
+            bwd.append(("dfd_bn_bwd_reduce", (gm, _ptr(rec["ylast"]), None, bl.mean, bl.rstd, N, ho * wo, b.cout, dt, bl.bs1, bl.bs2, BF(bl))))
+        else:
+            # gm = (dout + dout2) * (out > 0) is produced by the reduction itself (one pass over the block output instead of
+            # the residual add, the ReLU backward and the reduction)
+            bwd.append(("dfd_relu_bn_bwd_reduce", (dout, dout2, _ptr(rec["ylast"]), _ptr(rec["out"]), gm, bl.mean, bl.rstd, N, ho * wo,
+                                                   b.cout, dt, bl.bs1, bl.bs2)))
         bwd.append(bwd_finalize(bl, M2))
         bwd.append(("dfd_bn_bwd_apply", (gm, _ptr(rec["ylast"]), None, bl.cA, bl.cB, bl.cC, t1, N, ho * wo, b.cout, dt)))
         if b.kind == "basic":
@@ -296,20 +306,23 @@ def build_resnet(e):
             bwd.append(e._wgrad(t1, _ptr(rec["xs"]), G32(p + ".downsample.0.weight"), M2, b.cout, b.cin))
             if b.stride == 1:
                 bwd.append(("dfd_add_inplace", (t3, t2, M1 * b.cin, dt)))
-                new_dout = t3
+                new_dout = (t3, None)
             else:
-                # scatter the strided gradient back onto the input grid and add the main-path gradient
+                # scatter the strided gradient back onto the input grid and add the main-path gradient (the old dout buffer
+                # has been consumed by the reduction above: reused as the destination)
                 bwd.append(("dfd_col2im", (t2, t3, dout, N, h, w, b.cin, 1, b.stride, 0, dt)))
-                new_dout = dout
+                new_dout = (dout, None)
+        elif relu_fuse:
+            new_dout = (t3, gm)             # the block below adds them while it masks and reduces
         else:
             bwd.append(("dfd_add_inplace", (t3, gm, M1 * b.cin, dt)))
-            new_dout = t3
+            new_dout = (t3, None)
         e._flush_reduce(bwd)
-        allb = [dout] + free
-        free = [g for g in allb if g != new_dout]
-        dout = new_dout
+        dout, dout2 = new_dout
     # stem: maxpool -> relu/bn1 -> conv1 wgrad
-    t1, t2 = free[0], free[1]
+    if dout2 is not None:
+        bwd.append(("dfd_add_inplace", (dout, dout2, N * H2 * W2 * 64, dt)))
+    t1, t2 = [g for g in bufs if g != dout][:2]
     bwd.append(("dfd_maxpool_bwd", (dout, _ptr(e.pool_idx), t1, N, H1, W1, 64, dt)))
     bwd.append(("dfd_act_bwd", (t1, _ptr(y0), bn0.scale, bn0.shift, bn0.mean, bn0.rstd, None, None, t2, N, H1 * W1, 64,
                                 ACT_RELU, dt, bn0.bs1, bn0.bs2, BF(bn0))))

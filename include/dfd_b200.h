@@ -167,6 +167,10 @@ int dfd_pool(const void* y, const float* scale, const float* shift, float* poole
              int act, int dt, float* partial, int max_chunks, void* stream);
 int dfd_bn_bwd_reduce(const void* g, const void* y, const void* out, const float* mean, const float* rstd, int n,
                       long long hw, int C, int dt, double* s1, double* s2, const void* fin, void* stream);
+/* ReLU backward (and the residual add of the block above: g2 optional) fused into the reduction (ResNet block tail):
+ * gm = round16(g + g2) * (out > 0) is stored and reduced in one pass */
+int dfd_relu_bn_bwd_reduce(const void* g, const void* g2, const void* y, const void* out, void* gm, const float* mean,
+                           const float* rstd, int n, long long hw, int C, int dt, double* s1, double* s2, void* stream);
 int dfd_bn_bwd_finalize(const double* s1, const double* s2, double count, const float* gamma, const float* mean,
                         const float* rstd, float* dgamma, float* dbeta, float* cA, float* cB, float* cC, int C,
                         void* stream);

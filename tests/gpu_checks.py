@@ -711,6 +711,32 @@ def check_conv_implicit(N, H, W, Cin, Cout, k=3, dtype=torch.bfloat16, seed=0):
     return res
 
 
+def check_relu_bn_bwd_reduce(N, HW, C, dtype=torch.bfloat16, seed=0, two=False):
+    """dfd_relu_bn_bwd_reduce == dfd_relu_bwd followed by dfd_bn_bwd_reduce: the masked gradient bit for bit, the sums to fp64 rounding"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    gy = torch.randn(N, HW, C, device="cuda", generator=g).to(dtype)
+    y = torch.randn(N, HW, C, device="cuda", generator=g).to(dtype)
+    out = torch.relu(torch.randn(N, HW, C, device="cuda", generator=g)).to(dtype)
+    mean, rstd = torch.randn(C, device="cuda", generator=g) * 0.1, torch.rand(C, device="cuda", generator=g) + 0.5
+    d = DT[dtype]
+    gm_a, gm_b = torch.full_like(gy, float("nan")), torch.full_like(gy, float("nan"))
+    a1, a2, b1, b2 = stat_buf(C), stat_buf(C), stat_buf(C), stat_buf(C)
+    g2 = torch.randn(N, HW, C, device="cuda", generator=g).to(dtype) if two else None
+    gsum = gy
+    if two:                                     # the materialised residual add the fused kernel replaces
+        gsum = gy.clone()
+        _lib.call("dfd_add_inplace", P(gsum), P(g2), gsum.numel(), d, st())
+    _lib.call("dfd_relu_bwd", P(gsum), P(out), P(gm_a), gy.numel(), d, st())
+    _lib.call("dfd_bn_bwd_reduce", P(gm_a), P(y), None, P(mean), P(rstd), N, HW, C, d, P(a1), P(a2), None, st())
+    _lib.call("dfd_relu_bn_bwd_reduce", P(gy), P(g2) if two else None, P(y), P(out), P(gm_b), P(mean), P(rstd), N, HW, C, d, P(b1), P(b2), st())
+    torch.cuda.synchronize()
+    gmf = gsum.float() * (out.float() > 0)
+    xhat = (y.float() - mean) * rstd
+    return dict(gm_mismatch=int((gm_a.view(torch.int16) != gm_b.view(torch.int16)).sum()), s1_rel=relerr(b1.sum(0), a1.sum(0)),
+                s2_rel=relerr(b2.sum(0), a2.sum(0)), s1_ref=relerr(b1.sum(0), gmf.double().sum((0, 1))),
+                s2_ref=relerr(b2.sum(0), (gmf * xhat).double().sum((0, 1))))
+
+
 def check_maxpool_relu_pool(N, H, W, C, dtype=torch.bfloat16, seed=0):
     g = torch.Generator(device="cuda").manual_seed(seed)
     x = torch.relu(torch.randn(N, H, W, C, device="cuda", generator=g)).to(dtype)        # many exact ties at 0

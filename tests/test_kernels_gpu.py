@@ -176,6 +176,12 @@ def test_conv_implicit_fp16():
     assert r["wgrad_rel"] < 1e-4 and r["wgrad_det_bitwise"], r
 
 
+@pytest.mark.parametrize("N,HW,C,two", [(3, 49, 2048, False), (2, 3136, 256, True), (5, 196, 64, True), (2, 784, 512, False)])
+def test_relu_bn_bwd_reduce(N, HW, C, two):
+    r = _gc().check_relu_bn_bwd_reduce(N, HW, C, two=two)
+    assert r["gm_mismatch"] == 0 and r["s1_rel"] < 1e-6 and r["s2_rel"] < 1e-6 and r["s1_ref"] < 1e-5 and r["s2_ref"] < 1e-5, r
+
+
 @pytest.mark.parametrize("N,H,W,C", [(2, 16, 16, 64), (3, 15, 13, 64)])
 def test_maxpool_relu_pool(N, H, W, C):
     r = _gc().check_maxpool_relu_pool(N, H, W, C)
