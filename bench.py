@@ -96,6 +96,10 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------
 # algorithmic bytes of one launch of each kernel family (ideal: every operand once, 2 B / element)
 # ---------------------------------------------------------------------------------------------------
+def conv_out(h, k, s):
+    return (h + 2 * ((k - 1) // 2) - k) // s + 1
+
+
 def op_bytes(name, a):
     if name in ("dfd_gemm_tn", "dfd_gemm_tn_rowpack"):
         M, N, K = a[3], a[4], a[5]
@@ -107,11 +111,11 @@ def op_bytes(name, a):
         M, Nw, Kw = a[3], a[4], a[5]
         return 2 * M * (Nw + Kw) + 4 * Nw * Kw
     if name == "dfd_conv_tc":                              # input once, output once, weights once (no im2col matrix)
-        N, H, W, Cin, Cout, k = a[3:9]
-        return 2 * (N * H * W * (Cin + Cout) + k * k * Cin * Cout)
+        N, H, W, Cin, Cout, k, S = a[3:10]
+        return 2 * (N * (H * W * Cin + conv_out(H, k, S) * conv_out(W, k, S) * Cout) + k * k * Cin * Cout)
     if name == "dfd_conv_wgrad_tc":
-        N, H, W, Cin, Cout, k = a[3:9]
-        return 2 * N * H * W * (Cin + Cout) + 4 * k * k * Cin * Cout
+        N, H, W, Cin, Cout, k, S = a[3:10]
+        return 2 * N * (H * W * Cin + conv_out(H, k, S) * conv_out(W, k, S) * Cout) + 4 * k * k * Cin * Cout
     if name == "dfd_dwconv_fwd":
         N, H, W, C, k, s = a[5:11]
         return 2 * N * C * (H * W + ((H + s - 1) // s) * ((W + s - 1) // s))
@@ -166,9 +170,9 @@ def op_flops(name, a):
         return 2 * a[4] * a[5] * a[6]
     if name in ("dfd_gemm_wgrad_mma", "dfd_gemm_wgrad"):
         return 2 * a[3] * a[4] * a[5]
-    if name in ("dfd_conv_tc", "dfd_conv_wgrad_tc"):       # implicit GEMM: M = N*H*W pixels, K = k*k*Cin, N = Cout
-        N, H, W, Cin, Cout, k = a[3:9]
-        return 2 * N * H * W * Cout * k * k * Cin
+    if name in ("dfd_conv_tc", "dfd_conv_wgrad_tc"):       # implicit GEMM: M = N*Ho*Wo pixels, K = k*k*Cin, N = Cout
+        N, H, W, Cin, Cout, k, S = a[3:10]
+        return 2 * N * conv_out(H, k, S) * conv_out(W, k, S) * Cout * k * k * Cin
     return 0
 
 

@@ -18,9 +18,9 @@ SIGNATURES = {
     "dfd_memset_async": "pilp",
     "dfd_gemm_tn": "ppplii" "i" "ppp" "p",
     "dfd_gemm_tn_rowpack": "ppplii" "ii" "ppp" "p",
-    "dfd_conv_tc": "ppp" "iiiiiii" "ppp" "p",
-    "dfd_conv_wgrad_tc": "ppp" "iiiiiii" "pl" "p",
-    "dfd_conv_wgrad_splits": "iiiiii",
+    "dfd_conv_tc": "ppp" "iiiiiiii" "ppp" "p",
+    "dfd_conv_wgrad_tc": "ppp" "iiiiiiii" "pl" "p",
+    "dfd_conv_wgrad_splits": "iiiiiii",
     "dfd_blockdiag_weights": "piip",
     "dfd_gemm_tn_mma": "pppp" "lii" "i" "ppp",
     "dfd_gemm_wgrad_mma": "ppp" "lii" "i" "p",

@@ -171,6 +171,7 @@ struct TcParams {
     int cv_tiles_x, cv_tiles_y;       // patches per image row / column; M tile index = (n_tile * tiles_y + ty) * tiles_x + tx
     int cv_W, cv_H, cv_N;             // output (= input) extent
     int cv_k, cv_pad, cv_cpb;         // kernel size, padding, 64-channel blocks per tap
+    int cv_S;                         // convolution stride (1 or 2): the A box starts at S * patch origin + tap - pad
     int dbg;              // debug switches (DFD_DBG env): 1 = skip TMA store, 2 = skip stats pass, 4 = skip slabs, 8 = A from L2
     long long* ts;        // optional trace (DFD_TS env): CTA 0 records clock64 at 8 pipeline points for its first 32 tiles
 };
@@ -236,8 +237,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         const int tap = kb / p.cv_cpb, cb = kb - tap * p.cv_cpb;
                         const int kh = tap / p.cv_k, kw = tap - kh * p.cv_k;
                         mbar_arrive_expect_tx(full_bar + stage, (uint32_t)p.cv_rows * 128u + b_bytes);
-                        tma_load_4d(smem_a + (size_t)stage * a_bytes, &tmap_a, full_bar + stage, cb * BLOCK_K, cx0 + kw - p.cv_pad,
-                                    cy0 + kh - p.cv_pad, cn0);
+                        tma_load_4d(smem_a + (size_t)stage * a_bytes, &tmap_a, full_bar + stage, cb * BLOCK_K,
+                                    cx0 * p.cv_S + kw - p.cv_pad, cy0 * p.cv_S + kh - p.cv_pad, cn0);
                     } else {
                         mbar_arrive_expect_tx(full_bar + stage, a_bytes + b_bytes);
                         tma_load_2d(smem_a + (size_t)stage * a_bytes, &tmap_a, full_bar + stage, kb * BLOCK_K, (p.dbg & 8) ? 0 : m_idx * BLOCK_M);
@@ -470,7 +471,7 @@ struct WgParams {
     int conv;
     int cv_TW, cv_TH, cv_TN, cv_rows;
     int cv_tiles_x, cv_tiles_y;
-    int cv_k, cv_pad, cv_cpb;
+    int cv_k, cv_pad, cv_cpb, cv_S;
 };
 
 template <typename T>
@@ -543,8 +544,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constan
                     const int cx0 = txi * p.cv_TW, cy0 = (r % p.cv_tiles_y) * p.cv_TH, cn0 = (r / p.cv_tiles_y) * p.cv_TN;
                     tma_load_4d(a, &tmap_g, full_bar + stage, m0, cx0, cy0, cn0);
                     if (a_box1) tma_load_4d(a + WG_BOX_BYTES, &tmap_g, full_bar + stage, m0 + 64, cx0, cy0, cn0);
-                    tma_load_4d(b, &tmap_x, full_bar + stage, bt_c[0], cx0 + bt_dx[0], cy0 + bt_dy[0], cn0);
-                    if (b_box1) tma_load_4d(b + WG_BOX_BYTES, &tmap_x, full_bar + stage, bt_c[1], cx0 + bt_dx[1], cy0 + bt_dy[1], cn0);
+                    tma_load_4d(b, &tmap_x, full_bar + stage, bt_c[0], cx0 * p.cv_S + bt_dx[0], cy0 * p.cv_S + bt_dy[0], cn0);
+                    if (b_box1) tma_load_4d(b + WG_BOX_BYTES, &tmap_x, full_bar + stage, bt_c[1], cx0 * p.cv_S + bt_dx[1], cy0 * p.cv_S + bt_dy[1], cn0);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     continue;
                 }
@@ -661,13 +662,15 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, int cols, 
 
 
 // 4-D NHWC tensor [N, H, W, C] (16-bit) seen as dims {C, W, H, N}; box = {64 channels, bw, bh, bn}, 128-byte swizzle, OOB -> zeros
-static int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn, int is_bf16) {
+static int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn, int is_bf16,
+                         int es = 1) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return dfd_set_error(DFD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    // es = traversal stride in W and H (strided convolution): a box of (b - 1) * es + 1 tensor elements delivers b of them
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)((bw - 1) * es + 1), (cuuint32_t)((bh - 1) * es + 1), (cuuint32_t)bn};
+    cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
     CUresult r = fn(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -681,11 +684,13 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, 
 
 // Implicit-GEMM convolution on the kernel above (conv mode): y[N,H,W,Cout] = conv_{k x k, stride 1, pad (k-1)/2}(x[N,H,W,Cin]),
 // wpk = packed weight [Cout][kh][kw][Cin] (K-major rows of k*k*Cin). Cin % 64 == 0 keeps every 64-channel K block inside one tap.
-static int launch_conv_tc(const void* x, const void* wpk, void* y, int N, int H, int W, int Cin, int Cout, int k, int dt,
-                          double* dsum, double* dsq, const void* fin, void* stream) {
+static int launch_conv_tc(const void* x, const void* wpk, void* y, int N, int Hin, int Win, int Cin, int Cout, int k, int S,
+                          int dt, double* dsum, double* dsq, const void* fin, void* stream) {
     TcParams p;
     p.fin = (const BnFinDesc*)fin;
     p.conv = 1;
+    p.cv_S = S;
+    const int H = (Hin + 2 * ((k - 1) / 2) - k) / S + 1, W = (Win + 2 * ((k - 1) / 2) - k) / S + 1;     // output extents
     // output patch of an M tile: whole rows when they fit (W <= 128), as many rows as 128 / W allows, split evenly over the
     // image height; images stacked when a whole image is smaller than half a tile (7 x 7 -> two images per tile)
     int TW = W <= 128 ? W : 128;
@@ -720,7 +725,7 @@ static int launch_conv_tc(const void* x, const void* wpk, void* y, int N, int H,
     size_t smem = (size_t)stages * (a_bytes + b_stride) + fixed;
     CUtensorMap ma, mb, mc;
     int rc;
-    if ((rc = make_map_nhwc(&ma, x, N, H, W, Cin, TW, TH, TN, p.is_bf16))) return rc;
+    if ((rc = make_map_nhwc(&ma, x, N, Hin, Win, Cin, TW, TH, TN, p.is_bf16, S))) return rc;
     if ((rc = make_map(&mb, wpk, Cout, K, p.block_n, p.is_bf16))) return rc;
     if ((rc = make_map_nhwc(&mc, y, N, H, W, Cout, TW, TH, TN, p.is_bf16))) return rc;
     int device = 0, sms = 148;
@@ -862,12 +867,13 @@ int dfd_gemm_tn_rowpack(const void* A, const void* Bd, void* C, long long M, int
 // tensor (out-of-bounds rows arrive as zeros = the padding) straight into the swizzled MMA operand buffer.
 //   forward : x = input,  wpk = [Cout][kh][kw][Cin]                      (resnet.py:129-136,195-197: nn.Conv2d 3x3)
 //   dgrad   : x = dY,     wpk = [Cin][kh'][kw'][Cout] with flipped taps   (autograd input gradient of the same conv)
-int dfd_conv_tc(const void* x, const void* wpk, void* y, int N, int H, int W, int Cin, int Cout, int k, int dt, double* dsum,
-                double* dsq, const void* fin, void* stream) {
-    if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (Cin % 64) || (Cout % 64) || (k != 1 && k != 3 && k != 5 && k != 7))
-        return dfd_set_error(DFD_ERR_ARG, "dfd_conv_tc: Cin % 64, Cout % 64, k in {1,3,5,7}");
+int dfd_conv_tc(const void* x, const void* wpk, void* y, int N, int H, int W, int Cin, int Cout, int k, int stride, int dt,
+                double* dsum, double* dsq, const void* fin, void* stream) {
+    if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (Cin % 64) || (Cout % 64) || (k != 1 && k != 3 && k != 5 && k != 7) ||
+        (stride != 1 && stride != 2))
+        return dfd_set_error(DFD_ERR_ARG, "dfd_conv_tc: Cin % 64, Cout % 64, k in {1,3,5,7}, stride in {1,2}");
     if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_conv_tc: dtype");
-    return launch_conv_tc(x, wpk, y, N, H, W, Cin, Cout, k, dt, dsum, dsq, fin, stream);
+    return launch_conv_tc(x, wpk, y, N, H, W, Cin, Cout, k, stride, dt, dsum, dsq, fin, stream);
 }
 
 // table: device array of {src [N,K], dst [pack*N, pack*K], N, K, pack}; dst(j*N+n, j'*K+k) = (j == j') ? src(n,k) : 0
@@ -919,7 +925,7 @@ static WgPatch wg_patch(int N, int H, int W) {
 }
 
 static int launch_wgrad_tc(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* ws,
-                           long long ws_bytes, void* stream, int cvN, int cvH, int cvW, int cvCin, int cvk);
+                           long long ws_bytes, void* stream, int cvN, int cvH, int cvW, int cvCin, int cvk, int cvS = 1);
 
 int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* ws, long long ws_bytes,
                    void* stream) {
@@ -931,33 +937,39 @@ int dfd_gemm_wgrad(const void* G, const void* X, float* dW, long long M, int Nw,
 // Weight gradient of a dense k x k convolution (stride 1, padding (k-1)/2) as an IMPLICIT GEMM: dW[Cout][kh][kw][Cin] (fp32,
 // the packed order of dfd_repack_weights; accumulated, or written as split partials into `ws` like dfd_gemm_wgrad) =
 // sum over output pixels of dY[pixel, co] * x[pixel shifted by the tap, ci]; no im2col matrix in memory.
-int dfd_conv_wgrad_splits(int N, int H, int W, int Cin, int Cout, int k) {
-    if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return 0;
-    WgPatch pt = wg_patch(N, H, W);
-    return (int)wgrad_ws_splits((long long)N * H * W, Cout, k * k * Cin, 148, pt.patches);
+static inline int conv_out_extent(int h, int k, int s) { return (h + 2 * ((k - 1) / 2) - k) / s + 1; }
+int dfd_conv_wgrad_splits(int N, int H, int W, int Cin, int Cout, int k, int stride) {
+    if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || stride <= 0) return 0;
+    const int Ho = conv_out_extent(H, k, stride), Wo = conv_out_extent(W, k, stride);
+    WgPatch pt = wg_patch(N, Ho, Wo);
+    return (int)wgrad_ws_splits((long long)N * Ho * Wo, Cout, k * k * Cin, 148, pt.patches);
 }
 
-int dfd_conv_wgrad_tc(const void* dy, const void* x, float* dW, int N, int H, int W, int Cin, int Cout, int k, int dt, void* ws,
-                      long long ws_bytes, void* stream) {
-    if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (Cin % 64) || (Cout % 8) || (k != 1 && k != 3 && k != 5 && k != 7))
-        return dfd_set_error(DFD_ERR_ARG, "dfd_conv_wgrad_tc: Cin % 64, Cout % 8, k in {1,3,5,7}");
+int dfd_conv_wgrad_tc(const void* dy, const void* x, float* dW, int N, int H, int W, int Cin, int Cout, int k, int stride, int dt,
+                      void* ws, long long ws_bytes, void* stream) {
+    if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (Cin % 64) || (Cout % 8) || (k != 1 && k != 3 && k != 5 && k != 7) ||
+        (stride != 1 && stride != 2))
+        return dfd_set_error(DFD_ERR_ARG, "dfd_conv_wgrad_tc: Cin % 64, Cout % 8, k in {1,3,5,7}, stride in {1,2}");
     if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_conv_wgrad_tc: dtype");
-    return launch_wgrad_tc(dy, x, dW, (long long)N * H * W, Cout, k * k * Cin, dt, ws, ws_bytes, stream, N, H, W, Cin, k);
+    const int Ho = conv_out_extent(H, k, stride), Wo = conv_out_extent(W, k, stride);
+    return launch_wgrad_tc(dy, x, dW, (long long)N * Ho * Wo, Cout, k * k * Cin, dt, ws, ws_bytes, stream, N, H, W, Cin, k, stride);
 }
 
 static int launch_wgrad_tc(const void* G, const void* X, float* dW, long long M, int Nw, int Kw, int dt, void* ws,
-                           long long ws_bytes, void* stream, int cvN, int cvH, int cvW, int cvCin, int cvk) {
+                           long long ws_bytes, void* stream, int cvN, int cvH, int cvW, int cvCin, int cvk, int cvS) {
     WgParams p;
+    // cvH / cvW: INPUT extents of the convolution; the patches tile the OUTPUT pixels
+    const int cvHo = cvN > 0 ? conv_out_extent(cvH, cvk, cvS) : 0, cvWo = cvN > 0 ? conv_out_extent(cvW, cvk, cvS) : 0;
     p.M = M; p.Nw = Nw; p.Kw = Kw;
     p.is_bf16 = dt == DFD_DT_BF16;
     p.block_n = Kw >= 128 ? 128 : ((Kw + 15) / 16) * 16;
     p.kblocks = (M + WG_KP - 1) / WG_KP;
     p.conv = cvN > 0;
     if (p.conv) {
-        WgPatch pt = wg_patch(cvN, cvH, cvW);
+        WgPatch pt = wg_patch(cvN, cvHo, cvWo);
         p.cv_TW = pt.TW; p.cv_TH = pt.TH; p.cv_TN = pt.TN; p.cv_rows = pt.TW * pt.TH * pt.TN;
-        p.cv_tiles_x = cdiv(cvW, pt.TW); p.cv_tiles_y = cdiv(cvH, pt.TH);
-        p.cv_k = cvk; p.cv_pad = (cvk - 1) / 2; p.cv_cpb = cvCin / 64;
+        p.cv_tiles_x = cdiv(cvWo, pt.TW); p.cv_tiles_y = cdiv(cvHo, pt.TH);
+        p.cv_k = cvk; p.cv_pad = (cvk - 1) / 2; p.cv_cpb = cvCin / 64; p.cv_S = cvS;
         p.kblocks = pt.patches;
     }
     const int tm = cdiv(Nw, 128), tn = cdiv(Kw, p.block_n);
@@ -990,8 +1002,8 @@ static int launch_wgrad_tc(const void* G, const void* X, float* dW, long long M,
     CUtensorMap mg, mx;
     int rc;
     if (p.conv) {
-        if ((rc = make_map_nhwc(&mg, G, cvN, cvH, cvW, Nw, p.cv_TW, p.cv_TH, p.cv_TN, p.is_bf16))) return rc;
-        if ((rc = make_map_nhwc(&mx, X, cvN, cvH, cvW, cvCin, p.cv_TW, p.cv_TH, p.cv_TN, p.is_bf16))) return rc;
+        if ((rc = make_map_nhwc(&mg, G, cvN, cvHo, cvWo, Nw, p.cv_TW, p.cv_TH, p.cv_TN, p.is_bf16))) return rc;
+        if ((rc = make_map_nhwc(&mx, X, cvN, cvH, cvW, cvCin, p.cv_TW, p.cv_TH, p.cv_TN, p.is_bf16, cvS))) return rc;
     } else {
         if ((rc = make_map(&mg, G, M, Nw, WG_KP, p.is_bf16))) return rc;
         if ((rc = make_map(&mx, X, M, Kw, WG_KP, p.is_bf16))) return rc;

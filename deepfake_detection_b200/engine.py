@@ -239,15 +239,16 @@ class Engine:
         self._red_pending.append((off, dW, Nw * Kw, Nw * Kw, splits))
         return ("dfd_gemm_wgrad", [G, X, dW, M, Nw, Kw, self.dt, ("WS", off), nbytes])
 
-    def _wgrad_conv(self, dY, X, dW, N, H, W, Cin, Cout, k):
-        """implicit-GEMM weight gradient of a dense k x k stride-1 convolution into the packed [Cout][kh][kw][Cin] fp32 buffer"""
+    def _wgrad_conv(self, dY, X, dW, N, H, W, Cin, Cout, k, stride=1):
+        """implicit-GEMM weight gradient of a dense k x k convolution (H, W = input extents) into the packed
+        [Cout][kh][kw][Cin] fp32 buffer"""
         Kw = k * k * Cin
         if os.environ.get("DFD_NONDET"):
-            return ("dfd_conv_wgrad_tc", (dY, X, dW, N, H, W, Cin, Cout, k, self.dt, None, 0))
-        splits = self.L.cdll.dfd_conv_wgrad_splits(N, H, W, Cin, Cout, k)
+            return ("dfd_conv_wgrad_tc", (dY, X, dW, N, H, W, Cin, Cout, k, stride, self.dt, None, 0))
+        splits = self.L.cdll.dfd_conv_wgrad_splits(N, H, W, Cin, Cout, k, stride)
         off, nbytes = self._ws_take(splits * Cout * Kw * 4)
         self._red_pending.append((off, dW, Cout * Kw, Cout * Kw, splits))
-        return ("dfd_conv_wgrad_tc", [dY, X, dW, N, H, W, Cin, Cout, k, self.dt, ("WS", off), nbytes])
+        return ("dfd_conv_wgrad_tc", [dY, X, dW, N, H, W, Cin, Cout, k, stride, self.dt, ("WS", off), nbytes])
 
     def _dw_bwd(self, args, N, H, W, C, k, stride, fin=None):
         if os.environ.get("DFD_NONDET"):

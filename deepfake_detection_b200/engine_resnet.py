@@ -8,8 +8,10 @@ Dense 3x3 convolutions with stride 1 (13 of the 16 in resnet50, all but 3 in res
 map, no im2col matrix in memory) in the forward pass and for the input gradient (same kernel on dY with the tap-flipped
 [Cin][kh'][kw'][Cout] weights). The strided 3x3 convolutions keep the round-1 formulation (csrc/conv_dense.cu):
 materialised im2col -> tcgen05 GEMM (forward), GEMM -> col2im (input gradient). The weight gradient of every 3x3 is the
-MN-major tcgen05 wgrad GEMM: implicit too for the stride-1 layers (`dfd_conv_wgrad_tc`: one pipeline stage = one patch of
-<= 64 output pixels of dY and the input box shifted by the tap), on the re-computed im2col matrix for the strided ones. 1x1 convolutions are plain GEMMs on the NHWC tensors. BN + ReLU outputs are materialised (`dfd_bn_act`) because three consumers read them.
+MN-major tcgen05 wgrad GEMM, implicit too (`dfd_conv_wgrad_tc`: one pipeline stage = one patch of <= 64 output pixels of dY
+and the input box shifted by the tap). Stride-2 convolutions (the three strided 3x3 and the strided 1x1 downsample inputs) use
+the same kernels with TMA element strides {1, 2, 2, 1} in the forward pass and the weight gradient; only their INPUT
+gradient keeps GEMM + col2im. 1x1 convolutions are plain GEMMs on the NHWC tensors. BN + ReLU outputs are materialised (`dfd_bn_act`) because three consumers read them.
 """
 import os
 import struct
@@ -95,14 +97,16 @@ def build_resnet(e):
 
     implicit = e.gemm_impl == "tc" and not os.environ.get("DFD_NO_IMPLICIT_CONV")
     implicit_wgrad = not os.environ.get("DFD_NO_IMPLICIT_WGRAD")
+    implicit_s2 = not os.environ.get("DFD_NO_IMPLICIT_S2")          # stride-2 convolutions through TMA element strides
     e.n_implicit = 0
 
     def conv3x3(xin, name, y, h, w, cin, cout, stride, bn):
         """3x3 / padding 1 forward into y (+ BatchNorm statistics of y)"""
-        if implicit and stride == 1 and cin % 64 == 0 and cout % 64 == 0:
+        if implicit and (stride == 1 or implicit_s2) and cin % 64 == 0 and cout % 64 == 0:
             bn.fused = fused_fin
             e.n_implicit += 1
-            return [("dfd_conv_tc", (xin, PK(name), y, N, h, w, cin, cout, 3, dt, bn.fsum, bn.fsq, bn.fin if fused_fin else None))]
+            return [("dfd_conv_tc", (xin, PK(name), y, N, h, w, cin, cout, 3, stride, dt, bn.fsum, bn.fsq,
+                                     bn.fin if fused_fin else None))]
         ho, wo = conv_out(h, 3, stride, 1), conv_out(w, 3, stride, 1)
         return [("dfd_im2col", (xin, COLS, N, h, w, cin, 3, stride, 1, dt)),
                 gemm(COLS, PK(name), y, N * ho * wo, cout, 9 * cin, bn)]
@@ -192,12 +196,21 @@ def build_resnet(e):
             bnd = bns[p + ".downsample.1"]
             yd = e._alloc16(N, ho, wo, b.cout)
             r = e._alloc16(N, ho, wo, b.cout)
+            ds_implicit = (implicit and implicit_s2 and implicit_wgrad and b.stride == 2 and b.cin % 64 == 0 and b.cout % 64 == 0 and
+                           e._wgrad_name == "dfd_gemm_wgrad")
             if b.stride == 1:
                 xs = x
+                fwd.append(gemm(_ptr(xs), P16(p + ".downsample.0.weight"), _ptr(yd), M2, b.cout, b.cin, bnd))
+            elif ds_implicit:
+                # strided 1x1 convolution straight from the block input (k = 1, stride 2 implicit GEMM): no gathered copy
+                xs = None
+                bnd.fused = fused_fin
+                fwd.append(("dfd_conv_tc", (_ptr(x), P16(p + ".downsample.0.weight"), _ptr(yd), N, h, w, b.cin, b.cout, 1, b.stride, dt,
+                                            bnd.fsum, bnd.fsq, bnd.fin if fused_fin else None)))
             else:
                 xs = e._alloc16(N, ho, wo, b.cin)
                 fwd.append(("dfd_im2col", (_ptr(x), _ptr(xs), N, h, w, b.cin, 1, b.stride, 0, dt)))
-            fwd.append(gemm(_ptr(xs), P16(p + ".downsample.0.weight"), _ptr(yd), M2, b.cout, b.cin, bnd))
+                fwd.append(gemm(_ptr(xs), P16(p + ".downsample.0.weight"), _ptr(yd), M2, b.cout, b.cin, bnd))
             fwd.append(finalize(bnd, M2))
             fwd.append(("dfd_bn_act", (_ptr(yd), bnd.scale, bnd.shift, None, None, _ptr(r), N, ho * wo, b.cout, ACT_NONE, 0, dt)))
             rec.update(yd=yd, xs=xs, bnd=bnd)
@@ -228,13 +241,13 @@ def build_resnet(e):
         """dy [M_out, Cout] -> dx_out [N, n_h, n_w, Cin] (+dx_add) and the weight gradient of `name`"""
         if implicit and stride == 1 and dx_add is None and Cin % 64 == 0 and Cout % 64 == 0:
             # input gradient = the same implicit GEMM on dY with the tap-flipped [Cin][kh'][kw'][Cout] weights
-            ops = [("dfd_conv_tc", (dy, PKD(name), dx_out, N, n_h, n_w, Cout, Cin, 3, dt, None, None, None))]
+            ops = [("dfd_conv_tc", (dy, PKD(name), dx_out, N, n_h, n_w, Cout, Cin, 3, 1, dt, None, None, None))]
         else:
             ops = [gemm(dy, PKT(name), COLS, M_out, 9 * Cin, Cout),
                    ("dfd_col2im", (COLS, dx_add, dx_out, N, n_h, n_w, Cin, 3, stride, 1, dt))]
-        if implicit and implicit_wgrad and stride == 1 and Cin % 64 == 0 and e._wgrad_name == "dfd_gemm_wgrad":
+        if implicit and implicit_wgrad and (stride == 1 or implicit_s2) and Cin % 64 == 0 and e._wgrad_name == "dfd_gemm_wgrad":
             ops += [zero_gperm(Cout * 9 * Cin),
-                    e._wgrad_conv(dy, _ptr(xin_t), _ptr(e.gperm), N, n_h, n_w, Cin, Cout, 3)]
+                    e._wgrad_conv(dy, _ptr(xin_t), _ptr(e.gperm), N, n_h, n_w, Cin, Cout, 3, stride)]
         else:
             ops += [("dfd_im2col", (_ptr(xin_t), COLS, N, n_h, n_w, Cin, 3, stride, 1, dt)),
                     zero_gperm(Cout * 9 * Cin),
@@ -303,7 +316,10 @@ def build_resnet(e):
             bwd.append(bwd_finalize(bnd, M2))
             bwd.append(("dfd_bn_bwd_apply", (gm, _ptr(rec["yd"]), None, bnd.cA, bnd.cB, bnd.cC, t1, N, ho * wo, b.cout, dt)))
             bwd.append(gemm(t1, T16(p + ".downsample.0.weight"), t2, M2, b.cin, b.cout))
-            bwd.append(e._wgrad(t1, _ptr(rec["xs"]), G32(p + ".downsample.0.weight"), M2, b.cout, b.cin))
+            if rec["xs"] is None:      # strided 1x1: implicit weight gradient on the block input itself
+                bwd.append(e._wgrad_conv(t1, _ptr(xin), G32(p + ".downsample.0.weight"), N, h, w, b.cin, b.cout, 1, b.stride))
+            else:
+                bwd.append(e._wgrad(t1, _ptr(rec["xs"]), G32(p + ".downsample.0.weight"), M2, b.cout, b.cin))
             if b.stride == 1:
                 bwd.append(("dfd_add_inplace", (t3, t2, M1 * b.cin, dt)))
                 new_dout = (t3, None)

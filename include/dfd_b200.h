@@ -134,16 +134,18 @@ int dfd_repack_weights(const void* table, int count, int dt, void* stream);
  * rows arrive as zeros (= the padding). Replaces nn.Conv2d 3x3 stride 1 of BasicBlock / Bottleneck (resnet.py:129-136,195-197):
  *   forward: x = input [N,H,W,Cin],  wpk = dst_OHWI16,             y [N,H,W,Cout]; dsum/dsq = BatchNorm statistics of y
  *   dgrad  : x = dY    [N,H,W,Cout], wpk = dstD (flipped, [Cin]..), y = dX [N,H,W,Cin]  (call with Cin/Cout exchanged)
- * Cin % 64 == 0, Cout % 64 == 0. */
-int dfd_conv_tc(const void* x, const void* wpk, void* y, int N, int H, int W, int Cin, int Cout, int k, int dt, double* dsum,
-                double* dsq, const void* fin, void* stream);
+ * Cin % 64 == 0, Cout % 64 == 0. H, W = INPUT extents; stride 1 or 2 (2: the TMA box walks the input with element strides
+ * {1, 2, 2, 1}; forward / weight gradient only - the strided input gradient stays dfd_gemm_tn + dfd_col2im); k = 1 with
+ * stride 2 is the strided 1x1 downsample convolution (resnet.py:249-260) without its gather. */
+int dfd_conv_tc(const void* x, const void* wpk, void* y, int N, int H, int W, int Cin, int Cout, int k, int stride, int dt,
+                double* dsum, double* dsq, const void* fin, void* stream);
 /* Weight gradient of the same convolution, also an implicit GEMM (MN-major tcgen05 operands straight from the NHWC tensors,
  * one pipeline stage = one patch of <= 64 output pixels, its input box shifted by the tap): dW_OHWI fp32 [Cout][kh][kw][Cin]
  * += sum_pixels dY[pixel, co] * x[pixel + tap, ci]. `ws` / `ws_bytes` as for dfd_gemm_wgrad: when given, the split partials
  * (dfd_conv_wgrad_splits x Cout x k*k*Cin floats) are written there for dfd_ordered_reduce and dW is left alone. */
-int dfd_conv_wgrad_tc(const void* dy, const void* x, float* dW_ohwi, int N, int H, int W, int Cin, int Cout, int k, int dt,
-                      void* ws, long long ws_bytes, void* stream);
-int dfd_conv_wgrad_splits(int N, int H, int W, int Cin, int Cout, int k);
+int dfd_conv_wgrad_tc(const void* dy, const void* x, float* dW_ohwi, int N, int H, int W, int Cin, int Cout, int k, int stride,
+                      int dt, void* ws, long long ws_bytes, void* stream);
+int dfd_conv_wgrad_splits(int N, int H, int W, int Cin, int Cout, int k, int stride);
 int dfd_unpack_grad(const float* g_ohwi, float* g_oihw_accum, int O, int I, int k, void* stream);
 int dfd_maxpool_fwd(const void* x, void* out, void* argmax_u8, int N, int H, int W, int C, int dt, void* stream);
 int dfd_maxpool_bwd(const void* gy, const void* argmax_u8, void* gx, int N, int H, int W, int C, int dt, void* stream);

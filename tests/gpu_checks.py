@@ -649,12 +649,14 @@ def check_conv_dense(N, H, W, Cin, Cout, k, s, dtype=torch.bfloat16, seed=0):
     return res
 
 
-def check_conv_implicit(N, H, W, Cin, Cout, k=3, dtype=torch.bfloat16, seed=0):
-    """dfd_conv_tc (implicit GEMM, stride 1, "same" padding): forward + BatchNorm statistics and the input gradient (the same
-    kernel on dY with the tap-flipped weights) against F.conv2d and its autograd; also against the im2col formulation."""
+def check_conv_implicit(N, H, W, Cin, Cout, k=3, dtype=torch.bfloat16, seed=0, stride=1):
+    """dfd_conv_tc (implicit GEMM, padding (k-1)/2, stride 1 or 2): forward + BatchNorm statistics, the input gradient (stride 1: the
+    same kernel on dY with the tap-flipped weights) and the implicit weight gradient against fp64 F.conv2d / autograd; the forward
+    also bit for bit against the im2col formulation."""
     import struct
     g = torch.Generator(device="cuda").manual_seed(seed)
     pad = (k - 1) // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     x = torch.randn(N, H, W, Cin, device="cuda", generator=g).to(dtype)
     w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / math.sqrt(Cin * k * k)).to(dtype)
     wp = torch.zeros(Cout * k * k * Cin, device="cuda", dtype=dtype)
@@ -663,13 +665,13 @@ def check_conv_implicit(N, H, W, Cin, Cout, k=3, dtype=torch.bfloat16, seed=0):
                                                    Cout, Cin, k, 0)), dtype=torch.uint8).cuda()
     d = DT[dtype]
     _lib.call("dfd_repack_weights", P(table), 1, d, st())
-    y = torch.full((N, H, W, Cout), float("nan"), device="cuda", dtype=dtype)
+    y = torch.full((N, Ho, Wo, Cout), float("nan"), device="cuda", dtype=dtype)
     dsum, dsq = stat_buf(Cout), stat_buf(Cout)
-    _lib.call("dfd_conv_tc", P(x), P(wp), P(y), N, H, W, Cin, Cout, k, d, P(dsum), P(dsq), None, st())
+    _lib.call("dfd_conv_tc", P(x), P(wp), P(y), N, H, W, Cin, Cout, k, stride, d, P(dsum), P(dsq), None, st())
     torch.cuda.synchronize()
     xr = nchw(x.double()).requires_grad_(True)      # fp64: cuDNN's fp32 algorithm choice (TF32 / Winograd / FFT) is not a reference
     wr = w.double().clone().requires_grad_(True)
-    ref = F.conv2d(xr, wr, stride=1, padding=pad)
+    ref = F.conv2d(xr, wr, stride=stride, padding=pad)
     yf = y.float()
     res = dict(fwd_max=maxerr_scaled(nchw(yf), ref.detach()), nan=int(torch.isnan(yf).sum()))
     # the statistics are those of the STORED (rounded) output
@@ -677,30 +679,32 @@ def check_conv_implicit(N, H, W, Cin, Cout, k=3, dtype=torch.bfloat16, seed=0):
     res["sum_rel"] = relerr(s1, yf.double().sum((0, 1, 2)))
     res["sq_rel"] = relerr(s2, (yf.double() ** 2).sum((0, 1, 2)))
     # the im2col formulation computes the same products in the same K order: bit-identical output
-    cols = torch.zeros(N * H * W, k * k * Cin, device="cuda", dtype=dtype)
+    cols = torch.zeros(N * Ho * Wo, k * k * Cin, device="cuda", dtype=dtype)
     y2 = torch.zeros_like(y)
-    _lib.call("dfd_im2col", P(x), P(cols), N, H, W, Cin, k, 1, pad, d, st())
-    _lib.call("dfd_gemm_tn", P(cols), P(wp), P(y2), N * H * W, Cout, k * k * Cin, d, None, None, None, st())
+    _lib.call("dfd_im2col", P(x), P(cols), N, H, W, Cin, k, stride, pad, d, st())
+    _lib.call("dfd_gemm_tn", P(cols), P(wp), P(y2), N * Ho * Wo, Cout, k * k * Cin, d, None, None, None, st())
     torch.cuda.synchronize()
     res["vs_im2col_mismatch"] = int((y2.view(torch.int16) != y.view(torch.int16)).sum())
-    dy = (torch.randn(N, H, W, Cout, device="cuda", generator=g) * 0.1).to(dtype)
+    dy = (torch.randn(N, Ho, Wo, Cout, device="cuda", generator=g) * 0.1).to(dtype)
     ref.backward(nchw(dy.double()))
-    dx = torch.full((N, H, W, Cin), float("nan"), device="cuda", dtype=dtype)
-    _lib.call("dfd_conv_tc", P(dy), P(wpD), P(dx), N, H, W, Cout, Cin, k, d, None, None, None, st())
-    torch.cuda.synchronize()
-    res["dgrad_rel"] = relerr(nchw(dx.float()), xr.grad)
-    res["nan_b"] = int(torch.isnan(dx.float()).sum())
+    res["dgrad_rel"], res["nan_b"] = 0.0, 0
+    if stride == 1:
+        dx = torch.full((N, H, W, Cin), float("nan"), device="cuda", dtype=dtype)
+        _lib.call("dfd_conv_tc", P(dy), P(wpD), P(dx), N, H, W, Cout, Cin, k, 1, d, None, None, None, st())
+        torch.cuda.synchronize()
+        res["dgrad_rel"] = relerr(nchw(dx.float()), xr.grad)
+        res["nan_b"] = int(torch.isnan(dx.float()).sum())
     # weight gradient (implicit too): packed [Cout][kh][kw][Cin] fp32 -> OIHW; atomic flush and workspace partials + ordered reduce
     Kw = k * k * Cin
     gperm = torch.zeros(Cout, Kw, device="cuda")
-    _lib.call("dfd_conv_wgrad_tc", P(dy), P(x), P(gperm), N, H, W, Cin, Cout, k, d, None, 0, st())
+    _lib.call("dfd_conv_wgrad_tc", P(dy), P(x), P(gperm), N, H, W, Cin, Cout, k, stride, d, None, 0, st())
     gw = torch.zeros(Cout, Cin, k, k, device="cuda")
     _lib.call("dfd_unpack_grad", P(gperm), P(gw), Cout, Cin, k, st())
-    splits = _lib.lib().cdll.dfd_conv_wgrad_splits(N, H, W, Cin, Cout, k)
+    splits = _lib.lib().cdll.dfd_conv_wgrad_splits(N, H, W, Cin, Cout, k, stride)
     ws = torch.full((splits, Cout, Kw), float("nan"), device="cuda")
     det = [torch.zeros(Cout, Kw, device="cuda"), torch.zeros(Cout, Kw, device="cuda")]
     for t in det:
-        _lib.call("dfd_conv_wgrad_tc", P(dy), P(x), P(t), N, H, W, Cin, Cout, k, d, P(ws), ws.numel() * 4, st())
+        _lib.call("dfd_conv_wgrad_tc", P(dy), P(x), P(t), N, H, W, Cin, Cout, k, stride, d, P(ws), ws.numel() * 4, st())
         table = torch.frombuffer(bytearray(struct.pack("<QQqqii", P(ws), P(t), Cout * Kw, Cout * Kw, splits, 0)), dtype=torch.uint8).cuda()
         _lib.call("dfd_ordered_reduce", P(table), 1, P(t), min(1024, (Cout * Kw // 4 + 255) // 256), st())
         torch.cuda.synchronize()

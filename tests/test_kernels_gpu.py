@@ -170,6 +170,16 @@ def test_conv_implicit(N, H, W, Cin, Cout, k):
     assert r["wgrad_rel"] < 1e-4 and r["wgrad_det_bitwise"] and r["wgrad_det_vs_atomic"] < 1e-5, r
 
 
+# stride 2 (TMA element strides): the three strided 3x3 convolutions of resnet50 / resnet18 (56 -> 28, 28 -> 14, 14 -> 7), odd
+# extents, and k = 1 stride 2 = the strided downsample convolution without its gather
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k", [(2, 56, 56, 128, 128, 3), (3, 28, 28, 256, 256, 3), (5, 14, 14, 512, 512, 3),
+                                                 (2, 15, 21, 64, 128, 3), (3, 56, 56, 256, 512, 1), (2, 13, 9, 64, 64, 1)])
+def test_conv_implicit_stride2(N, H, W, Cin, Cout, k):
+    r = _gc().check_conv_implicit(N, H, W, Cin, Cout, k, stride=2)
+    assert r["nan"] == 0 and r["fwd_max"] < OUT16 and r["sum_rel"] < 1e-6 and r["sq_rel"] < 1e-6 and r["vs_im2col_mismatch"] == 0, r
+    assert r["wgrad_rel"] < 1e-4 and r["wgrad_det_bitwise"] and r["wgrad_det_vs_atomic"] < 1e-5, r
+
+
 def test_conv_implicit_fp16():
     r = _gc().check_conv_implicit(2, 14, 14, 64, 128, 3, dtype=torch.float16)
     assert r["nan"] == 0 and r["fwd_max"] < OUT16 and r["dgrad_rel"] < 6e-3 and r["vs_im2col_mismatch"] == 0, r

@@ -40,18 +40,18 @@ for (H, C) in [(56, 64), (28, 128), (14, 256), (7, 512)]:
         _lib.call("dfd_gemm_tn", P(cols), P(wp), P(y), M, C, 9 * C, 0, P(s1), P(s2), None, st())
 
     def fwd_new():
-        _lib.call("dfd_conv_tc", P(x), P(wp), P(y), N, H, H, C, C, 3, 0, P(s1), P(s2), None, st())
+        _lib.call("dfd_conv_tc", P(x), P(wp), P(y), N, H, H, C, C, 3, 1, 0, P(s1), P(s2), None, st())
 
     def dg_old():
         _lib.call("dfd_gemm_tn", P(y), P(wpT), P(cols), M, 9 * C, C, 0, None, None, None, st())
         _lib.call("dfd_col2im", P(cols), None, P(dx), N, H, H, C, 3, 1, 1, 0, st())
 
     def dg_new():
-        _lib.call("dfd_conv_tc", P(y), P(wpD), P(dx), N, H, H, C, C, 3, 0, None, None, None, st())
+        _lib.call("dfd_conv_tc", P(y), P(wpD), P(dx), N, H, H, C, C, 3, 1, 0, None, None, None, st())
 
     gperm = torch.zeros(C, 9 * C, device="cuda")
     sp_o = _lib.lib().cdll.dfd_gemm_wgrad_splits(M, C, 9 * C)
-    sp_n = _lib.lib().cdll.dfd_conv_wgrad_splits(N, H, H, C, C, 3)
+    sp_n = _lib.lib().cdll.dfd_conv_wgrad_splits(N, H, H, C, C, 3, 1)
     ws = torch.zeros(max(sp_o, sp_n) * C * 9 * C, device="cuda")
 
     def wg_old():
@@ -59,7 +59,7 @@ for (H, C) in [(56, 64), (28, 128), (14, 256), (7, 512)]:
         _lib.call("dfd_gemm_wgrad", P(y), P(cols), P(gperm), M, C, 9 * C, 0, P(ws), ws.numel() * 4, st())
 
     def wg_new():
-        _lib.call("dfd_conv_wgrad_tc", P(y), P(x), P(gperm), N, H, H, C, C, 3, 0, P(ws), ws.numel() * 4, st())
+        _lib.call("dfd_conv_wgrad_tc", P(y), P(x), P(gperm), N, H, H, C, C, 3, 1, 0, P(ws), ws.numel() * 4, st())
 
     a, b, c, d = timeit(fwd_old), timeit(fwd_new), timeit(dg_old), timeit(dg_new)
     e_, f_ = timeit(wg_old), timeit(wg_new)
