@@ -94,6 +94,7 @@ __global__ void repack_weights_kernel(const RepackDesc* __restrict__ table) {
     const long long total = (long long)d.O * d.I * kk;
     const long long step = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (dst) {
+#pragma unroll 4
         for (long long i = i0; i < total; i += step) {          // i = (o*kk + tap)*I + ci
             const int ci = (int)(i % d.I);
             const long long t = i / d.I;
@@ -102,6 +103,7 @@ __global__ void repack_weights_kernel(const RepackDesc* __restrict__ table) {
         }
     }
     if (dstT) {
+#pragma unroll 4
         for (long long i = i0; i < total; i += step) {          // i = (tap*I + ci)*O + o
             const int o = (int)(i % d.O);
             const long long t = i / d.O;
@@ -110,6 +112,7 @@ __global__ void repack_weights_kernel(const RepackDesc* __restrict__ table) {
         }
     }
     if (dstD) {
+#pragma unroll 4
         for (long long i = i0; i < total; i += step) {          // i = (ci*kk + tap')*O + o, tap' = kk-1-tap
             const int o = (int)(i % d.O);
             const long long t = i / d.O;
@@ -335,7 +338,7 @@ int dfd_col2im(const void* dcols, const void* add, void* dx, int N, int H, int W
 // table: device array of { const void* src; void* dst; void* dstT; void* dstD; int O, I, k; int pad_; }
 int dfd_repack_weights(const void* table, int count, int dt, void* stream) {
     if (count <= 0) return DFD_OK;
-    dim3 grid(148, count);
+    dim3 grid(148 * 8, count);       // latency-bound gather: many short grid-stride loops
     CD_T(dt, (repack_weights_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const RepackDesc*)table)));
     DFD_LAUNCH_CHECK();
     return DFD_OK;
