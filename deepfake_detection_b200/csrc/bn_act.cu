@@ -534,6 +534,9 @@ __global__ void se_bwd_reduce_kernel(const T* __restrict__ da, const T* __restri
 // registers: with them in registers (48 of 122) only 2 CTAs x 256 threads fit an SM and 4 x 16 bytes in flight per thread
 // (32 KB per SM) cannot cover the HBM latency (Little: ~44 KB). Layout [operand][half][V] float4, so that a warp's 16-byte
 // reads are consecutive (conflict-free); 12 LDS.128 per row of 8 channels next to ~100 ALU instructions.
+#ifndef ACTBWD_U_RELU
+#define ACTBWD_U_RELU 3
+#endif
 template <typename T, int ACT, bool HAS_DA, int MAXT, int OCC>
 __global__ void __launch_bounds__(MAXT, OCC) act_bwd_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
                                const float* __restrict__ shift, const float* __restrict__ mean,
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(MAXT, OCC) act_bwd_kernel(const T* __restrict_
     if (r1 > hw) r1 = hw;
     const size_t img = (size_t)blockIdx.y * hw * C + c0;
     // independent 16-byte loads in flight per thread: OCC 2 (128 registers, 512 threads per SM) 6; OCC 3 (80 registers) 4
-    constexpr int U = OCC == 3 ? 2 : (HAS_DA ? 3 : 4);
+    constexpr int U = OCC == 3 ? 2 : (HAS_DA ? (ACT == 1 ? 3 : ACTBWD_U_RELU) : 4);
     for (long long r = r0 + threadIdx.y; r < r1; r += (long long)U * blockDim.y) {
         uint4 draw_[U], yraw[U];
 #pragma unroll
