@@ -110,6 +110,9 @@ def op_bytes(name, a):
     if name in ("dfd_gemm_wgrad_mma", "dfd_gemm_wgrad"):
         M, Nw, Kw = a[3], a[4], a[5]
         return 2 * M * (Nw + Kw) + 4 * Nw * Kw
+    if name == "dfd_conv_dgrad_s2_tc":
+        N, H, W, Cin, Cout = a[3:8]
+        return 2 * (N * (H * W * Cin + conv_out(H, 3, 2) * conv_out(W, 3, 2) * Cout) + 9 * Cin * Cout)
     if name == "dfd_conv_tc":                              # input once, output once, weights once (no im2col matrix)
         N, H, W, Cin, Cout, k, S = a[3:10]
         return 2 * (N * (H * W * Cin + conv_out(H, k, S) * conv_out(W, k, S) * Cout) + k * k * Cin * Cout)
@@ -170,6 +173,9 @@ def op_flops(name, a):
         return 2 * a[4] * a[5] * a[6]
     if name in ("dfd_gemm_wgrad_mma", "dfd_gemm_wgrad"):
         return 2 * a[3] * a[4] * a[5]
+    if name == "dfd_conv_dgrad_s2_tc":                     # 9 taps x Cout per 4 input pixels
+        N, H, W, Cin, Cout = a[3:8]
+        return 2 * N * conv_out(H, 3, 2) * conv_out(W, 3, 2) * 9 * Cin * Cout
     if name in ("dfd_conv_tc", "dfd_conv_wgrad_tc"):       # implicit GEMM: M = N*Ho*Wo pixels, K = k*k*Cin, N = Cout
         N, H, W, Cin, Cout, k, S = a[3:10]
         return 2 * N * conv_out(H, k, S) * conv_out(W, k, S) * Cout * k * k * Cin

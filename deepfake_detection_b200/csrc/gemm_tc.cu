@@ -172,6 +172,10 @@ struct TcParams {
     int cv_W, cv_H, cv_N;             // output (= input) extent
     int cv_k, cv_pad, cv_cpb;         // kernel size, padding, 64-channel blocks per tap
     int cv_S;                         // convolution stride (1 or 2): the A box starts at S * patch origin + tap - pad
+    // explicit tap list (cv_ntaps > 0; the parity classes of a strided input gradient): tap t reads the A box at patch origin +
+    // (cv_tox[t], cv_toy[t]) against weight k-blocks (cv_tk[t] * cv_cpb + cb)
+    int cv_ntaps;
+    int cv_tox[9], cv_toy[9], cv_tk[9];
     int dbg;              // debug switches (DFD_DBG env): 1 = skip TMA store, 2 = skip stats pass, 4 = skip slabs, 8 = A from L2
     long long* ts;        // optional trace (DFD_TS env): CTA 0 records clock64 at 8 pipeline points for its first 32 tiles
 };
@@ -233,17 +237,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (int kb = 0; kb < p.num_k_blocks; kb++) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
                     if (p.ts && kb == 0 && blockIdx.x == 0 && lt < 32) p.ts[lt * 8 + 0] = clock64();
+                    int bk = kb * BLOCK_K;
                     if (p.conv) {
                         const int tap = kb / p.cv_cpb, cb = kb - tap * p.cv_cpb;
-                        const int kh = tap / p.cv_k, kw = tap - kh * p.cv_k;
+                        int ax, ay;
+                        if (p.cv_ntaps) {
+                            ax = cx0 + p.cv_tox[tap]; ay = cy0 + p.cv_toy[tap];
+                            bk = (p.cv_tk[tap] * p.cv_cpb + cb) * BLOCK_K;
+                        } else {
+                            const int kh = tap / p.cv_k, kw = tap - kh * p.cv_k;
+                            ax = cx0 * p.cv_S + kw - p.cv_pad; ay = cy0 * p.cv_S + kh - p.cv_pad;
+                        }
                         mbar_arrive_expect_tx(full_bar + stage, (uint32_t)p.cv_rows * 128u + b_bytes);
-                        tma_load_4d(smem_a + (size_t)stage * a_bytes, &tmap_a, full_bar + stage, cb * BLOCK_K,
-                                    cx0 * p.cv_S + kw - p.cv_pad, cy0 * p.cv_S + kh - p.cv_pad, cn0);
+                        tma_load_4d(smem_a + (size_t)stage * a_bytes, &tmap_a, full_bar + stage, cb * BLOCK_K, ax, ay, cn0);
                     } else {
                         mbar_arrive_expect_tx(full_bar + stage, a_bytes + b_bytes);
                         tma_load_2d(smem_a + (size_t)stage * a_bytes, &tmap_a, full_bar + stage, kb * BLOCK_K, (p.dbg & 8) ? 0 : m_idx * BLOCK_M);
                     }
-                    tma_load_2d(smem_b + (size_t)stage * b_stride, &tmap_b, full_bar + stage, kb * BLOCK_K, n_idx * p.block_n);
+                    tma_load_2d(smem_b + (size_t)stage * b_stride, &tmap_b, full_bar + stage, bk, n_idx * p.block_n);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -662,12 +673,14 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, int cols, 
 
 
 // 4-D NHWC tensor [N, H, W, C] (16-bit) seen as dims {C, W, H, N}; box = {64 channels, bw, bh, bn}, 128-byte swizzle, OOB -> zeros
+struct PixelView { long long sW, sH, sN; };      // byte strides between pixels / rows / images (a parity class of a tensor)
 static int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn, int is_bf16,
-                         int es = 1) {
+                         int es = 1, const PixelView* pv = nullptr) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return dfd_set_error(DFD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    if (pv) { strides[0] = (cuuint64_t)pv->sW; strides[1] = (cuuint64_t)pv->sH; strides[2] = (cuuint64_t)pv->sN; }
     // es = traversal stride in W and H (strided convolution): a box of (b - 1) * es + 1 tensor elements delivers b of them
     cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)((bw - 1) * es + 1), (cuuint32_t)((bh - 1) * es + 1), (cuuint32_t)bn};
     cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
@@ -684,13 +697,18 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, 
 
 // Implicit-GEMM convolution on the kernel above (conv mode): y[N,H,W,Cout] = conv_{k x k, stride 1, pad (k-1)/2}(x[N,H,W,Cin]),
 // wpk = packed weight [Cout][kh][kw][Cin] (K-major rows of k*k*Cin). Cin % 64 == 0 keeps every 64-channel K block inside one tap.
+struct ConvTaps { int n, ox[9], oy[9], kidx[9]; };
 static int launch_conv_tc(const void* x, const void* wpk, void* y, int N, int Hin, int Win, int Cin, int Cout, int k, int S,
-                          int dt, double* dsum, double* dsq, const void* fin, void* stream) {
+                          int dt, double* dsum, double* dsq, const void* fin, void* stream, const ConvTaps* taps = nullptr,
+                          int outH = 0, int outW = 0, const PixelView* out_view = nullptr, int wcols = 0) {
     TcParams p;
     p.fin = (const BnFinDesc*)fin;
     p.conv = 1;
     p.cv_S = S;
-    const int H = (Hin + 2 * ((k - 1) / 2) - k) / S + 1, W = (Win + 2 * ((k - 1) / 2) - k) / S + 1;     // output extents
+    p.cv_ntaps = taps ? taps->n : 0;
+    if (taps) for (int t = 0; t < taps->n; t++) { p.cv_tox[t] = taps->ox[t]; p.cv_toy[t] = taps->oy[t]; p.cv_tk[t] = taps->kidx[t]; }
+    // output extents (explicit tap list: the caller's output grid, e.g. one parity class of the input-gradient tensor)
+    const int H = taps ? outH : (Hin + 2 * ((k - 1) / 2) - k) / S + 1, W = taps ? outW : (Win + 2 * ((k - 1) / 2) - k) / S + 1;
     // output patch of an M tile: whole rows when they fit (W <= 128), as many rows as 128 / W allows, split evenly over the
     // image height; images stacked when a whole image is smaller than half a tile (7 x 7 -> two images per tile)
     int TW = W <= 128 ? W : 128;
@@ -704,14 +722,14 @@ static int launch_conv_tc(const void* x, const void* wpk, void* y, int N, int Hi
     p.cv_tiles_x = (W + TW - 1) / TW; p.cv_tiles_y = (H + TH - 1) / TH;
     p.cv_W = W; p.cv_H = H; p.cv_N = N;
     p.cv_k = k; p.cv_pad = (k - 1) / 2; p.cv_cpb = Cin / BLOCK_K;
-    const int K = k * k * Cin;
+    const int K = taps ? wcols : k * k * Cin;          // columns of the packed weight matrix
     p.M = N * H * W; p.N = Cout; p.K = K;
     p.stat_n = Cout;
     p.is_bf16 = dt == DFD_DT_BF16;
     p.block_n = Cout <= MAX_BLOCK_N ? ((Cout + 15) / 16) * 16 : MAX_BLOCK_N;
     p.num_m_tiles = p.cv_tiles_x * p.cv_tiles_y * ((N + TN - 1) / TN);
     p.num_n_tiles = cdiv(Cout, p.block_n);
-    p.num_k_blocks = k * k * p.cv_cpb;
+    p.num_k_blocks = (taps ? taps->n : k * k) * p.cv_cpb;
     p.dsum = dsum; p.dsq = dsq;
     { const char* e = getenv("DFD_DBG"); p.dbg = e ? atoi(e) : 0; }
     p.ts = nullptr;
@@ -727,7 +745,7 @@ static int launch_conv_tc(const void* x, const void* wpk, void* y, int N, int Hi
     int rc;
     if ((rc = make_map_nhwc(&ma, x, N, Hin, Win, Cin, TW, TH, TN, p.is_bf16, S))) return rc;
     if ((rc = make_map(&mb, wpk, Cout, K, p.block_n, p.is_bf16))) return rc;
-    if ((rc = make_map_nhwc(&mc, y, N, H, W, Cout, TW, TH, TN, p.is_bf16))) return rc;
+    if ((rc = make_map_nhwc(&mc, y, N, H, W, Cout, TW, TH, TN, p.is_bf16, 1, out_view))) return rc;
     int device = 0, sms = 148;
     cudaGetDevice(&device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -874,6 +892,43 @@ int dfd_conv_tc(const void* x, const void* wpk, void* y, int N, int H, int W, in
         return dfd_set_error(DFD_ERR_ARG, "dfd_conv_tc: Cin % 64, Cout % 64, k in {1,3,5,7}, stride in {1,2}");
     if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_conv_tc: dtype");
     return launch_conv_tc(x, wpk, y, N, H, W, Cin, Cout, k, stride, dt, dsum, dsq, fin, stream);
+}
+
+// Input gradient of a 3x3, stride-2, padding-1 convolution as FOUR implicit GEMMs, one per parity class (py, px) of the input
+// pixels: dx[2a+py][2b+px] = sum over the taps whose parity matches of dY[a + oy][b + ox] * W[kh][kw] - 1, 2, 2 and 4 taps.
+// Each class is a stride-1 implicit GEMM over dY (out-of-range rows / columns arrive as TMA zeros) whose output tensor map is
+// a strided VIEW of dx (every other pixel of every other row, offset by the parity): every dx element is written exactly once,
+// no 9 x Cin column matrix and no col2im scatter. wpkD = the tap-flipped [Cin][kh'][kw'][Cout] layout of dfd_repack_weights.
+int dfd_conv_dgrad_s2_tc(const void* dy, const void* wpkD, void* dx, int N, int H, int W, int Cin, int Cout, int dt, void* stream) {
+    if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (Cin % 64) || (Cout % 64))
+        return dfd_set_error(DFD_ERR_ARG, "dfd_conv_dgrad_s2_tc: Cin % 64, Cout % 64");
+    if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_conv_dgrad_s2_tc: dtype");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    for (int py = 0; py < 2; py++) {
+        for (int px = 0; px < 2; px++) {
+            const int Ha = (H - py + 1) / 2, Wb = (W - px + 1) / 2;
+            if (Ha <= 0 || Wb <= 0) continue;
+            ConvTaps t;
+            t.n = 0;
+            for (int kh = 0; kh < 3; kh++) {
+                if (((py + 1 - kh) & 1) != 0) continue;                 // iy + 1 - kh must be even
+                for (int kw = 0; kw < 3; kw++) {
+                    if (((px + 1 - kw) & 1) != 0) continue;
+                    t.oy[t.n] = (py + 1 - kh) / 2;                      // dY row = a + (py + 1 - kh) / 2
+                    t.ox[t.n] = (px + 1 - kw) / 2;
+                    t.kidx[t.n] = 8 - (kh * 3 + kw);                    // position of tap (kh, kw) in the flipped layout
+                    t.n++;
+                }
+            }
+            PixelView pv = {2LL * Cin * 2, 2LL * W * Cin * 2, (long long)H * W * Cin * 2};
+            void* base = (char*)dx + ((size_t)py * W + px) * Cin * 2;
+            // GEMM: M = N * Ha * Wb pixels of the class, K = taps x Cout (A = dY), N = Cin
+            int rc = launch_conv_tc(dy, wpkD, base, N, Ho, Wo, Cout, Cin, 3, 1, dt, nullptr, nullptr, nullptr, stream, &t, Ha, Wb, &pv,
+                                    9 * Cout);
+            if (rc) return rc;
+        }
+    }
+    return DFD_OK;
 }
 
 // table: device array of {src [N,K], dst [pack*N, pack*K], N, K, pack}; dst(j*N+n, j'*K+k) = (j == j') ? src(n,k) : 0

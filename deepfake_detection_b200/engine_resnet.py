@@ -10,8 +10,9 @@ map, no im2col matrix in memory) in the forward pass and for the input gradient 
 materialised im2col -> tcgen05 GEMM (forward), GEMM -> col2im (input gradient). The weight gradient of every 3x3 is the
 MN-major tcgen05 wgrad GEMM, implicit too (`dfd_conv_wgrad_tc`: one pipeline stage = one patch of <= 64 output pixels of dY
 and the input box shifted by the tap). Stride-2 convolutions (the three strided 3x3 and the strided 1x1 downsample inputs) use
-the same kernels with TMA element strides {1, 2, 2, 1} in the forward pass and the weight gradient; only their INPUT
-gradient keeps GEMM + col2im. 1x1 convolutions are plain GEMMs on the NHWC tensors. BN + ReLU outputs are materialised (`dfd_bn_act`) because three consumers read them.
+the same kernels with TMA element strides {1, 2, 2, 1} in the forward pass and the weight gradient; the input gradient of a
+strided 3x3 is four parity-class implicit GEMMs (`dfd_conv_dgrad_s2_tc`) storing through strided views of dx. Only the strided
+1x1 downsample input gradient keeps GEMM + col2im (a scatter fused with the main-path add). 1x1 convolutions are plain GEMMs on the NHWC tensors. BN + ReLU outputs are materialised (`dfd_bn_act`) because three consumers read them.
 """
 import os
 import struct
@@ -242,6 +243,10 @@ def build_resnet(e):
         if implicit and stride == 1 and dx_add is None and Cin % 64 == 0 and Cout % 64 == 0:
             # input gradient = the same implicit GEMM on dY with the tap-flipped [Cin][kh'][kw'][Cout] weights
             ops = [("dfd_conv_tc", (dy, PKD(name), dx_out, N, n_h, n_w, Cout, Cin, 3, 1, dt, None, None, None))]
+        elif implicit and implicit_s2 and stride == 2 and dx_add is None and Cin % 64 == 0 and Cout % 64 == 0 and \
+                not os.environ.get("DFD_NO_IMPLICIT_S2_DGRAD"):
+            # strided input gradient: four parity-class implicit GEMMs storing through strided views of dx
+            ops = [("dfd_conv_dgrad_s2_tc", (dy, PKD(name), dx_out, N, n_h, n_w, Cin, Cout, dt))]
         else:
             ops = [gemm(dy, PKT(name), COLS, M_out, 9 * Cin, Cout),
                    ("dfd_col2im", (COLS, dx_add, dx_out, N, n_h, n_w, Cin, 3, stride, 1, dt))]

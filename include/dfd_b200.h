@@ -146,6 +146,11 @@ int dfd_conv_tc(const void* x, const void* wpk, void* y, int N, int H, int W, in
 int dfd_conv_wgrad_tc(const void* dy, const void* x, float* dW_ohwi, int N, int H, int W, int Cin, int Cout, int k, int stride,
                       int dt, void* ws, long long ws_bytes, void* stream);
 int dfd_conv_wgrad_splits(int N, int H, int W, int Cin, int Cout, int k, int stride);
+/* Input gradient of a 3x3, stride-2, padding-1 convolution (the autograd dgrad of resnet.py:195-197 with stride 2) as four
+ * implicit GEMMs, one per parity class of the input pixels (1, 2, 2 and 4 taps), each storing through a strided tensor-map
+ * view of dx: dx [N,H,W,Cin] is written exactly once, no column matrix, no col2im. dy [N,Ho,Wo,Cout]; wpkD = the tap-flipped
+ * [Cin][kh'][kw'][Cout] layout of dfd_repack_weights. Cin % 64 == 0, Cout % 64 == 0. */
+int dfd_conv_dgrad_s2_tc(const void* dy, const void* wpkD, void* dx, int N, int H, int W, int Cin, int Cout, int dt, void* stream);
 int dfd_unpack_grad(const float* g_ohwi, float* g_oihw_accum, int O, int I, int k, void* stream);
 int dfd_maxpool_fwd(const void* x, void* out, void* argmax_u8, int N, int H, int W, int C, int dt, void* stream);
 int dfd_maxpool_bwd(const void* gy, const void* argmax_u8, void* gx, int N, int H, int W, int C, int dt, void* stream);

@@ -688,6 +688,19 @@ def check_conv_implicit(N, H, W, Cin, Cout, k=3, dtype=torch.bfloat16, seed=0, s
     dy = (torch.randn(N, Ho, Wo, Cout, device="cuda", generator=g) * 0.1).to(dtype)
     ref.backward(nchw(dy.double()))
     res["dgrad_rel"], res["nan_b"] = 0.0, 0
+    if stride == 2 and k == 3:
+        dx = torch.full((N, H, W, Cin), float("nan"), device="cuda", dtype=dtype)      # every element must be written exactly once
+        _lib.call("dfd_conv_dgrad_s2_tc", P(dy), P(wpD), P(dx), N, H, W, Cin, Cout, d, st())
+        torch.cuda.synchronize()
+        res["dgrad_rel"] = relerr(nchw(dx.float()), xr.grad)
+        res["nan_b"] = int(torch.isnan(dx.float()).sum())
+        # against the GEMM + col2im formulation (same products, different summation order inside a pixel: not bit-identical)
+        dcols = torch.zeros(N * Ho * Wo, k * k * Cin, device="cuda", dtype=dtype)
+        dx2 = torch.zeros_like(dx)
+        _lib.call("dfd_gemm_tn", P(dy), P(wpT), P(dcols), N * Ho * Wo, k * k * Cin, Cout, d, None, None, None, st())
+        _lib.call("dfd_col2im", P(dcols), None, P(dx2), N, H, W, Cin, k, 2, pad, d, st())
+        torch.cuda.synchronize()
+        res["dgrad_vs_col2im"] = relerr(dx.float(), dx2.float())
     if stride == 1:
         dx = torch.full((N, H, W, Cin), float("nan"), device="cuda", dtype=dtype)
         _lib.call("dfd_conv_tc", P(dy), P(wpD), P(dx), N, H, W, Cout, Cin, k, 1, d, None, None, None, st())

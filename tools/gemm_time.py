@@ -12,7 +12,8 @@ def t(M,N,K,stats=True, reps=20):
     e1.record(); torch.cuda.synchronize()
     ms=e0.elapsed_time(e1)/reps
     print("DBG=%s M=%d N=%d K=%d stats=%s ms=%.3f GB/s=%.0f"%(os.environ.get("DFD_DBG","0"),M,N,K,stats,ms,2*(M*K+M*N)/ms/1e6))
-shapes=[(3211264,96,16),(802816,144,24),(200704,240,40),(3211264,16,96),(50176,672,112)]
+shapes=[(3211264,96,16),(802816,144,24),(200704,240,40),(3211264,16,96),(50176,672,112),
+        (802816,256,64),(802816,64,256),(200704,512,128),(50176,1024,256),(12544,2048,512)]      # + resnet50 1x1 layers
 if os.environ.get("GT_ONE"): shapes=shapes[:1]+shapes[3:4]
 for shp in shapes:
     t(*shp); t(*shp, stats=False)
