@@ -173,6 +173,9 @@ def op_flops(name, a):
         return 2 * a[4] * a[5] * a[6]
     if name in ("dfd_gemm_wgrad_mma", "dfd_gemm_wgrad"):
         return 2 * a[3] * a[4] * a[5]
+    if name == "dfd_conv1x1_dgrad_add":
+        N, H, W, Cin, Cout, S = a[3:9]
+        return 2 * N * conv_out(H, 1, S) * conv_out(W, 1, S) * Cin * Cout
     if name == "dfd_conv_dgrad_s2_tc":                     # 9 taps x Cout per 4 input pixels
         N, H, W, Cin, Cout = a[3:8]
         return 2 * N * conv_out(H, 3, 2) * conv_out(W, 3, 2) * 9 * Cin * Cout

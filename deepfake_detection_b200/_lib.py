@@ -22,6 +22,7 @@ SIGNATURES = {
     "dfd_conv_wgrad_tc": "ppp" "iiiiiiii" "pl" "p",
     "dfd_conv_wgrad_splits": "iiiiiii",
     "dfd_conv_dgrad_s2_tc": "ppp" "iiiiii" "p",
+    "dfd_conv1x1_dgrad_add": "ppp" "iiiiiii" "p",
     "dfd_blockdiag_weights": "piip",
     "dfd_gemm_tn_mma": "pppp" "lii" "i" "ppp",
     "dfd_gemm_wgrad_mma": "ppp" "lii" "i" "p",

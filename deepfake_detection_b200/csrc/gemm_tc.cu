@@ -80,6 +80,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// TMA reduction store: global (16-bit) += shared tile, element-wise add performed in L2 (round to nearest in the tensor's type)
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -176,6 +181,7 @@ struct TcParams {
     // (cv_tox[t], cv_toy[t]) against weight k-blocks (cv_tk[t] * cv_cpb + cb)
     int cv_ntaps;
     int cv_tox[9], cv_toy[9], cv_tk[9];
+    int cv_accum;                     // conv mode: the output tile is ADDED to the destination (TMA reduction store)
     int dbg;              // debug switches (DFD_DBG env): 1 = skip TMA store, 2 = skip stats pass, 4 = skip slabs, 8 = A from L2
     long long* ts;        // optional trace (DFD_TS env): CTA 0 records clock64 at 8 pipeline points for its first 32 tiles
 };
@@ -380,7 +386,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 epi_barrier(wg);
                 if (leader && !(p.dbg & 1)) {
-                    if (p.conv) tma_store_4d(&tmap_c, cbuf, n_idx * p.block_n + s * SLAB, cx0, cy0, cn0);
+                    if (p.conv && p.cv_accum) tma_reduce_add_4d(&tmap_c, cbuf, n_idx * p.block_n + s * SLAB, cx0, cy0, cn0);
+                    else if (p.conv) tma_store_4d(&tmap_c, cbuf, n_idx * p.block_n + s * SLAB, cx0, cy0, cn0);
                     else tma_store_2d(&tmap_c, cbuf, n_idx * p.block_n + s * SLAB, m_idx * BLOCK_M);
                     tma_store_commit();
                 }
@@ -700,11 +707,12 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, 
 struct ConvTaps { int n, ox[9], oy[9], kidx[9]; };
 static int launch_conv_tc(const void* x, const void* wpk, void* y, int N, int Hin, int Win, int Cin, int Cout, int k, int S,
                           int dt, double* dsum, double* dsq, const void* fin, void* stream, const ConvTaps* taps = nullptr,
-                          int outH = 0, int outW = 0, const PixelView* out_view = nullptr, int wcols = 0) {
+                          int outH = 0, int outW = 0, const PixelView* out_view = nullptr, int wcols = 0, int accum = 0) {
     TcParams p;
     p.fin = (const BnFinDesc*)fin;
     p.conv = 1;
     p.cv_S = S;
+    p.cv_accum = accum;
     p.cv_ntaps = taps ? taps->n : 0;
     if (taps) for (int t = 0; t < taps->n; t++) { p.cv_tox[t] = taps->ox[t]; p.cv_toy[t] = taps->oy[t]; p.cv_tk[t] = taps->kidx[t]; }
     // output extents (explicit tap list: the caller's output grid, e.g. one parity class of the input-gradient tensor)
@@ -929,6 +937,22 @@ int dfd_conv_dgrad_s2_tc(const void* dy, const void* wpkD, void* dx, int N, int 
         }
     }
     return DFD_OK;
+}
+
+// Input gradient of a 1x1 convolution with stride s (the downsample branch, resnet.py:249-260) ADDED into dx, which already
+// holds the main-path gradient of the block input: dx[n, s*a, s*b, :] += dY[n, a, b, :] * W. One implicit GEMM (k = 1) whose
+// output map is the stride-s pixel view of dx and whose epilogue is a TMA reduction store (bf16 / fp16 add in L2) - replaces
+// GEMM -> scratch, then col2im scatter + add (stride 2) or add_inplace (stride 1). wT = the transposed [Cin][Cout] weight.
+int dfd_conv1x1_dgrad_add(const void* dy, const void* wT, void* dx, int N, int H, int W, int Cin, int Cout, int stride, int dt,
+                          void* stream) {
+    if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (Cin % 64) || (Cout % 64) || (stride != 1 && stride != 2))
+        return dfd_set_error(DFD_ERR_ARG, "dfd_conv1x1_dgrad_add: Cin % 64, Cout % 64, stride in {1,2}");
+    if (dt != DFD_DT_BF16 && dt != DFD_DT_FP16) return dfd_set_error(DFD_ERR_ARG, "dfd_conv1x1_dgrad_add: dtype");
+    const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+    ConvTaps t;
+    t.n = 1; t.ox[0] = 0; t.oy[0] = 0; t.kidx[0] = 0;
+    PixelView pv = {(long long)stride * Cin * 2, (long long)stride * W * Cin * 2, (long long)H * W * Cin * 2};
+    return launch_conv_tc(dy, wT, dx, N, Ho, Wo, Cout, Cin, 1, 1, dt, nullptr, nullptr, nullptr, stream, &t, Ho, Wo, &pv, Cout, 1);
 }
 
 // table: device array of {src [N,K], dst [pack*N, pack*K], N, K, pack}; dst(j*N+n, j'*K+k) = (j == j') ? src(n,k) : 0

@@ -320,12 +320,21 @@ def build_resnet(e):
             bwd.append(("dfd_bn_bwd_reduce", (gm, _ptr(rec["yd"]), None, bnd.mean, bnd.rstd, N, ho * wo, b.cout, dt, bnd.bs1, bnd.bs2, BF(bnd))))
             bwd.append(bwd_finalize(bnd, M2))
             bwd.append(("dfd_bn_bwd_apply", (gm, _ptr(rec["yd"]), None, bnd.cA, bnd.cB, bnd.cC, t1, N, ho * wo, b.cout, dt)))
-            bwd.append(gemm(t1, T16(p + ".downsample.0.weight"), t2, M2, b.cin, b.cout))
+            ds_add = (implicit and implicit_s2 and b.cin % 64 == 0 and b.cout % 64 == 0 and
+                      not os.environ.get("DFD_NO_DGRAD_ADD"))
+            if ds_add:
+                # the downsample input gradient is ADDED into t3 (main-path gradient) by the GEMM's own epilogue: a TMA reduction
+                # store through the stride-s pixel view of t3 - no scratch tensor, no col2im scatter / add pass
+                bwd.append(("dfd_conv1x1_dgrad_add", (t1, T16(p + ".downsample.0.weight"), t3, N, h, w, b.cin, b.cout, b.stride, dt)))
+            else:
+                bwd.append(gemm(t1, T16(p + ".downsample.0.weight"), t2, M2, b.cin, b.cout))
             if rec["xs"] is None:      # strided 1x1: implicit weight gradient on the block input itself
                 bwd.append(e._wgrad_conv(t1, _ptr(xin), G32(p + ".downsample.0.weight"), N, h, w, b.cin, b.cout, 1, b.stride))
             else:
                 bwd.append(e._wgrad(t1, _ptr(rec["xs"]), G32(p + ".downsample.0.weight"), M2, b.cout, b.cin))
-            if b.stride == 1:
+            if ds_add:
+                new_dout = (t3, None)
+            elif b.stride == 1:
                 bwd.append(("dfd_add_inplace", (t3, t2, M1 * b.cin, dt)))
                 new_dout = (t3, None)
             else:

@@ -151,6 +151,12 @@ int dfd_conv_wgrad_splits(int N, int H, int W, int Cin, int Cout, int k, int str
  * view of dx: dx [N,H,W,Cin] is written exactly once, no column matrix, no col2im. dy [N,Ho,Wo,Cout]; wpkD = the tap-flipped
  * [Cin][kh'][kw'][Cout] layout of dfd_repack_weights. Cin % 64 == 0, Cout % 64 == 0. */
 int dfd_conv_dgrad_s2_tc(const void* dy, const void* wpkD, void* dx, int N, int H, int W, int Cin, int Cout, int dt, void* stream);
+/* Input gradient of a 1x1 convolution with stride 1 or 2 (downsample branch, resnet.py:249-260) ADDED into dx [N,H,W,Cin],
+ * which already holds the main-path gradient: dx[n, s*a, s*b, :] += dY[n,a,b,:] * W - an implicit GEMM whose output map is
+ * the stride-s pixel view of dx and whose epilogue is a TMA reduction store (16-bit add in L2). wT = transposed [Cin][Cout]
+ * weight (dfd_transpose_weights). Replaces dfd_gemm_tn + dfd_col2im / dfd_add_inplace. */
+int dfd_conv1x1_dgrad_add(const void* dy, const void* wT, void* dx, int N, int H, int W, int Cin, int Cout, int stride, int dt,
+                          void* stream);
 int dfd_unpack_grad(const float* g_ohwi, float* g_oihw_accum, int O, int I, int k, void* stream);
 int dfd_maxpool_fwd(const void* x, void* out, void* argmax_u8, int N, int H, int W, int C, int dt, void* stream);
 int dfd_maxpool_bwd(const void* gy, const void* argmax_u8, void* gx, int N, int H, int W, int C, int dt, void* stream);

@@ -728,6 +728,29 @@ def check_conv_implicit(N, H, W, Cin, Cout, k=3, dtype=torch.bfloat16, seed=0, s
     return res
 
 
+def check_conv1x1_dgrad_add(N, H, W, Cin, Cout, stride, dtype=torch.bfloat16, seed=0):
+    """dfd_conv1x1_dgrad_add (TMA reduction store through a strided view) == dfd_gemm_tn + dfd_col2im(add) bit for bit"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    dy = (torch.randn(N, Ho, Wo, Cout, device="cuda", generator=g) * 0.1).to(dtype)
+    w = (torch.randn(Cout, Cin, device="cuda", generator=g) / math.sqrt(Cin)).to(dtype)
+    wT = w.t().contiguous()                                      # [Cin][Cout]
+    main = torch.randn(N, H, W, Cin, device="cuda", generator=g).to(dtype)
+    d = DT[dtype]
+    t2 = torch.zeros(N * Ho * Wo, Cin, device="cuda", dtype=dtype)
+    ref = torch.full_like(main, float("nan"))
+    _lib.call("dfd_gemm_tn", P(dy), P(wT), P(t2), N * Ho * Wo, Cin, Cout, d, None, None, None, st())
+    _lib.call("dfd_col2im", P(t2), P(main), P(ref), N, H, W, Cin, 1, stride, 0, d, st())
+    got = main.clone()
+    _lib.call("dfd_conv1x1_dgrad_add", P(dy), P(wT), P(got), N, H, W, Cin, Cout, stride, d, st())
+    torch.cuda.synchronize()
+    exact = (dy.float().reshape(-1, Cout) @ w.float()).reshape(N, Ho, Wo, Cin)
+    full = main.float().clone()
+    full[:, ::stride, ::stride, :] += exact
+    return dict(mismatch=int((got.view(torch.int16) != ref.view(torch.int16)).sum()), rel=relerr(got.float(), full),
+                nan=int(torch.isnan(got.float()).sum()))
+
+
 def check_relu_bn_bwd_reduce(N, HW, C, dtype=torch.bfloat16, seed=0, two=False):
     """dfd_relu_bn_bwd_reduce == dfd_relu_bwd followed by dfd_bn_bwd_reduce: the masked gradient bit for bit, the sums to fp64 rounding"""
     g = torch.Generator(device="cuda").manual_seed(seed)

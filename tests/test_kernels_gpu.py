@@ -182,6 +182,13 @@ def test_conv_implicit_stride2(N, H, W, Cin, Cout, k):
     assert r["wgrad_rel"] < 1e-4 and r["wgrad_det_bitwise"] and r["wgrad_det_vs_atomic"] < 1e-5, r
 
 
+@pytest.mark.parametrize("N,H,W,Cin,Cout,stride", [(3, 56, 56, 64, 256, 1), (2, 56, 56, 256, 512, 2), (5, 14, 14, 1024, 2048, 2),
+                                                      (2, 13, 9, 64, 128, 2)])
+def test_conv1x1_dgrad_add(N, H, W, Cin, Cout, stride):
+    r = _gc().check_conv1x1_dgrad_add(N, H, W, Cin, Cout, stride)
+    assert r["nan"] == 0 and r["mismatch"] == 0 and r["rel"] < 6e-3, r
+
+
 def test_conv_implicit_fp16():
     r = _gc().check_conv_implicit(2, 14, 14, 64, 128, 3, dtype=torch.float16)
     assert r["nan"] == 0 and r["fwd_max"] < OUT16 and r["dgrad_rel"] < 6e-3 and r["vs_im2col_mismatch"] == 0, r
