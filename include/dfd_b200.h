@@ -121,7 +121,10 @@ int dfd_pad_weight(const void* src16, void* dst16, int O, int taps, int Kp, int 
 int dfd_unpad_grad(const float* g_padded, float* g_accum, int O, int taps, int Kp, void* stream);
 
 /* ---- dense k x k convolution, max-pool, ReLU tail (ResNet: resnet.py:129-136,150-175,195-260,379-382,450-468).
- *      conv = im2col -> dfd_gemm_tn; dgrad = dfd_gemm_tn -> col2im; wgrad = dfd_gemm_wgrad_mma on the im2col matrix.
+ *      Product path: the IMPLICIT GEMMs further down (dfd_conv_tc, dfd_conv_wgrad_tc, dfd_conv_dgrad_s2_tc,
+ *      dfd_conv1x1_dgrad_add) for every 3x3 and strided 1x1 convolution; the materialised formulation below (conv = im2col ->
+ *      dfd_gemm_tn; dgrad = dfd_gemm_tn -> col2im; wgrad on the im2col matrix) serves the 7x7 stem, channel counts that are
+ *      not multiples of 64, and the bit-exact cross-checks in the tests.
  *      Column order of the im2col matrix / packed weights: (kh, kw, ci). ------------------------------------------- */
 int dfd_im2col(const void* x, void* cols, int N, int H, int W, int C, int k, int stride, int pad, int dt, void* stream);
 int dfd_col2im(const void* dcols, const void* add, void* dx, int N, int H, int W, int C, int k, int stride, int pad, int dt,
