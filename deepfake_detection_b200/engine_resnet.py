@@ -53,7 +53,9 @@ def build_resnet(e):
         ar._rtable_count = len(pk_off)
         ar._derived_dirty = True
     e.wpack16, e.wpackT16, e.wpackD16 = ar.wpack16, ar.wpackT16, ar.wpackD16
-    e.gperm = torch.zeros(max([O * I * k * k for (_, O, I, k) in pk_off.values()] + [8]), dtype=torch.float32, device=dev)
+    # two regions: a BasicBlock has two 3x3 convolutions whose packed gradients wait for the block's single ordered reduce
+    gperm_max = max([O * I * k * k for (_, O, I, k) in pk_off.values()] + [8])
+    e.gperm = torch.zeros(2 * gperm_max, dtype=torch.float32, device=dev)
 
     P32 = lambda n: _ptr(e.params32, e.p_off[n][0])
     G32 = lambda n: _ptr(e.grads32, e.p_off[n][0])
@@ -235,8 +237,17 @@ def build_resnet(e):
     e.target_f = torch.zeros(N, K, dtype=torch.float32, device=dev)
 
     # ---- backward ----------------------------------------------------------------------------------------
-    def zero_gperm(numel):
-        return ("dfd_memset_async", (_ptr(e.gperm), 0, numel * 4))
+    pending_unpack = []         # (gperm region pointer, name, Cout, Cin): unpacked after the block's ordered reduce
+
+    def zero_gperm(ptr, numel):
+        return ("dfd_memset_async", (ptr, 0, numel * 4))
+
+    def flush_block(ops):
+        """ONE ordered reduce per block (every weight gradient of the block), then the packed 3x3 gradients -> OIHW arena"""
+        e._flush_reduce(ops)
+        for gp, name, Cout, Cin in pending_unpack:
+            ops.append(("dfd_unpack_grad", (gp, G32(name), Cout, Cin, 3)))
+        del pending_unpack[:]
 
     def conv3x3_bwd(name, dy, M_out, Cin, Cout, xin_t, n_h, n_w, stride, dx_out, dx_add=None):
         """dy [M_out, Cout] -> dx_out [N, n_h, n_w, Cin] (+dx_add) and the weight gradient of `name`"""
@@ -250,15 +261,19 @@ def build_resnet(e):
         else:
             ops = [gemm(dy, PKT(name), COLS, M_out, 9 * Cin, Cout),
                    ("dfd_col2im", (COLS, dx_add, dx_out, N, n_h, n_w, Cin, 3, stride, 1, dt))]
+        gp = _ptr(e.gperm, len(pending_unpack) * gperm_max)         # this block's next free region
+        assert len(pending_unpack) < 2
         if implicit and implicit_wgrad and (stride == 1 or implicit_s2) and Cin % 64 == 0 and e._wgrad_name == "dfd_gemm_wgrad":
-            ops += [zero_gperm(Cout * 9 * Cin),
-                    e._wgrad_conv(dy, _ptr(xin_t), _ptr(e.gperm), N, n_h, n_w, Cin, Cout, 3, stride)]
+            ops += [zero_gperm(gp, Cout * 9 * Cin),
+                    e._wgrad_conv(dy, _ptr(xin_t), gp, N, n_h, n_w, Cin, Cout, 3, stride)]
         else:
             ops += [("dfd_im2col", (_ptr(xin_t), COLS, N, n_h, n_w, Cin, 3, stride, 1, dt)),
-                    zero_gperm(Cout * 9 * Cin),
-                    e._wgrad(dy, COLS, _ptr(e.gperm), M_out, Cout, 9 * Cin)]
-        e._flush_reduce(ops)             # the permuted gradient must be complete before it is unpacked into the arena
-        ops.append(("dfd_unpack_grad", (_ptr(e.gperm), G32(name), Cout, Cin, 3)))
+                    zero_gperm(gp, Cout * 9 * Cin),
+                    e._wgrad(dy, COLS, gp, M_out, Cout, 9 * Cin)]
+        if os.environ.get("DFD_NONDET"):
+            ops.append(("dfd_unpack_grad", (gp, G32(name), Cout, Cin, 3)))       # atomics: complete when the kernel is
+        else:
+            pending_unpack.append((gp, name, Cout, Cin))     # complete after the block's ordered reduce (flush_block)
         return ops
 
     bwd.append(("dfd_head_bwd", (_ptr(e.dlogits), _ptr(e.pooled), P32("fc.weight"), G32("fc.weight"), G32("fc.bias"),
@@ -347,7 +362,7 @@ def build_resnet(e):
         else:
             bwd.append(("dfd_add_inplace", (t3, gm, M1 * b.cin, dt)))
             new_dout = (t3, None)
-        e._flush_reduce(bwd)
+        flush_block(bwd)
         dout, dout2 = new_dout
     # stem: maxpool -> relu/bn1 -> conv1 wgrad
     if dout2 is not None:
