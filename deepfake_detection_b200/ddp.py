@@ -207,6 +207,10 @@ class GradReducer:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
             t.mul_(1.0 / self.world)
 
+    def reduce_all(self):
+        """one mean all-reduce over the whole gradient arena on the current stream (split-graph mode of the Trainer)"""
+        self._mean(self.arena.grads32)
+
     def backward_and_reduce(self, engine=None):
         """Runs `engine`'s backward plan (the one whose forward just ran) on the current stream, launching each bucket's
         mean all-reduce on the side stream as soon as the ops that produce it have been enqueued; joins at the end."""
